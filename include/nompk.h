@@ -1,0 +1,125 @@
+/*
+ * nompk.h -- C ABI of libnompk, the hand-written sm_100a kernel library that sits under
+ * libnomp's CUDA backend.
+ *
+ * libnomp (the reference, nomp-org/libnomp) has no hand-written device code: every kernel is a
+ * string printed by loopy and compiled by NVRTC (reference backends/unified-cuda-hip-impl.h:96-141,
+ * launched at :143-158).  This library is what replaces that generated code for the three loop
+ * families that dominate spectral-element runs.  The bridge (libnomp_b200/python/nomp_bridge) recognises
+ * the family at nomp_jit() time and the backend's knl_run() (reference include/nomp-impl.h:213-237)
+ * calls one of the entry points below instead of cuLaunchKernel().
+ *
+ * Conventions
+ *   - plain C: pointers are DEVICE pointers unless the name ends in _host; sizes are element counts;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function is asynchronous on `stream` and returns 0 on success, or a negative NOMPK_E*
+ *     code; nompk_last_error() gives the text of the last failure on the calling thread;
+ *   - no entry point allocates device memory; workspaces are caller-owned.
+ */
+#ifndef NOMPK_H_
+#define NOMPK_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOMPK_VERSION 100
+
+/* error codes */
+#define NOMPK_OK 0
+#define NOMPK_EINVAL (-1)   /* bad argument (unsupported dtype/op/n, NULL pointer, ...) */
+#define NOMPK_ECUDA (-2)    /* a CUDA runtime call or a launch failed */
+#define NOMPK_EUNSUPPORTED (-3)
+
+/* Scalar element types.  These are the six types of the reference test matrix
+ * (reference tests/nomp-generate-tests.h:1-49): int, unsigned, long, unsigned long, float, double. */
+typedef enum {
+  NOMPK_I32 = 0,
+  NOMPK_U32 = 1,
+  NOMPK_I64 = 2,
+  NOMPK_U64 = 3,
+  NOMPK_F32 = 4,
+  NOMPK_F64 = 5
+} nompk_dtype_t;
+
+/* Elementwise map family.  Each op is one canonical loop body, written the way the reference tests
+ * spell it (reference tests/nomp-api-200-impl.h:36-40, :64-68, :92-96; tests/nomp-api-600-impl.h:36-40).
+ * y is read-modify-write, x and z are read-only, alpha/beta are HOST scalars of the element type. */
+typedef enum {
+  NOMPK_MAP_ADD   = 0, /* y[i] = y[i] + x[i]                 "a[i] += b[i]"          */
+  NOMPK_MAP_SUB   = 1, /* y[i] = y[i] - x[i]                 "a[i] -= b[i]"          */
+  NOMPK_MAP_MUL   = 2, /* y[i] = y[i] * x[i]                 "a[i] *= b[i]"          */
+  NOMPK_MAP_AXPY  = 3, /* y[i] = y[i] + alpha * x[i]         "a[i] += alpha * b[i]"  */
+  NOMPK_MAP_XPAY  = 4, /* y[i] = x[i] + alpha * y[i]         "p[i] = r[i] + beta * p[i]" */
+  NOMPK_MAP_AXPBY = 5, /* y[i] = alpha * x[i] + beta * y[i]                          */
+  NOMPK_MAP_SCALE = 6, /* y[i] = alpha * y[i]                                        */
+  NOMPK_MAP_COPY  = 7, /* y[i] = x[i]                                                */
+  NOMPK_MAP_FILL  = 8, /* y[i] = alpha                                               */
+  NOMPK_MAP_ADD3  = 9, /* y[i] = x[i] + z[i]                 "c[i] = a[i] + b[i]"    */
+  NOMPK_MAP_OP_COUNT
+} nompk_map_op_t;
+
+/* Reduction family.  SUM and PROD are the reference's two operators (reference src/reduction.c:3-22,
+ * include/nomp-impl.h:99-102); MIN and MAX are additions named by the north star.  With y == NULL the
+ * reduced value is x[i]; with y != NULL it is x[i] * y[i] (dot product for SUM). */
+typedef enum {
+  NOMPK_RED_SUM  = 0,
+  NOMPK_RED_PROD = 1,
+  NOMPK_RED_MIN  = 2,
+  NOMPK_RED_MAX  = 3,
+  NOMPK_RED_OP_COUNT
+} nompk_red_op_t;
+
+int nompk_version(void);
+const char *nompk_last_error(void);
+size_t nompk_dtype_size(nompk_dtype_t dt);
+
+/* y <- op(y, x, z, alpha, beta) over n elements.  Unused operands may be NULL.
+ * Replaces: the loopy-generated one-element-per-thread map kernel launched by
+ * reference backends/unified-cuda-hip-impl.h:143-158 for the loops of tests 200/205/600.
+ * fp results are bit-identical to the serial C loop compiled without FMA contraction. */
+int nompk_map(nompk_map_op_t op, nompk_dtype_t dt, size_t n, void *y, const void *x, const void *z,
+              const void *alpha_host, const void *beta_host, void *stream);
+
+/* Bytes of device workspace nompk_reduce() needs (partials + a ticket counter).  The workspace must be
+ * zero-filled once before first use; the kernel leaves it ready for the next call on the same stream. */
+size_t nompk_reduce_workspace_bytes(void);
+
+/* result[0] <- reduce_op over i of (y ? x[i]*y[i] : x[i]),  i in [0,n).  n == 0 writes the identity.
+ * Single pass: per-thread accumulators, warp-shuffle tree, one partial per block, and the last block to
+ * take a ticket folds the partials in block order (deterministic run to run).  `result` is a device
+ * pointer (8-byte aligned); if result_host_mapped != NULL the same value is also stored through that
+ * pointer (device address of pinned, mapped host memory), so the host needs no D2H copy.
+ * Replaces: loopy's per-block tree (reference python/reduction.py:30-134) + the D2H of all partials and
+ * the serial host loop in reference src/reduction.c:33-88. */
+int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y,
+                 void *result, void *result_host_mapped, void *workspace, void *stream);
+
+/* Local Poisson operator on E hexahedral spectral elements with n = N+1 points per direction, fp64:
+ *   w_e = D^T_r (g1 Dr u + g2 Ds u + g3 Dt u) + D^T_s (g2 Dr u + g4 Ds u + g5 Dt u)
+ *       + D^T_t (g3 Dr u + g5 Ds u + g6 Dt u)                         (Nekbone ax_e / CEED BK5 form)
+ * Layouts: u, w  double[E][n][n][n]  (i fastest);  g  double[E][6][n][n][n]  (g1..g6 = G11,G12,G13,G22,G23,G33);
+ *          D  double[n][n] row-major, D[a][l] = d phi_l / dx at node a.
+ * The reference has no such operator (reference tests/sem.py:10-36 only tags loops); the canonical kernel
+ * string that the bridge maps onto this entry point is in libnomp_b200/python/nomp_bridge/families.py.
+ * Hand-written for n in {8, 10} (N = 7, 9); other n return NOMPK_EUNSUPPORTED and the bridge falls back to
+ * NVRTC.  D is staged into __constant__ memory on `stream` unless NOMPK_AX_D_CACHED is set, which asserts
+ * that the previous call with the same n used identical D values. */
+#define NOMPK_AX_D_CACHED 1
+int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
+                 unsigned flags, void *stream);
+int nompk_ax_supported(int n);
+/* Variant selector for benchmarking/profiling (0 = default). */
+int nompk_ax_set_variant(int variant);
+
+/* Launch bookkeeping used by bench.py's "gpu_launches" field: number of kernels this library has
+ * launched since load (monotonic, process-wide). */
+unsigned long long nompk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NOMPK_H_ */

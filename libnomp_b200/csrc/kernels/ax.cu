@@ -1,0 +1,394 @@
+// Spectral-element local Poisson operator  w = A_L u  on (N+1)^3 hexahedral elements, fp64 (Nekbone ax_e /
+// CEED BK5 form; definition in include/nompk.h and SURVEY.md 8(a-17)).  Not present in the reference
+// (reference tests/sem.py:10-36 only tags loops; the structural precursor is the element/dof kernel of
+// reference tests/nomp-api-400-impl.h:254-291 with one block per element and private temporaries).
+//
+// Roofline: 64 algorithmic B/DOF (u 8 + six geometric factors 48 + w 8; D is 8 n^2 bytes, constant) against
+// 12n+15 flop/DOF (111 at n = 8)  ->  1.7 flop/B, HBM-bound on B200 (fp64 ridge ~5 flop/B).  At the measured
+// copy bandwidth one SM has ~2.8 clocks per DOF, which allows ~350 B/DOF of shared-memory traffic and ~177
+// DFMA/DOF; the design below needs ~120 B/DOF and ~57 DFMA/DOF.
+//
+// Design
+//   * n even.  A "work item" is a PAIR of adjacent-i lines of n points; an element has T = n^2/2 items per
+//     direction, one item per lane.  n = 8: T = 32, one WARP per element, no block-level barrier at all
+//     (__syncwarp only).  n = 10: T = 50, two warps per element and a 64-thread named barrier.
+//   * Every global access is a 128-bit coalesced LDG/STG (a pair of adjacent i); a warp instruction moves 512
+//     contiguous bytes.  The six geometric factors (75 % of the traffic) go straight from HBM to registers and
+//     never touch shared memory; loads for slab k+kGeoAhead are in flight while slab k is consumed, and the next
+//     element's 28 KB are pulled into L2 with one bulk prefetch so those loads find their lines there.
+//   * D lives in __constant__ memory.  All contractions are fully unrolled, so every DFMA takes its D entry
+//     as a constant-bank operand: no register, no shared-memory read and no load instruction for D.
+//   * The three 1-D contractions (and their transposes) are done by the lane that owns the whole line in
+//     registers: 2 x n inputs -> 2 x n outputs, n^2 DFMAs each, 2n independent accumulation chains.  Between
+//     directions the data is transposed through three n^3 shared-memory buffers using only LDS.128/STS.128;
+//     the buffer layout (slab stride + XOR swizzle, tools/check_banks.py) makes all three access patterns
+//     bank-conflict-free for n = 8.
+//   * FP64 FMA on the CUDA cores; tensor cores are not used (the kernel is HBM-bound).
+#include <type_traits>
+#include <utility>
+
+#include "nompk_common.cuh"
+
+// D[a][l] at nompk_ax_cD[a * n + l].  C linkage: the kernel reads it through inline PTX by symbol name.
+extern "C" {
+__constant__ double nompk_ax_cD[12 * 12];
+}
+
+namespace nompk {
+namespace {
+
+
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory layout of one n^3 buffer, in 16-byte chunks (one chunk = two adjacent-i doubles).
+// ---------------------------------------------------------------------------------------------------
+template <int N> struct Layout {
+  static constexpr int NP = N / 2;  // chunks per i-line
+  static constexpr int SK = (N == 8) ? 36 : (N == 10) ? 53 : (N == 6) ? 19 : (N == 12) ? 78 : N * NP + 1;
+  static constexpr int kChunks = N * SK;
+  static constexpr int T = N * N / 2;              // work items per element and direction
+  static constexpr int WPE = (T + 31) / 32;        // warps per element
+  static constexpr int LPE = 32 * WPE;             // lanes per element
+  __device__ static __forceinline__ int at(int k, int j, int p) {
+    if constexpr (N == 8) return k * SK + j * NP + (p ^ ((j >> 1) & 3));
+    else return k * SK + j * NP + p;
+  }
+};
+
+__device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
+
+__device__ __forceinline__ double2 ldg2_stream(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int LPE> __device__ __forceinline__ void element_sync(int el_in_blk) {
+  if constexpr (LPE == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(el_in_blk + 1), "n"(LPE) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D entries as instruction operands.
+// In uniform control flow ptxas serves a __constant__ read with LDCU (uniform datapath) and feeds the DFMA from
+// the uniform register: a D entry costs no vector register and no LSU slot.  Left alone, though, both NVVM and
+// ptxas treat the n^2 reads as loop invariants, hoist them out of the element loop and pin 2 n^2 VECTOR registers
+// for the whole kernel (R2UR before every DFMA, heavy spilling).  So every stage indexes D with its own
+// "zero" that is derived from the loop counter (eb >> 56..62: always 0, but not provably so): the reads become
+// loop-variant, stay next to their DFMAs as `LDCU.64 URx, c[3][URz + imm]`, and are not merged across stages.
+// ---------------------------------------------------------------------------------------------------
+template <int IDX> __device__ __forceinline__ double ld_D(int z) { return nompk_ax_cD[IDX + z]; }
+
+template <int... Is, typename F>
+__device__ __forceinline__ void static_for(std::integer_sequence<int, Is...>, F &&f) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+
+// M(a, l) = D[a][l] (TRANS = false) or D[l][a] (TRANS = true)
+template <int N, bool TRANS, int A, int L_> struct DIdx {
+  static constexpr int value = TRANS ? L_ * N + A : A * N + L_;
+};
+
+// s += sum_l M(A, l) * in[l], for a PAIR of lines packed as double2 (same D entry for both).
+template <int N, bool TRANS, int A>
+__device__ __forceinline__ double2 dot_pair(const double2 (&in)[N], double2 s, int z) {
+  static_for(std::make_integer_sequence<int, N>{}, [&](auto Lc) {
+    constexpr int l = decltype(Lc)::value;
+    const double d = ld_D<DIdx<N, TRANS, A, l>::value>(z);
+    s.x = fma(d, in[l].x, s.x);
+    s.y = fma(d, in[l].y, s.y);
+  });
+  return s;
+}
+
+// Two i-lines held as chunks: v0[c], v1[c] = points (2c, 2c+1) of row 0 / row 1.  Returns output points
+// (2C, 2C+1) of both rows.
+template <int N, bool TRANS, int C>
+__device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const double2 (&v1)[N / 2], double2 &o0,
+                                         double2 &o1, int z) {
+  double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+  static_for(std::make_integer_sequence<int, N / 2>{}, [&](auto Cc) {
+    constexpr int c = decltype(Cc)::value;
+    {
+      const double d0 = ld_D<DIdx<N, TRANS, 2 * C, 2 * c>::value>(z);
+      const double d1 = ld_D<DIdx<N, TRANS, 2 * C + 1, 2 * c>::value>(z);
+      a0.x = fma(d0, v0[c].x, a0.x);
+      a1.x = fma(d0, v1[c].x, a1.x);
+      a0.y = fma(d1, v0[c].x, a0.y);
+      a1.y = fma(d1, v1[c].x, a1.y);
+    }
+    {
+      const double d0 = ld_D<DIdx<N, TRANS, 2 * C, 2 * c + 1>::value>(z);
+      const double d1 = ld_D<DIdx<N, TRANS, 2 * C + 1, 2 * c + 1>::value>(z);
+      a0.x = fma(d0, v0[c].y, a0.x);
+      a1.x = fma(d0, v1[c].y, a1.x);
+      a0.y = fma(d1, v0[c].y, a0.y);
+      a1.y = fma(d1, v1[c].y, a1.y);
+    }
+  });
+  o0 = a0;
+  o1 = a1;
+}
+
+// kGeoAhead: how many k-slabs of geometric factors are in flight in registers ahead of their use.
+// kPrefetchL2: pull the next element this warp group will process into L2 while working on the current one.
+//
+// Control flow is kept CTA-uniform on purpose: the element loop depends only on blockIdx; lanes beyond the T work
+// items of an element (n = 10: 14 of 64) and elements beyond E in the last group do not branch, they mirror
+// the last valid item / element and write the same values to the same addresses.  (Divergent regions would make
+// ptxas drop the uniform-register D operands and issue one vector LDC.64 per DFMA.)
+template <int N, int EPB, int kGeoAhead, bool kPrefetchL2, bool kStreamLoads, int kMinBlocks>
+__global__ void __launch_bounds__(EPB *Layout<N>::LPE, kMinBlocks)
+ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E) {
+  using L = Layout<N>;
+  using SeqN = std::make_integer_sequence<int, N>;
+  using SeqNP = std::make_integer_sequence<int, N / 2>;
+  constexpr int NP = L::NP, T = L::T, LPE = L::LPE;
+  constexpr int N3 = N * N * N;
+  constexpr int SLAB2 = N * NP;  // double2 per k-slab in global memory
+  extern __shared__ double2 smem[];
+
+  const int el_in_blk = threadIdx.x / LPE;
+  const int t = threadIdx.x % LPE;
+  const int tt = t < T ? t : T - 1;
+  // k-column item: (p, j);  j-line item: (p, k) -- the same split of t.
+  const int p = tt % NP, q = tt / NP;
+  // i-line items: rows r0 = 2t and r0 + 1 (same k, adjacent j).
+  const int rk = (2 * tt) / N, rj = (2 * tt) % N;
+
+  double2 *B0 = smem + (size_t)el_in_blk * 3 * L::kChunks;
+  double2 *B1 = B0 + L::kChunks;
+  double2 *B2 = B1 + L::kChunks;
+
+  const size_t estride = (size_t)gridDim.x * EPB;
+  for (size_t eb = (size_t)blockIdx.x * EPB; eb < E; eb += estride) {
+    const int z1 = (int)(eb >> 62), z2 = (int)(eb >> 61), z3 = (int)(eb >> 60), z5 = (int)(eb >> 59),
+              z6 = (int)(eb >> 58), z7 = (int)(eb >> 57);  // all zero, see ld_D
+    size_t e = eb + el_in_blk;
+    e = e < E ? e : E - 1;
+    const double2 *ue = reinterpret_cast<const double2 *>(u + e * N3) + q * NP + p;
+    const double2 *ge = reinterpret_cast<const double2 *>(g + e * 6 * N3) + q * NP + p;
+    double2 *we = reinterpret_cast<double2 *>(w + e * N3) + q * NP + p;
+
+    if constexpr (kPrefetchL2) {
+      const size_t en = e + estride;
+      if (t == 0 && en < E) {
+        prefetch_l2_bulk(u + en * N3, N3 * 8);
+        prefetch_l2_bulk(g + en * 6 * N3, 6 * N3 * 8);
+      }
+    }
+
+    // ---- S0: u k-column pair -> registers and B0 -----------------------------------------------------
+    double2 col[N];  // u column, later ut, later wt
+    double2 gq[kGeoAhead][6];
+#pragma unroll
+    for (int k = 0; k < N; k++) col[k] = kStreamLoads ? ldg2_stream(ue + k * SLAB2) : ldg2(ue + k * SLAB2);
+    // first slabs of geometric factors: in flight during S1..S3
+#pragma unroll
+    for (int a = 0; a < kGeoAhead; a++)
+#pragma unroll
+      for (int f = 0; f < 6; f++)
+        gq[a][f] = kStreamLoads ? ldg2_stream(ge + f * (N3 / 2) + a * SLAB2) : ldg2(ge + f * (N3 / 2) + a * SLAB2);
+#pragma unroll
+    for (int k = 0; k < N; k++) B0[L::at(k, q, p)] = col[k];
+    // ---- S1: ut = D_t u along the k-column, in registers ---------------------------------------------
+    {
+      double2 ut[N];
+      static_for(SeqN{}, [&](auto A) {
+        constexpr int a = decltype(A)::value;
+        ut[a] = dot_pair<N, false, a>(col, make_double2(0.0, 0.0), z1);
+      });
+#pragma unroll
+      for (int k = 0; k < N; k++) col[k] = ut[k];
+    }
+    element_sync<LPE>(el_in_blk);
+
+    // ---- S2: ur = D_r u on two i-lines -> B1 ----------------------------------------------------------
+    {
+      double2 v0[NP], v1[NP];
+#pragma unroll
+      for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
+      static_for(SeqNP{}, [&](auto C) {
+        constexpr int c = decltype(C)::value;
+        double2 o0, o1;
+        dot_rows<N, false, c>(v0, v1, o0, o1, z2);
+        B1[L::at(rk, rj, c)] = o0;
+        B1[L::at(rk, rj + 1, c)] = o1;
+      });
+    }
+    // ---- S3: us = D_s u on a j-line pair (p, k = q) -> B2 ---------------------------------------------
+    {
+      double2 in[N];
+#pragma unroll
+      for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
+      static_for(SeqN{}, [&](auto A) {
+        constexpr int j = decltype(A)::value;
+        B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
+      });
+    }
+    element_sync<LPE>(el_in_blk);
+
+    // ---- S4: geometric factors at the k-column (p, j = q); wr -> B1, ws -> B2, wt -> registers ---------
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const int slot = k % kGeoAhead;
+      double2 gk[6];
+#pragma unroll
+      for (int f = 0; f < 6; f++) gk[f] = gq[slot][f];
+      if (k + kGeoAhead < N) {
+#pragma unroll
+        for (int f = 0; f < 6; f++)
+          gq[slot][f] = kStreamLoads ? ldg2_stream(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2)
+                                     : ldg2(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2);
+      }
+      const int a = L::at(k, q, p);
+      const double2 ur = B1[a], us = B2[a], ut = col[k];
+      double2 wr, ws, wt;
+      wr.x = fma(gk[0].x, ur.x, fma(gk[1].x, us.x, gk[2].x * ut.x));
+      wr.y = fma(gk[0].y, ur.y, fma(gk[1].y, us.y, gk[2].y * ut.y));
+      ws.x = fma(gk[1].x, ur.x, fma(gk[3].x, us.x, gk[4].x * ut.x));
+      ws.y = fma(gk[1].y, ur.y, fma(gk[3].y, us.y, gk[4].y * ut.y));
+      wt.x = fma(gk[2].x, ur.x, fma(gk[4].x, us.x, gk[5].x * ut.x));
+      wt.y = fma(gk[2].y, ur.y, fma(gk[4].y, us.y, gk[5].y * ut.y));
+      B1[a] = wr;
+      B2[a] = ws;
+      col[k] = wt;
+    }
+    // ---- S5: w = D_t^T wt along the k-column, in registers --------------------------------------------
+    double2 wacc[N];
+    static_for(SeqN{}, [&](auto A) {
+      constexpr int a = decltype(A)::value;
+      wacc[a] = dot_pair<N, true, a>(col, make_double2(0.0, 0.0), z5);
+    });
+    element_sync<LPE>(el_in_blk);
+
+    // ---- S6: D_r^T wr on two i-lines: B1 -> B0 ----------------------------------------------------------
+    {
+      double2 v0[NP], v1[NP];
+#pragma unroll
+      for (int c = 0; c < NP; c++) v0[c] = B1[L::at(rk, rj, c)], v1[c] = B1[L::at(rk, rj + 1, c)];
+      static_for(SeqNP{}, [&](auto C) {
+        constexpr int c = decltype(C)::value;
+        double2 o0, o1;
+        dot_rows<N, true, c>(v0, v1, o0, o1, z6);
+        B0[L::at(rk, rj, c)] = o0;
+        B0[L::at(rk, rj + 1, c)] = o1;
+      });
+    }
+    element_sync<LPE>(el_in_blk);
+
+    // ---- S7: + D_s^T ws on the j-line pair (p, k = q): B2, B0 -> B0 -------------------------------------
+    {
+      double2 in[N];
+#pragma unroll
+      for (int l = 0; l < N; l++) in[l] = B2[L::at(q, l, p)];
+      static_for(SeqN{}, [&](auto A) {
+        constexpr int j = decltype(A)::value;
+        const int a = L::at(q, j, p);
+        B0[a] = dot_pair<N, true, j>(in, B0[a], z7);
+      });
+    }
+    element_sync<LPE>(el_in_blk);
+
+    // ---- S8: add the r/s part to the k-column and store w ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double2 rs = B0[L::at(k, q, p)];
+      double2 o;
+      o.x = wacc[k].x + rs.x;
+      o.y = wacc[k].y + rs.y;
+      we[k * SLAB2] = o;
+    }
+    // No barrier needed here: the next iteration's S0 writes exactly the B0 chunks this lane just read.
+  }
+}
+
+struct AxVariant {
+  int epb, geo_ahead, prefetch_l2, stream_loads, min_blocks;
+};
+
+int g_variant = 0;
+
+template <int N, int EPB, int GA, bool PF, bool ST, int MB>
+int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream) {
+  using L = Layout<N>;
+  auto kern = ax_kernel<N, EPB, GA, PF, ST, MB>;
+  const size_t smem = (size_t)EPB * 3 * L::kChunks * sizeof(double2);
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  if (!configured) {
+    NOMPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NOMPK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, EPB * L::LPE, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    configured = true;
+  }
+  size_t blocks = (E + EPB - 1) / EPB;
+  const size_t cap = (size_t)sm_count() * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, EPB * L::LPE, smem, stream>>>(u, g, w, E);
+  NOMPK_LAUNCH_CHECK("ax_kernel");
+  return NOMPK_OK;
+}
+
+template <int N> int dispatch_ax(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
+  // CTA = EPB0 elements.  MB128 / MB168 = resident CTAs per SM that cap the kernel at 128 / 168 registers.
+  constexpr int EPB0 = 128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1;
+  constexpr int kThreads = EPB0 * Layout<N>::LPE;
+  constexpr int MB128 = 65536 / (128 * kThreads), MB168 = 65536 / (168 * kThreads);
+  // Variants are kept for profiling (bench/profile scripts sweep them); 0 is the production choice.
+  switch (variant) {
+  default:
+  case 0: return launch_ax<N, EPB0, 2, true, false, MB128>(E, u, g, w, s);
+  case 1: return launch_ax<N, EPB0, 2, false, false, MB128>(E, u, g, w, s);
+  case 2: return launch_ax<N, EPB0, 1, true, false, MB128>(E, u, g, w, s);
+  case 3: return launch_ax<N, EPB0, 2, true, true, MB128>(E, u, g, w, s);
+  case 4: return launch_ax<N, EPB0, 2, true, false, MB168>(E, u, g, w, s);
+  case 5: return launch_ax<N, EPB0, 4, true, false, MB168>(E, u, g, w, s);
+  case 6: return launch_ax<N, EPB0, 2, true, false, 1>(E, u, g, w, s);
+  }
+}
+
+}  // namespace
+}  // namespace nompk
+
+extern "C" int nompk_ax_supported(int n) { return n == 8 || n == 10 || n == 6 || n == 12; }
+
+extern "C" int nompk_ax_set_variant(int variant) {
+  nompk::g_variant = variant;
+  return NOMPK_OK;
+}
+
+extern "C" int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
+                            unsigned flags, void *stream_) {
+  using namespace nompk;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!nompk_ax_supported(n)) {
+    set_error("nompk_ax_f64: n = %d has no hand-written kernel (supported: 6, 8, 10, 12)", n);
+    return NOMPK_EUNSUPPORTED;
+  }
+  if (E == 0) return NOMPK_OK;
+  if (!u || !g || !D || !w) {
+    set_error("nompk_ax_f64: NULL operand");
+    return NOMPK_EINVAL;
+  }
+  if (!is_aligned16(u) || !is_aligned16(g) || !is_aligned16(w)) {
+    set_error("nompk_ax_f64: u, g and w must be 16-byte aligned");
+    return NOMPK_EINVAL;
+  }
+  if (!(flags & NOMPK_AX_D_CACHED)) {
+    NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+  }
+  switch (n) {
+  case 6: return dispatch_ax<6>(g_variant, E, u, g, w, stream);
+  case 8: return dispatch_ax<8>(g_variant, E, u, g, w, stream);
+  case 10: return dispatch_ax<10>(g_variant, E, u, g, w, stream);
+  case 12: return dispatch_ax<12>(g_variant, E, u, g, w, stream);
+  }
+  return NOMPK_EUNSUPPORTED;
+}

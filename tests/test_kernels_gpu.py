@@ -1,0 +1,252 @@
+"""Parity of the hand-written sm_100a kernels (libnompk.so, called through the C ABI of include/nompk.h)
+against the CPU oracle (oracle/nomp_oracle.c) on the same seeded inputs.
+
+Bars: bit-exact for maps (all dtypes), integer reductions and exact-data (Set X) fp64 reductions / Ax;
+1e-12 relative against the compensated / extended-precision oracle for random fp64 data (Set R).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from libnomp_b200 import capi  # noqa: E402
+from oracle import ffi  # noqa: E402
+
+NP = ffi.NP_DTYPES
+TORCH_DT = {capi.I32: torch.int32, capi.U32: torch.int32, capi.I64: torch.int64, capi.U64: torch.int64,
+            capi.F32: torch.float32, capi.F64: torch.float64}
+
+
+def dev(a: np.ndarray):
+    """numpy -> device tensor holding the same bytes (unsigned types travel as their signed twin)."""
+    signed = {np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}.get(a.dtype)
+    t = torch.from_numpy(a.view(signed) if signed else a).cuda()
+    return t
+
+
+def host(t, npdt):
+    return t.cpu().numpy().view(npdt)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rand_array(dtype, n, seed):
+    rng = np.random.default_rng(seed)
+    npdt = NP[dtype]
+    if dtype in (capi.F32, capi.F64):
+        return rng.uniform(0.5, 1.5, n).astype(npdt)
+    info = np.iinfo(npdt)
+    return rng.integers(info.min, info.max, n, dtype=npdt, endpoint=True)
+
+
+MAP_OPS = [capi.MAP_ADD, capi.MAP_SUB, capi.MAP_MUL, capi.MAP_AXPY, capi.MAP_XPAY, capi.MAP_AXPBY, capi.MAP_SCALE,
+           capi.MAP_COPY, capi.MAP_FILL, capi.MAP_ADD3]
+
+
+@pytest.mark.parametrize("dtype", [capi.I32, capi.U32, capi.I64, capi.U64, capi.F32, capi.F64])
+@pytest.mark.parametrize("n", [0, 1, 10, 50, 70, 1023, 4099, (1 << 20) + 3])
+def test_map_bit_exact(dtype, n):
+    lib = capi.nompk()
+    npdt = NP[dtype]
+    for op in MAP_OPS:
+        y = rand_array(dtype, n, 1 + op)
+        x = rand_array(dtype, n, 100 + op)
+        z = rand_array(dtype, n, 200 + op)
+        alpha = npdt(3) if dtype not in (capi.F32, capi.F64) else npdt(0.37)
+        beta = npdt(5) if dtype not in (capi.F32, capi.F64) else npdt(-1.25)
+        want = ffi.map_(op, dtype, y.copy(), x, z, alpha, beta)
+        ty, tx, tz = dev(y), dev(x), dev(z)
+        a, b = np.array([alpha], npdt), np.array([beta], npdt)
+        rc = lib.nompk_map(op, dtype, n, ty.data_ptr(), tx.data_ptr(), tz.data_ptr(), a.ctypes.data, b.ctypes.data,
+                           stream())
+        capi.nompk_check(rc, "nompk_map")
+        got = host(ty, npdt)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), f"op {op} dtype {dtype} n {n}"
+
+
+def test_map_misaligned_operands():
+    """Sub-range mappings give pointers that are only element-aligned: the scalar path must agree too."""
+    lib = capi.nompk()
+    n = 5000
+    y = rand_array(capi.F64, n + 1, 3)
+    x = rand_array(capi.F64, n + 1, 4)
+    want = ffi.map_(capi.MAP_ADD, capi.F64, y[1:].copy(), x[1:].copy())
+    ty, tx = dev(y), dev(x)
+    rc = lib.nompk_map(capi.MAP_ADD, capi.F64, n, ty.data_ptr() + 8, tx.data_ptr() + 8, None, None, None, stream())
+    capi.nompk_check(rc)
+    assert np.array_equal(host(ty, np.float64)[1:], want)
+    assert host(ty, np.float64)[0] == y[0]
+
+
+def _reduce(op, dtype, x, y=None, mapped=False):
+    lib = capi.nompk()
+    npdt = NP[dtype]
+    ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.int64, device="cuda")
+    tx = dev(x)
+    ty = dev(y) if y is not None else None
+    rc = lib.nompk_reduce(op, dtype, x.size, tx.data_ptr(), ty.data_ptr() if ty is not None else None,
+                          res.data_ptr(), None, ws.data_ptr(), stream())
+    capi.nompk_check(rc, "nompk_reduce")
+    first = res.cpu().numpy().view(npdt)[0]
+    # second launch on the same workspace: the ticket must have been reset by the kernel
+    rc = lib.nompk_reduce(op, dtype, x.size, tx.data_ptr(), ty.data_ptr() if ty is not None else None,
+                          res.data_ptr(), None, ws.data_ptr(), stream())
+    capi.nompk_check(rc, "nompk_reduce")
+    second = res.cpu().numpy().view(npdt)[0]
+    assert first.tobytes() == second.tobytes(), "reduction is not deterministic / workspace not reset"
+    return first
+
+
+@pytest.mark.parametrize("dtype", [capi.I32, capi.U32, capi.I64, capi.U64])
+@pytest.mark.parametrize("n", [0, 1, 10, 50, 1000, 4099, (1 << 22) + 5])
+def test_reduce_integers_bit_exact(dtype, n):
+    x = rand_array(dtype, n, 11)
+    y = rand_array(dtype, n, 12)
+    for op in (capi.RED_SUM, capi.RED_PROD, capi.RED_MIN, capi.RED_MAX):
+        assert _reduce(op, dtype, x) == ffi.reduce_(op, dtype, x), (op, dtype, n)
+    assert _reduce(capi.RED_SUM, dtype, x, y) == ffi.reduce_(capi.RED_SUM, dtype, x, y)
+
+
+@pytest.mark.parametrize("n", [0, 1, 10, 50, 4099, (1 << 22) + 5])
+def test_reduce_f64_exact_data(n):
+    """Set X: integer-valued doubles -> every summation order is exact -> bitwise equality."""
+    x = ffi.fill_int_f64(n, 1, 0, 7)
+    y = ffi.fill_int_f64(n, 2, 0, 7)
+    assert _reduce(capi.RED_SUM, capi.F64, x) == ffi.reduce_(capi.RED_SUM, capi.F64, x)
+    assert _reduce(capi.RED_SUM, capi.F64, x, y) == ffi.reduce_(capi.RED_SUM, capi.F64, x, y)
+    assert _reduce(capi.RED_MIN, capi.F64, x) == ffi.reduce_(capi.RED_MIN, capi.F64, x)
+    assert _reduce(capi.RED_MAX, capi.F64, x) == ffi.reduce_(capi.RED_MAX, capi.F64, x)
+
+
+@pytest.mark.parametrize("n", [1000, (1 << 22) + 5, 1 << 25])
+def test_reduce_f64_random_data(n):
+    """Set R: U[0.5,1.5) -> compare with the compensated oracle, 1e-12 relative (reduction-order tolerance)."""
+    x = ffi.fill_uniform_f64(n, 1234, 0.5, 1.5)
+    y = ffi.fill_uniform_f64(n, 4321, 0.5, 1.5)
+    s = ffi.sum_compensated(x)
+    d = ffi.sum_compensated(x, y)
+    assert abs(_reduce(capi.RED_SUM, capi.F64, x) - s) <= 1e-12 * abs(s)
+    assert abs(_reduce(capi.RED_SUM, capi.F64, x, y) - d) <= 1e-12 * abs(d)
+
+
+def test_reduce_f32_small_ints():
+    for n in (10, 50):
+        x = np.arange(n, dtype=np.float32)
+        assert _reduce(capi.RED_SUM, capi.F32, x) == np.float32(n * (n - 1) / 2)
+        assert _reduce(capi.RED_SUM, capi.F32, x, x) == np.float32(n * (2 * n - 1) * (n - 1) / 6)
+
+
+def test_reduce_result_in_mapped_host_memory():
+    lib = capi.nompk()
+    n = 1 << 20
+    x = ffi.fill_int_f64(n, 9, 0, 7)
+    tx = dev(x)
+    ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    pinned = torch.zeros(1, dtype=torch.float64).pin_memory()
+    rc = lib.nompk_reduce(capi.RED_SUM, capi.F64, n, tx.data_ptr(), None, res.data_ptr(), pinned.data_ptr(),
+                          ws.data_ptr(), stream())
+    capi.nompk_check(rc)
+    torch.cuda.synchronize()
+    assert pinned.item() == x.sum() == res.item()
+
+
+def _ax(n, u, g, D, variant=0):
+    lib = capi.nompk()
+    lib.nompk_ax_set_variant(variant)
+    tu, tg, tD = dev(u), dev(g), dev(D)
+    tw = torch.full_like(tu, float("nan"))
+    E = u.size // n ** 3
+    rc = lib.nompk_ax_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), 0, stream())
+    capi.nompk_check(rc, "nompk_ax_f64")
+    lib.nompk_ax_set_variant(0)
+    return host(tw, np.float64)
+
+
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+@pytest.mark.parametrize("E", [1, 2, 7, 64, 1031])
+def test_ax_exact_data_bitwise(n, E):
+    """Set X: u in [-4,4], D in [-2,2], g in [0,3] integers -> all partial sums exact -> bitwise equality."""
+    u = ffi.fill_int_f64(E * n ** 3, 2, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 3, 0, 3)
+    D = ffi.fill_int_f64(n * n, 4, -2, 2)
+    want = ffi.ax(n, u, g, D)
+    got = _ax(n, u, g, D)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n", [8, 10])
+def test_ax_variants_agree(variant, n):
+    E = 333
+    u = ffi.fill_int_f64(E * n ** 3, 12, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 13, 0, 3)
+    D = ffi.fill_int_f64(n * n, 14, -2, 2)
+    assert np.array_equal(_ax(n, u, g, D, variant), ffi.ax(n, u, g, D))
+
+
+@pytest.mark.parametrize("n", [8, 10])
+def test_ax_random_data_vs_extended_oracle(n):
+    """Set R with the real GLL derivative matrix: ||w - w_ref||_inf / ||w_ref||_inf <= 1e-12."""
+    E = 257
+    D, _ = ffi.gll_derivative(n)
+    D = np.ascontiguousarray(D.ravel())
+    u = ffi.fill_uniform_f64(E * n ** 3, 1234, 0.5, 1.5)
+    g = ffi.fill_uniform_f64(E * 6 * n ** 3, 99, 0.5, 1.5)
+    ref = ffi.ax(n, u, g, D, "extended")
+    got = _ax(n, u, g, D)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [8, 10])
+def test_ax_properties_at_full_size(n):
+    """BASELINE size (E = 32768): size-independent properties instead of a full CPU recomputation.
+    constant u -> w == 0 (rows of D sum to 0);  linearity A(a u + v) = a Au + Av;  symmetry v.(Au) = u.(Av);
+    plus a sampled bit-for-bit check of 64 elements against the oracle on exact data."""
+    E = 32768
+    lib = capi.nompk()
+    D, _ = ffi.gll_derivative(n)
+    tD = torch.from_numpy(np.ascontiguousarray(D.ravel())).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.rand(E * n ** 3, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    v = torch.rand(E * n ** 3, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    g = torch.rand(E * 6 * n ** 3, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+
+    def A(x):
+        w = torch.empty_like(x)
+        capi.nompk_check(lib.nompk_ax_f64(n, E, x.data_ptr(), g.data_ptr(), tD.data_ptr(), w.data_ptr(), 0, stream()))
+        return w
+
+    Au, Av = A(u), A(v)
+    scale = Au.abs().max().item()
+    assert A(torch.ones_like(u)).abs().max().item() <= 1e-10 * scale
+    assert (A(2.5 * u + v) - (2.5 * Au + Av)).abs().max().item() <= 1e-12 * scale * 4
+    lhs, rhs = torch.dot(v, Au).item(), torch.dot(u, Av).item()
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
+
+    # exact data, sampled elements
+    ui = torch.randint(-4, 5, (E * n ** 3,), device="cuda", generator=gen).double()
+    gi = torch.randint(0, 4, (E * 6 * n ** 3,), device="cuda", generator=gen).double()
+    Di = ffi.fill_int_f64(n * n, 4, -2, 2)
+    tDi = torch.from_numpy(Di).cuda()
+    w = torch.empty_like(ui)
+    capi.nompk_check(lib.nompk_ax_f64(n, E, ui.data_ptr(), gi.data_ptr(), tDi.data_ptr(), w.data_ptr(), 0, stream()))
+    n3 = n ** 3
+    for e in list(range(0, E, E // 61)) + [E - 1]:
+        ue = ui[e * n3:(e + 1) * n3].cpu().numpy()
+        ge = gi[e * 6 * n3:(e + 1) * 6 * n3].cpu().numpy()
+        assert np.array_equal(w[e * n3:(e + 1) * n3].cpu().numpy(), ffi.ax(n, ue, ge, Di)), e
+
+
+def test_ax_unsupported_n_is_reported():
+    lib = capi.nompk()
+    t = torch.zeros(9 ** 3 * 6, dtype=torch.float64, device="cuda")
+    rc = lib.nompk_ax_f64(9, 1, t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, stream())
+    assert rc == -3 and b"n = 9" in lib.nompk_last_error()

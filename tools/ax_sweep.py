@@ -1,0 +1,107 @@
+#!/usr/bin/env python3
+"""Device-time sweep of the libnompk kernels (run on the GPU box): Ax variants, map and reduce bandwidth.
+Prints one JSON line per measurement to stdout and appends them to gpurun_out/sweep.jsonl."""
+import ctypes as C
+import json
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+
+from libnomp_b200 import capi  # noqa: E402
+
+PEAK = 6548.5
+try:
+    PEAK = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+except Exception:
+    pass
+
+out = ROOT / "gpurun_out"
+out.mkdir(exist_ok=True)
+log = open(out / "sweep.jsonl", "a")
+
+
+def emit(**kw):
+    s = json.dumps(kw)
+    print(s, flush=True)
+    log.write(s + "\n")
+    log.flush()
+
+
+def timeit(fn, reps=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    lib = capi.nompk()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    which = sys.argv[1:] or ["ax", "map", "reduce"]
+    if "ax" in which:
+        for n, E in ((8, 32768), (8, 262144), (10, 32768), (10, 131072)):
+            n3 = n ** 3
+            u = torch.rand(E * n3, dtype=torch.float64, device="cuda")
+            g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
+            D = torch.rand(n * n, dtype=torch.float64, device="cuda")
+            w = torch.empty_like(u)
+            for variant in range(7):
+                lib.nompk_ax_set_variant(variant)
+
+                def run():
+                    capi.nompk_check(lib.nompk_ax_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(),
+                                                      0, st))
+                med, best = timeit(run)
+                gb = E * n3 * 64 / 1e9
+                emit(kernel="ax", n=n, E=E, variant=variant, ms=med, ms_min=best, gdofs=E * n3 / med / 1e6,
+                     gbs=gb / med * 1e3, frac=gb / med * 1e3 / PEAK)
+            lib.nompk_ax_set_variant(0)
+            del u, g, w
+    if "map" in which:
+        for lg in (20, 24, 26, 28):
+            n = 1 << lg
+            x = torch.rand(n, dtype=torch.float64, device="cuda")
+            y = torch.rand(n, dtype=torch.float64, device="cuda")
+            alpha = C.c_double(0.5)
+            for op, name in ((capi.MAP_ADD, "add"), (capi.MAP_AXPY, "axpy")):
+                def run():
+                    capi.nompk_check(lib.nompk_map(op, capi.F64, n, y.data_ptr(), x.data_ptr(), None,
+                                                   C.addressof(alpha), None, st))
+                med, best = timeit(run)
+                emit(kernel="map_" + name, n=n, ms=med, ms_min=best, gbs=n * 24 / med / 1e6, frac=n * 24 / med / 1e6 / PEAK)
+            def cp():
+                y.copy_(x)
+            med, best = timeit(cp)
+            emit(kernel="torch_copy", n=n, ms=med, ms_min=best, gbs=n * 16 / med / 1e6, frac=n * 16 / med / 1e6 / PEAK)
+    if "reduce" in which:
+        ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+        res = torch.zeros(1, dtype=torch.float64, device="cuda")
+        for lg in (20, 24, 28):
+            n = 1 << lg
+            x = torch.rand(n, dtype=torch.float64, device="cuda")
+            y = torch.rand(n, dtype=torch.float64, device="cuda")
+            xi = torch.randint(-2 ** 62, 2 ** 62, (n,), dtype=torch.int64, device="cuda")
+            for name, dt, a, b, bytes_ in (("sum_f64", capi.F64, x, None, 8), ("dot_f64", capi.F64, x, y, 16),
+                                            ("sum_i64", capi.I64, xi, None, 8)):
+                def run():
+                    capi.nompk_check(lib.nompk_reduce(capi.RED_SUM, dt, n, a.data_ptr(),
+                                                      b.data_ptr() if b is not None else None, res.data_ptr(), None,
+                                                      ws.data_ptr(), st))
+                med, best = timeit(run)
+                emit(kernel=name, n=n, ms=med, ms_min=best, gbs=n * bytes_ / med / 1e6,
+                     frac=n * bytes_ / med / 1e6 / PEAK)
+
+
+if __name__ == "__main__":
+    main()
