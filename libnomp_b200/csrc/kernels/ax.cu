@@ -66,6 +66,10 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int LPE> __device__ __forceinline__ void element_sync(int el_in_blk) {
   if constexpr (LPE == 32) {
     __syncwarp();
@@ -137,13 +141,17 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 }
 
 // kGeoAhead: how many k-slabs of geometric factors are in flight in registers ahead of their use.
-// kPrefetchL2: pull the next element this warp group will process into L2 while working on the current one.
+// kPf: L2 prefetch policy.  0 = none; 1 = one bulk prefetch of the whole next element (measured: doubles DRAM reads,
+// the 66 MB that 2368 warps keep "reserved" do not survive in L2); >= 2 = rolling window: while slab k of the
+// geometric factors is consumed, the 24 lines of slab k + kPf (wrapping into the next element of this warp) are
+// requested with one fire-and-forget `prefetch.global.L2` per lane, so demand loads find their lines in L2 and the
+// HBM latency is paid by requests that hold no register and no scoreboard slot.
 //
 // Control flow is kept CTA-uniform on purpose: the element loop depends only on blockIdx; lanes beyond the T work
 // items of an element (n = 10: 14 of 64) and elements beyond E in the last group do not branch, they mirror
 // the last valid item / element and write the same values to the same addresses.  (Divergent regions would make
 // ptxas drop the uniform-register D operands and issue one vector LDC.64 per DFMA.)
-template <int N, int EPB, int kGeoAhead, bool kPrefetchL2, bool kStreamLoads, int kMinBlocks>
+template <int N, int EPB, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks>
 __global__ void __launch_bounds__(EPB *Layout<N>::LPE, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E) {
   using L = Layout<N>;
@@ -176,11 +184,22 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     const double2 *ge = reinterpret_cast<const double2 *>(g + e * 6 * N3) + q * NP + p;
     double2 *we = reinterpret_cast<double2 *>(w + e * N3) + q * NP + p;
 
-    if constexpr (kPrefetchL2) {
+    if constexpr (kPf == 1) {
       const size_t en = e + estride;
       if (t == 0 && en < E) {
         prefetch_l2_bulk(u + en * N3, N3 * 8);
         prefetch_l2_bulk(g + en * 6 * N3, 6 * N3 * 8);
+      }
+    }
+    // Rolling prefetch: line `pl` of factor `pf` of a slab (a slab of one factor is N*N*8 bytes).
+    constexpr int kLinesPerFactor = (N * N * 8 + 127) / 128;
+    const int pf_f = t / kLinesPerFactor, pf_l = t % kLinesPerFactor;
+    const size_t e_next = (e + estride < E) ? e + estride : e;
+    if constexpr (kPf >= 2) {
+      if (eb == (size_t)blockIdx.x * EPB) {  // first element of this CTA: warm the window
+#pragma unroll
+        for (int k = kGeoAhead; k < kPf && k < N; k++)
+          if (pf_f < 6) prefetch_l2(g + (e * 6 + pf_f) * N3 + k * N * N + pf_l * 16);
       }
     }
 
@@ -246,6 +265,21 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         for (int f = 0; f < 6; f++)
           gq[slot][f] = kStreamLoads ? ldg2_stream(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2)
                                      : ldg2(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2);
+      }
+      if constexpr (kPf >= 2) {
+        // slab k + kPf of this element, or slab (k + kPf - N) of the next one; next element's u with slab 0
+        const int ks = k + kPf;
+        if (ks < N) {
+          if (pf_f < 6) prefetch_l2(g + (e * 6 + pf_f) * N3 + ks * N * N + pf_l * 16);
+        } else if (ks - N < N) {
+          if (pf_f < 6) prefetch_l2(g + (e_next * 6 + pf_f) * N3 + (ks - N) * N * N + pf_l * 16);
+        }
+        if (k == 0) {
+          constexpr int kULines = (N3 * 8 + 127) / 128;
+#pragma unroll
+          for (int l0 = 0; l0 < kULines; l0 += LPE)
+            if (l0 + t < kULines) prefetch_l2(u + e_next * N3 + (l0 + t) * 16);
+        }
       }
       const int a = L::at(k, q, p);
       const double2 ur = B1[a], us = B2[a], ut = col[k];
@@ -315,7 +349,7 @@ struct AxVariant {
 
 int g_variant = 0;
 
-template <int N, int EPB, int GA, bool PF, bool ST, int MB>
+template <int N, int EPB, int GA, int PF, bool ST, int MB>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream) {
   using L = Layout<N>;
   auto kern = ax_kernel<N, EPB, GA, PF, ST, MB>;
@@ -344,13 +378,20 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   // Variants are kept for profiling (bench/profile scripts sweep them); 0 is the production choice.
   switch (variant) {
   default:
-  case 0: return launch_ax<N, EPB0, 2, true, false, MB128>(E, u, g, w, s);
-  case 1: return launch_ax<N, EPB0, 2, false, false, MB128>(E, u, g, w, s);
-  case 2: return launch_ax<N, EPB0, 1, true, false, MB128>(E, u, g, w, s);
-  case 3: return launch_ax<N, EPB0, 2, true, true, MB128>(E, u, g, w, s);
-  case 4: return launch_ax<N, EPB0, 2, true, false, MB168>(E, u, g, w, s);
-  case 5: return launch_ax<N, EPB0, 4, true, false, MB168>(E, u, g, w, s);
-  case 6: return launch_ax<N, EPB0, 2, true, false, 1>(E, u, g, w, s);
+  case 0:  // production choice (gpurun sweep of round 1, profiles/ax_sweep_r01.md)
+    if constexpr (N == 8) return launch_ax<N, EPB0, 3, 6, false, MB168>(E, u, g, w, s);
+    else return launch_ax<N, EPB0, 2, 4, false, MB168>(E, u, g, w, s);
+  case 1: return launch_ax<N, EPB0, 2, 4, false, MB128>(E, u, g, w, s);
+  case 2: return launch_ax<N, EPB0, 2, 3, false, MB128>(E, u, g, w, s);
+  case 3: return launch_ax<N, EPB0, 2, 2, false, MB128>(E, u, g, w, s);
+  case 4: return launch_ax<N, EPB0, 2, 0, false, MB128>(E, u, g, w, s);
+  case 5: return launch_ax<N, EPB0, 2, 4, true, MB128>(E, u, g, w, s);
+  case 6: return launch_ax<N, EPB0, 2, 0, false, 1>(E, u, g, w, s);
+  case 7: return launch_ax<N, EPB0, 2, 4, false, MB168>(E, u, g, w, s);
+  case 8: return launch_ax<N, EPB0, 3, 6, false, MB168>(E, u, g, w, s);
+  case 9: return launch_ax<N, EPB0, 2, 4, false, 1>(E, u, g, w, s);
+  case 10: return launch_ax<N, EPB0, 4, 6, false, 1>(E, u, g, w, s);
+  case 11: return launch_ax<N, EPB0, 3, 4, false, MB168>(E, u, g, w, s);
   }
 }
 

@@ -1,0 +1,638 @@
+"""Loop-family recogniser: decides which execution path a parsed kernel takes.
+
+  native map      -> nompk_map()       hand-written sm_100a kernel in libnompk.so
+  native reduce   -> nompk_reduce()
+  native ax       -> nompk_ax_f64()
+  map skeleton    -> NVRTC: any other single-loop elementwise kernel gets the same 128-bit grid-stride schedule
+  reduce skeleton -> NVRTC: any other single-loop reduce clause gets the same single-pass reduction schedule
+  generic         -> NVRTC: everything else, scheduled by the user's transform (emit_cuda.py)
+
+The canonical spellings are the ones the reference tests use (reference tests/nomp-api-200-impl.h:36-40,
+tests/nomp-api-600-impl.h:36-40, tests/nomp-api-500-impl.h:23-27, :47-51, :95-99, :180-184) plus the Ax kernel
+string below (the reference has no Ax).  The result is a one-line descriptor, `//!nomp key=value ...`, that
+travels to the backend as the first line of the `src` argument of knl_build() (reference
+include/nomp-impl.h:213-237 keeps the vtable signatures), followed by CUDA source for the NVRTC paths.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, List, Optional, Tuple
+
+from . import cparse as c
+from .emit_cuda import PRELUDE, cuda_type, expr_str, grid_expr_str, signature, const_int
+from .ir import Kernel, KernelError, expr_names, map_expr, map_stmts, walk
+
+# dtype / op codes of include/nompk.h
+DTYPE_CODE = {("int", False): 0, ("int", True): 1, ("long", False): 2, ("long", True): 3,
+              ("longlong", False): 2, ("longlong", True): 3, ("float", False): 4, ("double", False): 5}
+MAP_OPS = {"add": 0, "sub": 1, "mul": 2, "axpy": 3, "xpay": 4, "axpby": 5, "scale": 6, "copy": 7, "fill": 8, "add3": 9}
+RED_OPS = {"+": 0, "*": 1, "min": 2, "max": 3}
+
+# ----------------------------------------------------------------------------------------------------
+# The canonical Ax kernel string (layouts of include/nompk.h).  `n` is passed as NOMP_INT | NOMP_JIT.
+# It is plain nomp C: the generic path can run it for any n, the oracle compiles it with gcc, and the
+# recogniser maps it (up to renaming of identifiers) onto nompk_ax_f64 for the n that have a tuned kernel.
+# ----------------------------------------------------------------------------------------------------
+AX_KERNEL_SOURCE = """\
+void nomp_ax(double *w, const double *u, const double *g, const double *D, int E, int n) {
+  for (int e = 0; e < E; e++) {
+    double ur[n][n][n];
+    double us[n][n][n];
+    double ut[n][n][n];
+    for (int k = 0; k < n; k++)
+      for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+          double r = 0;
+          double s = 0;
+          double t = 0;
+          for (int l = 0; l < n; l++) {
+            r += D[i * n + l] * u[e * n * n * n + k * n * n + j * n + l];
+            s += D[j * n + l] * u[e * n * n * n + k * n * n + l * n + i];
+            t += D[k * n + l] * u[e * n * n * n + l * n * n + j * n + i];
+          }
+          ur[k][j][i] = g[(e * 6 + 0) * n * n * n + k * n * n + j * n + i] * r + g[(e * 6 + 1) * n * n * n + k * n * n + j * n + i] * s + g[(e * 6 + 2) * n * n * n + k * n * n + j * n + i] * t;
+          us[k][j][i] = g[(e * 6 + 1) * n * n * n + k * n * n + j * n + i] * r + g[(e * 6 + 3) * n * n * n + k * n * n + j * n + i] * s + g[(e * 6 + 4) * n * n * n + k * n * n + j * n + i] * t;
+          ut[k][j][i] = g[(e * 6 + 2) * n * n * n + k * n * n + j * n + i] * r + g[(e * 6 + 4) * n * n * n + k * n * n + j * n + i] * s + g[(e * 6 + 5) * n * n * n + k * n * n + j * n + i] * t;
+        }
+    for (int k = 0; k < n; k++)
+      for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+          double acc = 0;
+          for (int l = 0; l < n; l++) {
+            acc += D[l * n + i] * ur[k][j][l];
+            acc += D[l * n + j] * us[k][l][i];
+            acc += D[l * n + k] * ut[l][j][i];
+          }
+          w[e * n * n * n + k * n * n + j * n + i] = acc;
+        }
+  }
+}
+"""
+
+
+def _canonical_tokens(src: str) -> Tuple[List[str], List[str]]:
+    """Token list with identifiers renamed v0, v1, ... in order of first appearance (keywords/types kept)."""
+    keep = set(c._TYPE_WORDS) | {"for", "if", "else", "break", "continue"}
+    names: List[str] = []
+    out = []
+    for kind, text, _ in c.tokenize(src):
+        if kind == "id" and text not in keep:
+            if text not in names:
+                names.append(text)
+            out.append(f"v{names.index(text)}")
+        elif kind != "eof":
+            out.append(text)
+    return out, names
+
+
+_AX_TOKENS, _AX_NAMES = _canonical_tokens(AX_KERNEL_SOURCE)
+
+
+def match_ax(knl: Kernel) -> Optional[Dict[str, str]]:
+    """If the kernel text is the canonical Ax string up to renaming, return {role: user identifier}."""
+    try:
+        toks, names = _canonical_tokens(knl.source)
+    except Exception:
+        return None
+    if toks != _AX_TOKENS or len(names) != len(_AX_NAMES):
+        return None
+    return dict(zip(_AX_NAMES, names))
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers on the ORIGINAL (untransformed) function
+# ----------------------------------------------------------------------------------------------------
+
+def _dtype_code(t: c.CType) -> Optional[int]:
+    return DTYPE_CODE.get((t.base, t.unsigned))
+
+
+def _single_loop(func: c.Function) -> Optional[c.For]:
+    body = [n for n in func.body if not (isinstance(n, c.If) and not n.then and not n.other)]
+    if len(body) != 1 or not isinstance(body[0], c.For):
+        return None
+    loop = body[0]
+    if any(isinstance(n, (c.For, c.Bind)) for n in walk(loop.body)):
+        return None
+    return loop
+
+
+def _params(func: c.Function) -> Dict[str, c.Param]:
+    return {p.name: p for p in func.params}
+
+
+def _is_elem(e: c.Node, arrays: Dict[str, c.Param], var: str) -> Optional[str]:
+    """`a[i]` with a a pointer parameter and i the loop variable -> 'a'."""
+    if (isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays and len(e.index) == 1
+            and isinstance(e.index[0], c.Name) and e.index[0].id == var):
+        return e.base.id
+    return None
+
+
+def _terms(e: c.Node) -> Optional[List[List[c.Node]]]:
+    """Flatten e into a sum of products (no parenthesised sums inside products). None if not of that shape."""
+    if isinstance(e, c.BinOp) and e.op == "+":
+        a, b = _terms(e.left), _terms(e.right)
+        return None if a is None or b is None else a + b
+    factors: List[c.Node] = []
+
+    def prod(x) -> bool:
+        if isinstance(x, c.BinOp) and x.op == "*":
+            return prod(x.left) and prod(x.right)
+        if isinstance(x, (c.Name, c.Subscript, c.Num)):
+            factors.append(x)
+            return True
+        return False
+
+    return [factors] if prod(e) else None
+
+
+def _loop_count(loop: c.For, params: Dict[str, c.Param]) -> Optional[str]:
+    """Trip count as 'name' (int parameter) or a literal, for loops that start at 0."""
+    if const_int(loop.lo) != 0:
+        return None
+    if isinstance(loop.hi, c.Name) and loop.hi.id in params and not params[loop.hi.id].is_array \
+            and not params[loop.hi.id].ctype.is_float:
+        return loop.hi.id
+    v = const_int(loop.hi)
+    return str(v) if v is not None and v >= 0 else None
+
+
+# ----------------------------------------------------------------------------------------------------
+# native map
+# ----------------------------------------------------------------------------------------------------
+
+def match_native_map(func: c.Function) -> Optional[Dict[str, str]]:
+    loop = _single_loop(func)
+    if loop is None or len(loop.body) != 1 or not isinstance(loop.body[0], c.Assign):
+        return None
+    params = _params(func)
+    count = _loop_count(loop, params)
+    if count is None:
+        return None
+    arrays = {k: p for k, p in params.items() if p.is_array}
+    st: c.Assign = loop.body[0]
+    y = _is_elem(st.target, arrays, loop.var)
+    if y is None or arrays[y].ctype.const:
+        return None
+    dt = _dtype_code(arrays[y].ctype)
+    if dt is None:
+        return None
+    ytype = arrays[y].ctype
+
+    def same_type(p: c.Param) -> bool:
+        return (p.ctype.base, p.ctype.unsigned) == (ytype.base, ytype.unsigned) or \
+               ({p.ctype.base, ytype.base} <= {"long", "longlong"} and p.ctype.unsigned == ytype.unsigned)
+
+    value = st.value
+    if st.op in ("+=", "-=", "*="):
+        value = c.BinOp(st.op[0], st.target, st.value)
+    elif st.op != "=":
+        return None
+
+    def classify(f: c.Node):
+        """('y',) | ('x', name) | ('s', name) for y[i], other array element, scalar parameter."""
+        a = _is_elem(f, arrays, loop.var)
+        if a is not None:
+            if not same_type(arrays[a]):
+                return None
+            return ("y",) if a == y else ("x", a)
+        if isinstance(f, c.Name) and f.id in params and not params[f.id].is_array and same_type(params[f.id]):
+            return ("s", f.id)
+        return None
+
+    out = {"family": "map", "dtype": str(dt), "y": y, "n": count}
+
+    # y - x
+    if isinstance(value, c.BinOp) and value.op == "-":
+        l, r = classify(value.left), classify(value.right)
+        if l == ("y",) and r and r[0] == "x":
+            return {**out, "op": "sub", "x": r[1]}
+        return None
+    terms = _terms(value)
+    if terms is None:
+        return None
+    cls = []
+    for t in terms:
+        k = [classify(f) for f in t]
+        if any(x is None for x in k):
+            return None
+        cls.append(sorted(k))
+    cls.sort()
+    n_terms = len(cls)
+    if n_terms == 1:
+        t = cls[0]
+        if t == [("y",)]:
+            return None
+        if len(t) == 1 and t[0][0] == "x":
+            return {**out, "op": "copy", "x": t[0][1]}
+        if len(t) == 1 and t[0][0] == "s":
+            return {**out, "op": "fill", "alpha": t[0][1]}
+        if len(t) == 2 and t[0][0] == "s" and t[1] == ("y",):
+            return {**out, "op": "scale", "alpha": t[0][1]}
+        if len(t) == 2 and t[0][0] == "x" and t[1] == ("y",):
+            return {**out, "op": "mul", "x": t[0][1]}
+        return None
+    if n_terms == 2:
+        a, b = cls
+        flat = (tuple(a), tuple(b))
+        # y + x
+        if len(a) == 1 and len(b) == 1:
+            kinds = sorted([a[0], b[0]])
+            if kinds[0][0] == "x" and kinds[1] == ("y",):
+                return {**out, "op": "add", "x": kinds[0][1]}
+            if kinds[0][0] == "x" and kinds[1][0] == "x" and kinds[0][1] != kinds[1][1]:
+                # order of the two reads does not matter for a two-term sum
+                return {**out, "op": "add3", "x": kinds[0][1], "z": kinds[1][1]}
+            return None
+        one = [t for t in (a, b) if len(t) == 1]
+        two = [t for t in (a, b) if len(t) == 2]
+        if len(one) == 1 and len(two) == 1:
+            s_x = two[0]
+            # alpha * x  (+ y)   -> axpy ;  alpha * y (+ x) -> xpay
+            if s_x[0][0] == "s" and s_x[1][0] == "x" and one[0] == [("y",)]:
+                return {**out, "op": "axpy", "alpha": s_x[0][1], "x": s_x[1][1]}
+            if s_x[0][0] == "s" and s_x[1] == ("y",) and one[0][0][0] == "x":
+                return {**out, "op": "xpay", "alpha": s_x[0][1], "x": one[0][0][1]}
+            return None
+        if len(two) == 2:
+            # alpha * x + beta * y
+            tx = [t for t in two if t[0][0] == "s" and t[1][0] == "x"]
+            ty = [t for t in two if t[0][0] == "s" and t[1] == ("y",)]
+            if len(tx) == 1 and len(ty) == 1:
+                return {**out, "op": "axpby", "alpha": tx[0][0][1], "x": tx[0][1][1], "beta": ty[0][0][1]}
+        del flat
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# reductions
+# ----------------------------------------------------------------------------------------------------
+
+class ReductionInfo:
+    def __init__(self, loop: c.For, var: str, vtype: c.CType, op: str, rhs: c.Node, preds: List[c.Node],
+                 pre: List[c.Node]):
+        self.loop, self.var, self.vtype, self.op, self.rhs, self.preds, self.pre = loop, var, vtype, op, rhs, preds, pre
+
+
+def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
+    """Find `var[0] op= rhs` inside the single loop (reference python/reduction.py:37-48 requires one loop and a
+    subscripted accumulator; the lhs' incoming value is dropped, :68)."""
+    params = _params(func)
+    if var not in params or not params[var].is_array:
+        raise KernelError(f"reduce: {var!r} must be a pointer parameter of the kernel")
+    body = [n for n in func.body if not (isinstance(n, c.If) and not n.then and not n.other)]
+    if len(body) != 1 or not isinstance(body[0], c.For):
+        raise KernelError("reduce: the kernel must consist of exactly one loop")
+    loop = body[0]
+    if any(isinstance(n, (c.For, c.Bind)) for n in walk(loop.body)):
+        raise KernelError("reduce: nested loops are not supported in a reduction kernel")
+    vtype = params[var].ctype.scalar()
+
+    def is_acc(e: c.Node) -> bool:
+        return (isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id == var
+                and len(e.index) == 1 and const_int(e.index[0]) == 0)
+
+    found: List[Tuple[c.Assign, List[c.Node]]] = []
+    pre: List[c.Node] = []
+
+    def scan(nodes, preds, top):
+        for n in nodes:
+            if isinstance(n, c.Assign) and is_acc(n.target):
+                found.append((n, list(preds)))
+            elif isinstance(n, c.If):
+                scan(n.then, preds + [n.cond], False)
+                scan(n.other, preds + [c.UnOp("!", n.cond)], False)
+            elif top:
+                pre.append(n)
+            else:
+                raise KernelError("reduce: only the accumulation may appear under a condition")
+
+    scan(loop.body, [], True)
+    if len(found) != 1:
+        raise KernelError(f"reduce: expected exactly one update of {var}[0], found {len(found)}")
+    st, preds = found[0]
+    uses_acc = lambda e: var in expr_names(e)  # noqa: E731
+    binop = {"+": "+", "*": "*"}.get(op)
+    rhs = None
+    if op in ("+", "*"):
+        if st.op == f"{op}=":
+            rhs = st.value
+        elif st.op == "=" and isinstance(st.value, c.BinOp) and st.value.op == binop:
+            if is_acc(st.value.left):
+                rhs = st.value.right
+            elif is_acc(st.value.right):
+                rhs = st.value.left
+    else:  # min / max:  m[0] = (x < m[0]) ? x : m[0]   in any arrangement
+        if st.op == "=" and isinstance(st.value, c.Ternary):
+            cand = [b for b in (st.value.then, st.value.other) if not is_acc(b)]
+            if len(cand) == 1:
+                rhs = cand[0]
+    if rhs is None or uses_acc(rhs):
+        raise KernelError(f"reduce: the update of {var}[0] does not have the form of a '{op}' reduction")
+    for n in pre:
+        if isinstance(n, c.Assign):
+            tgt = n.target.base.id if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) else \
+                (n.target.id if isinstance(n.target, c.Name) else None)
+            if tgt in params:
+                raise KernelError("reduce: a reduction kernel may not write to its other arguments")
+    return ReductionInfo(loop, var, vtype, op, rhs, preds, pre)
+
+
+def match_native_reduce(func: c.Function, info: ReductionInfo) -> Optional[Dict[str, str]]:
+    if info.preds or info.pre:
+        return None
+    params = _params(func)
+    count = _loop_count(info.loop, params)
+    dt = _dtype_code(info.vtype)
+    if count is None or dt is None:
+        return None
+    arrays = {k: p for k, p in params.items() if p.is_array and k != info.var}
+
+    def elem(e):
+        a = _is_elem(e, arrays, info.loop.var)
+        if a is None:
+            return None
+        t = arrays[a].ctype
+        if (t.base, t.unsigned) != (info.vtype.base, info.vtype.unsigned):
+            return None
+        return a
+
+    out = {"family": "reduce", "dtype": str(dt), "op": str(RED_OPS[info.op]), "n": count, "out": info.var}
+    x = elem(info.rhs)
+    if x is not None:
+        return {**out, "x": x}
+    if isinstance(info.rhs, c.BinOp) and info.rhs.op == "*":
+        x, y = elem(info.rhs.left), elem(info.rhs.right)
+        if x is not None and y is not None:
+            return {**out, "x": x, "y": y}
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# NVRTC skeletons
+# ----------------------------------------------------------------------------------------------------
+_RED_IDENTITY = {"+": "0", "*": "1"}
+
+
+def _limits(t: c.CType, hi: bool) -> str:
+    if t.is_float:
+        return ("" if hi else "-") + ("__int_as_float(0x7f800000)" if t.base == "float" else "__longlong_as_double(0x7ff0000000000000LL)")
+    bits = t.size * 8
+    if t.unsigned:
+        return f"({cuda_type(t)})~({cuda_type(t)})0" if hi else "0"
+    if bits == 32:
+        return "2147483647" if hi else "(-2147483647 - 1)"
+    return "9223372036854775807LL" if hi else "(-9223372036854775807LL - 1)"
+
+
+def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tuple[str, List[str], List[str], List[str]]:
+    """Single-pass reduction kernel with the same structure as libnompk's reduce.cu, for an arbitrary rhs.
+    Returns (source, grid exprs, block exprs, kernel parameter names).  The trailing four parameters
+    (partials, ticket, result, result_host) are supplied by the backend."""
+    T = cuda_type(info.vtype)
+    func = knl.func
+    params = [p for p in func.params if p.name != info.var]
+    sig_parts = []
+    for prm in params:
+        t = prm.ctype
+        sig_parts.append(f"const {cuda_type(t)} *__restrict__ {prm.name}" if prm.is_array else f"{cuda_type(t)} {prm.name}")
+    sig_parts += [f"{T} *__restrict__ nomp_partials", "unsigned int *__restrict__ nomp_ticket",
+                  f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host"]
+    int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}
+    it = cuda_type(info.loop.vtype)
+    lo, hi = expr_str(info.loop.lo), expr_str(info.loop.hi)
+    if info.op in _RED_IDENTITY:
+        ident = f"({T}){_RED_IDENTITY[info.op]}"
+        comb = lambda a, b: f"({a}) {info.op} ({b})"  # noqa: E731
+    elif info.op == "min":
+        ident = _limits(info.vtype, True)
+        comb = lambda a, b: f"(({b}) < ({a}) ? ({b}) : ({a}))"  # noqa: E731
+    else:
+        ident = _limits(info.vtype, False)
+        comb = lambda a, b: f"(({b}) > ({a}) ? ({b}) : ({a}))"  # noqa: E731
+    pre_lines = []
+    from .emit_cuda import GenericEmitter
+    ge = GenericEmitter(knl)
+    ge.lines = []
+    ge.stmts(info.pre, 2, True, False)
+    pre_lines = ge.lines
+    cond = " && ".join(expr_str(p) for p in info.preds)
+    rhs = f"({T})({expr_str(info.rhs)})"
+    upd = f"nomp_acc = {comb('nomp_acc', 'nomp_v')};"
+    body = [f"const {T} nomp_v = {rhs};", upd]
+    if cond:
+        body = [f"if ({cond}) {{"] + ["  " + b for b in body] + ["}"]
+    shfl = f"nomp_o = __shfl_xor_sync(0xffffffffu, nomp_acc, nomp_s); nomp_acc = {comb('nomp_acc', 'nomp_o')};"
+    src = f"""{PRELUDE}
+// reduce clause on `{info.var}` (op {info.op}): single-pass schedule of libnompk reduce.cu with a generated right-hand side
+extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_parts)}) {{
+  {T} nomp_acc = {ident};
+  {T} nomp_o;
+  const long long nomp_lo = (long long)({lo}), nomp_hi = (long long)({hi});
+  for (long long nomp_i = nomp_lo + (long long)blockIdx.x * 256 + threadIdx.x; nomp_i < nomp_hi;
+       nomp_i += (long long)gridDim.x * 256) {{
+    const {it} {info.loop.var} = ({it})nomp_i;
+{chr(10).join(pre_lines)}
+    {(chr(10) + '    ').join(body)}
+  }}
+  __shared__ {T} nomp_warp[8];
+  __shared__ bool nomp_last;
+  for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+  if ((threadIdx.x & 31) == 0) nomp_warp[threadIdx.x >> 5] = nomp_acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {{
+    nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
+    for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+  }}
+  if (threadIdx.x == 0) {{
+    nomp_partials[blockIdx.x] = nomp_acc;
+    __threadfence();
+    nomp_last = (atomicAdd(nomp_ticket, 1u) == gridDim.x - 1);
+  }}
+  __syncthreads();
+  if (!nomp_last) return;
+  __threadfence();
+  nomp_acc = {ident};
+  for (unsigned int nomp_b = threadIdx.x; nomp_b < gridDim.x; nomp_b += 256) {{
+    nomp_o = __ldcg(nomp_partials + nomp_b);
+    nomp_acc = {comb('nomp_acc', 'nomp_o')};
+  }}
+  for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) nomp_warp[threadIdx.x >> 5] = nomp_acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {{
+    nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
+    for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+    if (threadIdx.x == 0) {{
+      *nomp_result = nomp_acc;
+      if (nomp_result_host) {{ *nomp_result_host = nomp_acc; __threadfence_system(); }}
+      *nomp_ticket = 0u;
+    }}
+  }}
+}}
+"""
+    extent = c.BinOp("-", info.loop.hi, info.loop.lo) if const_int(info.loop.lo) != 0 else info.loop.hi
+    try:
+        ext = grid_expr_str(extent, int_params)
+        grid = f"max(1, min(({ext} + 255) / 256, {max(1, sm_count) * 8}))"
+    except KernelError:
+        grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
+    names = [p.name for p in params] + ["nomp_partials", "nomp_ticket", "nomp_result", "nomp_result_host"]
+    return src, [grid, "1", "1"], ["256", "1", "1"], names
+
+
+def match_map_skeleton(func: c.Function) -> Optional[c.For]:
+    """Single loop whose every array access is `a[i]` on a pointer parameter, no local arrays, all arrays of one
+    element size: eligible for the vectorised grid-stride schedule."""
+    loop = _single_loop(func)
+    if loop is None:
+        return None
+    params = _params(func)
+    arrays = {k: p for k, p in params.items() if p.is_array}
+    sizes = set()
+    ok = True
+    written_scalars = set()
+
+    def check_expr(e):
+        nonlocal ok
+        if isinstance(e, c.Subscript):
+            a = _is_elem(e, arrays, loop.var)
+            if a is None:
+                ok = False
+            else:
+                sizes.add(arrays[a].ctype.size)
+        return e
+
+    for n in walk(loop.body):
+        if isinstance(n, (c.Break, c.Continue)):
+            return None
+        if isinstance(n, c.Decl):
+            if n.dims:
+                return None
+            map_expr(n.init, check_expr)
+        elif isinstance(n, c.Assign):
+            map_expr(n.target, check_expr)
+            map_expr(n.value, check_expr)
+            if isinstance(n.target, c.Name):
+                written_scalars.add(n.target.id)
+            elif isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) \
+                    and n.target.base.id in arrays and arrays[n.target.base.id].ctype.const:
+                return None
+        elif isinstance(n, c.If):
+            map_expr(n.cond, check_expr)
+    for b in (loop.lo, loop.hi):
+        if any(isinstance(x, c.Subscript) for x in _subexprs(b)):
+            return None
+    if not ok or len(sizes) != 1 or (written_scalars & set(params)) or sizes.pop() not in (4, 8):
+        return None
+    if loop.var in written_scalars:
+        return None
+    return loop
+
+
+def _subexprs(e):
+    acc = []
+    map_expr(e, lambda x: (acc.append(x), x)[1])
+    return acc
+
+
+def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, List[str], List[str]]:
+    """Vectorised elementwise kernel: 128-bit loads/stores when every operand is 16-byte aligned (checked in the
+    kernel, the branch is uniform), scalar grid-stride otherwise; same schedule as libnompk map.cu."""
+    func = knl.func
+    params = _params(func)
+    arrays = {k: p for k, p in params.items() if p.is_array}
+    used, written = [], []
+
+    def note(e):
+        if isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays and e.base.id not in used:
+            used.append(e.base.id)
+        return e
+
+    for n in walk(loop.body):
+        if isinstance(n, c.Assign):
+            map_expr(n.value, note)
+            map_expr(n.target, note)
+            if isinstance(n.target, c.Subscript) and n.target.base.id not in written:
+                written.append(n.target.base.id)
+        elif isinstance(n, c.Decl):
+            map_expr(n.init, note)
+        elif isinstance(n, c.If):
+            map_expr(n.cond, note)
+    esize = arrays[used[0]].ctype.size if used else 8
+    lanes = 16 // esize
+
+    def scalarise(e):
+        if isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays:
+            return c.Name(f"nomp_{e.base.id}_i")
+        return e
+
+    body_nodes = map_stmts(loop.body, scalarise)
+    from .emit_cuda import GenericEmitter
+    ge = GenericEmitter(knl)
+    ge.lines = []
+    ge.stmts(body_nodes, 4, True, False)
+    body = "\n".join(ge.lines)
+    ge.lines = []
+    ge.stmts(body_nodes, 3, True, False)
+    body_scalar = "\n".join(ge.lines)
+    it = cuda_type(loop.vtype)
+    lo, hi = expr_str(loop.lo), expr_str(loop.hi)
+    ety = {a: cuda_type(arrays[a].ctype) for a in used}
+    align = " | ".join(f"(nomp_u64_t)({a} + nomp_lo)" for a in used) or "0"
+    vec_decl = "\n".join(f"      struct __align__(16) {{ {ety[a]} v[{lanes}]; }} nomp_{a}_v;" for a in used)
+    vec_load = "\n".join(
+        f"      *reinterpret_cast<int4 *>(&nomp_{a}_v) = *reinterpret_cast<const int4 *>({a} + nomp_e);" for a in used)
+    vec_store = "\n".join(
+        f"      *reinterpret_cast<int4 *>({a} + nomp_e) = *reinterpret_cast<int4 *>(&nomp_{a}_v);" for a in written)
+    lane_in = "\n".join(f"        {ety[a]} nomp_{a}_i = nomp_{a}_v.v[nomp_l];" for a in used)
+    lane_out = "\n".join(f"        nomp_{a}_v.v[nomp_l] = nomp_{a}_i;" for a in written)
+    sc_in = "\n".join(f"      {ety[a]} nomp_{a}_i = {a}[nomp_e];" for a in used)
+    sc_out = "\n".join(f"      {a}[nomp_e] = nomp_{a}_i;" for a in written)
+    src = f"""{PRELUDE}
+// elementwise loop over `{loop.var}`: vectorised grid-stride schedule of libnompk map.cu with a generated body
+{signature(knl)} {{
+  const long long nomp_lo = (long long)({lo}), nomp_hi = (long long)({hi});
+  const long long nomp_n = nomp_hi - nomp_lo;
+  if (nomp_n <= 0) return;
+  const long long nomp_tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nomp_nthreads = (long long)gridDim.x * blockDim.x;
+  if ((({align}) & 15u) == 0) {{
+    const long long nomp_nvec = nomp_n / {lanes};
+    for (long long nomp_v = nomp_tid; nomp_v < nomp_nvec; nomp_v += nomp_nthreads) {{
+      const long long nomp_e = nomp_lo + nomp_v * {lanes};
+{vec_decl}
+{vec_load}
+#pragma unroll
+      for (int nomp_l = 0; nomp_l < {lanes}; nomp_l++) {{
+        const {it} {loop.var} = ({it})(nomp_e + nomp_l);
+{lane_in}
+{body}
+{lane_out}
+      }}
+{vec_store}
+    }}
+    for (long long nomp_e = nomp_lo + nomp_nvec * {lanes} + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
+      const {it} {loop.var} = ({it})nomp_e;
+{sc_in}
+{body_scalar}
+{sc_out}
+    }}
+  }} else {{
+    for (long long nomp_e = nomp_lo + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
+      const {it} {loop.var} = ({it})nomp_e;
+{sc_in}
+{body_scalar}
+{sc_out}
+    }}
+  }}
+}}
+"""
+    int_params = {p.name for p in func.params if not p.is_array and not p.ctype.is_float}
+    extent = c.BinOp("-", loop.hi, loop.lo) if const_int(loop.lo) != 0 else loop.hi
+    ext = grid_expr_str(extent, int_params)
+    per_block = 256 * lanes
+    grid = f"max(1, min(({ext} + {per_block - 1}) / {per_block}, {max(1, sm_count) * 8}))"
+    return src, [grid, "1", "1"], ["256", "1", "1"]

@@ -56,7 +56,7 @@ def main():
             g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
             D = torch.rand(n * n, dtype=torch.float64, device="cuda")
             w = torch.empty_like(u)
-            for variant in range(7):
+            for variant in range(12):
                 lib.nompk_ax_set_variant(variant)
 
                 def run():
