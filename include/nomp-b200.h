@@ -1,0 +1,34 @@
+/* nomp-b200.h -- additions of the B200 implementation to libnomp.so's exported surface.  None of them is needed by
+ * a program written against nomp.h; they exist for measurement (bench.py records CUDA events on the backend's own
+ * stream) and for multi-GPU runs.
+ *
+ * Multi-GPU (one process per GPU).  The reference is one process <-> one device (reference src/nomp.c:5,
+ * backends/unified-cuda-hip-impl.h:228) and has no collective.  Here nomp_init() joins an NCCL communicator when
+ * NOMP_COMM_SIZE > 1 (with NOMP_COMM_RANK and NOMP_COMM_ID_FILE, a path on a file system all ranks share, e.g.
+ * /dev/shm, through which rank 0 publishes the ncclUniqueId).  Each rank maps and loops over its own slice of the
+ * vectors / elements; the ONLY collective is an ncclAllReduce of the scalar a reduce clause produces, issued on
+ * the backend stream right after the single-pass device reduction. */
+#ifndef LIBNOMP_B200_EXT_H_
+#define LIBNOMP_B200_EXT_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t (as void*) on which this runtime issues copies and kernels; NULL before nomp_init(). */
+void *nomp_b200_stream(void);
+/* Device address that kernels receive for host pointer `hptr` (the address of host element 0), or NULL. */
+void *nomp_b200_device_ptr(void *hptr);
+/* Kernels launched by this runtime since load: NVRTC-built kernels + libnompk launches. */
+unsigned long long nomp_b200_launch_count(void);
+/* Rank / size of the NCCL communicator (0 / 1 when single-process). */
+int nomp_b200_comm_rank(void);
+int nomp_b200_comm_size(void);
+/* "kind=native family=map ..." descriptor of program `id` (valid until nomp_finalize), or NULL. */
+const char *nomp_b200_prog_info(int id);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LIBNOMP_B200_EXT_H_ */

@@ -1,0 +1,544 @@
+/* CUDA-only backend of libnomp for B200 (sm_100a).
+ *
+ * Fills the same six-entry vtable as the reference's CUDA backend (reference backends/cuda.c +
+ * backends/unified-cuda-hip-impl.h:70-246; vtable at reference include/nomp-impl.h:213-237) but
+ *   - knl_build() understands a one-line descriptor in front of the source: `kind=native` programs are bound to
+ *     the hand-written kernels of libnompk.so (include/nompk.h), `kind=nvrtc` programs are compiled by NVRTC
+ *     straight to a CUBIN for sm_100a (the reference asks NVRTC for PTX of sm_100 and lets the driver JIT it,
+ *     reference backends/cuda.c:21-22, unified-cuda-hip-impl.h:101-123) with FMA contraction off, so generated
+ *     code keeps the roundings of the C loop;
+ *   - all work is issued on one non-blocking stream owned by the backend (the reference uses the NULL stream and
+ *     cudaDeviceSynchronize, unified-cuda-hip-impl.h:151-169);
+ *   - a reduce clause is one kernel whose last block writes the result into mapped pinned host memory; across
+ *     ranks the scalar is all-reduced with NCCL first (reference: D2H of every partial + serial host loop,
+ *     src/reduction.c:33-88);
+ *   - there is no HIP / OpenCL / CPU path: if CUDA is unavailable nomp_init() fails with NOMP_CUDA_FAILURE.
+ * The driver API (module load, launch) is reached through cudaGetDriverEntryPoint, so the library has no
+ * link-time dependency on libcuda.so and loads on machines without a driver.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include "nomp-impl.h"
+#include "nomp-loopy.h"
+#include "nompk.h"
+
+static const char *ERR_STR_CUDA_FAILURE = "CUDA %s failure: %s.";
+
+#define check_runtime(call)                                                                                      \
+  do {                                                                                                           \
+    cudaError_t e_ = (call);                                                                                     \
+    if (e_ != cudaSuccess)                                                                                       \
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "runtime", cudaGetErrorName(e_));     \
+  } while (0)
+
+#define check_driver(call)                                                                                       \
+  do {                                                                                                           \
+    CUresult r_ = (call);                                                                                        \
+    if (r_ != CUDA_SUCCESS) {                                                                                    \
+      const char *m_ = "unknown";                                                                                \
+      if (drv.GetErrorName) drv.GetErrorName(r_, &m_);                                                           \
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "driver", m_);                        \
+    }                                                                                                            \
+  } while (0)
+
+#define check_nvrtc(call)                                                                                        \
+  do {                                                                                                           \
+    nvrtcResult r_ = (call);                                                                                     \
+    if (r_ != NVRTC_SUCCESS)                                                                                     \
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "nvrtc", nvrtcGetErrorString(r_));    \
+  } while (0)
+
+#define check_nompk(call)                                                                                        \
+  do {                                                                                                           \
+    int r_ = (call);                                                                                             \
+    if (r_ != NOMPK_OK)                                                                                          \
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "kernel library", nompk_last_error()); \
+  } while (0)
+
+/* driver entry points, resolved once per process */
+static struct {
+  CUresult (*ModuleLoadData)(CUmodule *, const void *);
+  CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+  CUresult (*ModuleUnload)(CUmodule);
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                           CUstream, void **, void **);
+  CUresult (*GetErrorName)(CUresult, const char **);
+  int resolved;
+} drv;
+
+static int resolve_driver(void) {
+  if (drv.resolved) return 0;
+  struct {
+    const char *name;
+    void **slot;
+  } table[] = {{"cuModuleLoadData", (void **)&drv.ModuleLoadData},
+               {"cuModuleGetFunction", (void **)&drv.ModuleGetFunction},
+               {"cuModuleUnload", (void **)&drv.ModuleUnload},
+               {"cuLaunchKernel", (void **)&drv.LaunchKernel},
+               {"cuGetErrorName", (void **)&drv.GetErrorName}};
+  for (unsigned i = 0; i < sizeof(table) / sizeof(table[0]); i++) {
+    enum cudaDriverEntryPointQueryResult status;
+    check_runtime(cudaGetDriverEntryPoint(table[i].name, table[i].slot, cudaEnableDefault, &status));
+    if (status != cudaDriverEntryPointSuccess || *table[i].slot == NULL)
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "driver entry point", table[i].name);
+  }
+  drv.resolved = 1;
+  return 0;
+}
+
+/* ---- backend state ------------------------------------------------------------------------------------------ */
+#define WORKSPACE_RESULT_OFFSET 16512 /* result slot inside the core's scratch buffer, after the nompk workspace */
+
+typedef struct {
+  int device;
+  struct cudaDeviceProp prop;
+  cudaStream_t stream;
+  void *pinned_host;   /* 64 bytes of mapped pinned memory: the host-visible reduction result */
+  void *pinned_dev;    /* its device alias */
+  void *red_partials;  /* device pointers handed to generated reduce kernels */
+  void *red_ticket;
+  void *red_result;
+  void *red_result_host;
+  /* D staging cache of the Ax family */
+  const void *ax_D;
+  unsigned long ax_D_version;
+  int ax_n;
+  unsigned long long nvrtc_launches;
+} cuda_state_t;
+
+static cuda_state_t *g_state = NULL; /* for the nomp_b200_* accessors */
+
+typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX } family_t;
+
+#define SLOT_NONE (-1)
+#define SLOT_PARTIALS (-2)
+#define SLOT_TICKET (-3)
+#define SLOT_RESULT (-4)
+#define SLOT_RESULT_HOST (-5)
+
+typedef struct {
+  family_t family;
+  /* nvrtc */
+  CUmodule module;
+  CUfunction function;
+  int nparams;
+  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 4]; /* index into prg->args, or SLOT_* */
+  int is_reduce;
+  /* native */
+  int op, dtype, ax_n;
+  int a_y, a_x, a_z, a_alpha, a_beta, a_n, a_out; /* argument indices (SLOT_NONE if unused) */
+  int a_u, a_g, a_D, a_w, a_E;
+  long n_literal; /* trip count when it is a literal in the source (a_n == SLOT_NONE) */
+} cuda_prog_t;
+
+/* ---- memory --------------------------------------------------------------------------------------------------- */
+static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direction_t op, size_t start, size_t end,
+                       size_t usize) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (op & NOMP_ALLOC) {
+    size_t bytes = NOMP_MEM_BYTES(start, end, usize);
+    check_runtime(cudaMalloc(&m->bptr, bytes ? bytes : 1));
+    m->bsize = bytes;
+    if (m == &bnd->scratch) { /* reduction workspace: the ticket counter must start at zero */
+      check_runtime(cudaMemsetAsync(m->bptr, 0, bytes, st->stream));
+      st->red_partials = m->bptr;
+      st->red_ticket = (char *)m->bptr + (nompk_reduce_workspace_bytes() - 64);
+      st->red_result = (char *)m->bptr + WORKSPACE_RESULT_OFFSET;
+    }
+  }
+  if (op & NOMP_TO) {
+    /* blocking on purpose: the caller may overwrite the host range as soon as nomp_update returns */
+    check_runtime(cudaMemcpyAsync((char *)m->bptr + NOMP_MEM_OFFSET(start - m->idx0, usize),
+                                  (const char *)m->hptr + NOMP_MEM_OFFSET(start, usize),
+                                  NOMP_MEM_BYTES(start, end, usize), cudaMemcpyHostToDevice, st->stream));
+    check_runtime(cudaStreamSynchronize(st->stream));
+    m->version++;
+  }
+  if (op == NOMP_FROM) {
+    check_runtime(cudaMemcpyAsync((char *)m->hptr + NOMP_MEM_OFFSET(start, usize),
+                                  (const char *)m->bptr + NOMP_MEM_OFFSET(start - m->idx0, usize),
+                                  NOMP_MEM_BYTES(start, end, usize), cudaMemcpyDeviceToHost, st->stream));
+    check_runtime(cudaStreamSynchronize(st->stream));
+  } else if (op == NOMP_FREE) {
+    check_runtime(cudaStreamSynchronize(st->stream));
+    check_runtime(cudaFree(m->bptr));
+    m->bptr = NULL; /* tells the core to drop the entry (reference src/nomp.c:360) */
+  }
+  return 0;
+}
+
+/* ---- descriptor parsing --------------------------------------------------------------------------------------- */
+/* value of `key=` in the first line of src, copied into buf; 0 if absent */
+static int desc_get(const char *src, const char *key, char *buf, size_t cap) {
+  const char *eol = strchr(src, '\n');
+  size_t linelen = eol ? (size_t)(eol - src) : strlen(src);
+  size_t klen = strlen(key);
+  for (const char *p = src; p + klen + 1 <= src + linelen; p++) {
+    if ((p == src || p[-1] == ' ') && !strncmp(p, key, klen) && p[klen] == '=') {
+      const char *v = p + klen + 1;
+      size_t n = 0;
+      while (v + n < src + linelen && v[n] != ' ' && n + 1 < cap) n++;
+      memcpy(buf, v, n);
+      buf[n] = '\0';
+      return 1;
+    }
+  }
+  return 0;
+}
+
+static int arg_index(const nomp_prog_t *prg, const char *name) {
+  for (unsigned i = 0; i < prg->nargs; i++)
+    if (!strncmp(prg->args[i].name, name, NOMP_MAX_BUFFER_SIZE)) return (int)i;
+  return SLOT_NONE;
+}
+
+/* resolve descriptor key -> argument index; "-" or absent means unused */
+static int desc_arg(const nomp_prog_t *prg, const char *src, const char *key, int required, int *out) {
+  char name[NOMP_MAX_BUFFER_SIZE + 1];
+  *out = SLOT_NONE;
+  if (!desc_get(src, key, name, sizeof(name)) || !strcmp(name, "-")) {
+    if (required)
+      return nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Kernel descriptor is missing \"%s\".", key);
+    return 0;
+  }
+  *out = arg_index(prg, name);
+  if (*out == SLOT_NONE)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
+                    "Kernel argument \"%s\" was not declared in nomp_jit().", name);
+  return 0;
+}
+
+static int desc_count(const nomp_prog_t *prg, const char *src, const char *key, int *idx, long *literal) {
+  char v[NOMP_MAX_BUFFER_SIZE + 1];
+  if (!desc_get(src, key, v, sizeof(v)))
+    return nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Kernel descriptor is missing \"%s\".", key);
+  if (v[0] >= '0' && v[0] <= '9') {
+    *idx = SLOT_NONE;
+    *literal = strtol(v, NULL, 10);
+    return 0;
+  }
+  *idx = arg_index(prg, v);
+  if (*idx == SLOT_NONE)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
+                    "Kernel argument \"%s\" was not declared in nomp_jit().", v);
+  return 0;
+}
+
+static void mark_const_args(nomp_prog_t *prg, const char *src) {
+  char list[BUFSIZ];
+  if (!desc_get(src, "ro", list, sizeof(list))) return;
+  for (char *tok = strtok(list, ","); tok; tok = strtok(NULL, ",")) {
+    int i = arg_index(prg, tok);
+    if (i >= 0) prg->args[i].is_const = 1;
+  }
+}
+
+/* ---- build ---------------------------------------------------------------------------------------------------- */
+static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, const char *source, const char *name) {
+  nomp_check(resolve_driver());
+
+  char params[BUFSIZ];
+  if (!desc_get(source, "params", params, sizeof(params))) params[0] = '\0';
+  cp->nparams = 0;
+  for (char *tok = strtok(params, ","); tok; tok = strtok(NULL, ",")) {
+    int slot;
+    if (!strcmp(tok, "nomp_partials")) slot = SLOT_PARTIALS;
+    else if (!strcmp(tok, "nomp_ticket")) slot = SLOT_TICKET;
+    else if (!strcmp(tok, "nomp_result")) slot = SLOT_RESULT;
+    else if (!strcmp(tok, "nomp_result_host")) slot = SLOT_RESULT_HOST;
+    else {
+      slot = arg_index(prg, tok);
+      if (slot == SLOT_NONE)
+        return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
+                        "Kernel argument \"%s\" was not declared in nomp_jit().", tok);
+    }
+    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 4)
+      return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Too many kernel arguments.");
+    cp->param_slot[cp->nparams++] = slot;
+  }
+  char flag[8];
+  cp->is_reduce = desc_get(source, "reduce", flag, sizeof(flag)) && flag[0] == '1';
+
+  nvrtcProgram prog;
+  check_nvrtc(nvrtcCreateProgram(&prog, source, name, 0, NULL, NULL));
+  char arch[64];
+  /* architecture-specific target ("a" suffix) for Hopper and newer: sm_100a on B200 */
+  snprintf(arch, sizeof(arch), "--gpu-architecture=sm_%d%d%s", st->prop.major, st->prop.minor,
+           st->prop.major >= 9 ? "a" : "");
+  const char *options[] = {arch, "--fmad=false", "--std=c++17", "-lineinfo"};
+  nvrtcResult result = nvrtcCompileProgram(prog, 4, options);
+  if (result != NVRTC_SUCCESS) {
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    char *log = nomp_calloc(char, log_size + 1);
+    nvrtcGetProgramLog(prog, log);
+    int err = nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "CUDA build failure: %s: %s.", nvrtcGetErrorString(result), log);
+    free(log);
+    nvrtcDestroyProgram(&prog);
+    return err;
+  }
+  size_t size = 0;
+  check_nvrtc(nvrtcGetCUBINSize(prog, &size));
+  char *cubin = nomp_calloc(char, size + 1);
+  check_nvrtc(nvrtcGetCUBIN(prog, cubin));
+  check_nvrtc(nvrtcDestroyProgram(&prog));
+  CUresult r = drv.ModuleLoadData(&cp->module, cubin);
+  free(cubin);
+  check_driver(r);
+  check_driver(drv.ModuleGetFunction(&cp->function, cp->module, name));
+  return 0;
+}
+
+static int cuda_knl_build(nomp_backend_t *bnd, nomp_prog_t *prg, const char *source, const char *name) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  char kind[32] = "", family[32] = "", num[32];
+  if (strncmp(source, "//!nomp ", 8) || !desc_get(source, "kind", kind, sizeof(kind)) ||
+      !desc_get(source, "family", family, sizeof(family)))
+    return nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Generated kernel \"%s\" has no descriptor line.", name);
+  mark_const_args(prg, source);
+
+  cuda_prog_t *cp = nomp_calloc(cuda_prog_t, 1);
+  cp->a_y = cp->a_x = cp->a_z = cp->a_alpha = cp->a_beta = cp->a_n = cp->a_out = SLOT_NONE;
+  cp->a_u = cp->a_g = cp->a_D = cp->a_w = cp->a_E = SLOT_NONE;
+  int err = 0;
+  if (!strcmp(kind, "nvrtc")) {
+    cp->family = FAM_NVRTC;
+    err = build_nvrtc(st, cp, prg, source, name);
+  } else if (!strcmp(kind, "native")) {
+    cp->op = desc_get(source, "op", num, sizeof(num)) ? atoi(num) : 0;
+    cp->dtype = desc_get(source, "dtype", num, sizeof(num)) ? atoi(num) : NOMPK_F64;
+    if (!strcmp(family, "map")) {
+      cp->family = FAM_MAP;
+      (void)((err = desc_arg(prg, source, "y", 1, &cp->a_y)) || (err = desc_arg(prg, source, "x", 0, &cp->a_x)) ||
+             (err = desc_arg(prg, source, "z", 0, &cp->a_z)) || (err = desc_arg(prg, source, "alpha", 0, &cp->a_alpha)) ||
+             (err = desc_arg(prg, source, "beta", 0, &cp->a_beta)) ||
+             (err = desc_count(prg, source, "n", &cp->a_n, &cp->n_literal)));
+    } else if (!strcmp(family, "reduce")) {
+      cp->family = FAM_REDUCE;
+      cp->is_reduce = 1;
+      (void)((err = desc_arg(prg, source, "x", 1, &cp->a_x)) || (err = desc_arg(prg, source, "y", 0, &cp->a_y)) ||
+             (err = desc_arg(prg, source, "out", 1, &cp->a_out)) ||
+             (err = desc_count(prg, source, "n", &cp->a_n, &cp->n_literal)));
+    } else if (!strcmp(family, "ax")) {
+      cp->family = FAM_AX;
+      cp->ax_n = desc_get(source, "n", num, sizeof(num)) ? atoi(num) : 0;
+      if (!nompk_ax_supported(cp->ax_n))
+        err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "No native Ax kernel for n = %d.", cp->ax_n);
+      else
+        (void)((err = desc_arg(prg, source, "u", 1, &cp->a_u)) || (err = desc_arg(prg, source, "g", 1, &cp->a_g)) ||
+               (err = desc_arg(prg, source, "D", 1, &cp->a_D)) || (err = desc_arg(prg, source, "w", 1, &cp->a_w)) ||
+               (err = desc_arg(prg, source, "E", 1, &cp->a_E)));
+    } else {
+      err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Unknown native kernel family \"%s\".", family);
+    }
+  } else {
+    err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Unknown kernel kind \"%s\".", kind);
+  }
+  if (err) {
+    free(cp);
+    return err;
+  }
+  prg->bptr = cp;
+  return 0;
+}
+
+/* ---- run ------------------------------------------------------------------------------------------------------ */
+static long int_arg(const nomp_prog_t *prg, int idx, long literal) {
+  if (idx < 0) return literal;
+  const nomp_arg_t *a = &prg->args[idx];
+  if (a->type == NOMP_UINT) return a->size == 8 ? (long)*(unsigned long *)a->ptr : (long)*(unsigned *)a->ptr;
+  return a->size == 8 ? *(long *)a->ptr : (long)*(int *)a->ptr;
+}
+
+static void *ptr_arg(const nomp_prog_t *prg, int idx) { return idx < 0 ? NULL : prg->args[idx].ptr; }
+
+static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
+  /* with several ranks the host-visible value must be the all-reduced one, so the kernel only fills the device slot */
+  void *result_host = nomp_comm_size() > 1 ? NULL : st->pinned_dev;
+
+  switch (cp->family) {
+  case FAM_MAP: {
+    long n = int_arg(prg, cp->a_n, cp->n_literal);
+    if (n < 0) n = 0;
+    check_nompk(nompk_map((nompk_map_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_y),
+                          ptr_arg(prg, cp->a_x), ptr_arg(prg, cp->a_z), ptr_arg(prg, cp->a_alpha),
+                          ptr_arg(prg, cp->a_beta), st->stream));
+    return 0;
+  }
+  case FAM_REDUCE: {
+    long n = int_arg(prg, cp->a_n, cp->n_literal);
+    if (n < 0) n = 0;
+    check_nompk(nompk_reduce((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
+                             ptr_arg(prg, cp->a_y), st->red_result, result_host, st->red_partials, st->stream));
+    return 0;
+  }
+  case FAM_AX: {
+    long E = int_arg(prg, cp->a_E, 0);
+    if (E < 0) E = 0;
+    const void *D = ptr_arg(prg, cp->a_D);
+    /* D is staged into __constant__ memory by a tiny D2D copy; skip it while the same device image is reused
+     * (the mapping's version changes on every nomp_update(TO) and whenever a kernel may have written to it) */
+    const nomp_mem_t *dm = (const nomp_mem_t *)prg->args[cp->a_D].mem;
+    const unsigned long version = dm ? dm->version : 0;
+    unsigned flags = 0;
+    if (dm && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
+    check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
+                             (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
+                             (double *)ptr_arg(prg, cp->a_w), flags, st->stream));
+    st->ax_D = D, st->ax_n = cp->ax_n, st->ax_D_version = version;
+    return 0;
+  }
+  case FAM_NVRTC: {
+    st->red_result_host = result_host;
+    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 4];
+    for (int i = 0; i < cp->nparams; i++) {
+      int s = cp->param_slot[i];
+      if (s == SLOT_PARTIALS) vargs[i] = &st->red_partials;
+      else if (s == SLOT_TICKET) vargs[i] = &st->red_ticket;
+      else if (s == SLOT_RESULT) vargs[i] = &st->red_result;
+      else if (s == SLOT_RESULT_HOST) vargs[i] = &st->red_result_host;
+      else if (prg->args[s].type == NOMP_PTR) vargs[i] = &prg->args[s].ptr; /* device pointer by value */
+      else vargs[i] = prg->args[s].ptr;                                       /* the caller's scalar */
+    }
+    const size_t *g = prg->global, *l = prg->local;
+    if (g[0] == 0 || g[1] == 0 || g[2] == 0) return 0; /* empty iteration space */
+    check_driver(drv.LaunchKernel(cp->function, (unsigned)g[0], (unsigned)g[1], (unsigned)g[2], (unsigned)l[0],
+                                  (unsigned)l[1], (unsigned)l[2], 0, (CUstream)st->stream, vargs, NULL));
+    st->nvrtc_launches++;
+    return 0;
+  }
+  }
+  return 0;
+}
+
+int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
+  size_t size = (size_t)prg->reduction_size;
+  if (size != 4 && size != 8)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Reduction variable must be 4 or 8 bytes wide.");
+  if (cp->family == FAM_NVRTC && (prg->global[0] == 0)) {
+    /* empty loop: the result is the identity */
+    memset(prg->reduction_ptr, 0, size);
+    if (prg->reduction_op == NOMP_PROD) {
+      if (prg->reduction_type == NOMP_FLOAT) {
+        if (size == 4) *(float *)prg->reduction_ptr = 1.0f; else *(double *)prg->reduction_ptr = 1.0;
+      } else {
+        ((char *)prg->reduction_ptr)[0] = 1;
+      }
+    }
+    return 0;
+  }
+  if (nomp_comm_size() > 1) {
+    int dtype;
+    switch (prg->reduction_type) {
+    case NOMP_INT: dtype = size == 4 ? NOMPK_I32 : NOMPK_I64; break;
+    case NOMP_UINT: dtype = size == 4 ? NOMPK_U32 : NOMPK_U64; break;
+    default: dtype = size == 4 ? NOMPK_F32 : NOMPK_F64; break;
+    }
+    nomp_check(nomp_comm_allreduce(st->red_result, dtype, (int)prg->reduction_op, st->stream));
+    check_runtime(cudaMemcpyAsync(st->pinned_host, st->red_result, 8, cudaMemcpyDeviceToHost, st->stream));
+  }
+  /* the reduce clause's result is valid on the host when nomp_run returns (reference
+   * tests/nomp-api-500-impl.h:29-34 read it with no nomp_sync in between) */
+  check_runtime(cudaStreamSynchronize(st->stream));
+  memcpy(prg->reduction_ptr, st->pinned_host, size);
+  return 0;
+}
+
+static int cuda_knl_free(nomp_prog_t *prg) {
+  cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
+  if (cp == NULL) return 0;
+  if (cp->family == FAM_NVRTC && cp->module && drv.resolved) check_driver(drv.ModuleUnload(cp->module));
+  free(cp);
+  prg->bptr = NULL;
+  return 0;
+}
+
+static int cuda_sync(nomp_backend_t *bnd) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  check_runtime(cudaStreamSynchronize(st->stream));
+  return 0;
+}
+
+static int cuda_finalize(nomp_backend_t *bnd) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (st == NULL) return 0;
+  nomp_comm_finalize();
+  if (st->stream) {
+    cudaStreamSynchronize(st->stream);
+    cudaStreamDestroy(st->stream);
+  }
+  if (st->pinned_host) cudaFreeHost(st->pinned_host);
+  if (g_state == st) g_state = NULL;
+  free(st);
+  bnd->bptr = NULL;
+  return 0;
+}
+
+static int cuda_device_query(nomp_backend_t *bnd, cuda_state_t *st) {
+  check_runtime(cudaGetDeviceProperties(&st->prop, st->device));
+  nomp_py_dict_set_str(bnd->py_context, "device::name", st->prop.name);
+  nomp_py_dict_set_str(bnd->py_context, "device::vendor", "NVIDIA");
+  char arch[32];
+  snprintf(arch, sizeof(arch), "sm_%d%d", st->prop.major, st->prop.minor);
+  nomp_py_dict_set_str(bnd->py_context, "device::arch", arch);
+  int driver = 0;
+  check_runtime(cudaDriverGetVersion(&driver));
+  nomp_py_dict_set_long(bnd->py_context, "device::driver", driver);
+  nomp_py_dict_set_long(bnd->py_context, "device::max_threads_per_block", st->prop.maxThreadsPerBlock);
+  nomp_py_dict_set_long(bnd->py_context, "device::multiprocessor_count", st->prop.multiProcessorCount);
+  return 0;
+}
+
+int cuda_init(nomp_backend_t *bnd, int platform, int device) {
+  (void)platform; /* validated by the core, meaningless for CUDA (reference unified-cuda-hip-impl.h:219) */
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess)
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "runtime", cudaGetErrorName(e));
+  if (device < 0 || device >= count)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, ERR_STR_USER_DEVICE_IS_INVALID, device);
+  check_runtime(cudaSetDevice(device));
+  check_runtime(cudaFree(0));
+
+  cuda_state_t *st = nomp_calloc(cuda_state_t, 1);
+  st->device = device;
+  int err = cuda_device_query(bnd, st);
+  if (!err) {
+    e = cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc(&st->pinned_host, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&st->pinned_dev, st->pinned_host, 0);
+    if (e != cudaSuccess)
+      err = nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "runtime", cudaGetErrorName(e));
+  }
+  if (!err) err = nomp_comm_init(device);
+  if (err) {
+    if (st->stream) cudaStreamDestroy(st->stream);
+    if (st->pinned_host) cudaFreeHost(st->pinned_host);
+    free(st);
+    return err;
+  }
+  memset(st->pinned_host, 0, 64);
+
+  bnd->bptr = st;
+  bnd->update = cuda_update;
+  bnd->knl_build = cuda_knl_build;
+  bnd->knl_run = cuda_knl_run;
+  bnd->knl_free = cuda_knl_free;
+  bnd->sync = cuda_sync;
+  bnd->finalize = cuda_finalize;
+  g_state = st;
+  return 0;
+}
+
+/* ---- include/nomp-b200.h ---------------------------------------------------------------------------------------- */
+NOMP_EXPORT void *nomp_b200_stream(void) { return g_state ? (void *)g_state->stream : NULL; }
+
+NOMP_EXPORT unsigned long long nomp_b200_launch_count(void) {
+  return nompk_launch_count() + (g_state ? g_state->nvrtc_launches : 0);
+}

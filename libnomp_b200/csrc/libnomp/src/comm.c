@@ -1,0 +1,133 @@
+/* NCCL communicator for multi-GPU runs (one process per GPU).
+ *
+ * The reference has no collective of any kind.  The only exchange on the north-star path is the
+ * scalar of a reduce clause, e.g. the dot products of a CG iteration: each rank reduces its slice in one kernel
+ * and this file all-reduces the 4/8-byte result in place on the backend stream (NVLink 5 / NVSwitch).
+ *
+ * Bootstrap without MPI: NOMP_COMM_SIZE, NOMP_COMM_RANK and NOMP_COMM_ID_FILE.  Rank 0 creates the ncclUniqueId and
+ * publishes it by writing <file>.tmp and renaming it to <file>; the other ranks poll for <file>.  The caller must
+ * pick a path that is fresh for every job (bench.py derives it from MASTER_PORT and a broadcast token).
+ * NCCL is dlopen()ed on first use, so single-GPU programs and the nomp-api tests never load it.
+ */
+#include <dlfcn.h>
+#include <nccl.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "nomp-aux.h"
+#include "nomp-impl.h"
+#include "nompk.h"
+
+static struct {
+  void *handle;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char *(*GetErrorString)(ncclResult_t);
+} nccl;
+
+static ncclComm_t comm = NULL;
+static int comm_rank = 0, comm_size = 1;
+
+#define check_nccl(call)                                                                                         \
+  do {                                                                                                           \
+    ncclResult_t r_ = (call);                                                                                    \
+    if (r_ != ncclSuccess)                                                                                       \
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "NCCL failure: %s.", nccl.GetErrorString(r_));              \
+  } while (0)
+
+static int load_nccl(void) {
+  if (nccl.handle) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (unsigned i = 0; i < 2 && !nccl.handle; i++) nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!nccl.handle) return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "NCCL failure: cannot load libnccl.so.2 (%s).", dlerror());
+#define RESOLVE(field, sym)                                                                                      \
+  if (!(*(void **)&nccl.field = dlsym(nccl.handle, sym)))                                                        \
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "NCCL failure: symbol %s not found.", sym);
+  RESOLVE(GetUniqueId, "ncclGetUniqueId")
+  RESOLVE(CommInitRank, "ncclCommInitRank")
+  RESOLVE(AllReduce, "ncclAllReduce")
+  RESOLVE(CommDestroy, "ncclCommDestroy")
+  RESOLVE(GetErrorString, "ncclGetErrorString")
+#undef RESOLVE
+  return 0;
+}
+
+static int env_int(const char *name, int fallback) {
+  const char *v = getenv(name);
+  if (!v) return fallback;
+  return nomp_str_toui(v, NOMP_MAX_BUFFER_SIZE);
+}
+
+int nomp_comm_rank(void) { return comm_rank; }
+int nomp_comm_size(void) { return comm_size; }
+NOMP_EXPORT int nomp_b200_comm_rank(void) { return comm_rank; }
+NOMP_EXPORT int nomp_b200_comm_size(void) { return comm_size; }
+
+int nomp_comm_init(int device) {
+  (void)device;
+  comm_rank = 0, comm_size = 1;
+  const int size = env_int("NOMP_COMM_SIZE", 1);
+  if (size == 1) return 0;
+  const int rank = env_int("NOMP_COMM_RANK", -1);
+  const char *path = getenv("NOMP_COMM_ID_FILE");
+  if (size < 1 || rank < 0 || rank >= size || !path || !path[0])
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
+                    "NOMP_COMM_SIZE > 1 needs a valid NOMP_COMM_RANK and NOMP_COMM_ID_FILE.");
+  nomp_check(load_nccl());
+
+  ncclUniqueId id;
+  if (rank == 0) {
+    check_nccl(nccl.GetUniqueId(&id));
+    char *tmp = nomp_str_cat(2, PATH_MAX, path, ".tmp");
+    FILE *f = fopen(tmp, "wb");
+    int ok = f && fwrite(&id, sizeof(id), 1, f) == 1;
+    if (f) ok = (fclose(f) == 0) && ok;
+    ok = ok && rename(tmp, path) == 0;
+    free(tmp);
+    if (!ok) return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Cannot publish the NCCL id through \"%s\".", path);
+  } else {
+    int got = 0;
+    for (int tries = 0; tries < 12000 && !got; tries++) { /* up to 120 s */
+      FILE *f = fopen(path, "rb");
+      if (f) {
+        got = fread(&id, sizeof(id), 1, f) == 1;
+        fclose(f);
+      }
+      if (!got) {
+        struct timespec ts = {0, 10 * 1000 * 1000};
+        nanosleep(&ts, NULL);
+      }
+    }
+    if (!got) return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Timed out waiting for the NCCL id in \"%s\".", path);
+  }
+  check_nccl(nccl.CommInitRank(&comm, size, id, rank));
+  comm_rank = rank, comm_size = size;
+  return 0;
+}
+
+int nomp_comm_finalize(void) {
+  if (comm) {
+    nccl.CommDestroy(comm);
+    comm = NULL;
+  }
+  comm_rank = 0, comm_size = 1;
+  return 0;
+}
+
+int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *stream) {
+  if (comm_size == 1) return 0;
+  ncclDataType_t dt;
+  switch (dtype) {
+  case NOMPK_I32: dt = ncclInt32; break;
+  case NOMPK_U32: dt = ncclUint32; break;
+  case NOMPK_I64: dt = ncclInt64; break;
+  case NOMPK_U64: dt = ncclUint64; break;
+  case NOMPK_F32: dt = ncclFloat32; break;
+  default: dt = ncclFloat64; break;
+  }
+  ncclRedOp_t rop = op == NOMP_PROD ? ncclProd : op == NOMP_MIN ? ncclMin : op == NOMP_MAX ? ncclMax : ncclSum;
+  check_nccl(nccl.AllReduce(dev_scalar, dev_scalar, 1, dt, rop, comm, (cudaStream_t)stream));
+  return 0;
+}
