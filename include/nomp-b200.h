@@ -11,6 +11,8 @@
 #ifndef LIBNOMP_B200_EXT_H_
 #define LIBNOMP_B200_EXT_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -24,6 +26,9 @@ unsigned long long nomp_b200_launch_count(void);
 /* Rank / size of the NCCL communicator (0 / 1 when single-process). */
 int nomp_b200_comm_rank(void);
 int nomp_b200_comm_size(void);
+/* File rendezvous used to distribute the ncclUniqueId: rank 0 publishes `bytes` bytes through `path`, the other
+ * ranks wait for the file and read them.  0 on success, a log id otherwise. */
+int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 /* "kind=native family=map ..." descriptor of program `id` (valid until nomp_finalize), or NULL. */
 const char *nomp_b200_prog_info(int id);
 

@@ -44,7 +44,7 @@ NOMP_SYMBOLS = [
     "nomp_finalize", "nomp_finalize_excluding_interpreter", "nomp_copy_env",
     # extensions declared in include/nomp-b200.h
     "nomp_b200_stream", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
-    "nomp_b200_comm_size", "nomp_b200_prog_info",
+    "nomp_b200_comm_size", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
 ]
 
 
@@ -124,6 +124,8 @@ def nomp() -> C.CDLL:
         lib.nomp_b200_comm_size.restype = C.c_int
         lib.nomp_b200_prog_info.restype = C.c_char_p
         lib.nomp_b200_prog_info.argtypes = [C.c_int]
+        lib.nomp_b200_exchange_blob.restype = C.c_int
+        lib.nomp_b200_exchange_blob.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
         _nomp = lib
     return _nomp
 

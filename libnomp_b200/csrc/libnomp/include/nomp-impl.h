@@ -118,6 +118,7 @@ int nomp_comm_rank(void);
 int nomp_comm_size(void);
 /* in-place allreduce of one scalar on `stream`; dtype codes of include/nompk.h, op = nomp_reduction_op_t */
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *stream);
+int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 
 extern const char *ERR_STR_USER_MAP_PTR_IS_INVALID;
 extern const char *ERR_STR_USER_DEVICE_IS_INVALID;

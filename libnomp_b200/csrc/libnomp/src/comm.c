@@ -65,6 +65,33 @@ int nomp_comm_size(void) { return comm_size; }
 NOMP_EXPORT int nomp_b200_comm_rank(void) { return comm_rank; }
 NOMP_EXPORT int nomp_b200_comm_size(void) { return comm_size; }
 
+/* Rank 0 publishes `bytes` bytes through the file `path` (write <path>.tmp, then rename: readers never see a partial
+ * file); every other rank polls for the file (up to 120 s) and reads them.  Exported so that the rendezvous can be
+ * tested without GPUs (tests/test_multirank_cpu.py). */
+NOMP_EXPORT int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes) {
+  if (rank == 0) {
+    char *tmp = nomp_str_cat(2, PATH_MAX, path, ".tmp");
+    FILE *f = fopen(tmp, "wb");
+    int ok = f && fwrite(blob, bytes, 1, f) == 1;
+    if (f) ok = (fclose(f) == 0) && ok;
+    ok = ok && rename(tmp, path) == 0;
+    free(tmp);
+    if (!ok) return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Cannot publish the NCCL id through \"%s\".", path);
+    return 0;
+  }
+  for (int tries = 0; tries < 12000; tries++) {
+    FILE *f = fopen(path, "rb");
+    if (f) {
+      int got = fread(blob, bytes, 1, f) == 1;
+      fclose(f);
+      if (got) return 0;
+    }
+    struct timespec ts = {0, 10 * 1000 * 1000};
+    nanosleep(&ts, NULL);
+  }
+  return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Timed out waiting for the NCCL id in \"%s\".", path);
+}
+
 int nomp_comm_init(int device) {
   (void)device;
   comm_rank = 0, comm_size = 1;
@@ -78,30 +105,8 @@ int nomp_comm_init(int device) {
   nomp_check(load_nccl());
 
   ncclUniqueId id;
-  if (rank == 0) {
-    check_nccl(nccl.GetUniqueId(&id));
-    char *tmp = nomp_str_cat(2, PATH_MAX, path, ".tmp");
-    FILE *f = fopen(tmp, "wb");
-    int ok = f && fwrite(&id, sizeof(id), 1, f) == 1;
-    if (f) ok = (fclose(f) == 0) && ok;
-    ok = ok && rename(tmp, path) == 0;
-    free(tmp);
-    if (!ok) return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Cannot publish the NCCL id through \"%s\".", path);
-  } else {
-    int got = 0;
-    for (int tries = 0; tries < 12000 && !got; tries++) { /* up to 120 s */
-      FILE *f = fopen(path, "rb");
-      if (f) {
-        got = fread(&id, sizeof(id), 1, f) == 1;
-        fclose(f);
-      }
-      if (!got) {
-        struct timespec ts = {0, 10 * 1000 * 1000};
-        nanosleep(&ts, NULL);
-      }
-    }
-    if (!got) return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Timed out waiting for the NCCL id in \"%s\".", path);
-  }
+  if (rank == 0) check_nccl(nccl.GetUniqueId(&id));
+  nomp_check(nomp_b200_exchange_blob(path, rank, &id, sizeof(id)));
   check_nccl(nccl.CommInitRank(&comm, size, id, rank));
   comm_rank = rank, comm_size = size;
   return 0;

@@ -1,0 +1,143 @@
+"""The C-ABI boundary without a GPU: both shared libraries load, export every function their headers declare, and the
+parts of the public API that need no device behave like the reference (error ids, messages, configuration parsing)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from libnomp_b200 import INSTALL_DIR, capi  # noqa: E402
+
+DECL = re.compile(r"^\s*(?:const\s+)?(?:unsigned\s+long\s+long|unsigned|int|void|char|size_t)\s*\*?\s*(nomp\w+|nompk\w+)\s*\(", re.M)
+
+
+def declared(header):
+    text = (ROOT / "include" / header).read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(DECL.findall(text)))
+
+
+def test_headers_and_libraries_agree():
+    k, n = capi.nompk(), capi.nomp()
+    want_k = declared("nompk.h")
+    assert len(want_k) >= 10
+    for sym in want_k:
+        assert hasattr(k, sym), f"libnompk.so does not export {sym}"
+    want_n = declared("nomp.h") + declared("nomp-aux.h") + declared("nomp-b200.h")
+    assert {"nomp_init", "nomp_update", "nomp_jit", "nomp_run", "nomp_sync", "nomp_get_err_str", "nomp_get_err_no",
+            "nomp_finalize", "nomp_finalize_excluding_interpreter", "nomp_copy_env"} <= set(want_n)
+    for sym in want_n:
+        assert hasattr(n, sym), f"libnomp.so does not export {sym}"
+    assert sorted(capi.NOMPK_SYMBOLS) == want_k
+    assert k.nompk_version() == 100 and k.nompk_reduce_workspace_bytes() >= 2048 * 8
+    assert [k.nompk_dtype_size(d) for d in range(6)] == [4, 4, 8, 8, 4, 8]
+    assert [k.nompk_ax_supported(x) for x in (6, 7, 8, 9, 10, 12)] == [1, 0, 1, 0, 1, 1]
+
+
+def test_public_enum_values_are_the_reference_abi():
+    text = (ROOT / "include" / "nomp.h").read_text()
+    for name, value in dict(NOMP_INT=2048, NOMP_UINT=4096, NOMP_FLOAT=8192, NOMP_PTR=16384, NOMP_ALLOC=1, NOMP_TO=2,
+                            NOMP_FROM=4, NOMP_FREE=8, NOMP_JIT=1).items():
+        assert re.search(rf"\b{name}\s*=\s*{value}\b", text), name
+    for name, value in dict(NOMP_USER_INPUT_IS_INVALID=-128, NOMP_USER_MAP_PTR_IS_INVALID=-130, NOMP_USER_MAP_OP_IS_INVALID=-132,
+                            NOMP_USER_LOG_ID_IS_INVALID=-134, NOMP_INITIALIZE_FAILURE=-256, NOMP_FINALIZE_FAILURE=-258,
+                            NOMP_PY_CALL_FAILURE=-384, NOMP_LOOPY_CONVERSION_FAILURE=-386, NOMP_LOOPY_KNL_NAME_NOT_FOUND=-388,
+                            NOMP_LOOPY_CODEGEN_FAILURE=-390, NOMP_LOOPY_GRIDSIZE_FAILURE=-392, NOMP_CUDA_FAILURE=-512).items():
+        assert re.search(rf"#define {name} \({value}\)", text), name
+
+
+def test_kernel_library_has_only_sm_100a_code():
+    """No multi-architecture dispatch: the fat binary holds exactly one target."""
+    out = subprocess.run(["cuobjdump", "--list-elf", str(ROOT / "libnomp_b200" / "lib" / "libnompk.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+# The following run in a child process: nomp_init() touches process-wide state (embedded interpreter, CUDA).
+CHILD = r"""
+import ctypes as C, sys, os
+sys.path.insert(0, {root!r})
+from libnomp_b200 import capi
+lib = capi.nomp()
+def argv(*a):
+    return len(a), (C.c_char_p * len(a))(*[x.encode() for x in a])
+out = []
+# finalize before init: the raw code, and it is not a valid log id
+e = lib.nomp_finalize(); out.append(("finalize_first", e, lib.nomp_get_err_no(C.c_uint(e & 0xffffffff))))
+# missing value after the last flag
+e = lib.nomp_init(*argv("--nomp-backend", "cuda", "--nomp-device", "0", "--nomp-platform")); out.append(("missing_value",) + capi.err_info(e))
+# backend / install dir missing
+os.environ.pop("NOMP_INSTALL_DIR", None)
+e = lib.nomp_init(*argv("prog", "--nomp-backend", "cuda")); out.append(("no_install_dir",) + capi.err_info(e))
+e = lib.nomp_init(*argv("prog", "--nomp-install-dir", {inst!r})); out.append(("no_backend",) + capi.err_info(e))
+# invalid numeric values, from the environment (which overrides the command line)
+os.environ["NOMP_DEVICE"] = "invalid"
+e = lib.nomp_init(*argv("prog", "--nomp-backend", "cuda", "--nomp-install-dir", {inst!r}, "--nomp-device", "0")); out.append(("bad_device",) + capi.err_info(e))
+del os.environ["NOMP_DEVICE"]
+os.environ["NOMP_BACKEND"] = "invalid"
+e = lib.nomp_init(*argv("prog", "--nomp-backend", "cuda", "--nomp-install-dir", {inst!r})); out.append(("bad_backend",) + capi.err_info(e))
+del os.environ["NOMP_BACKEND"]
+e = lib.nomp_init(*argv("prog", "--nomp-backend", "OpenCL", "--nomp-install-dir", {inst!r})); out.append(("opencl",) + capi.err_info(e))
+# every failed init leaves the runtime uninitialised
+out.append(("finalize_after_failures", lib.nomp_finalize()))
+out.append(("run_invalid",) + capi.err_info(lib.nomp_run(C.c_int(-1))))
+out.append(("bad_id", lib.nomp_get_err_no(C.c_uint(0)), lib.nomp_get_err_no(C.c_uint(100000))))
+for o in out: print(repr(o))
+"""
+
+
+def test_configuration_and_error_registry_without_a_device():
+    code = CHILD.format(root=str(ROOT), inst=str(INSTALL_DIR))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("NOMP_")}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = {}
+    for line in r.stdout.splitlines():
+        t = eval(line)
+        rows[t[0]] = t[1:]
+    assert rows["finalize_first"] == (capi.NOMP_FINALIZE_FAILURE, capi.NOMP_USER_LOG_ID_IS_INVALID)
+    no, text = rows["missing_value"]
+    assert no == capi.NOMP_USER_INPUT_IS_INVALID and re.search(r"libnomp/src/nomp\.c:\d+ Missing argument value after: --nomp-platform\.", text)
+    assert rows["no_install_dir"][0] == capi.NOMP_USER_INPUT_IS_INVALID and "NOMP_INSTALL_DIR is missing or invalid" in rows["no_install_dir"][1]
+    assert rows["no_backend"][0] == capi.NOMP_USER_INPUT_IS_INVALID and "NOMP_BACKEND is missing or invalid" in rows["no_backend"][1]
+    assert rows["bad_device"][0] == capi.NOMP_USER_INPUT_IS_INVALID and "NOMP_DEVICE is missing or invalid" in rows["bad_device"][1]
+    assert rows["bad_backend"] == (capi.NOMP_USER_INPUT_IS_INVALID, rows["bad_backend"][1]) and "Invalid backend: invalid." in rows["bad_backend"][1]
+    assert "Invalid backend: opencl." in rows["opencl"][1], "CUDA is the only backend; names are lower-cased"
+    assert rows["finalize_after_failures"] == (capi.NOMP_FINALIZE_FAILURE,)
+    no, text = rows["run_invalid"]
+    assert no == capi.NOMP_USER_INPUT_IS_INVALID and re.search(r"\[Error\] .*/src/nomp\.c:\d+ Kernel id -1 passed to nomp_run is not valid\.", text)
+    assert rows["bad_id"] == (capi.NOMP_USER_LOG_ID_IS_INVALID, capi.NOMP_USER_LOG_ID_IS_INVALID)
+
+
+def test_product_does_not_reference_the_oracle():
+    """No CPU fallback: neither library links the oracle, and no product source mentions it."""
+    for lib in ("libnomp.so", "libnompk.so"):
+        out = subprocess.run(["ldd", str(ROOT / "libnomp_b200" / "lib" / lib)], capture_output=True, text=True).stdout
+        assert "oracle" not in out
+    for path in list((ROOT / "libnomp_b200").rglob("*.c")) + list((ROOT / "libnomp_b200").rglob("*.cu")) + \
+            list((ROOT / "libnomp_b200").rglob("*.py")):
+        if "build" in path.parts:
+            continue
+        text = path.read_text()
+        assert "libnomp_oracle" not in text and "from oracle" not in text and "import oracle" not in text or path.name == "build.py", path
+
+
+def test_aux_helpers():
+    lib = capi.nomp()
+    lib.nomp_str_toui.argtypes = [C.c_char_p, C.c_size_t]
+    assert [lib.nomp_str_toui(s, 128) for s in (b"0", b"17", b"invalid", b"-3", b"", b"12x")] == [0, 17, -1, -1, -1, -1]
+    lib.nomp_copy_env.restype = C.c_void_p
+    lib.nomp_copy_env.argtypes = [C.c_char_p, C.c_size_t]
+    os.environ["NOMP_TEST_ENV_VALUE"] = "hello world"
+    p = lib.nomp_copy_env(b"NOMP_TEST_ENV_VALUE", 5)
+    assert C.string_at(p) == b"hello"
+    assert lib.nomp_copy_env(b"NOMP_TEST_ENV_UNSET", 5) is None
+    lib.nomp_max.restype = C.c_int
+    assert lib.nomp_max(C.c_uint(3), C.c_int(-5), C.c_int(9), C.c_int(2)) == 9

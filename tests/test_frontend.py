@@ -1,0 +1,383 @@
+"""Host-side jit logic without a GPU: the C-subset parser, the loop transformations user scripts call through the
+`loopy` shim, the loop-family recogniser, and the CUDA emitter (every generated kernel is compiled by NVRTC for
+sm_100a and, where threads are independent, executed on the host through tests/cuda_emulation.py and compared with the
+kernel string itself compiled by gcc)."""
+import ctypes as C
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "libnomp_b200" / "python"))
+
+import loopy as lp  # noqa: E402  (the shim)
+import nomp_bridge as nb  # noqa: E402
+from nomp_bridge import cparse, families  # noqa: E402
+from nomp_bridge.gridexpr_py import evaluate as grid_eval  # noqa: E402
+
+from tests.cuda_emulation import emulate, nvrtc_compile  # noqa: E402
+from tests.kernel_oracle import run_kernel  # noqa: E402
+
+CTX = {"backend::name": "cuda", "device::max_threads_per_block": 1024, "device::multiprocessor_count": 148}
+TYPES = ["int", "long", "unsigned", "unsigned long", "double", "float"]
+NP = {"int": np.int32, "long": np.int64, "unsigned": np.uint32, "unsigned long": np.uint64, "double": np.float64,
+      "float": np.float32}
+
+
+def tile(knl, context):
+    (iname,) = knl.default_entrypoint.all_inames()
+    bs = min(512, context["device::max_threads_per_block"])
+    knl = lp.split_iname(knl, iname, bs, inner_iname=f"{iname}_inner", outer_iname=f"{iname}_outer")
+    return lp.tag_inames(knl, {f"{iname}_outer": "g.0", f"{iname}_inner": "l.0"})
+
+
+def tile_outer(knl, context):
+    (i, j) = sorted(knl.default_entrypoint.all_inames())
+    knl = lp.split_iname(knl, i, 512, inner_iname=f"{i}_inner", outer_iname=f"{i}_outer")
+    return lp.tag_inames(knl, {f"{i}_outer": "g.0", f"{i}_inner": "l.0", j: "for"})
+
+
+def tile2d(knl, context):
+    bs = int(math.sqrt(min(1024, context["device::max_threads_per_block"])))
+    knl = lp.split_iname(knl, "i", bs)
+    knl = lp.split_iname(knl, "j", bs)
+    return lp.tag_inames(knl, {"i_outer": "g.0", "i_inner": "l.0", "j_outer": "g.1", "j_inner": "l.1"})
+
+
+def plan(src, transform=None, reduce=None, fixed=None):
+    k = nb.c_to_loopy(src, "cuda")
+    if transform:
+        k = transform(k, CTX)
+    if reduce:
+        k = nb.realize_reduction(k, reduce[0], reduce[1], CTX)
+    if fixed:
+        k = nb.fix_parameters(k, fixed)
+    text = nb.get_knl_src(k, CTX)
+    header, _, body = text.partition("\n")
+    desc = dict(kv.split("=", 1) for kv in header.split()[1:])
+    return desc, body, nb.get_grid_size(k, CTX), k
+
+
+# ---- parser --------------------------------------------------------------------------------------------------------
+
+def test_parser_accepts_the_reference_subset():
+    f = cparse.parse_kernel("""
+        void foo(const double *a, unsigned long *b, int N, float alpha) {
+          for (int i = 0; i < N; i++) {
+            int t = 0;
+            double s[4][2];
+            for (unsigned j = b[i]; j <= b[i + 1]; j++) {
+              if ((!(j < 3) && (j < 5)) || j == 1) continue;
+              t += (j % 2 == 0) ? 1 : 2;
+              if (t > 100) break;
+            }
+            b[i] = ~b[i] ^ (t << 2) | 1;
+          }
+        }""")
+    assert f.name == "foo" and [p.name for p in f.params] == ["a", "b", "N", "alpha"]
+    assert f.params[0].ctype.const and f.params[0].is_array and not f.params[2].is_array
+    assert f.params[1].ctype.unsigned and f.params[1].ctype.base == "long"
+    loop = f.body[0]
+    assert isinstance(loop, cparse.For) and loop.var == "i"
+    inner = [n for n in loop.body if isinstance(n, cparse.For)][0]
+    assert isinstance(inner.hi, cparse.BinOp) and inner.hi.op == "+"       # <= became < hi + 1
+
+
+@pytest.mark.parametrize("bad", [
+    "void foo(int *a, int N) { for (int i = 0; i < N; i++) a[i] = i }",            # missing ';' (reference test 100)
+    "void foo(int *a, int N) { for (int i = 0; i < N; i--) a[i] = i; }",           # update must be ++
+    "void foo(int *a, int N) { for (int i = 0; i > N; i++) a[i] = i; }",           # condition must be < or <=
+    "void foo(int *a, int N) { int i; for (i = 0; i < N; i++) a[i] = i; }",        # variable must be declared in init
+    "void foo(int *a, int N) { while (N) a[0] = 1; }",
+    "void foo(int *a, int N) { for (int i = 0; i < N; i++) a[i] = i; } int x;",
+    "int main",
+    "void foo(int *a, int N) { for (int i = 0; i < N; i++) { a[i] = i; }",        # unbalanced
+    "void foo(int *a, int N) { for (int i = 0; i < N; i++) a[i] = i++; }",
+])
+def test_parser_rejects(bad):
+    with pytest.raises(SyntaxError):
+        nb.c_to_loopy(bad, "cuda")
+
+
+def test_reserved_prefix_is_rejected():
+    with pytest.raises(SyntaxError):
+        nb.c_to_loopy("void f(int *a, int N) { for (int i = 0; i < N; i++) { int _nomp_var0 = 1; a[i] = _nomp_var0; } }")
+
+
+# ---- loopy shim ------------------------------------------------------------------------------------------------------
+
+def test_split_and_tag_inames():
+    k = nb.c_to_loopy("void f(double *a, int N) { for (int i = 0; i < N; i++) a[i] = i; }")
+    assert k.default_entrypoint.all_inames() == frozenset({"i"})
+    k2 = lp.split_iname(k, "i", 128)
+    assert set(k2.default_entrypoint.all_inames()) == {"i_outer", "i_inner"}
+    assert k.default_entrypoint.all_inames() == frozenset({"i"}), "transformations must not mutate their argument"
+    k3 = lp.tag_inames(k2, [("i_outer", "g.0"), ("i_inner", "l.0")])
+    assert k3.tags() == {"i_outer": "g.0", "i_inner": "l.0"}
+    with pytest.raises(lp.LoopyError):
+        lp.tag_inames(k2, {"nope": "g.0"})
+    with pytest.raises(lp.LoopyError):
+        lp.tag_inames(k2, {"i_outer": "g.7"})
+    with pytest.raises(lp.LoopyError):
+        lp.split_iname(k2, "i", 32)          # i no longer exists
+
+
+def test_glob_tags_and_repeated_loop_names():
+    k = nb.c_to_loopy("""void f(double *b, const double *a, int n) { for (int i = 0; i < n; i++) { double s[32];
+        for (int j = 0; j < 32; j++) s[j] = a[i * 32 + j];
+        for (int j = 0; j < 32; j++) b[i * 32 + j] = s[j]; } }""")
+    assert sorted(k.default_entrypoint.all_inames()) == ["i", "j"]
+    k = lp.tag_inames(k, {"i": "g.0", "j*": "l.0"})
+    assert [l.tag for l in k.loops()] == ["g.0", "l.0", "l.0"]
+
+
+def test_sem_annotation_script_semantics():
+    """grid_loop -> split + g.0/l.0; element_loop -> g.0; dof_loop's result is discarded by the reference script
+    (reference tests/sem.py:20-24), which must be tolerated."""
+    k = nb.c_to_loopy("void f(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] += b[i]; }")
+    assert lp.translation_unit.TranslationUnit is type(k)
+    bs = min(512, CTX["device::max_threads_per_block"])
+    lp.split_iname(k, "i", bs, inner_tag="l.0")          # discarded, no side effect
+    assert k.tags() == {"i": None}
+    g = lp.tag_inames(lp.split_iname(k, "i", bs), [("i_outer", "g.0"), ("i_inner", "l.0")])
+    assert g.tags() == {"i_outer": "g.0", "i_inner": "l.0"}
+
+
+# ---- family recogniser -------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("body,op,extra", [
+    ("a[i] += b[i];", "add", {"x": "b"}),
+    ("a[i] = b[i] + a[i];", "add", {"x": "b"}),
+    ("a[i] -= b[i];", "sub", {"x": "b"}),
+    ("a[i] *= b[i];", "mul", {"x": "b"}),
+    ("a[i] = a[i] * b[i];", "mul", {"x": "b"}),
+    ("a[i] += s * b[i];", "axpy", {"x": "b", "alpha": "s"}),
+    ("a[i] = a[i] + b[i] * s;", "axpy", {"x": "b", "alpha": "s"}),
+    ("a[i] = b[i] + s * a[i];", "xpay", {"x": "b", "alpha": "s"}),
+    ("a[i] = s * b[i] + t * a[i];", "axpby", {"x": "b", "alpha": "s", "beta": "t"}),
+    ("a[i] = s * a[i];", "scale", {"alpha": "s"}),
+    ("a[i] = b[i];", "copy", {"x": "b"}),
+    ("a[i] = s;", "fill", {"alpha": "s"}),
+    ("a[i] = b[i] + c[i];", "add3", {"x": "b", "z": "c"}),
+])
+def test_native_map_recognition(body, op, extra):
+    for T in ("double", "float", "int", "unsigned long"):
+        src = f"void f({T} *a, const {T} *b, const {T} *c, {T} s, {T} t, int N) {{ for (int i = 0; i < N; i++) {body} }}"
+        desc, cuda, grid, _ = plan(src, tile)
+        assert desc["kind"] == "native" and desc["family"] == "map", (body, desc)
+        assert int(desc["op"]) == families.MAP_OPS[op] and desc["y"] == "a" and desc["n"] == "N"
+        for k, v in extra.items():
+            assert desc[k] == v
+        assert cuda == "" and grid == (("1", "1", "1"), ("1", "1", "1"))
+
+
+@pytest.mark.parametrize("body", [
+    "a[i] -= b[i] + 1;", "a[i] = a[i] * a[i] + b[i] * b[i];", "a[i] = 2 * b[i] + 1;", "a[i] = a[i] + 3 * b[i] + 2 * c[i];",
+    "a[i] = i;", "a[i] = a[i] & 3;", "a[i] = ~a[i];", "a[i] = (b[i] > 0) ? b[i] : c[i];",
+])
+def test_other_elementwise_loops_get_the_vector_skeleton(body):
+    for T in ("int", "unsigned long", "double", "float"):
+        if T in ("double", "float") and ("&" in body or "~" in body):
+            continue
+        src = f"void f({T} *a, const {T} *b, const {T} *c, int N) {{ for (int i = 0; i < N; i++) {body} }}"
+        desc, cuda, grid, _ = plan(src, tile)
+        assert desc["kind"] == "nvrtc" and desc["family"] == "map" and desc["params"] == "a,b,c,N"
+        ok, log = nvrtc_compile(cuda)
+        assert ok, log
+        assert "int4" in cuda and grid[1] == ("256", "1", "1")
+
+
+def test_mixed_width_or_offset_access_is_not_a_map():
+    desc, _, _, _ = plan("void f(double *a, const int *b, int N) { for (int i = 0; i < N; i++) a[i] = b[i]; }", tile)
+    assert desc["family"] == "generic"
+    desc, _, _, _ = plan("void f(double *a, const double *b, int N) { for (int i = 0; i < N; i++) a[i] = b[i + 1]; }", tile)
+    assert desc["family"] == "generic"
+
+
+def test_reduce_recognition_and_errors():
+    desc, _, _, _ = plan("void f(double *a, int N, double *s) { for (int i = 0; i < N; i++) { s[0] += a[i]; } }", None, ("s", "+"))
+    assert (desc["kind"], desc["family"], desc["x"], desc["y"], desc["out"], int(desc["dtype"])) == ("native", "reduce", "a", "-", "s", 5)
+    desc, _, _, _ = plan("void f(long *a, long *b, int N, long *t) { for (int i = 0; i < N; i++) t[0] += a[i] * b[i]; }", None, ("t", "+"))
+    assert (desc["x"], desc["y"], int(desc["dtype"]), int(desc["op"])) == ("a", "b", 2, 0)
+    desc, _, _, _ = plan("void f(float *a, int N, float *m) { for (int i = 0; i < N; i++) m[0] = (a[i] < m[0]) ? a[i] : m[0]; }", None, ("m", "min"))
+    assert (desc["family"], int(desc["op"])) == ("reduce", 2) and desc["kind"] == "native"
+    for body in ("s[0] += 1;", "s[0] += i;", "if (a[i] > 0) s[0] += 1;", "s[0] += a[i] * a[i] + 1;"):
+        desc, cuda, grid, _ = plan(f"void f(double *a, int N, double *s) {{ for (int i = 0; i < N; i++) {{ {body} }} }}", None, ("s", "+"))
+        assert desc["kind"] == "nvrtc" and desc["family"] == "reduce" and desc["out"] == "s"
+        assert desc["params"].endswith("nomp_partials,nomp_ticket,nomp_result,nomp_result_host")
+        ok, log = nvrtc_compile(cuda)
+        assert ok, log
+    with pytest.raises(nb.KernelError):   # two loops
+        plan("void f(double *a, int N, double *s) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) s[0] += a[i]; }", None, ("s", "+"))
+    with pytest.raises(nb.KernelError):   # not a parameter
+        plan("void f(double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", None, ("q", "+"))
+    with pytest.raises(nb.KernelError):   # bad operator
+        plan("void f(double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", None, ("s", "-"))
+
+
+def test_ax_recognition():
+    k = nb.c_to_loopy(families.AX_KERNEL_SOURCE)
+    for n in (6, 8, 10, 12):
+        kn = nb.fix_parameters(k, {"n": n})
+        header = nb.get_knl_src(kn, CTX)
+        assert header.startswith(f"//!nomp kind=native family=ax n={n} E=E u=u g=g D=D w=w ro=u,g,D")
+    import re
+    renamed = families.AX_KERNEL_SOURCE
+    for old, new in (("nomp_ax", "my_ax"), ("ur", "gr"), ("w", "out"), ("E", "nel")):
+        renamed = re.sub(rf"\b{old}\b", new, renamed)
+    kr = nb.fix_parameters(nb.c_to_loopy(renamed), {"n": 8})
+    assert "family=ax" in nb.get_knl_src(kr, CTX) and "w=out" in nb.get_knl_src(kr, CTX) and "E=nel" in nb.get_knl_src(kr, CTX)
+    # an n without a hand-written kernel falls back to one thread per element through NVRTC
+    k9 = nb.fix_parameters(k, {"n": 9})
+    text = nb.get_knl_src(k9, CTX)
+    assert "kind=nvrtc family=generic" in text
+    ok, log = nvrtc_compile(text)
+    assert ok, log
+    assert nb.get_grid_size(k9, CTX) == (("((E + 31) / 32)", "1", "1"), ("32", "1", "1"))
+    # a changed loop body is not the Ax family
+    other = nb.fix_parameters(nb.c_to_loopy(families.AX_KERNEL_SOURCE.replace("double acc = 0;", "double acc = 1;")), {"n": 8})
+    assert "family=ax" not in nb.get_knl_src(other, CTX)
+
+
+# ---- generic emitter: compile with NVRTC and execute on the host -----------------------------------------------------------
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_generic_inner_loop_with_continue_break_and_ternary(T):
+    src = f"""void foo({T} *a, int N) {{
+      for (int i = 0; i < N; i++) {{
+        int t = 0;
+        for (int j = 0; j < 10; j++) {{
+          if ((!(j < 3) && (j < 5)) || j == 1) continue;
+          t += (j == 7) ? 3 : 1;
+          if (j == 8) break;
+        }}
+        a[i] = t + i;
+      }}
+    }}"""
+    desc, cuda, (grid, block), _ = plan(src, tile_outer)
+    assert desc["family"] == "generic" and block[0] == "512"
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    n = 700
+    want = np.zeros(n, dtype=NP[T])
+    run_kernel(src, want, n)
+    got = np.zeros(n, dtype=NP[T])
+    g = (grid_eval(grid[0], {"N": n}), 1, 1)
+    emulate(cuda, "foo", g, (512, 1, 1), [f"{'unsigned long long' if T == 'unsigned long' else ('long long' if T == 'long' else T)} *", "int"],
+            [_ptr(got), C.c_int(n)])
+    assert np.array_equal(got, want)
+
+
+def test_generic_data_dependent_bounds():
+    src = """void foo(double *a, int *b, int N) { for (int i = 0; i < N; i++) { int t = 0;
+        for (int j = b[i]; j < b[i + 1] + 1; j++) { t += 1; } a[i] = t; } }"""
+    desc, cuda, (grid, block), _ = plan(src, tile_outer)
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    n = 50
+    b = (2 * np.arange(n + 1)).astype(np.int32)
+    got = np.zeros(n)
+    emulate(cuda, "foo", (1, 1, 1), (512, 1, 1), ["double *", "int *", "int"], [_ptr(got), _ptr(b), C.c_int(n)])
+    assert np.array_equal(got, np.full(n, 3.0))
+
+
+def test_generic_2d_tiling_transpose_and_matmul():
+    src = """void foo(double *a, double *b, int rows, int cols) { for (int j = 0; j < rows; j++)
+        for (int i = 0; i < cols; i++) a[j + i * rows] = b[i + j * cols]; }"""
+    desc, cuda, (grid, block), _ = plan(src, tile2d)
+    assert grid[:2] == ("((cols + 31) / 32)", "((rows + 31) / 32)") and block[:2] == ("32", "32")
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    rows, cols = 40, 5
+    b = np.arange(rows * cols, dtype=np.float64)
+    got = np.zeros(rows * cols)
+    g = (grid_eval(grid[0], dict(rows=rows, cols=cols)), grid_eval(grid[1], dict(rows=rows, cols=cols)), 1)
+    emulate(cuda, "foo", g, (32, 32, 1), ["double *", "double *", "int", "int"], [_ptr(got), _ptr(b), C.c_int(rows), C.c_int(cols)])
+    assert np.array_equal(got.reshape(cols, rows), b.reshape(rows, cols).T)
+
+    mm = """void foo(long *a, long *b, long *c, int size) { for (unsigned i = 0; i < size; i++) { for (unsigned j = 0; j < size; j++) {
+        double dot = 0; for (unsigned k = 0; k < size; k++) dot += a[i * size + k] * b[k * size + j]; c[i * size + j] = dot; } } }"""
+    desc, cuda, (grid, block), k = plan(mm, lambda kn, ctx: lp.tag_inames(tile2d(kn, ctx), {"k": "for"}))
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    n = 10
+    a = np.tile(np.arange(n, dtype=np.int64), n)
+    bm = np.repeat(np.arange(n, dtype=np.int64), n)
+    got = np.zeros(n * n, dtype=np.int64)
+    emulate(cuda, "foo", (1, 1, 1), (32, 32, 1), ["long long *"] * 3 + ["int"], [_ptr(a), _ptr(bm), _ptr(got), C.c_int(n)])
+    assert np.all(got == sum(i * i for i in range(n)))
+
+
+def test_block_level_arrays_become_shared_memory_with_barriers():
+    src = """void foo(double *b, const double *a, int n, int m) { for (int i = 0; i < n; i++) { double s[m][m];
+        for (int j = 0; j < m; j++) s[j][4] = a[i * m + j];
+        for (int j = 0; j < m; j++) s[j][4] += s[j][4];
+        for (int j = 0; j < m; j++) b[i * m + j] = s[j][4]; } }"""
+    desc, cuda, (grid, block), _ = plan(src, lambda k, c: lp.tag_inames(k, {"i": "g.0", "j*": "l.0"}), fixed={"m": 16})
+    assert desc["params"] == "b,a,n" and grid[0] == "n" and block[0] == "16"
+    assert "__shared__ double s[16][16];" in cuda and cuda.count("__syncthreads();") == 3
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    n, m = 16, 16
+    a = np.repeat(np.arange(n, dtype=np.float64), m)
+    got = np.zeros(n * m)
+    emulate(cuda, "foo", (n, 1, 1), (m, 1, 1), ["double *", "const double *", "int"], [_ptr(got), _ptr(a), C.c_int(n)])
+    assert np.array_equal(got, 2 * a)
+    with pytest.raises(nb.KernelError):     # VLA extent must be fixed at jit time
+        plan(src, lambda k, c: lp.tag_inames(k, {"i": "g.0", "j*": "l.0"}))
+
+
+def test_untransformed_kernel_runs_as_a_single_thread():
+    desc, cuda, (grid, block), _ = plan("void f(double *a, int *b, int N) { for (int i = 0; i < N; i++) a[b[i]] = i; }")
+    assert desc["family"] == "generic" and grid == ("1", "1", "1") and block == ("1", "1", "1")
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+
+
+def test_map_skeleton_executes_correctly_on_the_host():
+    src = "void foo(unsigned *a, const unsigned *b, int N) { for (int i = 0; i < N; i++) a[i] = (a[i] ^ b[i]) + (i << 1); }"
+    desc, cuda, (grid, block), _ = plan(src, tile)
+    assert desc["family"] == "map" and desc["kind"] == "nvrtc"
+    for n in (0, 1, 5, 1000, 1027):
+        a = np.arange(n, dtype=np.uint32) * 7
+        b = np.arange(n, dtype=np.uint32) * 13 + 1
+        want = a.copy()
+        run_kernel(src, want, b, n)
+        emulate(cuda, "foo", (grid_eval(grid[0], {"N": n}), 1, 1), (256, 1, 1), ["unsigned *", "const unsigned *", "int"],
+                [_ptr(a), _ptr(b), C.c_int(n)])
+        assert np.array_equal(a, want), n
+
+
+# ---- launch-size expressions ---------------------------------------------------------------------------------------------
+
+def test_grid_expression_grammar_matches_the_c_evaluator():
+    """src/gridexpr.c compiled standalone and compared with the Python mirror on the expressions the emitter prints."""
+    import subprocess
+    import tempfile
+    d = Path(tempfile.mkdtemp())
+    stub = d / "stub.c"
+    stub.write_text('#include <stddef.h>\nint nomp_log_(const char *f, unsigned l, int e, int t, const char *fmt, ...) { return 1; }\n'
+                    'unsigned nomp_log_get_verbose(void) { return 0; }\n')
+    inc = ROOT / "libnomp_b200" / "csrc" / "libnomp"
+    import sysconfig
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(d / "gx.so"), str(inc / "src" / "gridexpr.c"), str(stub),
+                    "-I", str(inc / "include"), "-I", str(ROOT / "include"), "-I", sysconfig.get_paths()["include"]], check=True)
+    lib = C.CDLL(str(d / "gx.so"))
+    names = (C.c_char_p * 3)(b"N", b"rows", b"cols")
+    values = (C.c_long * 3)(1000, 40, 5)
+    env = {"N": 1000, "rows": 40, "cols": 5}
+    for expr in ["1", "((N + 511) / 512)", "max(1, min((N + 1023) / 1024, 1184))", "((cols + 31) / 32)", "N", "rows * cols - 3 % 2",
+                 "max(((rows + 31) / 32), 7)", "-(N) + 2000", "min(N, rows) * 2"]:
+        out = C.c_long()
+        assert lib.nomp_gridexpr_eval(expr.encode(), names, values, 3, C.byref(out)) == 0, expr
+        assert out.value == grid_eval(expr, env), expr
+    for bad in ["N +", "foo", "(N", "N / 0", "max(N)", "N N"]:
+        out = C.c_long()
+        assert lib.nomp_gridexpr_eval(bad.encode(), names, values, 3, C.byref(out)) != 0, bad

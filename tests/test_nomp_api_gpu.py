@@ -1,0 +1,497 @@
+"""The public C API on a B200 (ctypes -> libnomp.so -> CUDA backend), compared with the kernel string compiled by gcc
+(tests/kernel_oracle.py) or the oracle library, on the same inputs.  Mirrors what the reference's tests/nomp-api-*.c
+pin and adds large sizes, random data and the north-star additions (min/max, Ax, extensions)."""
+import ctypes as C
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "libnomp_b200" / "python"))
+
+from libnomp_b200 import capi  # noqa: E402
+from oracle import ffi  # noqa: E402
+from tests.kernel_oracle import run_kernel  # noqa: E402
+
+P, I, U, F, JIT = capi.NOMP_PTR, capi.NOMP_INT, capi.NOMP_UINT, capi.NOMP_FLOAT, capi.NOMP_JIT
+TYPES = {"int": (np.int32, I), "long": (np.int64, I), "unsigned": (np.uint32, U), "unsigned long": (np.uint64, U),
+         "double": (np.float64, F), "float": (np.float32, F)}
+TR = "nomp_test_transforms"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def runtime():
+    capi.check(capi.init(backend="cuda", device=0, verbose=0, scripts_dir=ROOT / "tests" / "scripts",
+                         annotations_script="nomp_test_annotations"))
+    yield capi.nomp()
+    assert capi.nomp().nomp_finalize_excluding_interpreter() == 0
+
+
+def rand(T, n, seed):
+    dt = TYPES[T][0]
+    rng = np.random.default_rng(seed)
+    if np.issubdtype(dt, np.floating):
+        return rng.uniform(0.5, 1.5, n).astype(dt)
+    return rng.integers(0, 1000, n).astype(dt)
+
+
+class Mapped:
+    """nomp_update(TO) on entry, FROM (for outputs) + FREE on exit."""
+
+    def __init__(self, *arrays, out=()):
+        self.arrays, self.out = arrays, out
+
+    def __enter__(self):
+        for a in self.arrays:
+            capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_TO))
+        return self
+
+    def __exit__(self, *exc):
+        for a in self.arrays:
+            if any(a is o for o in self.out):
+                capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_FROM))
+            capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_FREE))
+
+
+def jit(src, clauses, args):
+    err, kid = capi.jit(src, clauses, args)
+    capi.check(err)
+    return kid
+
+
+def family(kid):
+    info = capi.nomp().nomp_b200_prog_info(kid).decode()
+    d = dict(kv.split("=", 1) for kv in info.split())
+    return d["kind"], d["family"]
+
+
+# ---- nomp_update ----------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_update_subranges_and_errors(T):
+    dt = TYPES[T][0]
+    a = np.zeros(50, dtype=dt)
+    for op in (capi.NOMP_FREE, capi.NOMP_FROM):
+        err = capi.update(a.ctypes.data, 2, 8, a.itemsize, op)
+        no, text = capi.err_info(err)
+        assert no == capi.NOMP_USER_MAP_OP_IS_INVALID
+        assert re.search(r"\[Error\] .*libnomp/src/nomp\.c:\d+ NOMP_FREE or NOMP_FROM can only be called on a pointer "
+                         r"which is already on the device\.", text)
+    for s, e in ((0, 10), (5, 10), (2, 8)):
+        a[:] = 0
+        a[s:e] = np.arange(s, e)
+        capi.check(capi.update(a.ctypes.data, s, e, a.itemsize, capi.NOMP_TO))
+        capi.check(capi.update(a.ctypes.data, s, e, a.itemsize, capi.NOMP_TO))     # twice is fine
+        a[:] = 0
+        capi.check(capi.update(a.ctypes.data, s, e, a.itemsize, capi.NOMP_FROM))
+        capi.check(capi.update(a.ctypes.data, s, e, a.itemsize, capi.NOMP_FROM))
+        want = np.zeros(50, dtype=dt)
+        want[s:e] = np.arange(s, e)
+        assert np.array_equal(a, want)
+        capi.check(capi.update(a.ctypes.data, s, e, a.itemsize, capi.NOMP_FREE))
+    # partial transfers inside a mapping: [0,20) mapped, refresh [0,5) and [15,20), read back everything
+    a[:] = 0
+    capi.check(capi.update(a.ctypes.data, 0, 20, a.itemsize, capi.NOMP_TO))
+    a[:20] = np.arange(20)
+    capi.check(capi.update(a.ctypes.data, 0, 5, a.itemsize, capi.NOMP_TO))
+    capi.check(capi.update(a.ctypes.data, 15, 20, a.itemsize, capi.NOMP_TO))
+    a[:] = 0
+    capi.check(capi.update(a.ctypes.data, 5, 15, a.itemsize, capi.NOMP_FROM))
+    assert not a.any()
+    capi.check(capi.update(a.ctypes.data, 0, 20, a.itemsize, capi.NOMP_FROM))
+    assert np.array_equal(a[:20], np.concatenate([np.arange(5), np.zeros(10), np.arange(15, 20)]).astype(dt))
+    capi.check(capi.update(a.ctypes.data, 0, 20, a.itemsize, capi.NOMP_FREE))
+    # a char buffer re-typed: the lookup is by pointer AND byte range
+    raw = np.zeros(64, dtype=np.uint8)
+    capi.check(capi.update(raw.ctypes.data, 0, 64, 1, capi.NOMP_ALLOC))
+    typed = raw.view(dt)
+    typed[:] = np.arange(typed.size)
+    capi.check(capi.update(raw.ctypes.data, 0, typed.size, typed.itemsize, capi.NOMP_TO))
+    typed[:] = 0
+    capi.check(capi.update(raw.ctypes.data, 0, typed.size, typed.itemsize, capi.NOMP_FROM))
+    assert np.array_equal(typed, np.arange(typed.size).astype(dt))
+    capi.check(capi.update(raw.ctypes.data, 0, 64, 1, capi.NOMP_FREE))
+
+
+def test_kernels_index_submappings_like_the_host():
+    """A mapping of [lo, hi) gives the kernel the device address of host element 0, so `a[i]` means the same element
+    on both sides (the reference hands over the start of the buffer)."""
+    a = np.arange(40, dtype=np.float64)
+    lo, hi = 7, 29
+    capi.check(capi.update(a.ctypes.data, lo, hi, 8, capi.NOMP_TO))
+    kid = jit("void inc(double *a, int lo, int hi) { for (int i = lo; i < hi; i++) a[i] = a[i] * 2 + 1; }",
+              capi.clauses(("transform", TR, "tile")), [("a", 8, P), ("lo", 4, I), ("hi", 4, I)])
+    capi.check(capi.run(kid, a.ctypes.data, C.c_int(lo), C.c_int(hi)))
+    want = a.copy()
+    want[lo:hi] = want[lo:hi] * 2 + 1
+    a[:] = -1
+    capi.check(capi.update(a.ctypes.data, lo, hi, 8, capi.NOMP_FROM))
+    assert np.array_equal(a[lo:hi], want[lo:hi]) and np.all(a[:lo] == -1) and np.all(a[hi:] == -1)
+    assert capi.nomp().nomp_b200_device_ptr(C.c_void_p(a.ctypes.data)) is not None
+    capi.check(capi.update(a.ctypes.data, lo, hi, 8, capi.NOMP_FREE))
+    assert capi.nomp().nomp_b200_device_ptr(C.c_void_p(a.ctypes.data)) is None
+
+
+# ---- nomp_jit / nomp_run error paths -------------------------------------------------------------------------------------
+VALID = "void foo(int *a, int N) { for (int i = 0; i < N; i++) a[i] = i; }"
+ARGS = [("a", 4, P), ("N", 4, I)]
+
+
+def expect(err, errno, pattern):
+    no, text = capi.err_info(err)
+    assert no == errno, (no, text)
+    assert re.search(pattern, text), text
+
+
+def test_jit_error_paths():
+    err, _ = capi.jit(VALID, capi.clauses(("transform", "no_such_module", "tile")), ARGS)
+    expect(err, capi.NOMP_PY_CALL_FAILURE, r'\[Error\] .*src/.*\.c:\d+ Importing Python module "no_such_module" failed\.')
+    err, _ = capi.jit(VALID, capi.clauses(("transform", TR, "no_such_function")), ARGS)
+    expect(err, capi.NOMP_PY_CALL_FAILURE,
+           rf'\[Error\] .*src/loopy\.c:\d+ Importing Python function "no_such_function" from module "{TR}" failed\.')
+    for triple in (("transform", None, "tile"), ("transform", TR, None)):
+        err, _ = capi.jit(VALID, capi.clauses(triple), ARGS)
+        expect(err, capi.NOMP_USER_INPUT_IS_INVALID, r"Module name and/or function name not provided\.")
+    err, _ = capi.jit(VALID, capi.clauses(("invalid-clause", TR, "tile")), ARGS)
+    expect(err, capi.NOMP_USER_INPUT_IS_INVALID, r'Clause "invalid-clause" passed into nomp_jit is not a valid clause\.')
+    err, _ = capi.jit(VALID.replace("= i;", "= i"), capi.clauses(("transform", TR, "tile")), ARGS)
+    expect(err, capi.NOMP_LOOPY_CONVERSION_FAILURE, r"Converting C source to loopy kernel failed\.")
+    err, _ = capi.jit(VALID, capi.clauses(("transform", TR, "raises")), ARGS)
+    expect(err, capi.NOMP_PY_CALL_FAILURE, rf'Calling Python function "raises" from module "{TR}" failed\.')
+    err, _ = capi.jit(VALID, capi.clauses(("transform", TR, "returns_garbage")), ARGS)
+    assert capi.err_info(err)[0] in (capi.NOMP_LOOPY_KNL_NAME_NOT_FOUND, capi.NOMP_LOOPY_CODEGEN_FAILURE, capi.NOMP_PY_CALL_FAILURE)
+    err, _ = capi.jit("void f(double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }",
+                      capi.clauses(("reduce", "s", "/")), [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    expect(err, capi.NOMP_USER_INPUT_IS_INVALID, r'Reduction operator "/" is not one of')
+    # a cache hit does not even look at its arguments
+    kid = C.c_int(5)
+    assert capi.nomp().nomp_jit(C.byref(kid), None, None, C.c_int(0)) == 0 and kid.value == 5
+    jit(VALID, capi.clauses(("transform", TR, "checks_context")), ARGS)
+
+
+def test_run_error_paths():
+    kid = jit("void foo(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] = a[i] * b[i]; }",
+              capi.clauses(("transform", TR, "tile")), [("a", 8, P), ("b", 8, P), ("N", 4, I)])
+    a, b = np.ones(20), np.ones(20)
+    expect(capi.run(-1, a.ctypes.data, b.ctypes.data, C.c_int(20)), capi.NOMP_USER_INPUT_IS_INVALID,
+           r"\[Error\] .*/src/nomp\.c:\d+ Kernel id -1 passed to nomp_run is not valid\.")
+    expect(capi.run(10 ** 6, a.ctypes.data, b.ctypes.data, C.c_int(20)), capi.NOMP_USER_INPUT_IS_INVALID, r"is not valid")
+    with Mapped(a):
+        expect(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(20)), capi.NOMP_USER_MAP_PTR_IS_INVALID,
+               r"\[Error\] .*/src/.*\.c:\d+ Map pointer 0[xX][0-9a-fA-F]* was not found on device\.")
+
+
+# ---- maps ----------------------------------------------------------------------------------------------------------------
+MAP_BODIES = [
+    ("a[i] += b[i];", ("native", "map")),
+    ("a[i] -= b[i] + 1;", ("nvrtc", "map")),
+    ("a[i] *= b[i] + 1;", ("nvrtc", "map")),
+    ("a[i] = a[i] * b[i];", ("native", "map")),
+    ("a[i] = a[i] * a[i] + b[i] * b[i];", ("nvrtc", "map")),
+    ("a[i] = 2 * b[i] + 1;", ("nvrtc", "map")),
+    ("a[i] = a[i] + b[i] + c[i];", ("nvrtc", "map")),
+    ("a[i] = a[i] * b[i] + c[i];", ("nvrtc", "map")),
+    ("a[i] = a[i] + 3 * b[i] + 2 * c[i];", ("nvrtc", "map")),
+    ("a[i] = b[i] + c[i];", ("native", "map")),
+    ("a[i] = i;", ("nvrtc", "map")),
+]
+
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_elementwise_maps_bit_exact(T):
+    dt, _ = TYPES[T]
+    for body, fam in MAP_BODIES:
+        src = f"void foo({T} *a, const {T} *b, const {T} *c, int N) {{ for (int i = 0; i < N; i++) {body} }}"
+        kid = jit(src, capi.clauses(("transform", TR, "tile")), [("a", dt().itemsize, P), ("b", dt().itemsize, P),
+                                                                 ("c", dt().itemsize, P), ("N", 4, I)])
+        assert family(kid) == fam, (body, family(kid))
+        for n in (10, 50, 70, 1000, 100003):       # the same kernel id serves every size (launch sizes re-evaluated)
+            a, b, c = rand(T, n, 1), rand(T, n, 2), rand(T, n, 3)
+            want = a.copy()
+            run_kernel(src, want, b, c, n)
+            with Mapped(a, b, c, out=(a,)):
+                capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, c.ctypes.data, C.c_int(n)))
+                capi.check(capi.nomp().nomp_sync())
+            assert np.array_equal(a.view(np.uint8), want.view(np.uint8)), (T, body, n)
+
+
+@pytest.mark.parametrize("T", ["double", "float", "long"])
+def test_scalar_arguments_axpy_family(T):
+    dt, kind = TYPES[T]
+    sz = dt().itemsize
+    for body, fam in (("y[i] += alpha * x[i];", ("native", "map")), ("y[i] = x[i] + alpha * y[i];", ("native", "map")),
+                      ("y[i] = alpha * x[i] + beta * y[i];", ("native", "map")), ("y[i] = alpha * y[i];", ("native", "map")),
+                      ("y[i] = alpha;", ("native", "map")), ("y[i] = alpha * x[i] * x[i] - beta;", ("nvrtc", "map"))):
+        src = f"void k({T} *y, const {T} *x, {T} alpha, {T} beta, int N) {{ for (int i = 0; i < N; i++) {body} }}"
+        kid = jit(src, capi.clauses(), [("y", sz, P), ("x", sz, P), ("alpha", sz, kind), ("beta", sz, kind), ("N", 4, I)])
+        assert family(kid) == fam, body
+        n = 12345
+        x, y = rand(T, n, 5), rand(T, n, 6)
+        alpha, beta = dt(3), dt(2)
+        if T != "long":
+            alpha, beta = dt(0.37), dt(-1.25)
+        want = y.copy()
+        ca = {"double": C.c_double, "float": C.c_float, "long": C.c_long}[T]
+        run_kernel(src, want, x, ca(alpha.item()), ca(beta.item()), n)
+        with Mapped(x, y, out=(y,)):
+            capi.check(capi.run(kid, y.ctypes.data, x.ctypes.data, ca(alpha.item()), ca(beta.item()), C.c_int(n)))
+        assert np.array_equal(y.view(np.uint8), want.view(np.uint8)), (T, body)
+
+
+@pytest.mark.parametrize("T", ["int", "long", "unsigned", "unsigned long"])
+def test_bitwise_operators(T):
+    dt, _ = TYPES[T]
+    for body in ("a[i] = a[i] & 3;", "a[i] = i | 3;", "a[i] = i ^ 3;", "a[i] = a[i] << 3;", "a[i] = a[i] >> 3;", "a[i] = ~ a[i];"):
+        src = f"void foo({T} *a, int N) {{ for (int i = 0; i < N; i++) {body} }}"
+        kid = jit(src, capi.clauses(("transform", TR, "tile")), [("a", dt().itemsize, P), ("N", 4, I)])
+        for n in (10, 70):
+            a = np.arange(n).astype(dt)
+            want = a.copy()
+            run_kernel(src, want, n)
+            with Mapped(a, out=(a,)):
+                capi.check(capi.run(kid, a.ctypes.data, C.c_int(n)))
+            assert np.array_equal(a, want), (T, body)
+
+
+# ---- generic loop nests ----------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_sequential_inner_loops(T):
+    dt, _ = TYPES[T]
+    kernels = [
+        f"""void foo({T} *a, int *b, int N) {{ for (int i = 0; i < N; i++) {{ int t = 0;
+              for (int j = 0; j < 10; j++) {{ if ((!(j < 3) && (j < 5)) || j == 1) continue; t += 1; }} a[i] = t; }} }}""",
+        f"""void foo({T} *a, int *b, int N) {{ for (int i = 0; i < N; i++) {{ int t = 0;
+              for (int j = 0; j < 10; j++) {{ t = ((!(j < 3) && (j < 5)) || j == 1) ? t : t + 1; t += (j == 4) ? 0 : 1; }} a[i] = t; }} }}""",
+        f"""void foo({T} *a, int *b, int N) {{ for (int i = 0; i < N; i++) {{ int t = 0;
+              for (int j = 0; j < 10; j++) {{ t += 1; if (j == 5) break; }} a[i] = t; }} }}""",
+        f"""void foo({T} *a, int *b, int N) {{ for (int i = 0; i < N; i++) {{ int t = 0;
+              for (int j = b[i]; j < b[i + 1] + 1; j++) {{ t += 1; }} a[i] = t; }} }}""",
+    ]
+    for src in kernels:
+        kid = jit(src, capi.clauses(("transform", TR, "tile_outer")), [("a", dt().itemsize, P), ("b", 4, P), ("N", 4, I)])
+        assert family(kid) == ("nvrtc", "generic")
+        for n in (10, 50, 700):
+            a = np.zeros(n, dtype=dt)
+            b = (2 * np.arange(n + 1)).astype(np.int32)
+            want = a.copy()
+            run_kernel(src, want, b, n)
+            with Mapped(a, b, out=(a,)):
+                capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(n)))
+            assert np.array_equal(a, want)
+
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_two_dimensional_tiling(T):
+    dt, _ = TYPES[T]
+    sz = dt().itemsize
+    add = f"void foo({T} *a, {T} *b, int rows, int cols) {{ for (int j = 0; j < rows; j++) for (int i = 0; i < cols; i++) a[j * cols + i] = a[j * cols + i] + b[j * cols + i]; }}"
+    tr = f"void foo({T} *a, {T} *b, int rows, int cols) {{ for (int j = 0; j < rows; j++) for (int i = 0; i < cols; i++) a[j + i * rows] = b[i + j * cols]; }}"
+    for src in (add, tr):
+        kid = jit(src, capi.clauses(("transform", TR, "tile_2d")), [("a", sz, P), ("b", sz, P), ("rows", 4, I), ("cols", 4, I)])
+        for rows, cols in ((40, 5), (16, 16), (100, 37)):
+            a, b = rand(T, rows * cols, 1), rand(T, rows * cols, 2)
+            want = a.copy()
+            run_kernel(src, want, b, rows, cols)
+            with Mapped(a, b, out=(a,)):
+                capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(rows), C.c_int(cols)))
+            assert np.array_equal(a, want)
+    mm = f"""void foo({T} *a, {T} *b, {T} *c, int size) {{ for (unsigned i = 0; i < size; i++) {{ for (unsigned j = 0; j < size; j++) {{
+               double dot = 0; for (unsigned k = 0; k < size; k++) dot += a[i * size + k] * b[k * size + j]; c[i * size + j] = dot; }} }} }}"""
+    kid = jit(mm, capi.clauses(("transform", TR, "tile_2d")), [("a", sz, P), ("b", sz, P), ("c", sz, P), ("size", 4, I)])
+    for n in (10, 40):
+        a = np.tile(np.arange(n), n).astype(dt)
+        b = np.repeat(np.arange(n), n).astype(dt)
+        c = np.zeros(n * n, dtype=dt)
+        with Mapped(a, b, c, out=(c,)):
+            capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, c.ctypes.data, C.c_int(n)))
+        assert np.all(c == dt(sum(i * i for i in range(n))))
+
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_per_element_temporaries_fixed_and_jit_sized(T):
+    dt, _ = TYPES[T]
+    sz = dt().itemsize
+    shapes = [("s[32]", "s[j]", None, 32), ("s[32][8]", "s[j][4]", None, 32), ("s[2][2][32]", "s[1][1][j]", None, 32),
+              ("s[m]", "s[j]", 16, 16), ("s[m][m]", "s[j][4]", 32, 32), ("s[m][m][m]", "s[j][0][0]", 8, 8)]
+    for decl, ref, m, width in shapes:
+        bound = "m" if m else "32"
+        src = f"""void foo({T} *b, const {T} *a, int n{', int m' if m else ''}) {{ for (int i = 0; i < n; i++) {{ {T} {decl};
+              for (int j = 0; j < {bound}; j++) {ref} = a[i * {bound} + j];
+              for (int j = 0; j < {bound}; j++) {ref} += {ref};
+              for (int j = 0; j < {bound}; j++) b[i * {bound} + j] = {ref}; }} }}"""
+        args = [("b", sz, P), ("a", sz, P), ("n", 4, I)]
+        if m:
+            args.append(("m", 4, I | JIT, C.c_int(m)))
+        kid = jit(src, capi.clauses(("transform", TR, "element_dof")), args)
+        n = 16
+        a = np.repeat(np.arange(n), width).astype(dt)
+        b = np.zeros(n * width, dtype=dt)
+        with Mapped(a, b, out=(b,)):
+            capi.check(capi.run(kid, b.ctypes.data, a.ctypes.data, C.c_int(n)))   # the JIT argument is not passed at run time
+        assert np.array_equal(b, 2 * a), (T, decl)
+
+
+def test_annotate_clause_goes_through_the_annotations_script():
+    src = "void foo(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] = a[i] * b[i] + i; }"
+    kid = jit(src, capi.clauses(("annotate", "grid_loop", "i")), [("a", 8, P), ("b", 8, P), ("N", 4, I)])
+    n = 5000
+    a, b = rand("double", n, 1), rand("double", n, 2)
+    want = a.copy()
+    run_kernel(src, want, b, n)
+    with Mapped(a, b, out=(a,)):
+        capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(n)))
+    assert np.array_equal(a, want)
+    # element_loop on a kernel that is not elementwise: schedule comes from the annotation
+    src2 = "void foo(double *a, const int *b, int N) { for (int i = 0; i < N; i++) a[i] = b[N - 1 - i]; }"
+    kid2 = jit(src2, capi.clauses(("annotate", "element_loop", "i")), [("a", 8, P), ("b", 4, P), ("N", 4, I)])
+    assert family(kid2) == ("nvrtc", "generic")
+    a2, b2 = np.zeros(300), np.arange(300, dtype=np.int32)
+    with Mapped(a2, b2, out=(a2,)):
+        capi.check(capi.run(kid2, a2.ctypes.data, b2.ctypes.data, C.c_int(300)))
+    assert np.array_equal(a2, np.arange(300)[::-1])
+
+
+# ---- reductions ------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("T", list(TYPES))
+def test_reduce_clause_golden_values(T):
+    """Closed forms of the reference's reduce tests; the result overwrites the output and is valid when nomp_run returns
+    (no nomp_sync), the incoming value of the accumulator is ignored."""
+    dt, kind = TYPES[T]
+    sz = dt().itemsize
+    red = capi.clauses(("reduce", "s", "+"))
+    k_const = jit(f"void f({T} *s, int N) {{ for (int i = 0; i < N; i++) {{ s[0] += 1; }} }}", red, [("s", sz, kind), ("N", 4, I)])
+    k_index = jit(f"void f({T} *s, int N) {{ for (int i = 0; i < N; i++) {{ s[0] += i; }} }}", red, [("s", sz, kind), ("N", 4, I)])
+    k_sum = jit(f"void f({T} *a, int N, {T} *s) {{ for (int i = 0; i < N; i++) {{ s[0] += a[i]; }} }}", red,
+                [("a", sz, P), ("N", 4, I), ("s", sz, kind)])
+    k_dot = jit(f"void f({T} *a, {T} *b, int N, {T} *s) {{ for (int i = 0; i < N; i++) {{ s[0] += a[i] * b[i]; }} }}", red,
+                [("a", 8, P), ("b", sz, P), ("N", 4, I), ("s", sz, kind)])
+    assert family(k_sum) == ("native", "reduce") and family(k_dot) == ("native", "reduce") and family(k_const) == ("nvrtc", "reduce")
+    for N in (10, 50):
+        out = np.full(4, 77, dtype=dt)       # garbage in: must be overwritten
+        capi.check(capi.run(k_const, out.ctypes.data, C.c_int(N)))
+        assert out[0] == dt(N) and np.all(out[1:] == 77)
+        capi.check(capi.run(k_index, out.ctypes.data, C.c_int(N)))
+        assert out[0] == dt(N * (N - 1) // 2)
+        a = np.arange(N).astype(dt)
+        with Mapped(a):
+            capi.check(capi.run(k_sum, a.ctypes.data, C.c_int(N), out.ctypes.data))
+            assert out[0] == dt(N * (N - 1) // 2)
+            capi.check(capi.run(k_dot, a.ctypes.data, a.ctypes.data, C.c_int(N), out.ctypes.data))
+            assert out[0] == dt(N * (2 * N - 1) * (N - 1) // 6)
+        for it in range(1, 5):                # the same kernel, new data, several times
+            a = (it * np.arange(N)).astype(dt)
+            with Mapped(a):
+                capi.check(capi.run(k_sum, a.ctypes.data, C.c_int(N), out.ctypes.data))
+            assert out[0] == dt((N - 1) * N * it // 2)
+    capi.check(capi.run(k_const, out.ctypes.data, C.c_int(0)))      # empty loop -> identity
+    assert out[0] == 0
+
+
+def test_reduce_large_sizes():
+    n = (1 << 24) + 11
+    red = capi.clauses(("reduce", "s", "+"))
+    x = ffi.fill_uniform_f64(n, 1234, 0.5, 1.5)
+    y = ffi.fill_uniform_f64(n, 4321, 0.5, 1.5)
+    xi = ffi.fill_i64(n, 1)
+    k_sum = jit("void f(const double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", red,
+                [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    k_dot = jit("void f(const double *a, const double *b, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i] * b[i]; }",
+                red, [("a", 8, P), ("b", 8, P), ("N", 4, I), ("s", 8, F)])
+    k_isum = jit("void f(const long *a, int N, long *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", red,
+                 [("a", 8, P), ("N", 4, I), ("s", 8, I)])
+    k_cond = jit("void f(const double *a, int N, double *s) { for (int i = 0; i < N; i++) { if (a[i] > 1) s[0] += 1; } }", red,
+                 [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    k_sq = jit("void f(const double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i] * a[i] + 1; }", red,
+               [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    s, si = C.c_double(), C.c_long()
+    with Mapped(x, y, xi):
+        capi.check(capi.run(k_sum, x.ctypes.data, C.c_int(n), s))
+        ref = ffi.sum_compensated(x)
+        assert abs(s.value - ref) <= 1e-12 * abs(ref)                      # fp64: reduction-order tolerance 1e-12 relative
+        capi.check(capi.run(k_dot, x.ctypes.data, y.ctypes.data, C.c_int(n), s))
+        ref = ffi.sum_compensated(x, y)
+        assert abs(s.value - ref) <= 1e-12 * abs(ref)
+        capi.check(capi.run(k_isum, xi.ctypes.data, C.c_int(n), si))
+        assert si.value == ffi.reduce_(0, ffi.I64, xi)                      # int64: bit-exact
+        capi.check(capi.run(k_cond, x.ctypes.data, C.c_int(n), s))
+        assert s.value == float((x > 1).sum())
+        capi.check(capi.run(k_sq, x.ctypes.data, C.c_int(n), s))
+        ref = ffi.sum_compensated(x, x) + n
+        assert abs(s.value - ref) <= 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("T", ["int", "unsigned long", "double", "float"])
+def test_min_max_and_product_clauses(T):
+    dt, kind = TYPES[T]
+    sz = dt().itemsize
+    n = 100003
+    a = rand(T, n, 9)
+    kmin = jit(f"void f(const {T} *a, int N, {T} *m) {{ for (int i = 0; i < N; i++) m[0] = (a[i] < m[0]) ? a[i] : m[0]; }}",
+               capi.clauses(("reduce", "m", "min")), [("a", sz, P), ("N", 4, I), ("m", sz, kind)])
+    kmax = jit(f"void f(const {T} *a, int N, {T} *m) {{ for (int i = 0; i < N; i++) m[0] = (m[0] > a[i]) ? m[0] : a[i]; }}",
+               capi.clauses(("reduce", "m", "max")), [("a", sz, P), ("N", 4, I), ("m", sz, kind)])
+    kprod = jit(f"void f(const {T} *a, int N, {T} *m) {{ for (int i = 0; i < N; i++) m[0] *= a[i]; }}",
+                capi.clauses(("reduce", "m", "*")), [("a", sz, P), ("N", 4, I), ("m", sz, kind)])
+    assert family(kmin) == ("native", "reduce")
+    out = np.zeros(1, dtype=dt)
+    with Mapped(a):
+        capi.check(capi.run(kmin, a.ctypes.data, C.c_int(n), out.ctypes.data))
+        assert out[0] == a.min()
+        capi.check(capi.run(kmax, a.ctypes.data, C.c_int(n), out.ctypes.data))
+        assert out[0] == a.max()
+    small = (np.arange(12) % 3 + 1).astype(dt)
+    with Mapped(small):
+        capi.check(capi.run(kprod, small.ctypes.data, C.c_int(12), out.ctypes.data))
+    assert out[0] == dt(np.prod(small.astype(np.float64)))
+
+
+# ---- Ax through the API ------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,expect_family", [(8, ("native", "ax")), (10, ("native", "ax")), (6, ("native", "ax")), (4, ("nvrtc", "generic")),
+                                             (5, ("nvrtc", "generic"))])
+def test_ax_kernel_string(n, expect_family):
+    from nomp_bridge.families import AX_KERNEL_SOURCE
+    E = 37
+    u = ffi.fill_int_f64(E * n ** 3, 5, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 6, 0, 3)
+    D = ffi.fill_int_f64(n * n, 7, -2, 2)
+    w = np.zeros_like(u)
+    kid = jit(AX_KERNEL_SOURCE, capi.clauses(), [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I),
+                                                 ("n", 4, I | JIT, C.c_int(n))])
+    assert family(kid) == expect_family
+    with Mapped(u, g, D, w, out=(w,)):
+        capi.check(capi.run(kid, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E)))
+        first = w.copy()
+        # D changes on the device: the cached __constant__ copy must be refreshed
+        D2 = D * 2
+        D[:] = D2
+        capi.check(capi.update(D.ctypes.data, 0, D.size, 8, capi.NOMP_TO))
+        capi.check(capi.run(kid, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E)))
+        capi.check(capi.update(w.ctypes.data, 0, w.size, 8, capi.NOMP_FROM))
+        assert np.array_equal(w, ffi.ax(n, u, g, D))
+        capi.check(capi.update(first.ctypes.data, 0, 1, 8, capi.NOMP_ALLOC))
+        capi.check(capi.update(first.ctypes.data, 0, 1, 8, capi.NOMP_FREE))
+    assert np.array_equal(w, ffi.ax(n, u, g, D))
+    assert np.array_equal(w, 4 * ffi.ax(n, u, g, D / 2))
+
+
+def test_extensions_and_launch_counter():
+    lib = capi.nomp()
+    assert lib.nomp_b200_stream() is not None
+    assert lib.nomp_b200_comm_size() == 1 and lib.nomp_b200_comm_rank() == 0
+    before = lib.nomp_b200_launch_count()
+    a, b = np.ones(1000), np.ones(1000)
+    kid = jit("void foo(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] += b[i]; }", capi.clauses(),
+              [("a", 8, P), ("b", 8, P), ("N", 4, I)])
+    with Mapped(a, b, out=(a,)):
+        for _ in range(3):
+            capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(1000)))
+    assert lib.nomp_b200_launch_count() - before == 3 and np.all(a == 4)
