@@ -271,8 +271,15 @@ def run_ours(args):
         capi.check(lib.nomp_sync())
 
     # ---- device-resident timing ----------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: at least W steps, and at least ~0.3 s of work so that the SM clocks have left their idle state
+    warm = max(args.warmup, 3)
+    t_warm = time.perf_counter()
+    done_warm = 0
+    while done_warm < warm or time.perf_counter() - t_warm < 0.3:
         ax_step()
+        done_warm += 1
+        if done_warm % 8 == 0:
+            sync()
     sync()
     barrier()
     launches0 = lib.nomp_b200_launch_count()

@@ -70,11 +70,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int LPE> __device__ __forceinline__ void element_sync(int el_in_blk) {
-  if constexpr (LPE == 32) {
+template <int GL> __device__ __forceinline__ void element_sync(int grp) {
+  if constexpr (GL == 32) {
     __syncwarp();
   } else {
-    asm volatile("bar.sync %0, %1;" ::"r"(el_in_blk + 1), "n"(LPE) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GL) : "memory");
   }
 }
 
@@ -84,7 +84,7 @@ template <int LPE> __device__ __forceinline__ void element_sync(int el_in_blk) {
 // the uniform register: a D entry costs no vector register and no LSU slot.  Left alone, though, both NVVM and
 // ptxas treat the n^2 reads as loop invariants, hoist them out of the element loop and pin 2 n^2 VECTOR registers
 // for the whole kernel (R2UR before every DFMA, heavy spilling).  So every stage indexes D with its own
-// "zero" that is derived from the loop counter (eb >> 56..62: always 0, but not provably so): the reads become
+// "zero" that is derived from the loop counter (iteration counter >> 24..29: always 0, but not provably so): the reads become
 // loop-variant, stay next to their DFMAs as `LDCU.64 URx, c[3][URz + imm]`, and are not merged across stages.
 // ---------------------------------------------------------------------------------------------------
 template <int IDX> __device__ __forceinline__ double ld_D(int z) { return nompk_ax_cD[IDX + z]; }
@@ -151,34 +151,44 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // items of an element (n = 10: 14 of 64) and elements beyond E in the last group do not branch, they mirror
 // the last valid item / element and write the same values to the same addresses.  (Divergent regions would make
 // ptxas drop the uniform-register D operands and issue one vector LDC.64 per DFMA.)
-template <int N, int EPB, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks>
-__global__ void __launch_bounds__(EPB *Layout<N>::LPE, kMinBlocks)
+template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks>
+__global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E) {
   using L = Layout<N>;
   using SeqN = std::make_integer_sequence<int, N>;
   using SeqNP = std::make_integer_sequence<int, N / 2>;
-  constexpr int NP = L::NP, T = L::T, LPE = L::LPE;
+  // A GROUP of W warps works on G elements at a time: G*T work items on 32*W lanes (n = 8: 1 element per warp,
+  // 100 %; n = 10: 3 elements on 5 warps, 150/160 lanes = 94 % instead of 50/64 = 78 % with one element on 2 warps).
+  constexpr int NP = L::NP, T = L::T, GL = 32 * W;
+  static_assert(G * T <= GL, "group too small for its elements");
   constexpr int N3 = N * N * N;
   constexpr int SLAB2 = N * NP;  // double2 per k-slab in global memory
   extern __shared__ double2 smem[];
 
-  const int el_in_blk = threadIdx.x / LPE;
-  const int t = threadIdx.x % LPE;
-  const int tt = t < T ? t : T - 1;
+  const int grp = threadIdx.x / GL;             // group within the CTA
+  const int gid = threadIdx.x % GL;             // lane within the group
+  const int gidc = gid < G * T ? gid : G * T - 1;  // surplus lanes mirror the last work item (no divergence)
+  const int el = gidc / T;                      // element within the group
+  const int tt = gidc % T;                      // work item within the element
+  const int t = tt;
   // k-column item: (p, j);  j-line item: (p, k) -- the same split of t.
   const int p = tt % NP, q = tt / NP;
   // i-line items: rows r0 = 2t and r0 + 1 (same k, adjacent j).
   const int rk = (2 * tt) / N, rj = (2 * tt) % N;
 
-  double2 *B0 = smem + (size_t)el_in_blk * 3 * L::kChunks;
+  double2 *B0 = smem + (size_t)(grp * G + el) * 3 * L::kChunks;
   double2 *B1 = B0 + L::kChunks;
   double2 *B2 = B1 + L::kChunks;
 
+  constexpr int EPB = GPC * G;  // elements per CTA and iteration
   const size_t estride = (size_t)gridDim.x * EPB;
+  int it = 0;
   for (size_t eb = (size_t)blockIdx.x * EPB; eb < E; eb += estride) {
-    const int z1 = (int)(eb >> 62), z2 = (int)(eb >> 61), z3 = (int)(eb >> 60), z5 = (int)(eb >> 59),
-              z6 = (int)(eb >> 58), z7 = (int)(eb >> 57);  // all zero, see ld_D
-    size_t e = eb + el_in_blk;
+    // always-zero, loop-variant offsets for the D reads (see ld_D): one per stage, derived from a counter that
+    // depends on nothing but the iteration number so that ptxas keeps it in a uniform register
+    const int z1 = it >> 24, z2 = it >> 25, z3 = it >> 26, z5 = it >> 27, z6 = it >> 28, z7 = it >> 29;
+    it++;
+    size_t e = eb + grp * G + el;
     e = e < E ? e : E - 1;
     const double2 *ue = reinterpret_cast<const double2 *>(u + e * N3) + q * NP + p;
     const double2 *ge = reinterpret_cast<const double2 *>(g + e * 6 * N3) + q * NP + p;
@@ -226,7 +236,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
       for (int k = 0; k < N; k++) col[k] = ut[k];
     }
-    element_sync<LPE>(el_in_blk);
+    element_sync<GL>(grp);
 
     // ---- S2: ur = D_r u on two i-lines -> B1 ----------------------------------------------------------
     {
@@ -251,7 +261,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
       });
     }
-    element_sync<LPE>(el_in_blk);
+    element_sync<GL>(grp);
 
     // ---- S4: geometric factors at the k-column (p, j = q); wr -> B1, ws -> B2, wt -> registers ---------
 #pragma unroll
@@ -277,7 +287,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         if (k == 0) {
           constexpr int kULines = (N3 * 8 + 127) / 128;
 #pragma unroll
-          for (int l0 = 0; l0 < kULines; l0 += LPE)
+          for (int l0 = 0; l0 < kULines; l0 += T)
             if (l0 + t < kULines) prefetch_l2(u + e_next * N3 + (l0 + t) * 16);
         }
       }
@@ -300,7 +310,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       constexpr int a = decltype(A)::value;
       wacc[a] = dot_pair<N, true, a>(col, make_double2(0.0, 0.0), z5);
     });
-    element_sync<LPE>(el_in_blk);
+    element_sync<GL>(grp);
 
     // ---- S6: D_r^T wr on two i-lines: B1 -> B0 ----------------------------------------------------------
     {
@@ -315,7 +325,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         B0[L::at(rk, rj + 1, c)] = o1;
       });
     }
-    element_sync<LPE>(el_in_blk);
+    element_sync<GL>(grp);
 
     // ---- S7: + D_s^T ws on the j-line pair (p, k = q): B2, B0 -> B0 -------------------------------------
     {
@@ -328,7 +338,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         B0[a] = dot_pair<N, true, j>(in, B0[a], z7);
       });
     }
-    element_sync<LPE>(el_in_blk);
+    element_sync<GL>(grp);
 
     // ---- S8: add the r/s part to the k-column and store w ------------------------------------------------
 #pragma unroll
@@ -343,55 +353,61 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   }
 }
 
-struct AxVariant {
-  int epb, geo_ahead, prefetch_l2, stream_loads, min_blocks;
-};
-
 int g_variant = 0;
 
-template <int N, int EPB, int GA, int PF, bool ST, int MB>
+template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, EPB, GA, PF, ST, MB>;
-  const size_t smem = (size_t)EPB * 3 * L::kChunks * sizeof(double2);
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB>;
+  constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
+  const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
     NOMPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NOMPK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, EPB * L::LPE, smem));
+    NOMPK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     configured = true;
   }
-  size_t blocks = (E + EPB - 1) / EPB;
+  size_t blocks = (E + kElems - 1) / kElems;
   const size_t cap = (size_t)sm_count() * blocks_per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, EPB * L::LPE, smem, stream>>>(u, g, w, E);
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E);
   NOMPK_LAUNCH_CHECK("ax_kernel");
   return NOMPK_OK;
 }
 
+// Group shapes: <elements per group, warps per group, groups per CTA>.
+template <int N> struct Shape;
+template <> struct Shape<6> { static constexpr int G = 7, W = 4, GPC = 1; };    // 126 / 128 lanes
+template <> struct Shape<8> { static constexpr int G = 1, W = 1, GPC = 4; };    // 32 / 32, warps independent
+template <> struct Shape<10> { static constexpr int G = 3, W = 5, GPC = 1; };   // 150 / 160
+template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   // 144 / 160
+
 template <int N> int dispatch_ax(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
-  // CTA = EPB0 elements.  MB128 / MB168 = resident CTAs per SM that cap the kernel at 128 / 168 registers.
-  constexpr int EPB0 = 128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1;
-  constexpr int kThreads = EPB0 * Layout<N>::LPE;
-  constexpr int MB128 = 65536 / (128 * kThreads), MB168 = 65536 / (168 * kThreads);
-  // Variants are kept for profiling (bench/profile scripts sweep them); 0 is the production choice.
+  // MBr = resident CTAs per SM that cap the kernel at r registers per thread.
+  constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
+  constexpr int kThreads = GPC * W * 32;
+  constexpr int MB128 = 65536 / (128 * kThreads), MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  // Variants are kept for profiling (tools/ax_sweep.py sweeps them); 0 is the production choice.
   switch (variant) {
   default:
-  case 0:  // production choice (gpurun sweep of round 1, profiles/ax_sweep_r01.md)
-    if constexpr (N == 8) return launch_ax<N, EPB0, 3, 6, false, MB168>(E, u, g, w, s);
-    else return launch_ax<N, EPB0, 2, 4, false, MB168>(E, u, g, w, s);
-  case 1: return launch_ax<N, EPB0, 2, 4, false, MB128>(E, u, g, w, s);
-  case 2: return launch_ax<N, EPB0, 2, 3, false, MB128>(E, u, g, w, s);
-  case 3: return launch_ax<N, EPB0, 2, 2, false, MB128>(E, u, g, w, s);
-  case 4: return launch_ax<N, EPB0, 2, 0, false, MB128>(E, u, g, w, s);
-  case 5: return launch_ax<N, EPB0, 2, 4, true, MB128>(E, u, g, w, s);
-  case 6: return launch_ax<N, EPB0, 2, 0, false, 1>(E, u, g, w, s);
-  case 7: return launch_ax<N, EPB0, 2, 4, false, MB168>(E, u, g, w, s);
-  case 8: return launch_ax<N, EPB0, 3, 6, false, MB168>(E, u, g, w, s);
-  case 9: return launch_ax<N, EPB0, 2, 4, false, 1>(E, u, g, w, s);
-  case 10: return launch_ax<N, EPB0, 4, 6, false, 1>(E, u, g, w, s);
-  case 11: return launch_ax<N, EPB0, 3, 4, false, MB168>(E, u, g, w, s);
+  case 0:  // production choice (gpurun sweeps of round 1, profiles/r01_kernel_sweeps.jsonl)
+    if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
+    else return launch_ax<N, G, W, GPC, 3, 6, false, MB168>(E, u, g, w, s);
+  case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
+  case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
+  case 3: return launch_ax<N, G, W, GPC, 2, 2, false, MB128>(E, u, g, w, s);
+  case 4: return launch_ax<N, G, W, GPC, 2, 0, false, MB128>(E, u, g, w, s);
+  case 5: return launch_ax<N, G, W, GPC, 2, 4, true, MB128>(E, u, g, w, s);
+  case 6: return launch_ax<N, G, W, GPC, 2, 0, false, 1>(E, u, g, w, s);
+  case 7: return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
+  case 8: return launch_ax<N, G, W, GPC, 3, 6, false, MB168>(E, u, g, w, s);
+  case 9: return launch_ax<N, G, W, GPC, 2, 4, false, 1>(E, u, g, w, s);
+  case 10: return launch_ax<N, G, W, GPC, 4, 6, false, 1>(E, u, g, w, s);
+  case 11: return launch_ax<N, G, W, GPC, 3, 4, false, MB168>(E, u, g, w, s);
+  case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
+    return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }
 }
 

@@ -182,7 +182,7 @@ def test_ax_exact_data_bitwise(n, E):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", list(range(12)))
+@pytest.mark.parametrize("variant", list(range(13)))
 @pytest.mark.parametrize("n", [8, 10])
 def test_ax_variants_agree(variant, n):
     E = 333

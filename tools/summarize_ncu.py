@@ -1,0 +1,80 @@
+#!/usr/bin/env python3
+"""Turn `ncu` outputs brought back in gpurun_out/ into the small text summaries kept under profiles/.
+
+  summarize_ncu.py launches <launches.csv>             -> per-kernel launch counts / total time / share
+  summarize_ncu.py report <file.ncu-rep> [title]       -> key counters of the first profiled launch
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.per_cycle_active",
+    "smsp__inst_executed.sum", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr, agg = None, collections.OrderedDict()
+    for r in rows:
+        if r[0] == "ID":
+            hdr = r
+            continue
+        if hdr is None:
+            continue
+        d = dict(zip(hdr, r))
+        if d.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(d["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(d["Metric Unit"], 1.0)
+        name = d["Kernel Name"].split("(")[0][-90:]
+        a = agg.setdefault(name, [0, 0.0, d["Grid Size"], d["Block Size"]])
+        a[0] += 1
+        a[1] += v
+    total = sum(a[1] for a in agg.values())
+    print("| kernel | launches | total us | avg us | share | grid | block |")
+    print("|---|---:|---:|---:|---:|---|---|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {a[1] / a[0]:.1f} | {100 * a[1] / total:.1f}% | {a[2]} | {a[3]} |")
+
+
+def report(path, title=None):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    col = {h: i for i, h in enumerate(hdr)}
+    print(f"### {title or path}")
+    print(f"kernel: `{vals[col['Kernel Name']][:140]}`\n")
+    print("| counter | value | unit |")
+    print("|---|---:|---|")
+    for k in KEYS:
+        if k in col:
+            print(f"| {k} | {vals[col[k]]} | {units[col[k]]} |")
+    print()
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        report(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
