@@ -43,6 +43,15 @@ METRIC = "SEM Ax GDOF/s (N=7 fp64)"
 UNIT = "GDOF/s"
 
 
+def ncu_traffic(n, E):
+    """DRAM bytes per launch of the Ax kernel from the committed ncu capture of the same shape, else None."""
+    try:
+        t = json.load(open(ROOT / "profiles" / "ncu_traffic.json"))["ax_kernel"].get(f"n{n}_E{E}")
+        return None if t is None else t["read_bytes"] + t["write_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         return float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]), "measured"
@@ -365,7 +374,7 @@ def run_ours(args):
                    "l2": f"no flush needed: each step streams {ndof * BYTES_PER_DOF / 1e6:.0f} MB per GPU, larger than the 126 MB L2",
                    "kernel": info},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                     "traffic": ncu_traffic(n, E), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                      "kernel": "nompk::ax_kernel<8,...>", "algorithmic_bytes_per_launch": ndof * BYTES_PER_DOF,
                      "avg_launch_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ndof * 8 * world, "d2h_bytes_per_step": ndof * 8 * world,

@@ -111,6 +111,17 @@ def build_libnomp(force=False):
     return out
 
 
+def build_tools(force=False):
+    """C drivers under tools/ (launch-overhead sweep of BASELINE.json configs[4])."""
+    OBJ.mkdir(exist_ok=True)
+    out = OBJ / "launch_overhead"
+    src = ROOT / "tools" / "launch_overhead.c"
+    if force or _stale(out, [src, LIB / "libnomp.so"]):
+        _run(["gcc", "-O2", "-I", str(ROOT / "include"), str(src), "-o", str(out), "-L", str(LIB), "-lnomp",
+              f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
+    return out
+
+
 def build_oracle(force=False):
     out = ROOT / "oracle" / "libnomp_oracle.so"
     if force or _stale(out, [ROOT / "oracle" / "nomp_oracle.c"]):
@@ -135,6 +146,8 @@ def build_all(force=False, only=None):
         built["kernels"] = build_kernels(force)
     if only in (None, "libnomp"):
         built["libnomp"] = build_libnomp(force)
+    if only in (None, "tools"):
+        built["tools"] = build_tools(force)
     if only in (None, "oracle"):
         built["oracle"] = build_oracle(force)
     if only in (None, "ref-tests"):
@@ -145,7 +158,7 @@ def build_all(force=False, only=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
-    ap.add_argument("--only", choices=["kernels", "libnomp", "oracle", "ref-tests"])
+    ap.add_argument("--only", choices=["kernels", "libnomp", "tools", "oracle", "ref-tests"])
     a = ap.parse_args()
     for k, v in build_all(a.force, a.only).items():
         print(f"{k}: {v}")
