@@ -26,6 +26,8 @@ unsigned long long nomp_b200_launch_count(void);
 /* Rank / size of the NCCL communicator (0 / 1 when single-process). */
 int nomp_b200_comm_rank(void);
 int nomp_b200_comm_size(void);
+/* 1 if multi-GPU reduce clauses use libnompk's NVLink one-shot all-reduce kernel, 0 if they use ncclAllReduce. */
+int nomp_b200_comm_uses_nvlink_kernel(void);
 /* File rendezvous used to distribute the ncclUniqueId: rank 0 publishes `bytes` bytes through `path`, the other
  * ranks wait for the file and read them.  0 on success, a log id otherwise. */
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);

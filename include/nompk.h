@@ -90,12 +90,27 @@ size_t nompk_reduce_workspace_bytes(void);
 /* result[0] <- reduce_op over i of (y ? x[i]*y[i] : x[i]),  i in [0,n).  n == 0 writes the identity.
  * Single pass: per-thread accumulators, warp-shuffle tree, one partial per block, and the last block to
  * take a ticket folds the partials in block order (deterministic run to run).  `result` is a device
- * pointer (8-byte aligned); if result_host_mapped != NULL the same value is also stored through that
- * pointer (device address of pinned, mapped host memory), so the host needs no D2H copy.
+ * pointer (8-byte aligned); if result_host_mapped != NULL (device address of 16 bytes of pinned, mapped host memory)
+ * the value is also stored at its bytes [0,8) and then host_seq at bytes [8,16), so the host needs no D2H copy and
+ * may spin on the sequence number instead of synchronising the stream.
  * Replaces: loopy's per-block tree (reference python/reduction.py:30-134) + the D2H of all partials and
  * the serial host loop in reference src/reduction.c:33-88. */
 int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y,
-                 void *result, void *result_host_mapped, void *workspace, void *stream);
+                 void *result, void *result_host_mapped, unsigned long long host_seq, void *workspace,
+                 void *stream);
+
+/* One-shot all-reduce of one scalar across `world` processes (one GPU each) over NVLink peer memory.
+ * `value` (device, 8-byte aligned) holds this rank's contribution and receives the result, identical bit for bit on
+ * every rank (contributions are folded in rank order).  peer_xchg is a DEVICE array of `world` pointers: entry r is
+ * rank r's exchange buffer of nompk_allreduce_xchg_bytes(world) zero-initialised bytes, as mapped into THIS process
+ * (own allocation for r == rank, cudaIpcOpenMemHandle otherwise).  `seq` numbers the collective calls: 1, 2, 3, ...
+ * in the same order on all ranks.  result_host_mapped / host_seq as in nompk_reduce.
+ * Replaces: nothing in the reference (it has no collective); in this implementation it replaces ncclAllReduce for the
+ * 4/8-byte result of a reduce clause (NCCL stays as the fallback when peer access is unavailable). */
+size_t nompk_allreduce_xchg_bytes(int world);
+int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
+                           unsigned long long host_seq, void *const *peer_xchg, int rank, int world,
+                           unsigned long long seq, void *stream);
 
 /* Local Poisson operator on E hexahedral spectral elements with n = N+1 points per direction, fp64:
  *   w_e = D^T_r (g1 Dr u + g2 Ds u + g3 Dt u) + D^T_s (g2 Dr u + g4 Ds u + g5 Dt u)

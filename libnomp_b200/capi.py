@@ -37,14 +37,14 @@ NOMP_CUDA_FAILURE = -512
 
 NOMPK_SYMBOLS = [
     "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes",
-    "nompk_reduce", "nompk_ax_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
+    "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
 ]
 NOMP_SYMBOLS = [
     "nomp_init", "nomp_update", "nomp_jit", "nomp_run", "nomp_sync", "nomp_get_err_str", "nomp_get_err_no",
     "nomp_finalize", "nomp_finalize_excluding_interpreter", "nomp_copy_env",
     # extensions declared in include/nomp-b200.h
     "nomp_b200_stream", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
-    "nomp_b200_comm_size", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
+    "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
 ]
 
 
@@ -79,7 +79,12 @@ def nompk() -> C.CDLL:
         lib.nompk_reduce_workspace_bytes.restype = C.c_size_t
         lib.nompk_reduce.restype = C.c_int
         lib.nompk_reduce.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p]
+                                     C.c_ulonglong, C.c_void_p, C.c_void_p]
+        lib.nompk_allreduce_xchg_bytes.restype = C.c_size_t
+        lib.nompk_allreduce_xchg_bytes.argtypes = [C.c_int]
+        lib.nompk_allreduce_scalar.restype = C.c_int
+        lib.nompk_allreduce_scalar.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_ulonglong, C.c_void_p]
         lib.nompk_ax_f64.restype = C.c_int
         lib.nompk_ax_f64.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
                                      C.c_void_p]
@@ -122,6 +127,7 @@ def nomp() -> C.CDLL:
         lib.nomp_b200_launch_count.restype = C.c_ulonglong
         lib.nomp_b200_comm_rank.restype = C.c_int
         lib.nomp_b200_comm_size.restype = C.c_int
+        lib.nomp_b200_comm_uses_nvlink_kernel.restype = C.c_int
         lib.nomp_b200_prog_info.restype = C.c_char_p
         lib.nomp_b200_prog_info.argtypes = [C.c_int]
         lib.nomp_b200_exchange_blob.restype = C.c_int

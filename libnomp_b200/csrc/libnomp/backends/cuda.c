@@ -95,7 +95,8 @@ typedef struct {
   int device;
   struct cudaDeviceProp prop;
   cudaStream_t stream;
-  void *pinned_host;   /* 64 bytes of mapped pinned memory: the host-visible reduction result */
+  void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
+  unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
   void *red_partials;  /* device pointers handed to generated reduce kernels */
   void *red_ticket;
@@ -117,6 +118,7 @@ typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX } family_t;
 #define SLOT_TICKET (-3)
 #define SLOT_RESULT (-4)
 #define SLOT_RESULT_HOST (-5)
+#define SLOT_SEQ (-6)
 
 typedef struct {
   family_t family;
@@ -124,7 +126,7 @@ typedef struct {
   CUmodule module;
   CUfunction function;
   int nparams;
-  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 4]; /* index into prg->args, or SLOT_* */
+  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 5]; /* index into prg->args, or SLOT_* */
   int is_reduce;
   /* native */
   int op, dtype, ax_n;
@@ -248,13 +250,14 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
     else if (!strcmp(tok, "nomp_ticket")) slot = SLOT_TICKET;
     else if (!strcmp(tok, "nomp_result")) slot = SLOT_RESULT;
     else if (!strcmp(tok, "nomp_result_host")) slot = SLOT_RESULT_HOST;
+    else if (!strcmp(tok, "nomp_seq")) slot = SLOT_SEQ;
     else {
       slot = arg_index(prg, tok);
       if (slot == SLOT_NONE)
         return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
                         "Kernel argument \"%s\" was not declared in nomp_jit().", tok);
     }
-    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 4)
+    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 5)
       return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Too many kernel arguments.");
     cp->param_slot[cp->nparams++] = slot;
   }
@@ -373,7 +376,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     long n = int_arg(prg, cp->a_n, cp->n_literal);
     if (n < 0) n = 0;
     check_nompk(nompk_reduce((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
-                             ptr_arg(prg, cp->a_y), st->red_result, result_host, st->red_partials, st->stream));
+                             ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_partials,
+                             st->stream));
     return 0;
   }
   case FAM_AX: {
@@ -394,13 +398,15 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   }
   case FAM_NVRTC: {
     st->red_result_host = result_host;
-    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 4];
+    if (cp->is_reduce) ++st->host_seq;
+    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 5];
     for (int i = 0; i < cp->nparams; i++) {
       int s = cp->param_slot[i];
       if (s == SLOT_PARTIALS) vargs[i] = &st->red_partials;
       else if (s == SLOT_TICKET) vargs[i] = &st->red_ticket;
       else if (s == SLOT_RESULT) vargs[i] = &st->red_result;
       else if (s == SLOT_RESULT_HOST) vargs[i] = &st->red_result_host;
+      else if (s == SLOT_SEQ) vargs[i] = &st->host_seq;
       else if (prg->args[s].type == NOMP_PTR) vargs[i] = &prg->args[s].ptr; /* device pointer by value */
       else vargs[i] = prg->args[s].ptr;                                       /* the caller's scalar */
     }
@@ -440,12 +446,36 @@ int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg) {
     case NOMP_UINT: dtype = size == 4 ? NOMPK_U32 : NOMPK_U64; break;
     default: dtype = size == 4 ? NOMPK_F32 : NOMPK_F64; break;
     }
-    nomp_check(nomp_comm_allreduce(st->red_result, dtype, (int)prg->reduction_op, st->stream));
-    check_runtime(cudaMemcpyAsync(st->pinned_host, st->red_result, 8, cudaMemcpyDeviceToHost, st->stream));
+    /* all-reduce the device scalar in place; the NVLink one-shot kernel also publishes {value, seq} to the host,
+     * the NCCL fallback needs an explicit 8-byte copy */
+    int published = 0;
+    nomp_check(nomp_comm_allreduce(st->red_result, dtype, (int)prg->reduction_op, st->pinned_dev, st->host_seq,
+                                   st->stream, &published));
+    if (!published) {
+      check_runtime(cudaMemcpyAsync(st->pinned_host, st->red_result, 8, cudaMemcpyDeviceToHost, st->stream));
+      check_runtime(cudaStreamSynchronize(st->stream));
+      memcpy(prg->reduction_ptr, st->pinned_host, size);
+      return 0;
+    }
   }
-  /* the reduce clause's result is valid on the host when nomp_run returns (reference
-   * tests/nomp-api-500-impl.h:29-34 read it with no nomp_sync in between) */
-  check_runtime(cudaStreamSynchronize(st->stream));
+  /* The reduce clause's result is valid on the host when nomp_run returns (reference
+   * tests/nomp-api-500-impl.h:29-34 read it with no nomp_sync in between).  The kernel stores the value and then the
+   * sequence number into mapped pinned memory; spinning on the sequence number is a few microseconds faster than
+   * cudaStreamSynchronize.  The stream is polled now and then so that a failed launch cannot hang the caller. */
+  volatile unsigned long long *seq = (volatile unsigned long long *)((char *)st->pinned_host + 8);
+  for (unsigned long spins = 1; *seq != st->host_seq; spins++) {
+    if ((spins & 0xfff) == 0) {
+      cudaError_t q = cudaStreamQuery(st->stream);
+      if (q == cudaSuccess) {
+        if (*seq == st->host_seq) break;
+        return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "reduction", "result was not published");
+      }
+      if (q != cudaErrorNotReady)
+        return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "runtime", cudaGetErrorName(q));
+    }
+    __builtin_ia32_pause();
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
   memcpy(prg->reduction_ptr, st->pinned_host, size);
   return 0;
 }

@@ -116,8 +116,10 @@ int nomp_comm_init(int device);
 int nomp_comm_finalize(void);
 int nomp_comm_rank(void);
 int nomp_comm_size(void);
-/* in-place allreduce of one scalar on `stream`; dtype codes of include/nompk.h, op = nomp_reduction_op_t */
-int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *stream);
+/* in-place allreduce of one scalar on `stream`; dtype codes of include/nompk.h, op = nomp_reduction_op_t.
+ * *published = 1 if {value, host_seq} was also written to result_host_mapped (NVLink one-shot path). */
+int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
+                        void *stream, int *published);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 
 extern const char *ERR_STR_USER_MAP_PTR_IS_INVALID;

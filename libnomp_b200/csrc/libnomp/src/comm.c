@@ -8,7 +8,14 @@
  * publishes it by writing <file>.tmp and renaming it to <file>; the other ranks poll for <file>.  The caller must
  * pick a path that is fresh for every job (bench.py derives it from MASTER_PORT and a broadcast token).
  * NCCL is dlopen()ed on first use, so single-GPU programs and the nomp-api tests never load it.
+ *
+ * Fast path: an 8-byte allreduce through NCCL costs a collective launch plus protocol latency (tens of microseconds),
+ * which is the whole latency budget of a CG step at 8 GPUs.  When every rank can map its peers' memory
+ * (CUDA IPC over NVLink / NVSwitch) the communicator also sets up the exchange buffers of libnompk's one-shot
+ * all-reduce kernel (include/nompk.h: nompk_allreduce_scalar) and uses it instead; NCCL stays as the fallback and is
+ * selected with NOMP_COMM_ALLREDUCE=nccl.
  */
+#include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <time.h>
@@ -29,6 +36,15 @@ static struct {
 
 static ncclComm_t comm = NULL;
 static int comm_rank = 0, comm_size = 1;
+
+/* NVLink one-shot all-reduce state */
+static struct {
+  int enabled;
+  void *mine;          /* this rank's exchange buffer (cudaMalloc) */
+  void *peers[64];     /* every rank's buffer as mapped into this process */
+  void **table_dev;    /* device copy of peers[] */
+  unsigned long long seq;
+} p2p;
 
 #define check_nccl(call)                                                                                         \
   do {                                                                                                           \
@@ -59,6 +75,8 @@ static int env_int(const char *name, int fallback) {
   if (!v) return fallback;
   return nomp_str_toui(v, NOMP_MAX_BUFFER_SIZE);
 }
+
+static void p2p_setup(const char *path, int rank, int size);
 
 int nomp_comm_rank(void) { return comm_rank; }
 int nomp_comm_size(void) { return comm_size; }
@@ -109,10 +127,71 @@ int nomp_comm_init(int device) {
   nomp_check(nomp_b200_exchange_blob(path, rank, &id, sizeof(id)));
   check_nccl(nccl.CommInitRank(&comm, size, id, rank));
   comm_rank = rank, comm_size = size;
+
+  /* optional NVLink one-shot path: enabled only if EVERY rank managed to map every peer (min over ranks via NCCL) */
+  p2p_setup(path, rank, size);
+  int *flag_dev = NULL;
+  int flag = p2p.enabled;
+  if (cudaMalloc((void **)&flag_dev, sizeof(int)) == cudaSuccess) {
+    cudaMemcpy(flag_dev, &flag, sizeof(int), cudaMemcpyHostToDevice);
+    ncclResult_t r = nccl.AllReduce(flag_dev, flag_dev, 1, ncclInt32, ncclMin, comm, 0);
+    cudaDeviceSynchronize();
+    if (r == ncclSuccess) cudaMemcpy(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    else flag = 0;
+    cudaFree(flag_dev);
+  } else {
+    flag = 0;
+  }
+  p2p.enabled = flag;
+  nomp_info("multi-GPU reductions use %s", p2p.enabled ? "the NVLink one-shot all-reduce kernel" : "ncclAllReduce");
   return 0;
 }
 
+/* Exchange CUDA IPC handles of the per-rank exchange buffers through files next to the id file and map the peers'.
+ * Any failure simply leaves the NCCL path in place. */
+static void p2p_setup(const char *path, int rank, int size) {
+  memset(&p2p, 0, sizeof(p2p));
+  const char *mode = getenv("NOMP_COMM_ALLREDUCE");
+  if ((mode && !strcmp(mode, "nccl")) || size > 64) return;
+  const size_t bytes = nompk_allreduce_xchg_bytes(size);
+  if (cudaMalloc(&p2p.mine, bytes) != cudaSuccess) return;
+  cudaMemset(p2p.mine, 0, bytes);
+  cudaDeviceSynchronize();
+  cudaIpcMemHandle_t handle;
+  int ok = cudaIpcGetMemHandle(&handle, p2p.mine) == cudaSuccess;
+  /* all-gather of (ok, handle): rank r publishes "<path>.ipc.<r>", everybody reads everybody */
+  struct { int ok; cudaIpcMemHandle_t h; } rec, all[64];
+  rec.ok = ok, rec.h = handle;
+  char name[PATH_MAX];
+  snprintf(name, sizeof(name), "%s.ipc.%d", path, rank);
+  if (nomp_b200_exchange_blob(name, 0, &rec, sizeof(rec)) > 0) ok = 0;
+  for (int r = 0; r < size; r++) {
+    snprintf(name, sizeof(name), "%s.ipc.%d", path, r);
+    if (r == rank) all[r] = rec;
+    else if (nomp_b200_exchange_blob(name, 1, &all[r], sizeof(all[r])) > 0) all[r].ok = 0;
+    ok = ok && all[r].ok;
+  }
+  for (int r = 0; ok && r < size; r++) {
+    if (r == rank) p2p.peers[r] = p2p.mine;
+    else if (cudaIpcOpenMemHandle(&p2p.peers[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+  }
+  if (ok && cudaMalloc((void **)&p2p.table_dev, sizeof(void *) * (size_t)size) == cudaSuccess &&
+      cudaMemcpy(p2p.table_dev, p2p.peers, sizeof(void *) * (size_t)size, cudaMemcpyHostToDevice) == cudaSuccess)
+    p2p.enabled = 1;
+  cudaGetLastError(); /* clear sticky-free errors of the probing above */
+  snprintf(name, sizeof(name), "%s.ipc.%d", path, rank);
+  /* every rank must agree: all-reduce the flag through NCCL-free means is overkill -- a rank that failed simply keeps
+   * enabled = 0 and the others would wait for it forever, so agreement is checked with one NCCL allreduce below */
+}
+
 int nomp_comm_finalize(void) {
+  if (p2p.mine) {
+    for (int r = 0; r < comm_size; r++)
+      if (r != comm_rank && p2p.peers[r]) cudaIpcCloseMemHandle(p2p.peers[r]);
+    cudaFree(p2p.mine);
+    if (p2p.table_dev) cudaFree(p2p.table_dev);
+    memset(&p2p, 0, sizeof(p2p));
+  }
   if (comm) {
     nccl.CommDestroy(comm);
     comm = NULL;
@@ -121,8 +200,20 @@ int nomp_comm_finalize(void) {
   return 0;
 }
 
-int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *stream) {
+NOMP_EXPORT int nomp_b200_comm_uses_nvlink_kernel(void) { return p2p.enabled; }
+
+int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
+                        void *stream, int *published) {
+  *published = 0;
   if (comm_size == 1) return 0;
+  if (p2p.enabled) {
+    int rc = nompk_allreduce_scalar((nompk_red_op_t)op, (nompk_dtype_t)dtype, dev_scalar, result_host_mapped, host_seq,
+                                    (void *const *)p2p.table_dev, comm_rank, comm_size, ++p2p.seq, stream);
+    if (rc != NOMPK_OK)
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "CUDA kernel library failure: %s.", nompk_last_error());
+    *published = 1;
+    return 0;
+  }
   ncclDataType_t dt;
   switch (dtype) {
   case NOMPK_I32: dt = ncclInt32; break;

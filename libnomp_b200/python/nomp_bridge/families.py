@@ -388,8 +388,8 @@ def _limits(t: c.CType, hi: bool) -> str:
 
 def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tuple[str, List[str], List[str], List[str]]:
     """Single-pass reduction kernel with the same structure as libnompk's reduce.cu, for an arbitrary rhs.
-    Returns (source, grid exprs, block exprs, kernel parameter names).  The trailing four parameters
-    (partials, ticket, result, result_host) are supplied by the backend."""
+    Returns (source, grid exprs, block exprs, kernel parameter names).  The trailing five parameters
+    (partials, ticket, result, result_host, seq) are supplied by the backend."""
     T = cuda_type(info.vtype)
     func = knl.func
     params = [p for p in func.params if p.name != info.var]
@@ -398,7 +398,7 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         t = prm.ctype
         sig_parts.append(f"const {cuda_type(t)} *__restrict__ {prm.name}" if prm.is_array else f"{cuda_type(t)} {prm.name}")
     sig_parts += [f"{T} *__restrict__ nomp_partials", "unsigned int *__restrict__ nomp_ticket",
-                  f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host"]
+                  f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host", "unsigned long long nomp_seq"]
     int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}
     it = cuda_type(info.loop.vtype)
     lo, hi = expr_str(info.loop.lo), expr_str(info.loop.hi)
@@ -467,7 +467,11 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
     if (threadIdx.x == 0) {{
       *nomp_result = nomp_acc;
-      if (nomp_result_host) {{ *nomp_result_host = nomp_acc; __threadfence_system(); }}
+      if (nomp_result_host) {{
+        *(volatile {T} *)nomp_result_host = nomp_acc;
+        __threadfence_system();
+        *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
+      }}
       *nomp_ticket = 0u;
     }}
   }}
@@ -479,7 +483,7 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
         grid = f"max(1, min(({ext} + 255) / 256, {max(1, sm_count) * 8}))"
     except KernelError:
         grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
-    names = [p.name for p in params] + ["nomp_partials", "nomp_ticket", "nomp_result", "nomp_result_host"]
+    names = [p.name for p in params] + ["nomp_partials", "nomp_ticket", "nomp_result", "nomp_result_host", "nomp_seq"]
     return src, [grid, "1", "1"], ["256", "1", "1"], names
 
 

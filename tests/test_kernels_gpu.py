@@ -92,12 +92,12 @@ def _reduce(op, dtype, x, y=None, mapped=False):
     tx = dev(x)
     ty = dev(y) if y is not None else None
     rc = lib.nompk_reduce(op, dtype, x.size, tx.data_ptr(), ty.data_ptr() if ty is not None else None,
-                          res.data_ptr(), None, ws.data_ptr(), stream())
+                          res.data_ptr(), None, 0, ws.data_ptr(), stream())
     capi.nompk_check(rc, "nompk_reduce")
     first = res.cpu().numpy().view(npdt)[0]
     # second launch on the same workspace: the ticket must have been reset by the kernel
     rc = lib.nompk_reduce(op, dtype, x.size, tx.data_ptr(), ty.data_ptr() if ty is not None else None,
-                          res.data_ptr(), None, ws.data_ptr(), stream())
+                          res.data_ptr(), None, 0, ws.data_ptr(), stream())
     capi.nompk_check(rc, "nompk_reduce")
     second = res.cpu().numpy().view(npdt)[0]
     assert first.tobytes() == second.tobytes(), "reduction is not deterministic / workspace not reset"
@@ -150,12 +150,13 @@ def test_reduce_result_in_mapped_host_memory():
     tx = dev(x)
     ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
     res = torch.zeros(1, dtype=torch.float64, device="cuda")
-    pinned = torch.zeros(1, dtype=torch.float64).pin_memory()
-    rc = lib.nompk_reduce(capi.RED_SUM, capi.F64, n, tx.data_ptr(), None, res.data_ptr(), pinned.data_ptr(),
+    pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
+    rc = lib.nompk_reduce(capi.RED_SUM, capi.F64, n, tx.data_ptr(), None, res.data_ptr(), pinned.data_ptr(), 41,
                           ws.data_ptr(), stream())
     capi.nompk_check(rc)
     torch.cuda.synchronize()
-    assert pinned.item() == x.sum() == res.item()
+    assert pinned[0].item() == x.sum() == res.item()
+    assert pinned.view(torch.int64)[1].item() == 41        # the sequence number follows the value
 
 
 def _ax(n, u, g, D, variant=0):

@@ -51,12 +51,14 @@ import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, {root!r})
 rank, world = int(sys.argv[1]), int(sys.argv[2])
-os.environ.update(NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(rank), NOMP_COMM_ID_FILE=sys.argv[3])
+os.environ.update(NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(rank), NOMP_COMM_ID_FILE=sys.argv[3], NOMP_COMM_ALLREDUCE=sys.argv[4])
 from libnomp_b200 import capi
 from oracle import ffi
 capi.check(capi.init(backend="cuda", device=rank, verbose=1))
 lib = capi.nomp()
 assert lib.nomp_b200_comm_size() == world and lib.nomp_b200_comm_rank() == rank
+if sys.argv[4] == "nccl":
+    assert lib.nomp_b200_comm_uses_nvlink_kernel() == 0
 P, I, F = capi.NOMP_PTR, capi.NOMP_INT, capi.NOMP_FLOAT
 n = 1 << 20
 x = ffi.fill_int_f64(n, 11, 0, 7); y = ffi.fill_int_f64(n, 12, 0, 7); xi = ffi.fill_i64(n, 5)
@@ -77,23 +79,27 @@ capi.check(capi.run(ki, xil.ctypes.data, C.c_int(hi - lo), si)); assert si.value
 capi.check(capi.run(kc, xl.ctypes.data, C.c_int(hi - lo), s)); assert s.value == float((x > 3).sum())
 capi.check(capi.run(km, xl.ctypes.data, C.c_int(hi - lo), s)); assert s.value == x.max()
 assert lib.nomp_finalize_excluding_interpreter() == 0
-print("rank", rank, "ok")
+print("rank", rank, "ok", "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else "nccl")
 """
 
 
-def test_nccl_allreduce_of_reduce_clause(tmp_path):
+@pytest.mark.parametrize("mode", ["auto", "nccl"])
+def test_allreduce_of_reduce_clause_across_gpus(tmp_path, mode):
+    """auto = the NVLink one-shot kernel when peers can be mapped (else NCCL); nccl = forced ncclAllReduce."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least two GPUs")
     script = tmp_path / "worker.py"
     script.write_text(NCCL_WORKER.format(root=str(ROOT)))
-    idfile = f"/dev/shm/nomp-test-nccl-{os.getpid()}"
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), idfile], stdout=subprocess.PIPE,
+    idfile = f"/dev/shm/nomp-test-nccl-{os.getpid()}-{mode}"
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), idfile, mode], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
-    try:
-        os.unlink(idfile)
-    except OSError:
-        pass
+    for f in [idfile] + [f"{idfile}.ipc.{r}" for r in range(world)]:
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]
+    print(outs[0].strip().splitlines()[-1])

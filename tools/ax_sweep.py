@@ -106,7 +106,7 @@ def main():
                                             ("sum_i64", capi.I64, xi, None, 8)):
                 def run():
                     capi.nompk_check(lib.nompk_reduce(capi.RED_SUM, dt, n, a.data_ptr(),
-                                                      b.data_ptr() if b is not None else None, res.data_ptr(), None,
+                                                      b.data_ptr() if b is not None else None, res.data_ptr(), None, 0,
                                                       ws.data_ptr(), st))
                 med, best = timeit(run)
                 emit(kernel=name, n=n, ms=med, ms_min=best, gbs=n * bytes_ / med / 1e6,

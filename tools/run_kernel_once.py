@@ -37,5 +37,5 @@ else:
     res = torch.zeros(1, dtype=torch.float64, device="cuda")
     for _ in range(reps):
         capi.nompk_check(lib.nompk_reduce(capi.RED_SUM, capi.F64, size, x.data_ptr(), y.data_ptr() if n else None,
-                                          res.data_ptr(), None, ws.data_ptr(), st))
+                                          res.data_ptr(), None, 0, ws.data_ptr(), st))
 torch.cuda.synchronize()
