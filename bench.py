@@ -358,8 +358,17 @@ def run_ours(args):
                "sample": f"Ax N=7 on E={E_sample} elements x {reps} repetitions ({dt:.1f} s), serial C loop nest of "
                          "oracle/nomp_oracle.c (gcc -O2 -march=native -ffp-contract=off)"}
 
+    allreduce_path = "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else ("nccl" if world > 1 else "none")
     capi.check(lib.nomp_finalize_excluding_interpreter())
     if world > 1:
+        dist.barrier()
+        if rank == 0:   # rendezvous files of this job
+            import glob
+            for f in glob.glob(os.environ["NOMP_COMM_ID_FILE"] + "*"):
+                try:
+                    os.unlink(f)
+                except OSError:
+                    pass
         dist.destroy_process_group()
     if rank != 0:
         return 0
@@ -372,7 +381,7 @@ def run_ours(args):
                                f"{E} per GPU (element-partitioned), through nomp_jit/nomp_run",
                    "E_total": E_TOTAL, "E_per_gpu": E, "n": n, "bytes_per_dof": BYTES_PER_DOF,
                    "l2": f"no flush needed: each step streams {ndof * BYTES_PER_DOF / 1e6:.0f} MB per GPU, larger than the 126 MB L2",
-                   "kernel": info},
+                   "kernel": info, "allreduce": allreduce_path},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(n, E), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                      "kernel": "nompk::ax_kernel<8,...>", "algorithmic_bytes_per_launch": ndof * BYTES_PER_DOF,
@@ -427,7 +436,7 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
     out["axpy_f64"] = {"n_per_gpu": nvec, "ms": ms, "GB/s_per_gpu": nvec * 24 / ms / 1e6, "frac_of_peak": nvec * 24 / ms / 1e6 / peak}
     ms = timed(lambda: capi.check(capi.run(sum_id, up, n_c, s)), 20)
     out["sum_f64"] = {"n_per_gpu": nvec, "ms": ms, "GB/s_per_gpu": nvec * 8 / ms / 1e6, "frac_of_peak": nvec * 8 / ms / 1e6 / peak,
-                      "note": "includes the host-visible result (and the NCCL allreduce when n_gpus > 1)"}
+                      "note": "includes the host-visible result (and the allreduce over ranks when n_gpus > 1)"}
     ms = timed(lambda: capi.check(capi.run(dot_id, up, wp, n_c, s)), 20)
     out["dot_f64"] = {"n_per_gpu": nvec, "ms": ms, "GB/s_per_gpu": nvec * 16 / ms / 1e6, "frac_of_peak": nvec * 16 / ms / 1e6 / peak}
 
@@ -448,7 +457,7 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
 
     ms = timed(cg_step, 20)
     total_dof = ndof * world
-    out["cg_step"] = {"what": "Ax + dot (NCCL allreduce) + axpy, 104 B/DOF", "ms": ms, "GDOF/s": total_dof / ms / 1e6,
+    out["cg_step"] = {"what": "Ax + dot (allreduce over ranks) + axpy, 104 B/DOF", "ms": ms, "GDOF/s": total_dof / ms / 1e6,
                       "GB/s_per_gpu": ndof * 104 / ms / 1e6, "frac_of_peak": ndof * 104 / ms / 1e6 / peak, "pAp": s.value}
     return out
 

@@ -78,8 +78,9 @@ for _ in range(3):
 capi.check(capi.run(ki, xil.ctypes.data, C.c_int(hi - lo), si)); assert si.value == ffi.reduce_(0, ffi.I64, xi)
 capi.check(capi.run(kc, xl.ctypes.data, C.c_int(hi - lo), s)); assert s.value == float((x > 3).sum())
 capi.check(capi.run(km, xl.ctypes.data, C.c_int(hi - lo), s)); assert s.value == x.max()
+path = "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else "nccl"
 assert lib.nomp_finalize_excluding_interpreter() == 0
-print("rank", rank, "ok", "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else "nccl")
+print("rank", rank, "ok", path)
 """
 
 
