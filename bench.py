@@ -314,27 +314,75 @@ def run_ours(args):
     achieved = ndof * BYTES_PER_DOF / (kernel_ms * 1e-3) / 1e9
 
     # ---- end to end: host buffers in, host buffers out ----------------------------------------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
+    # (a) blocking, reference API only: nomp_update(u, TO); nomp_run; nomp_update(w, FROM)
+    e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_step():
+    def e2e_blocking_step():
         capi.check(capi.update(up, 0, ndof, 8, capi.NOMP_TO))
         ax_step()
         capi.check(capi.update(wp, 0, ndof, 8, capi.NOMP_FROM))
 
-    for _ in range(2):
-        e2e_step()
-    sync()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    sync()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = E_TOTAL * n3 * e2e_steps / float(t.item()) / 1e9
+    def timed_wall(fn, reps):
+        fn()
+        sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        sync()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_blocking = E_TOTAL * n3 * e2e_steps / timed_wall(e2e_blocking_step, e2e_steps) / 1e9
     checksum = float(w_host[:: max(1, ndof // 4096)].sum())
+
+    # (b) pipelined: the arrays are mapped in NCHUNK element blocks; per block nomp_b200_update_async(u_c, TO),
+    # nomp_run on the block, nomp_b200_update_async(w_c, FROM); one nomp_sync per step.  Both PCIe directions and the
+    # kernel overlap.  The big mappings of u, w, g are released first (same host buffers, new device images).
+    NCHUNK = 8
+    Ec = E // NCHUNK
+    e2e_value, e2e_note = e2e_blocking, "blocking only (E per GPU not divisible into 8 blocks)"
+    if Ec * NCHUNK == E and Ec > 0:
+        for ptr, cnt in ((up, ndof), (wp, ndof), (gp, 6 * ndof)):
+            capi.check(capi.update(ptr, 0, cnt, 8, capi.NOMP_FREE))
+        cdof = Ec * n3
+        Ec_c = C.c_int(Ec)
+        blocks = []
+        for c in range(NCHUNK):
+            uc, wc, gc = up + c * cdof * 8, wp + c * cdof * 8, gp + c * 6 * cdof * 8
+            capi.check(capi.update(uc, 0, cdof, 8, capi.NOMP_TO))
+            capi.check(capi.update(wc, 0, cdof, 8, capi.NOMP_ALLOC))
+            capi.check(capi.update(gc, 0, 6 * cdof, 8, capi.NOMP_ALLOC))
+            capi.check(capi.run(fill_id, gc, C.c_int(6 * cdof), C.c_int(17 + rank + 6 * c * cdof)))
+            blocks.append((uc, wc, gc))
+
+        def e2e_pipelined_step():
+            for uc, wc, gc in blocks:
+                capi.check(capi.update_async(uc, 0, cdof, 8, capi.NOMP_TO))
+                capi.check(capi.run(ax_id, wc, uc, gc, Dp, Ec_c))
+                capi.check(capi.update_async(wc, 0, cdof, 8, capi.NOMP_FROM))
+            sync()
+
+        w_host.zero_()
+        e2e_value = E_TOTAL * n3 * e2e_steps / timed_wall(e2e_pipelined_step, e2e_steps) / 1e9
+        checksum_p = float(w_host[:: max(1, ndof // 4096)].sum())
+        if abs(checksum_p - checksum) > 1e-9 * abs(checksum):
+            raise SystemExit(f"pipelined e2e result differs from the blocking one: {checksum_p} vs {checksum}")
+        e2e_note = (f"per step and per block of {Ec} elements ({NCHUNK} blocks): nomp_b200_update_async(u, TO) from pinned "
+                    "host memory, nomp_run(Ax), nomp_b200_update_async(w, FROM); one nomp_sync per step; geometric "
+                    "factors and D stay mapped.  blocking_value: the same step with the blocking reference calls "
+                    "nomp_update(TO) / nomp_run / nomp_update(FROM) on the whole arrays")
+        # hand the extras their big mappings back
+        for uc, wc, gc in blocks:
+            for ptr, cnt in ((uc, cdof), (wc, cdof), (gc, 6 * cdof)):
+                capi.check(capi.update(ptr, 0, cnt, 8, capi.NOMP_FREE))
+        capi.check(capi.update(up, 0, ndof, 8, capi.NOMP_TO))
+        capi.check(capi.update(wp, 0, ndof, 8, capi.NOMP_ALLOC))
+        capi.check(capi.update(gp, 0, 6 * ndof, 8, capi.NOMP_ALLOC))
+        capi.check(capi.run(fill_id, gp, C.c_int(6 * ndof), C.c_int(17 + rank)))
 
     # ---- extras: maps, reductions, CG-style step ---------------------------------------------------------------------------
     extras = {}
@@ -387,9 +435,7 @@ def run_ours(args):
                      "kernel": "nompk::ax_kernel<8,...>", "algorithmic_bytes_per_launch": ndof * BYTES_PER_DOF,
                      "avg_launch_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ndof * 8 * world, "d2h_bytes_per_step": ndof * 8 * world,
-                "steps": e2e_steps, "checksum": checksum,
-                "note": "per step: nomp_update(u, TO) from pinned host memory, nomp_run(Ax), nomp_update(w, FROM); "
-                        "geometric factors and D stay mapped"},
+                "steps": e2e_steps, "blocking_value": e2e_blocking, "checksum": checksum, "note": e2e_note},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "cpu_baseline": cpu,

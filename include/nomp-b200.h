@@ -19,6 +19,11 @@ extern "C" {
 
 /* cudaStream_t (as void*) on which this runtime issues copies and kernels; NULL before nomp_init(). */
 void *nomp_b200_stream(void);
+/* Asynchronous nomp_update for an EXISTING mapping, op = NOMP_TO or NOMP_FROM.  Host-to-device and device-to-host
+ * copies run on two dedicated streams (both PCIe directions at once when the host memory is pinned); a copy starts
+ * after all kernels issued so far, kernels issued later see the data of the NOMP_TO copies issued so far.  The host
+ * range must not be touched until nomp_sync() returns.  (nomp_update itself stays blocking, as in the reference.) */
+int nomp_b200_update_async(void *ptr, size_t start_index, size_t end_index, size_t unit_size, int op);
 /* Device address that kernels receive for host pointer `hptr` (the address of host element 0), or NULL. */
 void *nomp_b200_device_ptr(void *hptr);
 /* Kernels launched by this runtime since load: NVRTC-built kernels + libnompk launches. */

@@ -43,7 +43,7 @@ NOMP_SYMBOLS = [
     "nomp_init", "nomp_update", "nomp_jit", "nomp_run", "nomp_sync", "nomp_get_err_str", "nomp_get_err_no",
     "nomp_finalize", "nomp_finalize_excluding_interpreter", "nomp_copy_env",
     # extensions declared in include/nomp-b200.h
-    "nomp_b200_stream", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
+    "nomp_b200_stream", "nomp_b200_update_async", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
     "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
 ]
 
@@ -122,6 +122,8 @@ def nomp() -> C.CDLL:
         lib.nomp_finalize.restype = C.c_int
         lib.nomp_finalize_excluding_interpreter.restype = C.c_int
         lib.nomp_b200_stream.restype = C.c_void_p
+        lib.nomp_b200_update_async.restype = C.c_int
+        lib.nomp_b200_update_async.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
         lib.nomp_b200_device_ptr.restype = C.c_void_p
         lib.nomp_b200_device_ptr.argtypes = [C.c_void_p]
         lib.nomp_b200_launch_count.restype = C.c_ulonglong
@@ -210,3 +212,7 @@ def run(kid: int, *ptrs):
 
 def update(ptr: int, i0: int, i1: int, usize: int, op: int):
     return nomp().nomp_update(C.c_void_p(ptr), i0, i1, usize, op)
+
+
+def update_async(ptr: int, i0: int, i1: int, usize: int, op: int):
+    return nomp().nomp_b200_update_async(C.c_void_p(ptr), i0, i1, usize, op)

@@ -95,6 +95,9 @@ typedef struct {
   int device;
   struct cudaDeviceProp prop;
   cudaStream_t stream;
+  cudaStream_t stream_h2d, stream_d2h; /* copy streams of nomp_b200_update_async (created on first use) */
+  cudaEvent_t ev_compute, ev_h2d;
+  int async_used;
   void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
   unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
@@ -492,6 +495,42 @@ static int cuda_knl_free(nomp_prog_t *prg) {
 static int cuda_sync(nomp_backend_t *bnd) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
   check_runtime(cudaStreamSynchronize(st->stream));
+  if (st->async_used) {
+    check_runtime(cudaStreamSynchronize(st->stream_h2d));
+    check_runtime(cudaStreamSynchronize(st->stream_d2h));
+  }
+  return 0;
+}
+
+/* Asynchronous variant of update() for the two copy directions (include/nomp-b200.h: nomp_b200_update_async).
+ * H2D copies run on their own stream, D2H copies on another, so that with pinned host memory both PCIe directions
+ * are busy at once while kernels run on the compute stream.  Ordering: a copy starts only after every kernel issued
+ * so far (it may read or write the range); kernels issued later wait for the H2D copies issued so far.  The caller
+ * must not touch the host range until nomp_sync(). */
+int nomp_cuda_update_async(nomp_backend_t *bnd, nomp_mem_t *m, nomp_map_direction_t op, size_t start, size_t end,
+                           size_t usize) {
+  cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (!st->stream_h2d) {
+    check_runtime(cudaStreamCreateWithFlags(&st->stream_h2d, cudaStreamNonBlocking));
+    check_runtime(cudaStreamCreateWithFlags(&st->stream_d2h, cudaStreamNonBlocking));
+    check_runtime(cudaEventCreateWithFlags(&st->ev_compute, cudaEventDisableTiming));
+    check_runtime(cudaEventCreateWithFlags(&st->ev_h2d, cudaEventDisableTiming));
+  }
+  st->async_used = 1;
+  cudaStream_t cs = op == NOMP_TO ? st->stream_h2d : st->stream_d2h;
+  check_runtime(cudaEventRecord(st->ev_compute, st->stream));
+  check_runtime(cudaStreamWaitEvent(cs, st->ev_compute, 0));
+  char *dev = (char *)m->bptr + NOMP_MEM_OFFSET(start - m->idx0, usize);
+  char *host = (char *)m->hptr + NOMP_MEM_OFFSET(start, usize);
+  const size_t bytes = NOMP_MEM_BYTES(start, end, usize);
+  if (op == NOMP_TO) {
+    check_runtime(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, cs));
+    check_runtime(cudaEventRecord(st->ev_h2d, cs));
+    check_runtime(cudaStreamWaitEvent(st->stream, st->ev_h2d, 0));
+    m->version++;
+  } else {
+    check_runtime(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, cs));
+  }
   return 0;
 }
 
@@ -502,6 +541,11 @@ static int cuda_finalize(nomp_backend_t *bnd) {
   if (st->stream) {
     cudaStreamSynchronize(st->stream);
     cudaStreamDestroy(st->stream);
+  }
+  if (st->stream_h2d) {
+    cudaStreamSynchronize(st->stream_h2d), cudaStreamSynchronize(st->stream_d2h);
+    cudaStreamDestroy(st->stream_h2d), cudaStreamDestroy(st->stream_d2h);
+    cudaEventDestroy(st->ev_compute), cudaEventDestroy(st->ev_h2d);
   }
   if (st->pinned_host) cudaFreeHost(st->pinned_host);
   if (g_state == st) g_state = NULL;

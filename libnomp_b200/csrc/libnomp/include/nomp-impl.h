@@ -105,6 +105,9 @@ int cuda_init(nomp_backend_t *backend, int platform, int device);
  * Replaces nomp_host_side_reduction (reference src/reduction.c:33-88). */
 int nomp_cuda_reduction_finish(nomp_backend_t *backend, nomp_prog_t *prg);
 
+int nomp_cuda_update_async(nomp_backend_t *backend, nomp_mem_t *m, nomp_map_direction_t op, size_t start, size_t end,
+                           size_t usize);
+
 /* core helpers used by the backend */
 nomp_mem_t *nomp_lookup_mem(const void *hptr);
 

@@ -219,6 +219,18 @@ NOMP_EXPORT int nomp_update(void *ptr, size_t idx0, size_t idx1, size_t unit_siz
   return 0;
 }
 
+/* include/nomp-b200.h: asynchronous NOMP_TO / NOMP_FROM on an EXISTING mapping; completion at nomp_sync(). */
+NOMP_EXPORT int nomp_b200_update_async(void *ptr, size_t idx0, size_t idx1, size_t unit_size, nomp_map_direction_t op) {
+  if (!initialized) return nomp_log(NOMP_INITIALIZE_FAILURE, NOMP_ERROR, "libnomp is not initialized.");
+  if (op != NOMP_TO && op != NOMP_FROM)
+    return nomp_log(NOMP_USER_MAP_OP_IS_INVALID, NOMP_ERROR, "nomp_b200_update_async supports NOMP_TO and NOMP_FROM only.");
+  mem_node_t *node = lookup_range(ptr, idx0, idx1, unit_size);
+  if (node == NULL)
+    return nomp_log(NOMP_USER_MAP_OP_IS_INVALID, NOMP_ERROR,
+                    "nomp_b200_update_async can only be called on a range which is already on the device.");
+  return nomp_cuda_update_async(&nomp, &node->m, op, idx0, idx1, unit_size);
+}
+
 NOMP_EXPORT void *nomp_b200_device_ptr(void *hptr) {
   nomp_mem_t *m = nomp_lookup_mem(hptr);
   return m ? (char *)m->bptr - m->idx0 * m->usize : NULL;

@@ -483,6 +483,33 @@ def test_ax_kernel_string(n, expect_family):
     assert np.array_equal(w, 4 * ffi.ax(n, u, g, D / 2))
 
 
+def test_async_update_pipeline():
+    """nomp_b200_update_async: H2D and D2H on their own streams, ordered against the kernels; data valid after nomp_sync."""
+    n, nblk = 1 << 20, 4
+    x = torch.arange(n * nblk, dtype=torch.float64).pin_memory()
+    y = torch.zeros(n * nblk, dtype=torch.float64).pin_memory()
+    kid = jit("void k(double *y, const double *x, int N) { for (int i = 0; i < N; i++) y[i] = 2 * x[i] + 1; }", capi.clauses(),
+              [("y", 8, P), ("x", 8, P), ("N", 4, I)])
+    blocks = [(x.data_ptr() + b * n * 8, y.data_ptr() + b * n * 8) for b in range(nblk)]
+    err = capi.update_async(blocks[0][0], 0, n, 8, capi.NOMP_TO)
+    assert capi.err_info(err)[0] == capi.NOMP_USER_MAP_OP_IS_INVALID          # not mapped yet
+    for xb, yb in blocks:
+        capi.check(capi.update(xb, 0, n, 8, capi.NOMP_ALLOC))
+        capi.check(capi.update(yb, 0, n, 8, capi.NOMP_ALLOC))
+    for rep in range(3):
+        x.add_(1.0)
+        for xb, yb in blocks:
+            capi.check(capi.update_async(xb, 0, n, 8, capi.NOMP_TO))
+            capi.check(capi.run(kid, yb, xb, C.c_int(n)))
+            capi.check(capi.update_async(yb, 0, n, 8, capi.NOMP_FROM))
+        capi.check(capi.nomp().nomp_sync())
+        assert torch.equal(y, 2 * x + 1)
+    assert capi.err_info(capi.update_async(blocks[0][0], 0, n, 8, capi.NOMP_FREE))[0] == capi.NOMP_USER_MAP_OP_IS_INVALID
+    for xb, yb in blocks:
+        capi.check(capi.update(xb, 0, n, 8, capi.NOMP_FREE))
+        capi.check(capi.update(yb, 0, n, 8, capi.NOMP_FREE))
+
+
 def test_extensions_and_launch_counter():
     lib = capi.nomp()
     assert lib.nomp_b200_stream() is not None
