@@ -501,6 +501,31 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
         capi.check(capi.run(dot_id, up, wp, nd, s))
         capi.check(capi.run(axpy_id, wp, up, alpha, nd))
 
+    # the same step with p.Ap fused into the Ax kernel (row f): Ax+dot (allreduce) + axpy -> 88 B/DOF
+    try:
+        from nomp_bridge.families import AX_DOT_KERNEL_SOURCE
+        err, axdot_id = capi.jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")),
+                                 [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I),
+                                  ("n", 4, I | capi.NOMP_JIT, C.c_int(N_POINTS)), ("pap", 8, F)])
+        capi.check(err)
+        s2 = C.c_double(0.0)
+
+        def cg_step_fused():
+            capi.check(capi.run(axdot_id, wp, up, gp, Dp, E_c, s2))
+            capi.check(capi.run(axpy_id, wp, up, alpha, nd))
+
+        # a fresh w for both variants so that the two p.Ap values are comparable
+        capi.check(capi.run(ax_id, wp, up, gp, Dp, E_c))
+        capi.check(capi.run(dot_id, up, wp, nd, s))
+        capi.check(capi.run(axdot_id, wp, up, gp, Dp, E_c, s2))
+        rel = abs(s.value - s2.value) / max(abs(s.value), 1e-300)
+        ms_f = timed(cg_step_fused, 20)
+        out["cg_step_fused"] = {"what": "Ax with p.Ap fused (allreduce over ranks) + axpy, 88 B/DOF", "ms": ms_f,
+                                "GDOF/s": ndof * world / ms_f / 1e6, "GB/s_per_gpu": ndof * 88 / ms_f / 1e6,
+                                "frac_of_peak": ndof * 88 / ms_f / 1e6 / peak, "pAp_rel_diff_vs_unfused": rel}
+    except Exception as exc:
+        out["cg_step_fused"] = {"error": repr(exc)}
+
     ms = timed(cg_step, 20)
     total_dof = ndof * world
     out["cg_step"] = {"what": "Ax + dot (allreduce over ranks) + axpy, 104 B/DOF", "ms": ms, "GDOF/s": total_dof / ms / 1e6,

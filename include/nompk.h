@@ -125,6 +125,14 @@ int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, voi
 #define NOMPK_AX_D_CACHED 1
 int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                  unsigned flags, void *stream);
+/* The same operator fused with the dot product  result = u . (A u)  (the p.Ap of a conjugate-gradient iteration):
+ * one pass over u and g instead of Ax followed by a 16 B/DOF dot kernel.  Evaluated in its energy form
+ * sum over points of (ur wr + us ws + ut wt), which equals sum u_i w_i in exact arithmetic and needs no extra load.
+ * result / result_host_mapped / host_seq / workspace as in nompk_reduce (same workspace, same publication protocol,
+ * deterministic for a given grid). */
+int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, double *result,
+                     double *result_host_mapped, unsigned long long host_seq, void *workspace, unsigned flags,
+                     void *stream);
 int nompk_ax_supported(int n);
 /* Variant selector for benchmarking/profiling (0 = default). */
 int nompk_ax_set_variant(int variant);

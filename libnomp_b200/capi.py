@@ -37,7 +37,7 @@ NOMP_CUDA_FAILURE = -512
 
 NOMPK_SYMBOLS = [
     "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes",
-    "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
+    "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_dot_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
 ]
 NOMP_SYMBOLS = [
     "nomp_init", "nomp_update", "nomp_jit", "nomp_run", "nomp_sync", "nomp_get_err_str", "nomp_get_err_no",
@@ -88,6 +88,9 @@ def nompk() -> C.CDLL:
         lib.nompk_ax_f64.restype = C.c_int
         lib.nompk_ax_f64.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
                                      C.c_void_p]
+        lib.nompk_ax_dot_f64.restype = C.c_int
+        lib.nompk_ax_dot_f64.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_uint, C.c_void_p]
         lib.nompk_ax_supported.restype = C.c_int
         lib.nompk_ax_supported.argtypes = [C.c_int]
         lib.nompk_ax_set_variant.restype = C.c_int

@@ -151,9 +151,22 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // items of an element (n = 10: 14 of 64) and elements beyond E in the last group do not branch, they mirror
 // the last valid item / element and write the same values to the same addresses.  (Divergent regions would make
 // ptxas drop the uniform-register D operands and issue one vector LDC.64 per DFMA.)
-template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks>
+//
+// kDot: also return u . (A u), the p.Ap of a CG iteration, without reading u or w again: with ur, us, ut the reference-
+// space gradient of u and (wr, ws, wt) = G (ur, us, ut), u . A u = sum over points of ur wr + us ws + ut wt, and all six
+// values are in registers in the geometric stage.  Finished like libnompk's reductions: block tree, one partial per
+// CTA, atomic ticket, the last CTA folds the partials in CTA order (deterministic) and publishes the scalar.
+struct AxDotArgs {
+  double *partials;
+  unsigned int *ticket;
+  double *result;
+  double *result_host;
+  unsigned long long host_seq;
+};
+
+template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
-ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E) {
+ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot) {
   using L = Layout<N>;
   using SeqN = std::make_integer_sequence<int, N>;
   using SeqNP = std::make_integer_sequence<int, N / 2>;
@@ -183,12 +196,15 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   constexpr int EPB = GPC * G;  // elements per CTA and iteration
   const size_t estride = (size_t)gridDim.x * EPB;
   int it = 0;
+  double energy = 0.0;  // kDot: this lane's share of u . A u
   for (size_t eb = (size_t)blockIdx.x * EPB; eb < E; eb += estride) {
     // always-zero, loop-variant offsets for the D reads (see ld_D): one per stage, derived from a counter that
     // depends on nothing but the iteration number so that ptxas keeps it in a uniform register
     const int z1 = it >> 24, z2 = it >> 25, z3 = it >> 26, z5 = it >> 27, z6 = it >> 28, z7 = it >> 29;
     it++;
     size_t e = eb + grp * G + el;
+    // lanes that only mirror another work item / element must not contribute to the dot product
+    const double dot_weight = (gid < G * T && e < E) ? 1.0 : 0.0;
     e = e < E ? e : E - 1;
     const double2 *ue = reinterpret_cast<const double2 *>(u + e * N3) + q * NP + p;
     const double2 *ge = reinterpret_cast<const double2 *>(g + e * 6 * N3) + q * NP + p;
@@ -300,6 +316,11 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       ws.y = fma(gk[1].y, ur.y, fma(gk[3].y, us.y, gk[4].y * ut.y));
       wt.x = fma(gk[2].x, ur.x, fma(gk[4].x, us.x, gk[5].x * ut.x));
       wt.y = fma(gk[2].y, ur.y, fma(gk[4].y, us.y, gk[5].y * ut.y));
+      if constexpr (kDot) {
+        double ex = fma(ur.x, wr.x, fma(us.x, ws.x, ut.x * wt.x));
+        double ey = fma(ur.y, wr.y, fma(us.y, ws.y, ut.y * wt.y));
+        energy = fma(dot_weight, ex + ey, energy);
+      }
       B1[a] = wr;
       B2[a] = ws;
       col[k] = wt;
@@ -351,14 +372,51 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     }
     // No barrier needed here: the next iteration's S0 writes exactly the B0 chunks this lane just read.
   }
+
+  if constexpr (kDot) {
+    constexpr int kWarps = GPC * W;
+    __shared__ double warp_part[kWarps];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_part[warp] = energy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < kWarps; i++) s += warp_part[i];
+      dot.partials[blockIdx.x] = s;
+      __threadfence();
+      is_last = (atomicAdd(dot.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp == 0) {
+      double s = 0.0;
+      // CTA order; lane l adds partials l, l+32, ... and the warp tree combines the 32 strided sums: a fixed association
+      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(dot.partials + b);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) {
+        *dot.result = s;
+        if (dot.result_host) {
+          *reinterpret_cast<volatile double *>(dot.result_host) = s;
+          __threadfence_system();
+          *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(dot.result_host) + 8) = dot.host_seq;
+        }
+        *dot.ticket = 0u;
+      }
+    }
+  }
 }
 
 int g_variant = 0;
 
-template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB>
-int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream) {
+template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false>
+int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
   static bool configured = false;
@@ -372,7 +430,7 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
   size_t blocks = (E + kElems - 1) / kElems;
   const size_t cap = (size_t)sm_count() * blocks_per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E);
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E, dot);
   NOMPK_LAUNCH_CHECK("ax_kernel");
   return NOMPK_OK;
 }
@@ -383,6 +441,15 @@ template <> struct Shape<6> { static constexpr int G = 7, W = 4, GPC = 1; };    
 template <> struct Shape<8> { static constexpr int G = 1, W = 1, GPC = 4; };    // 32 / 32, warps independent
 template <> struct Shape<10> { static constexpr int G = 3, W = 5, GPC = 1; };   // 150 / 160
 template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   // 144 / 160
+
+// Ax fused with u . A u (production shapes only).
+template <int N> int dispatch_ax_dot(size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
+  constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
+  constexpr int kThreads = GPC * W * 32;
+  constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
+  else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true>(E, u, g, w, s, dot);
+}
 
 template <int N> int dispatch_ax(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
   // MBr = resident CTAs per SM that cap the kernel at r registers per thread.
@@ -421,10 +488,43 @@ extern "C" int nompk_ax_set_variant(int variant) {
   return NOMPK_OK;
 }
 
+static int ax_common(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
+                     cudaStream_t stream, const nompk::AxDotArgs *dot);
+
 extern "C" int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                             unsigned flags, void *stream_) {
+  return ax_common(n, E, u, g, D, w, flags, static_cast<cudaStream_t>(stream_), nullptr);
+}
+
+extern "C" int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
+                                double *result, double *result_host_mapped, unsigned long long host_seq,
+                                void *workspace, unsigned flags, void *stream_) {
   using namespace nompk;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!result || !workspace) {
+    set_error("nompk_ax_dot_f64: NULL result/workspace");
+    return NOMPK_EINVAL;
+  }
+  AxDotArgs dot;
+  dot.partials = static_cast<double *>(workspace);
+  dot.ticket = reinterpret_cast<unsigned int *>(static_cast<char *>(workspace) + nompk_reduce_workspace_bytes() - 64);
+  dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
+  if (E == 0) {  // identity, through the same publication protocol
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NOMPK_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(double), stream));
+    if (result_host_mapped) {
+      NOMPK_CUDA_TRY(cudaMemsetAsync(result_host_mapped, 0, sizeof(double), stream));
+      NOMPK_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(result_host_mapped) + 8, &dot.host_seq, 8,
+                                     cudaMemcpyHostToDevice, stream));
+      NOMPK_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return NOMPK_OK;
+  }
+  return ax_common(n, E, u, g, D, w, flags, static_cast<cudaStream_t>(stream_), &dot);
+}
+
+static int ax_common(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
+                     cudaStream_t stream, const nompk::AxDotArgs *dot) {
+  using namespace nompk;
   if (!nompk_ax_supported(n)) {
     set_error("nompk_ax_f64: n = %d has no hand-written kernel (supported: 6, 8, 10, 12)", n);
     return NOMPK_EUNSUPPORTED;
@@ -440,6 +540,15 @@ extern "C" int nompk_ax_f64(int n, size_t E, const double *u, const double *g, c
   }
   if (!(flags & NOMPK_AX_D_CACHED)) {
     NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (dot) {
+    switch (n) {
+    case 6: return dispatch_ax_dot<6>(E, u, g, w, stream, *dot);
+    case 8: return dispatch_ax_dot<8>(E, u, g, w, stream, *dot);
+    case 10: return dispatch_ax_dot<10>(E, u, g, w, stream, *dot);
+    case 12: return dispatch_ax_dot<12>(E, u, g, w, stream, *dot);
+    }
+    return NOMPK_EUNSUPPORTED;
   }
   switch (n) {
   case 6: return dispatch_ax<6>(g_variant, E, u, g, w, stream);

@@ -114,7 +114,7 @@ typedef struct {
 
 static cuda_state_t *g_state = NULL; /* for the nomp_b200_* accessors */
 
-typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX } family_t;
+typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT } family_t;
 
 #define SLOT_NONE (-1)
 #define SLOT_PARTIALS (-2)
@@ -327,15 +327,17 @@ static int cuda_knl_build(nomp_backend_t *bnd, nomp_prog_t *prg, const char *sou
       (void)((err = desc_arg(prg, source, "x", 1, &cp->a_x)) || (err = desc_arg(prg, source, "y", 0, &cp->a_y)) ||
              (err = desc_arg(prg, source, "out", 1, &cp->a_out)) ||
              (err = desc_count(prg, source, "n", &cp->a_n, &cp->n_literal)));
-    } else if (!strcmp(family, "ax")) {
-      cp->family = FAM_AX;
+    } else if (!strcmp(family, "ax") || !strcmp(family, "axdot")) {
+      cp->family = !strcmp(family, "ax") ? FAM_AX : FAM_AXDOT;
+      cp->is_reduce = cp->family == FAM_AXDOT;
       cp->ax_n = desc_get(source, "n", num, sizeof(num)) ? atoi(num) : 0;
       if (!nompk_ax_supported(cp->ax_n))
         err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "No native Ax kernel for n = %d.", cp->ax_n);
       else
         (void)((err = desc_arg(prg, source, "u", 1, &cp->a_u)) || (err = desc_arg(prg, source, "g", 1, &cp->a_g)) ||
                (err = desc_arg(prg, source, "D", 1, &cp->a_D)) || (err = desc_arg(prg, source, "w", 1, &cp->a_w)) ||
-               (err = desc_arg(prg, source, "E", 1, &cp->a_E)));
+               (err = desc_arg(prg, source, "E", 1, &cp->a_E)) ||
+               (cp->family == FAM_AXDOT && (err = desc_arg(prg, source, "out", 1, &cp->a_out))));
     } else {
       err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Unknown native kernel family \"%s\".", family);
     }
@@ -383,7 +385,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
                              st->stream));
     return 0;
   }
-  case FAM_AX: {
+  case FAM_AX:
+  case FAM_AXDOT: {
     long E = int_arg(prg, cp->a_E, 0);
     if (E < 0) E = 0;
     const void *D = ptr_arg(prg, cp->a_D);
@@ -393,9 +396,15 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     const unsigned long version = dm ? dm->version : 0;
     unsigned flags = 0;
     if (dm && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
-    check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
-                             (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
-                             (double *)ptr_arg(prg, cp->a_w), flags, st->stream));
+    if (cp->family == FAM_AXDOT)
+      check_nompk(nompk_ax_dot_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
+                                   (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
+                                   (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result, (double *)result_host,
+                                   ++st->host_seq, st->red_partials, flags, st->stream));
+    else
+      check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
+                               (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
+                               (double *)ptr_arg(prg, cp->a_w), flags, st->stream));
     st->ax_D = D, st->ax_n = cp->ax_n, st->ax_D_version = version;
     return 0;
   }

@@ -48,6 +48,11 @@ def realize_reduction(knl: Kernel, var: str, op: str, context: Dict) -> Kernel:
         raise KernelError("reduce: operator must be one of '+', '*', 'min', 'max'")
     new = knl.copy()
     new.original = getattr(knl, "original", knl.func)
+    roles = fam.match_ax_dot(knl)
+    if roles is not None and roles["pap"] == var and op == "+":
+        new.reduction = (var, op)
+        new.ax_dot = roles          # the one reduction over a loop NEST that has a native kernel
+        return new
     fam.analyse_reduction(new.original, var, op)
     new.reduction = (var, op)
     return new
@@ -57,6 +62,8 @@ def fix_parameters(knl: Kernel, params: Dict) -> Kernel:
     new = _fix_parameters(knl, **params)
     orig = Kernel(getattr(knl, "original", knl.func))
     new.original = _fix_parameters(orig, **params).func
+    if hasattr(knl, "ax_dot"):
+        new.ax_dot = knl.ax_dot
     return new
 
 
@@ -87,6 +94,16 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
     sm_count = int(context.get("device::multiprocessor_count", 148) or 148)
     original = getattr(knl, "original", knl.func)
     one = ["1", "1", "1"]
+
+    roles = getattr(knl, "ax_dot", None)
+    if knl.reduction is not None and roles is not None:
+        n_val = knl.fixed.get(roles["n"])
+        if n_val is None or int(n_val) not in _SUPPORTED_AX_N:
+            raise KernelError(f"the fused Ax + dot kernel needs n as a NOMP_JIT argument, one of {_SUPPORTED_AX_N}")
+        plan = (_header(original, kind="native", family="axdot", n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
+                        D=roles["D"], w=roles["w"], out=roles["pap"]), one, one)
+        knl._plan = plan
+        return plan
 
     if knl.reduction is not None:
         var, op = knl.reduction

@@ -70,6 +70,17 @@ void nomp_ax(double *w, const double *u, const double *g, const double *D, int E
 """
 
 
+# Ax fused with the dot product u . (A u) (p.Ap of a CG iteration): the same loop nest with one more statement and a
+# reduce clause on `pap`.
+AX_DOT_KERNEL_SOURCE = AX_KERNEL_SOURCE.replace(
+    "void nomp_ax(double *w, const double *u, const double *g, const double *D, int E, int n) {",
+    "void nomp_ax_dot(double *w, const double *u, const double *g, const double *D, int E, int n, double *pap) {").replace(
+    "          w[e * n * n * n + k * n * n + j * n + i] = acc;\n",
+    "          w[e * n * n * n + k * n * n + j * n + i] = acc;\n"
+    "          pap[0] += u[e * n * n * n + k * n * n + j * n + i] * acc;\n")
+assert "pap[0]" in AX_DOT_KERNEL_SOURCE and "nomp_ax_dot" in AX_DOT_KERNEL_SOURCE
+
+
 def _canonical_tokens(src: str) -> Tuple[List[str], List[str]]:
     """Token list with identifiers renamed v0, v1, ... in order of first appearance (keywords/types kept)."""
     keep = set(c._TYPE_WORDS) | {"for", "if", "else", "break", "continue"}
@@ -86,6 +97,23 @@ def _canonical_tokens(src: str) -> Tuple[List[str], List[str]]:
 
 
 _AX_TOKENS, _AX_NAMES = _canonical_tokens(AX_KERNEL_SOURCE)
+
+
+_AX_DOT_TOKENS, _AX_DOT_NAMES = None, None
+
+
+def match_ax_dot(knl: Kernel) -> Optional[Dict[str, str]]:
+    """Same for the Ax + dot string."""
+    global _AX_DOT_TOKENS, _AX_DOT_NAMES
+    if _AX_DOT_TOKENS is None:
+        _AX_DOT_TOKENS, _AX_DOT_NAMES = _canonical_tokens(AX_DOT_KERNEL_SOURCE)
+    try:
+        toks, names = _canonical_tokens(knl.source)
+    except Exception:
+        return None
+    if toks != _AX_DOT_TOKENS or len(names) != len(_AX_DOT_NAMES):
+        return None
+    return dict(zip(_AX_DOT_NAMES, names))
 
 
 def match_ax(knl: Kernel) -> Optional[Dict[str, str]]:
@@ -330,12 +358,17 @@ def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
                 rhs = cand[0]
     if rhs is None or uses_acc(rhs):
         raise KernelError(f"reduce: the update of {var}[0] does not have the form of a '{op}' reduction")
-    for n in pre:
+    # Statements in front of the accumulation may update other arrays, but only elementwise (index == loop variable):
+    # iteration i is then owned by exactly one thread and fusing the update with the reduction is safe
+    # (e.g. the CG update  x[i] += a*p[i]; r[i] -= a*w[i]; rr[0] += r[i]*r[i];).
+    arrays = {k for k, p in params.items() if p.is_array}
+    for n in walk(pre):
         if isinstance(n, c.Assign):
-            tgt = n.target.base.id if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) else \
-                (n.target.id if isinstance(n.target, c.Name) else None)
-            if tgt in params:
-                raise KernelError("reduce: a reduction kernel may not write to its other arguments")
+            if isinstance(n.target, c.Name) and n.target.id in params:
+                raise KernelError("reduce: a reduction kernel may not assign to its scalar arguments")
+            if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) and n.target.base.id in arrays:
+                if _is_elem(n.target, {k: params[k] for k in arrays}, loop.var) is None:
+                    raise KernelError("reduce: other arguments may only be written elementwise (a[i]) in a reduction kernel")
     return ReductionInfo(loop, var, vtype, op, rhs, preds, pre)
 
 
@@ -393,10 +426,17 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
     T = cuda_type(info.vtype)
     func = knl.func
     params = [p for p in func.params if p.name != info.var]
+    written = set()
+    for node in walk(info.pre):
+        if isinstance(node, c.Assign) and isinstance(node.target, c.Subscript) and isinstance(node.target.base, c.Name):
+            written.add(node.target.base.id)
     sig_parts = []
     for prm in params:
         t = prm.ctype
-        sig_parts.append(f"const {cuda_type(t)} *__restrict__ {prm.name}" if prm.is_array else f"{cuda_type(t)} {prm.name}")
+        if prm.is_array:
+            sig_parts.append(f"{cuda_type(t)} *{prm.name}" if prm.name in written else f"const {cuda_type(t)} *__restrict__ {prm.name}")
+        else:
+            sig_parts.append(f"{cuda_type(t)} {prm.name}")
     sig_parts += [f"{T} *__restrict__ nomp_partials", "unsigned int *__restrict__ nomp_ticket",
                   f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host", "unsigned long long nomp_seq"]
     int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}

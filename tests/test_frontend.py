@@ -242,6 +242,25 @@ def test_ax_recognition():
     assert "family=ax" not in nb.get_knl_src(other, CTX)
 
 
+def test_fused_cg_families():
+    k = nb.c_to_loopy(families.AX_DOT_KERNEL_SOURCE)
+    k = nb.fix_parameters(nb.realize_reduction(k, "pap", "+", CTX), {"n": 10})
+    assert nb.get_knl_src(k, CTX).startswith("//!nomp kind=native family=axdot n=10 E=E u=u g=g D=D w=w out=pap ro=u,g,D")
+    with pytest.raises(nb.KernelError):        # no generic fallback for a reduction over a loop nest
+        nb.get_knl_src(nb.fix_parameters(nb.realize_reduction(nb.c_to_loopy(families.AX_DOT_KERNEL_SOURCE), "pap", "+", CTX), {"n": 9}), CTX)
+    with pytest.raises(nb.KernelError):        # the plain Ax string with a reduce clause is not a known family
+        nb.realize_reduction(nb.c_to_loopy(families.AX_KERNEL_SOURCE), "w", "+", CTX)
+    upd = ("void upd(double *x, double *r, const double *p, const double *w, double alpha, int N, double *rr) {"
+           " for (int i = 0; i < N; i++) { x[i] += alpha * p[i]; r[i] -= alpha * w[i]; rr[0] += r[i] * r[i]; } }")
+    desc, cuda, grid, _ = plan(upd, None, ("rr", "+"))
+    assert desc["kind"] == "nvrtc" and desc["family"] == "reduce" and desc["ro"] == "p,w"
+    assert "double *x, double *r, const double *__restrict__ p" in cuda
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    with pytest.raises(nb.KernelError):
+        plan("void bad(double *x, int N, double *s) { for (int i = 0; i < N; i++) { x[0] = i; s[0] += x[i]; } }", None, ("s", "+"))
+
+
 # ---- generic emitter: compile with NVRTC and execute on the host -----------------------------------------------------------
 
 def _ptr(a):

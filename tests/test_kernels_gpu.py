@@ -246,6 +246,45 @@ def test_ax_properties_at_full_size(n):
         assert np.array_equal(w[e * n3:(e + 1) * n3].cpu().numpy(), ffi.ax(n, ue, ge, Di)), e
 
 
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_fused_with_dot_product(n):
+    """nompk_ax_dot_f64: w as nompk_ax_f64, and u.(A u) from the energy form; exact data -> both bitwise equal to the
+    oracle's w and to sum(u * w); random SPD-like data -> 1e-12 relative."""
+    lib = capi.nompk()
+    ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
+    for E in (1, 5, 333, 4099):
+        u = ffi.fill_int_f64(E * n ** 3, 21, -4, 4)
+        g = ffi.fill_int_f64(E * 6 * n ** 3, 22, 0, 3)
+        D = ffi.fill_int_f64(n * n, 23, -2, 2)
+        tu, tg, tD = dev(u), dev(g), dev(D)
+        tw = torch.full_like(tu, float("nan"))
+        for rep in (1, 2):      # twice: the ticket must be reset
+            rc = lib.nompk_ax_dot_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), res.data_ptr(),
+                                      pinned.data_ptr(), 100 * E + rep, ws.data_ptr(), 0, stream())
+            capi.nompk_check(rc, "nompk_ax_dot_f64")
+            torch.cuda.synchronize()
+            w = ffi.ax(n, u, g, D)
+            assert np.array_equal(host(tw, np.float64), w)
+            assert res.item() == float(u @ w) == pinned[0].item(), (n, E)
+            assert pinned.view(torch.int64)[1].item() == 100 * E + rep
+    E = 257
+    Dr = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    u = ffi.fill_uniform_f64(E * n ** 3, 1234, 0.5, 1.5)
+    g = ffi.fill_uniform_f64(E * 6 * n ** 3, 99, -0.1, 0.1).reshape(E, 6, n ** 3)
+    g[:, (0, 3, 5), :] += 1.0          # G11, G22, G33 dominant: symmetric positive definite metric
+    g = np.ascontiguousarray(g.ravel())
+    tu, tg, tD = dev(u), dev(g), dev(Dr)
+    tw = torch.empty_like(tu)
+    capi.nompk_check(lib.nompk_ax_dot_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), res.data_ptr(),
+                                          None, 0, ws.data_ptr(), 0, stream()))
+    ref_w = ffi.ax(n, u, g, Dr, "extended")
+    ref = ffi.sum_compensated(u, ref_w)
+    assert np.abs(host(tw, np.float64) - ref_w).max() <= 1e-12 * np.abs(ref_w).max()
+    assert abs(res.item() - ref) <= 1e-12 * abs(ref)
+
+
 def test_ax_unsupported_n_is_reported():
     lib = capi.nompk()
     t = torch.zeros(9 ** 3 * 6, dtype=torch.float64, device="cuda")

@@ -483,6 +483,48 @@ def test_ax_kernel_string(n, expect_family):
     assert np.array_equal(w, 4 * ffi.ax(n, u, g, D / 2))
 
 
+def test_fused_cg_kernels():
+    """Row (f): Ax fused with p.Ap through the canonical Ax+dot kernel string, and the fused CG update
+    x += a p; r -= a w; rr = r.r through the reduce skeleton (elementwise writes in front of the accumulation)."""
+    from nomp_bridge.families import AX_DOT_KERNEL_SOURCE
+    n, E = 8, 53
+    u = ffi.fill_int_f64(E * n ** 3, 5, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 6, 0, 3)
+    D = ffi.fill_int_f64(n * n, 7, -2, 2)
+    w = np.zeros_like(u)
+    kid = jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")),
+              [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | JIT, C.c_int(n)), ("pap", 8, F)])
+    assert family(kid) == ("native", "axdot")
+    pap = C.c_double(-1)
+    with Mapped(u, g, D, w, out=(w,)):
+        for _ in range(2):
+            capi.check(capi.run(kid, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E), pap))
+    want = ffi.ax(n, u, g, D)
+    assert np.array_equal(w, want) and pap.value == float(u @ want)
+    err, _ = capi.jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")),
+                      [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | JIT, C.c_int(9)), ("pap", 8, F)])
+    assert capi.err_info(err)[0] in (capi.NOMP_LOOPY_CODEGEN_FAILURE, capi.NOMP_PY_CALL_FAILURE)
+
+    src = """void upd(double *x, double *r, const double *p, const double *w, double alpha, int N, double *rr) {
+               for (int i = 0; i < N; i++) { x[i] += alpha * p[i]; r[i] -= alpha * w[i]; rr[0] += r[i] * r[i]; } }"""
+    kid = jit(src, capi.clauses(("reduce", "rr", "+")), [("x", 8, P), ("r", 8, P), ("p", 8, P), ("w", 8, P), ("alpha", 8, F),
+                                                        ("N", 4, I), ("rr", 8, F)])
+    assert family(kid) == ("nvrtc", "reduce")
+    N = 100003
+    x, r, p, ww = (rand("double", N, s) for s in (1, 2, 3, 4))
+    xr, rr_ = x.copy(), r.copy()
+    rr_ref = np.zeros(1)
+    run_kernel(src, xr, rr_, p, ww, 0.37, N, rr_ref)
+    rr = C.c_double()
+    with Mapped(x, r, p, ww, out=(x, r)):
+        capi.check(capi.run(kid, x.ctypes.data, r.ctypes.data, p.ctypes.data, ww.ctypes.data, C.c_double(0.37), C.c_int(N), rr))
+    assert np.array_equal(x, xr) and np.array_equal(r, rr_)
+    assert abs(rr.value - ffi.sum_compensated(rr_, rr_)) <= 1e-12 * rr.value
+    err, _ = capi.jit("void bad(double *x, int N, double *s) { for (int i = 0; i < N; i++) { x[0] = i; s[0] += x[i]; } }",
+                      capi.clauses(("reduce", "s", "+")), [("x", 8, P), ("N", 4, I), ("s", 8, F)])
+    assert capi.err_info(err)[0] == capi.NOMP_PY_CALL_FAILURE       # non-elementwise write in a reduction kernel
+
+
 def test_async_update_pipeline():
     """nomp_b200_update_async: H2D and D2H on their own streams, ordered against the kernels; data valid after nomp_sync."""
     n, nblk = 1 << 20, 4
