@@ -104,7 +104,8 @@ int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, c
  * every rank (contributions are folded in rank order).  peer_xchg is a DEVICE array of `world` pointers: entry r is
  * rank r's exchange buffer of nompk_allreduce_xchg_bytes(world) zero-initialised bytes, as mapped into THIS process
  * (own allocation for r == rank, cudaIpcOpenMemHandle otherwise).  `seq` numbers the collective calls: 1, 2, 3, ...
- * in the same order on all ranks.  result_host_mapped / host_seq as in nompk_reduce.
+ * in the same order on all ranks.  result_host_mapped / host_seq as in nompk_reduce, except that the host block is
+ * 24 bytes: if a peer does not arrive within 20 s the kernel gives up (no GPU hang) and stores `seq` at bytes [16,24).
  * Replaces: nothing in the reference (it has no collective); in this implementation it replaces ncclAllReduce for the
  * 4/8-byte result of a reduce clause (NCCL stays as the fallback when peer access is unavailable). */
 size_t nompk_allreduce_xchg_bytes(int world);

@@ -164,9 +164,14 @@ struct AxDotArgs {
   unsigned long long host_seq;
 };
 
-template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot>
+// kPersistent: the grid has as many CTAs as fit on the device and each strides over the elements; otherwise one CTA
+// per GPC*G elements (the hardware scheduler streams the CTAs) and `pf_stride` = elements of all resident CTAs is only
+// the distance of the L2 prefetch (what will be scheduled next on SOME SM).
+template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
+          bool kPersistent>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
-ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot) {
+ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
+          size_t pf_stride) {
   using L = Layout<N>;
   using SeqN = std::make_integer_sequence<int, N>;
   using SeqNP = std::make_integer_sequence<int, N / 2>;
@@ -194,10 +199,10 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   double2 *B2 = B1 + L::kChunks;
 
   constexpr int EPB = GPC * G;  // elements per CTA and iteration
-  const size_t estride = (size_t)gridDim.x * EPB;
+  const size_t estride = kPersistent ? (size_t)gridDim.x * EPB : pf_stride;
   int it = 0;
   double energy = 0.0;  // kDot: this lane's share of u . A u
-  for (size_t eb = (size_t)blockIdx.x * EPB; eb < E; eb += estride) {
+  for (size_t eb = (size_t)blockIdx.x * EPB; eb < E; eb += (kPersistent ? estride : E)) {
     // always-zero, loop-variant offsets for the D reads (see ld_D): one per stage, derived from a counter that
     // depends on nothing but the iteration number so that ptxas keeps it in a uniform register
     const int z1 = it >> 24, z2 = it >> 25, z3 = it >> 26, z5 = it >> 27, z6 = it >> 28, z7 = it >> 29;
@@ -413,10 +418,10 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 
 int g_variant = 0;
 
-template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false>
+template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
   static bool configured = false;
@@ -429,8 +434,8 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
   }
   size_t blocks = (E + kElems - 1) / kElems;
   const size_t cap = (size_t)sm_count() * blocks_per_sm;
-  if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E, dot);
+  if (PERSISTENT && blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E, dot, cap * kElems);
   NOMPK_LAUNCH_CHECK("ax_kernel");
   return NOMPK_OK;
 }
@@ -461,6 +466,8 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   default:
   case 0:  // production choice (gpurun sweeps of round 1, profiles/r01_kernel_sweeps.jsonl)
     if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
+    else if constexpr (N == 6) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, false>(E, u, g, w, s);
+    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
     else return launch_ax<N, G, W, GPC, 3, 6, false, MB168>(E, u, g, w, s);
   case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
   case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
@@ -473,6 +480,11 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 9: return launch_ax<N, G, W, GPC, 2, 4, false, 1>(E, u, g, w, s);
   case 10: return launch_ax<N, G, W, GPC, 4, 6, false, 1>(E, u, g, w, s);
   case 11: return launch_ax<N, G, W, GPC, 3, 4, false, MB168>(E, u, g, w, s);
+  case 13: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, false>(E, u, g, w, s);   // one CTA per group
+  case 14: return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, false>(E, u, g, w, s);
+  case 15: return launch_ax<N, G, W, GPC, 2, 4, false, MB128, false, false>(E, u, g, w, s);
+  case 16: return launch_ax<N, G, W, GPC, 2, 0, false, MB168, false, false>(E, u, g, w, s);
+  case 17: return launch_ax<N, G, W, GPC, 2, 8, false, MB168, false, false>(E, u, g, w, s);
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }

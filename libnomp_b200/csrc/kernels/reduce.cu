@@ -243,13 +243,23 @@ template <int OP> reduce_fn pick_dtype(nompk_dtype_t dt) {
 // whose cost is one NVLink round trip.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 64;
+constexpr unsigned long long kAllreduceTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int OP, typename T>
 __global__ void __launch_bounds__(kMaxRanks)
 allreduce_scalar_kernel(T *__restrict__ value, T *__restrict__ result_host, unsigned long long host_seq,
                         void *const *__restrict__ peer_xchg, int rank, int world, unsigned long long seq) {
   __shared__ T vals[kMaxRanks];
+  __shared__ int timed_out;
   const int r = threadIdx.x;
+  if (r == 0) timed_out = 0;
+  __syncthreads();
   const size_t slot = (size_t)(seq & 1ull) * (size_t)world;
   if (r < world) {
     const T mine = *value;
@@ -258,17 +268,30 @@ allreduce_scalar_kernel(T *__restrict__ value, T *__restrict__ result_host, unsi
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long *>(dst + 8) = seq;
     char *src = static_cast<char *>(peer_xchg[rank]) + (slot + (size_t)r) * 16;
+    // A peer that never arrives (crashed rank, mismatched call order) must not hang the GPU: give up after
+    // kAllreduceTimeoutNs and report it through the error word of the host block.
+    const unsigned long long t0 = global_timer_ns();
+    bool ok = true;
     while (*reinterpret_cast<volatile unsigned long long *>(src + 8) != seq) {
+      if (global_timer_ns() - t0 > kAllreduceTimeoutNs) {
+        ok = false;
+        break;
+      }
     }
     __threadfence_system();
     vals[r] = *reinterpret_cast<volatile T *>(src);
+    if (!ok) atomicExch(&timed_out, 1);
   }
   __syncthreads();
   if (r == 0) {
     T acc = vals[0];
     for (int i = 1; i < world; i++) acc = red_combine<OP, T>(acc, vals[i]);
     *value = acc;
-    if (result_host) publish_to_host(result_host, acc, host_seq);
+    if (result_host) {
+      if (timed_out)
+        *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = seq;
+      publish_to_host(result_host, acc, host_seq);
+    }
   }
 }
 

@@ -488,6 +488,11 @@ int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg) {
     __builtin_ia32_pause();
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  if (*(volatile unsigned long long *)((char *)st->pinned_host + 16) != 0) { /* set by the NVLink all-reduce kernel */
+    *(volatile unsigned long long *)((char *)st->pinned_host + 16) = 0;
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "all-reduce",
+                    "a rank did not join the reduction within 20 s");
+  }
   memcpy(prg->reduction_ptr, st->pinned_host, size);
   return 0;
 }

@@ -677,6 +677,8 @@ def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, Lis
     int_params = {p.name for p in func.params if not p.is_array and not p.ctype.is_float}
     extent = c.BinOp("-", loop.hi, loop.lo) if const_int(loop.lo) != 0 else loop.hi
     ext = grid_expr_str(extent, int_params)
+    # one vector per thread, one tile per CTA: on B200 the hardware CTA scheduler streams faster than a persistent
+    # grid-stride loop (tools/exp/exp_map.cu); the loops in the kernel still stride, so any grid size is correct
     per_block = 256 * lanes
-    grid = f"max(1, min(({ext} + {per_block - 1}) / {per_block}, {max(1, sm_count) * 8}))"
+    grid = f"max(1, ({ext} + {per_block - 1}) / {per_block})"
     return src, [grid, "1", "1"], ["256", "1", "1"]

@@ -183,7 +183,7 @@ def test_ax_exact_data_bitwise(n, E):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", list(range(13)))
+@pytest.mark.parametrize("variant", list(range(18)))
 @pytest.mark.parametrize("n", [8, 10])
 def test_ax_variants_agree(variant, n):
     E = 333

@@ -60,13 +60,13 @@ def main():
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     which = sys.argv[1:] or ["ax", "map", "reduce"]
     if "ax" in which:
-        for n, E in ((8, 32768), (8, 262144), (10, 32768), (10, 131072)):
+        for n, E in ((8, 32768), (8, 262144), (10, 16384), (10, 131072), (12, 65536), (6, 524288)):
             n3 = n ** 3
             u = torch.rand(E * n3, dtype=torch.float64, device="cuda")
             g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
             D = torch.rand(n * n, dtype=torch.float64, device="cuda")
             w = torch.empty_like(u)
-            for variant in range(13):
+            for variant in range(18):
                 lib.nompk_ax_set_variant(variant)
 
                 def run():
