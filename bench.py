@@ -392,7 +392,7 @@ def run_ours(args):
         extras = {"error": repr(exc)}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle's serial loop nest on a bounded sample ------------------------------
-    cpu = None
+    cpu = cpu_all = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         E_sample = 32768
         ffi, cu, cg_, cD, cw = cpu_ax_sample(E_sample, n)
@@ -407,6 +407,20 @@ def run_ours(args):
         cpu = {"value": E_sample * n3 * reps / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"Ax N=7 on E={E_sample} elements (1/8 of the workload) x {reps} repetitions ({dt:.1f} s), serial C "
                          "loop nest of oracle/nomp_oracle.c (gcc -O2 -march=native -ffp-contract=off)"}
+        # the same loop nest on all host cores: stand-in for the reference's OpenCL backend on a CPU OpenCL platform
+        # (pocl), which cannot be installed here
+        fn_mt = ffi.lib().oracle_ax_f64_mt
+        cores = ffi.lib().oracle_num_threads()
+        fn_mt(n, E_sample, cu.ctypes.data, cg_.ctypes.data, cD.ctypes.data, cw.ctypes.data)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 2000):
+            fn_mt(n, E_sample, cu.ctypes.data, cg_.ctypes.data, cD.ctypes.data, cw.ctypes.data)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_all = {"value": E_sample * n3 * reps / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"same loop nest split over {cores} host threads (pthreads), E={E_sample} x {reps} repetitions "
+                             f"({dt:.1f} s); stand-in for libnomp's OpenCL backend on pocl, not installable here"}
 
     allreduce_path = "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else ("nccl" if world > 1 else "none")
     capi.check(lib.nomp_finalize_excluding_interpreter())
@@ -441,6 +455,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "cpu_baseline": cpu,
+        "cpu_baseline_all_cores": cpu_all,
         "extras": extras,
     }
     print(json.dumps(line), flush=True)

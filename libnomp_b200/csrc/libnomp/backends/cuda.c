@@ -433,31 +433,11 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   return 0;
 }
 
-int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg) {
+/* Backend half of the reduce finish (the type bookkeeping is in src/reduction.c): all-reduce the device scalar over the
+ * ranks if there are several, then wait for the kernel to publish {value, sequence number} to the host. */
+int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg, int dtype, size_t size) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
-  cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
-  size_t size = (size_t)prg->reduction_size;
-  if (size != 4 && size != 8)
-    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Reduction variable must be 4 or 8 bytes wide.");
-  if (cp->family == FAM_NVRTC && (prg->global[0] == 0)) {
-    /* empty loop: the result is the identity */
-    memset(prg->reduction_ptr, 0, size);
-    if (prg->reduction_op == NOMP_PROD) {
-      if (prg->reduction_type == NOMP_FLOAT) {
-        if (size == 4) *(float *)prg->reduction_ptr = 1.0f; else *(double *)prg->reduction_ptr = 1.0;
-      } else {
-        ((char *)prg->reduction_ptr)[0] = 1;
-      }
-    }
-    return 0;
-  }
   if (nomp_comm_size() > 1) {
-    int dtype;
-    switch (prg->reduction_type) {
-    case NOMP_INT: dtype = size == 4 ? NOMPK_I32 : NOMPK_I64; break;
-    case NOMP_UINT: dtype = size == 4 ? NOMPK_U32 : NOMPK_U64; break;
-    default: dtype = size == 4 ? NOMPK_F32 : NOMPK_F64; break;
-    }
     /* all-reduce the device scalar in place; the NVLink one-shot kernel also publishes {value, seq} to the host,
      * the NCCL fallback needs an explicit 8-byte copy */
     int published = 0;

@@ -101,9 +101,10 @@ extern "C" {
 /* The one backend of this implementation (reference include/nomp-impl.h:319-323 lists opencl/cuda/hip). */
 int cuda_init(nomp_backend_t *backend, int platform, int device);
 
-/* Device-side reduction finish: (allreduce across ranks,) wait, store the result through prg->reduction_ptr.
- * Replaces nomp_host_side_reduction (reference src/reduction.c:33-88). */
-int nomp_cuda_reduction_finish(nomp_backend_t *backend, nomp_prog_t *prg);
+/* Reduce-clause finish: src/reduction.c (type bookkeeping) -> backend (all-reduce across ranks, wait, store the
+ * result through prg->reduction_ptr).  Replaces nomp_host_side_reduction (reference src/reduction.c:33-88). */
+int nomp_device_side_reduction(nomp_backend_t *backend, nomp_prog_t *prg);
+int nomp_cuda_reduction_finish(nomp_backend_t *backend, nomp_prog_t *prg, int dtype, size_t size);
 
 int nomp_cuda_update_async(nomp_backend_t *backend, nomp_mem_t *m, nomp_map_direction_t op, size_t start, size_t end,
                            size_t usize);

@@ -10,7 +10,7 @@
  *     allocation on the nomp_run path (reference: 3 SymEngine objects per integer argument per run);
  *   - kernels receive the device address of host element 0 (bptr - idx0 * usize), so a loop over a sub-range
  *     mapping indexes the same elements on host and device;
- *   - the reduce clause is finished on the device by the backend (nomp_cuda_reduction_finish).
+ *   - the reduce clause is finished on the device (src/reduction.c -> backend).
  */
 #include <ctype.h>
 
@@ -452,7 +452,7 @@ NOMP_EXPORT int nomp_run(int id, ...) {
   for (unsigned i = 0; i < prg->nargs; i++) {
     if (args[i].mem && !args[i].is_const) ((nomp_mem_t *)args[i].mem)->version++;
   }
-  if (prg->reduction_index >= 0) nomp_check(nomp_cuda_reduction_finish(&nomp, prg));
+  if (prg->reduction_index >= 0) nomp_check(nomp_device_side_reduction(&nomp, prg));
   return 0;
 }
 
