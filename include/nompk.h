@@ -83,13 +83,16 @@ size_t nompk_dtype_size(nompk_dtype_t dt);
 int nompk_map(nompk_map_op_t op, nompk_dtype_t dt, size_t n, void *y, const void *x, const void *z,
               const void *alpha_host, const void *beta_host, void *stream);
 
-/* Bytes of device workspace nompk_reduce() needs (partials + a ticket counter).  The workspace must be
- * zero-filled once before first use; the kernel leaves it ready for the next call on the same stream. */
+/* Bytes of device workspace nompk_reduce() needs (partials of two levels + ticket counters, 536 KiB).  The workspace
+ * must be zero-filled once before first use; the kernels leave it ready for the next call on the same stream.
+ * nompk_reduce_workspace_layout() returns the byte offsets {global ticket, group tickets, level-2 partials, level-1
+ * partials}; generated reduction kernels (python/nomp_bridge/reduction.py) follow the same layout. */
 size_t nompk_reduce_workspace_bytes(void);
+void nompk_reduce_workspace_layout(size_t offsets[4]);
 
 /* result[0] <- reduce_op over i of (y ? x[i]*y[i] : x[i]),  i in [0,n).  n == 0 writes the identity.
- * Single pass: per-thread accumulators, warp-shuffle tree, one partial per block, and the last block to
- * take a ticket folds the partials in block order (deterministic run to run).  `result` is a device
+ * Single pass: per-thread accumulators, warp-shuffle tree, one partial per CTA, and two levels of atomic tickets fold
+ * the partials with a fixed association (deterministic run to run).  `result` is a device
  * pointer (8-byte aligned); if result_host_mapped != NULL (device address of 16 bytes of pinned, mapped host memory)
  * the value is also stored at its bytes [0,8) and then host_seq at bytes [8,16), so the host needs no D2H copy and
  * may spin on the sequence number instead of synchronising the stream.

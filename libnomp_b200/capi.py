@@ -36,7 +36,7 @@ NOMP_LOOPY_GRIDSIZE_FAILURE = -392
 NOMP_CUDA_FAILURE = -512
 
 NOMPK_SYMBOLS = [
-    "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes",
+    "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes", "nompk_reduce_workspace_layout",
     "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_dot_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
 ]
 NOMP_SYMBOLS = [
@@ -77,6 +77,8 @@ def nompk() -> C.CDLL:
         lib.nompk_map.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]
         lib.nompk_reduce_workspace_bytes.restype = C.c_size_t
+        lib.nompk_reduce_workspace_layout.restype = None
+        lib.nompk_reduce_workspace_layout.argtypes = [C.POINTER(C.c_size_t)]
         lib.nompk_reduce.restype = C.c_int
         lib.nompk_reduce.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_ulonglong, C.c_void_p, C.c_void_p]

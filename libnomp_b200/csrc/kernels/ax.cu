@@ -28,6 +28,7 @@
 #include <utility>
 
 #include "nompk_common.cuh"
+#include "nompk_gridreduce.cuh"
 
 // D[a][l] at nompk_ax_cD[a * n + l].  C linkage: the kernel reads it through inline PTX by symbol name.
 extern "C" {
@@ -157,8 +158,7 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // values are in registers in the geometric stage.  Finished like libnompk's reductions: block tree, one partial per
 // CTA, atomic ticket, the last CTA folds the partials in CTA order (deterministic) and publishes the scalar.
 struct AxDotArgs {
-  double *partials;
-  unsigned int *ticket;
+  void *workspace;
   double *result;
   double *result_host;
   unsigned long long host_seq;
@@ -381,38 +381,19 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   if constexpr (kDot) {
     constexpr int kWarps = GPC * W;
     __shared__ double warp_part[kWarps];
-    __shared__ bool is_last;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, off);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) warp_part[warp] = energy;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
+    double s = 0.0;
+    if (threadIdx.x == 0)
       for (int i = 0; i < kWarps; i++) s += warp_part[i];
-      dot.partials[blockIdx.x] = s;
-      __threadfence();
-      is_last = (atomicAdd(dot.ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (warp == 0) {
-      double s = 0.0;
-      // CTA order; lane l adds partials l, l+32, ... and the warp tree combines the 32 strided sums: a fixed association
-      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(dot.partials + b);
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      if (lane == 0) {
-        *dot.result = s;
-        if (dot.result_host) {
-          *reinterpret_cast<volatile double *>(dot.result_host) = s;
-          __threadfence_system();
-          *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(dot.result_host) + 8) = dot.host_seq;
-        }
-        *dot.ticket = 0u;
-      }
-    }
+    struct Sum {
+      static __device__ __forceinline__ double identity() { return 0.0; }
+      static __device__ __forceinline__ double combine(double a, double b) { return a + b; }
+    };
+    grid_finish<Sum, double, (kWarps * 32 < 64 ? 64 : kWarps * 32)>(s, dot.workspace, dot.result, dot.result_host, dot.host_seq);
   }
 }
 
@@ -517,8 +498,7 @@ extern "C" int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *
     return NOMPK_EINVAL;
   }
   AxDotArgs dot;
-  dot.partials = static_cast<double *>(workspace);
-  dot.ticket = reinterpret_cast<unsigned int *>(static_cast<char *>(workspace) + nompk_reduce_workspace_bytes() - 64);
+  dot.workspace = workspace;
   dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
   if (E == 0) {  // identity, through the same publication protocol
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

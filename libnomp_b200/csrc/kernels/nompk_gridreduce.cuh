@@ -1,0 +1,94 @@
+// Deterministic single-pass grid-wide finish of a reduction, shared by reduce.cu and the fused Ax + dot kernel (and
+// mirrored in text by the generated reduce skeleton, python/nomp_bridge/reduction.py).
+//
+// The streaming front ends run fastest with MANY small CTAs (one tile each; the hardware CTA scheduler beats a
+// persistent grid, tools/exp/exp_map.cu), so a launch can have up to kMaxCtas = 65536 partials -- too many for one
+// CTA to fold at the end.  Two levels of atomic tickets keep the fold short and its association fixed:
+//   level 1: CTA b stores its partial, then takes ticket[b / 32]; the CTA that takes the last ticket of a group of
+//            32 folds the group's partials with one warp (lane i <- partial i, shuffle tree) into a level-2 partial;
+//   level 2: that CTA then takes the global ticket; the last one folds the <= 2048 level-2 partials (256 threads, 8
+//            each, block tree) and publishes the result.
+// Every fold has a fixed shape, so the result does not depend on the order in which CTAs finish.  All tickets are
+// reset by the CTA that consumes them: the workspace is ready for the next launch on the same stream.
+#pragma once
+
+#include "nompk_common.cuh"
+
+namespace nompk {
+
+constexpr int kRedGroup = 32;
+constexpr int kRedMaxGroups = 2048;
+constexpr int kRedMaxCtas = kRedGroup * kRedMaxGroups;              // 65536
+constexpr size_t kWsTicket = 0;                                     // unsigned int
+constexpr size_t kWsGroupTicket = 64;                               // unsigned int[2048]
+constexpr size_t kWsL2 = kWsGroupTicket + 4 * kRedMaxGroups;        // 8-byte slots[2048]
+constexpr size_t kWsL1 = kWsL2 + 8 * kRedMaxGroups;                 // 8-byte slots[65536]
+constexpr size_t kWsBytes = kWsL1 + 8 * (size_t)kRedMaxCtas;        // 548928
+
+// Host-visible result: mapped pinned memory, [0,8) the value, [8,16) a sequence number written AFTER the value
+// (system-scope fence in between).  The host spins on the sequence number instead of synchronising the stream.
+template <typename T> __device__ __forceinline__ void publish_to_host(T *result_host, T value, unsigned long long seq) {
+  *reinterpret_cast<volatile T *>(result_host) = value;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 8) = seq;
+}
+
+// Combine functor interface: Op::identity(), Op::combine(a, b).
+// `v` must hold the CTA's partial in thread 0.  Every thread of the CTA must call; kThreads >= 64, multiple of 32.
+template <typename Op, typename T, int kThreads>
+__device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result_host, unsigned long long host_seq) {
+  char *ws = static_cast<char *>(ws_);
+  unsigned int *ticket = reinterpret_cast<unsigned int *>(ws + kWsTicket);
+  unsigned int *group_ticket = reinterpret_cast<unsigned int *>(ws + kWsGroupTicket);
+  T *l2 = reinterpret_cast<T *>(ws + kWsL2);   // 8-byte slots: T occupies the first sizeof(T) bytes
+  T *l1 = reinterpret_cast<T *>(ws + kWsL1);
+  constexpr int kSlot = 8 / sizeof(T);          // stride between slots in units of T
+  __shared__ int role;                          // 0: done, 1: last of its group, 2: last of all
+  __shared__ T warp_part[kThreads / 32];
+
+  const unsigned int b = blockIdx.x, nb = gridDim.x;
+  const unsigned int group = b / kRedGroup, ngroups = (nb + kRedGroup - 1) / kRedGroup;
+  const unsigned int gsize = (group == ngroups - 1) ? nb - group * kRedGroup : kRedGroup;
+  if (threadIdx.x == 0) {
+    l1[(size_t)b * kSlot] = v;
+    __threadfence();
+    role = (atomicAdd(&group_ticket[group], 1u) == gsize - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (role == 0) return;
+
+  if (threadIdx.x < 32) {
+    __threadfence();
+    T g = threadIdx.x < gsize ? __ldcg(l1 + ((size_t)group * kRedGroup + threadIdx.x) * kSlot) : Op::identity();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) g = Op::combine(g, __shfl_xor_sync(0xffffffffu, g, off));
+    if (threadIdx.x == 0) {
+      l2[(size_t)group * kSlot] = g;
+      group_ticket[group] = 0u;
+      __threadfence();
+      role = (atomicAdd(ticket, 1u) == ngroups - 1) ? 2 : 0;
+    }
+  }
+  __syncthreads();
+  if (role != 2) return;
+
+  __threadfence();
+  T w = Op::identity();
+  for (unsigned int i = threadIdx.x; i < ngroups; i += kThreads) w = Op::combine(w, __ldcg(l2 + (size_t)i * kSlot));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) w = Op::combine(w, __shfl_xor_sync(0xffffffffu, w, off));
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    w = threadIdx.x < kThreads / 32 ? warp_part[threadIdx.x] : Op::identity();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) w = Op::combine(w, __shfl_xor_sync(0xffffffffu, w, off));
+    if (threadIdx.x == 0) {
+      *result = w;
+      if (result_host) publish_to_host(result_host, w, host_seq);
+      *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace nompk

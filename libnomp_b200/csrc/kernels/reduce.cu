@@ -4,11 +4,11 @@
 // group (reference python/reduction.py:30-134), then synchronises, copies ALL partials to the host and folds
 // them in a serial loop (reference src/reduction.c:33-88; one partial per 512 elements, so n = 2^28 would need
 // 4 MiB of a 256 KiB scratch buffer).  Here the whole reduction is one launch:
-//   1. each thread strides over the array with 128-bit loads, kUnroll vectors in flight, one accumulator per
-//      vector slot (independent dependency chains);
-//   2. warp-shuffle tree, then one shared-memory slot per warp, then one partial per block to the workspace;
-//   3. a ticket counter (atomicAdd + __threadfence) elects the last block, which folds the <= kMaxBlocks
-//      partials in block order -> the result does not depend on block scheduling (deterministic);
+//   1. one CTA per tile of 256 threads x kUnroll 128-bit loads (up to 65536 CTAs, beyond that the CTAs stride): all
+//      loads of a thread are issued before the first use, one accumulator per vector slot (independent chains);
+//   2. warp-shuffle tree, then one shared-memory slot per warp, then one partial per CTA to the workspace;
+//   3. two levels of atomic tickets (nompk_gridreduce.cuh) fold the partials with a fixed association -> the result
+//      does not depend on CTA scheduling (deterministic);
 //   4. the result is stored to device memory and, optionally, straight into mapped pinned host memory.
 // Integer sums/products wrap mod 2^32 / 2^64 exactly like the reference's C loop, in any order (bit-exact).
 // fp64 sums differ from the serial loop only by association; the error bound is ~log2(n) ulp per partial tree
@@ -19,16 +19,13 @@
 #include <type_traits>
 
 #include "nompk_common.cuh"
+#include "nompk_gridreduce.cuh"
 
 namespace nompk {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kCtasPerSM = 4;
 constexpr int kUnroll = 4;
-constexpr int kMaxBlocks = 2048;                   // upper bound on the grid (148 * 4 = 592 on B200)
-constexpr size_t kTicketOffset = kMaxBlocks * 8;   // workspace: [partials | ticket]
-constexpr size_t kWorkspaceBytes = kTicketOffset + 64;
 
 template <typename T> struct Limits;
 template <> struct Limits<int> { static __device__ int lo() { return INT_MIN; } static __device__ int hi() { return INT_MAX; } };
@@ -87,20 +84,15 @@ template <int OP, typename T> __device__ __forceinline__ T block_reduce(T v) {
   return v;
 }
 
-// Host-visible result: 16 bytes of mapped pinned memory, [0,8) the value, [8,16) a sequence number written AFTER
-// the value (system-scope fence in between).  The host can spin on the sequence number instead of synchronising
-// the stream, which takes several microseconds off the latency of a reduce clause.
-template <typename T> __device__ __forceinline__ void publish_to_host(T *result_host, T value, unsigned long long seq) {
-  *reinterpret_cast<volatile T *>(result_host) = value;
-  __threadfence_system();
-  *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 8) = seq;
-}
+template <int OP, typename T> struct RedOp {
+  static __device__ __forceinline__ T identity() { return red_identity<OP, T>(); }
+  static __device__ __forceinline__ T combine(T a, T b) { return red_combine<OP, T>(a, b); }
+};
 
 template <int OP, bool DOT, bool VEC, typename T>
-__global__ void __launch_bounds__(kBlock, kCtasPerSM)
-reduce_kernel(const T *__restrict__ x, const T *__restrict__ y, size_t n, T *__restrict__ partials,
-              unsigned int *__restrict__ ticket, T *__restrict__ result, T *__restrict__ result_host,
-              unsigned long long host_seq) {
+__global__ void __launch_bounds__(kBlock)
+reduce_kernel(const T *__restrict__ x, const T *__restrict__ y, size_t n, void *__restrict__ workspace,
+              T *__restrict__ result, T *__restrict__ result_host, unsigned long long host_seq) {
   T acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++) acc[u] = red_identity<OP, T>();
@@ -152,26 +144,7 @@ reduce_kernel(const T *__restrict__ x, const T *__restrict__ y, size_t n, T *__r
   for (int u = 1; u < kUnroll; u++) v = red_combine<OP, T>(v, acc[u]);
   v = block_reduce<OP, T>(v);
 
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = v;
-    __threadfence();  // partial visible device-wide before the ticket is taken
-    const unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-
-  // Last block: fold the partials in block order (fixed association -> deterministic).
-  __threadfence();
-  T w = red_identity<OP, T>();
-  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock) w = red_combine<OP, T>(w, __ldcg(partials + b));
-  w = block_reduce<OP, T>(w);
-  if (threadIdx.x == 0) {
-    *result = w;
-    if (result_host) publish_to_host(result_host, w, host_seq);
-    *ticket = 0u;  // ready for the next launch on this stream
-  }
+  grid_finish<RedOp<OP, T>, T, kBlock>(v, workspace, result, result_host, host_seq);
 }
 
 template <int OP, typename T>
@@ -183,27 +156,24 @@ int launch_reduce(size_t n, const void *x_, const void *y_, void *result, void *
     set_error("nompk_reduce: NULL result/workspace/operand");
     return NOMPK_EINVAL;
   }
-  T *partials = static_cast<T *>(workspace);
-  unsigned int *ticket = reinterpret_cast<unsigned int *>(static_cast<char *>(workspace) + kTicketOffset);
   T *res = static_cast<T *>(result);
   T *res_h = static_cast<T *>(result_host);
 
   constexpr int L = Vec16<T>::kLanes;
   const bool vec = is_aligned16(x) && (!y || is_aligned16(y));
   const size_t per_block = vec ? (size_t)kBlock * kUnroll * L : (size_t)kBlock;
+  // one tile per CTA (up to 65536 CTAs, then the CTAs stride): many small CTAs stream faster than a persistent grid
   size_t blocks = (n + per_block - 1) / per_block;
-  const size_t cap = (size_t)sm_count() * kCtasPerSM;
-  if (blocks > cap) blocks = cap;
-  if (blocks > (size_t)kMaxBlocks) blocks = kMaxBlocks;
+  if (blocks > (size_t)kRedMaxCtas) blocks = kRedMaxCtas;
   if (blocks == 0) blocks = 1;
   const unsigned g = (unsigned)blocks;
 
   if (y) {
-    if (vec) reduce_kernel<OP, true, true, T><<<g, kBlock, 0, stream>>>(x, y, n, partials, ticket, res, res_h, host_seq);
-    else reduce_kernel<OP, true, false, T><<<g, kBlock, 0, stream>>>(x, y, n, partials, ticket, res, res_h, host_seq);
+    if (vec) reduce_kernel<OP, true, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
+    else reduce_kernel<OP, true, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
   } else {
-    if (vec) reduce_kernel<OP, false, true, T><<<g, kBlock, 0, stream>>>(x, y, n, partials, ticket, res, res_h, host_seq);
-    else reduce_kernel<OP, false, false, T><<<g, kBlock, 0, stream>>>(x, y, n, partials, ticket, res, res_h, host_seq);
+    if (vec) reduce_kernel<OP, false, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
+    else reduce_kernel<OP, false, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
   }
   NOMPK_LAUNCH_CHECK("reduce_kernel");
   return NOMPK_OK;
@@ -351,7 +321,11 @@ extern "C" int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void 
   return fn(value, result_host_mapped, host_seq, peer_xchg, rank, world, seq, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t nompk_reduce_workspace_bytes(void) { return nompk::kWorkspaceBytes; }
+extern "C" size_t nompk_reduce_workspace_bytes(void) { return nompk::kWsBytes; }
+
+extern "C" void nompk_reduce_workspace_layout(size_t offsets[4]) {
+  offsets[0] = nompk::kWsTicket, offsets[1] = nompk::kWsGroupTicket, offsets[2] = nompk::kWsL2, offsets[3] = nompk::kWsL1;
+}
 
 extern "C" int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y,
                             void *result, void *result_host_mapped, unsigned long long host_seq, void *workspace,

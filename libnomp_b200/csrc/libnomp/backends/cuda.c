@@ -89,7 +89,6 @@ static int resolve_driver(void) {
 }
 
 /* ---- backend state ------------------------------------------------------------------------------------------ */
-#define WORKSPACE_RESULT_OFFSET 16512 /* result slot inside the core's scratch buffer, after the nompk workspace */
 
 typedef struct {
   int device;
@@ -101,9 +100,8 @@ typedef struct {
   void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
   unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
-  void *red_partials;  /* device pointers handed to generated reduce kernels */
-  void *red_ticket;
-  void *red_result;
+  void *red_ws;        /* reduction workspace of libnompk inside the core's scratch buffer */
+  void *red_result;    /* device slot of the reduced scalar, right after the workspace */
   void *red_result_host;
   /* D staging cache of the Ax family */
   const void *ax_D;
@@ -117,8 +115,7 @@ static cuda_state_t *g_state = NULL; /* for the nomp_b200_* accessors */
 typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT } family_t;
 
 #define SLOT_NONE (-1)
-#define SLOT_PARTIALS (-2)
-#define SLOT_TICKET (-3)
+#define SLOT_WS (-2)
 #define SLOT_RESULT (-4)
 #define SLOT_RESULT_HOST (-5)
 #define SLOT_SEQ (-6)
@@ -148,9 +145,10 @@ static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direct
     m->bsize = bytes;
     if (m == &bnd->scratch) { /* reduction workspace: the ticket counter must start at zero */
       check_runtime(cudaMemsetAsync(m->bptr, 0, bytes, st->stream));
-      st->red_partials = m->bptr;
-      st->red_ticket = (char *)m->bptr + (nompk_reduce_workspace_bytes() - 64);
-      st->red_result = (char *)m->bptr + WORKSPACE_RESULT_OFFSET;
+      if (bytes < nompk_reduce_workspace_bytes() + 64)
+        return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "scratch", "buffer smaller than the reduction workspace");
+      st->red_ws = m->bptr;
+      st->red_result = (char *)m->bptr + nompk_reduce_workspace_bytes();
     }
   }
   if (op & NOMP_TO) {
@@ -249,8 +247,7 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
   cp->nparams = 0;
   for (char *tok = strtok(params, ","); tok; tok = strtok(NULL, ",")) {
     int slot;
-    if (!strcmp(tok, "nomp_partials")) slot = SLOT_PARTIALS;
-    else if (!strcmp(tok, "nomp_ticket")) slot = SLOT_TICKET;
+    if (!strcmp(tok, "nomp_ws")) slot = SLOT_WS;
     else if (!strcmp(tok, "nomp_result")) slot = SLOT_RESULT;
     else if (!strcmp(tok, "nomp_result_host")) slot = SLOT_RESULT_HOST;
     else if (!strcmp(tok, "nomp_seq")) slot = SLOT_SEQ;
@@ -381,7 +378,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     long n = int_arg(prg, cp->a_n, cp->n_literal);
     if (n < 0) n = 0;
     check_nompk(nompk_reduce((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
-                             ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_partials,
+                             ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_ws,
                              st->stream));
     return 0;
   }
@@ -400,7 +397,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
       check_nompk(nompk_ax_dot_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                    (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
                                    (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result, (double *)result_host,
-                                   ++st->host_seq, st->red_partials, flags, st->stream));
+                                   ++st->host_seq, st->red_ws, flags, st->stream));
     else
       check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
@@ -414,8 +411,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 5];
     for (int i = 0; i < cp->nparams; i++) {
       int s = cp->param_slot[i];
-      if (s == SLOT_PARTIALS) vargs[i] = &st->red_partials;
-      else if (s == SLOT_TICKET) vargs[i] = &st->red_ticket;
+      if (s == SLOT_WS) vargs[i] = &st->red_ws;
       else if (s == SLOT_RESULT) vargs[i] = &st->red_result;
       else if (s == SLOT_RESULT_HOST) vargs[i] = &st->red_result_host;
       else if (s == SLOT_SEQ) vargs[i] = &st->host_seq;

@@ -4,7 +4,7 @@
 
 #define NOMP_MAX_BUFFER_SIZE 128
 #define NOMP_MAX_KERNEL_ARGS_SIZE 64
-#define NOMP_MAX_SCRATCH_SIZE 32768 /* doubles */
+#define NOMP_MAX_SCRATCH_SIZE 131072 /* doubles: reduction workspace of libnompk (536 KiB) + result slot */
 
 #define NOMP_DEFAULT_VERBOSE 2
 #define NOMP_DEFAULT_PROFILE 0

@@ -149,6 +149,11 @@ def match_native_reduce(func: c.Function, info: ReductionInfo) -> Optional[Dict[
 # ---- generated single-pass reduction kernel -------------------------------------------------------------------
 _RED_IDENTITY = {"+": "0", "*": "1"}
 
+# workspace layout of libnompk (csrc/kernels/nompk_gridreduce.cuh; tests compare with nompk_reduce_workspace_layout())
+WS_TICKET, WS_GROUP_TICKET, WS_L2, WS_L1 = 0, 64, 64 + 4 * 2048, 64 + 4 * 2048 + 8 * 2048
+RED_GROUP, RED_MAX_GROUPS = 32, 2048
+RED_MAX_CTAS = RED_GROUP * RED_MAX_GROUPS
+
 
 def _limits(t: c.CType, hi: bool) -> str:
     if t.is_float:
@@ -161,26 +166,71 @@ def _limits(t: c.CType, hi: bool) -> str:
     return "9223372036854775807LL" if hi else "(-9223372036854775807LL - 1)"
 
 
+def _elementwise_arrays(func: c.Function, info: "ReductionInfo"):
+    """If every access to a pointer parameter in the loop body is `a[i]` and all those arrays have one element size
+    (4 or 8 bytes), return (arrays read or written, arrays written); else None -> scalar, non-substituting schedule."""
+    from .ir import map_expr
+    params = _params(func)
+    arrays = {k: p for k, p in params.items() if p.is_array and k != info.var}
+    used, written, ok = [], [], [True]
+
+    def visit(e):
+        if isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays:
+            if _is_elem(e, arrays, info.loop.var) is None:
+                ok[0] = False
+            elif e.base.id not in used:
+                used.append(e.base.id)
+        return e
+
+    for n in walk(info.pre):
+        if isinstance(n, c.Assign):
+            map_expr(n.target, visit)
+            map_expr(n.value, visit)
+            if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) and n.target.base.id in arrays \
+                    and n.target.base.id not in written:
+                written.append(n.target.base.id)
+        elif isinstance(n, c.Decl):
+            if n.dims:
+                ok[0] = False
+            map_expr(n.init, visit)
+        elif isinstance(n, c.If):
+            map_expr(n.cond, visit)
+        elif isinstance(n, (c.Break, c.Continue)):
+            ok[0] = False
+    for p_ in info.preds:
+        map_expr(p_, visit)
+    map_expr(info.rhs, visit)
+    sizes = {arrays[a].ctype.size for a in used}
+    if not ok[0] or len(sizes) > 1 or (sizes and sizes.pop() not in (4, 8)):
+        return None
+    return used, written
+
+
 def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tuple[str, List[str], List[str], List[str]]:
-    """Single-pass reduction kernel with the same structure as libnompk's reduce.cu, for an arbitrary rhs.
-    Returns (source, grid exprs, block exprs, kernel parameter names).  The trailing five parameters
-    (partials, ticket, result, result_host, seq) are supplied by the backend."""
+    """Single-pass reduction kernel with the schedule of libnompk's reduce.cu for an arbitrary right-hand side, with
+    optional conditions and elementwise updates in front of the accumulation.  One tile of 256 threads per CTA (up to
+    65536 CTAs, then the CTAs stride), 128-bit loads/stores when every array is elementwise and 16-byte aligned, and
+    the two-level deterministic ticket finish of nompk_gridreduce.cuh.
+    Returns (source, grid exprs, block exprs, kernel parameter names); the trailing four parameters
+    (workspace, result, result_host, seq) are supplied by the backend."""
+    from .emit_cuda import GenericEmitter
+    from .ir import map_expr, map_stmts
     T = cuda_type(info.vtype)
     func = knl.func
     params = [p for p in func.params if p.name != info.var]
-    written = set()
+    written_any = set()
     for node in walk(info.pre):
         if isinstance(node, c.Assign) and isinstance(node.target, c.Subscript) and isinstance(node.target.base, c.Name):
-            written.add(node.target.base.id)
+            written_any.add(node.target.base.id)
     sig_parts = []
     for prm in params:
         t = prm.ctype
         if prm.is_array:
-            sig_parts.append(f"{cuda_type(t)} *{prm.name}" if prm.name in written else f"const {cuda_type(t)} *__restrict__ {prm.name}")
+            sig_parts.append(f"{cuda_type(t)} *{prm.name}" if prm.name in written_any else f"const {cuda_type(t)} *__restrict__ {prm.name}")
         else:
             sig_parts.append(f"{cuda_type(t)} {prm.name}")
-    sig_parts += [f"{T} *__restrict__ nomp_partials", "unsigned int *__restrict__ nomp_ticket",
-                  f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host", "unsigned long long nomp_seq"]
+    sig_parts += ["void *__restrict__ nomp_ws", f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host",
+                  "unsigned long long nomp_seq"]
     int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}
     it = cuda_type(info.loop.vtype)
     lo, hi = expr_str(info.loop.lo), expr_str(info.loop.hi)
@@ -193,60 +243,139 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
     else:
         ident = _limits(info.vtype, False)
         comb = lambda a, b: f"(({b}) > ({a}) ? ({b}) : ({a}))"  # noqa: E731
-    pre_lines = []
-    from .emit_cuda import GenericEmitter
-    ge = GenericEmitter(knl)
-    ge.lines = []
-    ge.stmts(info.pre, 2, True, False)
-    pre_lines = ge.lines
-    cond = " && ".join(expr_str(p) for p in info.preds)
-    rhs = f"({T})({expr_str(info.rhs)})"
-    upd = f"nomp_acc = {comb('nomp_acc', 'nomp_v')};"
-    body = [f"const {T} nomp_v = {rhs};", upd]
-    if cond:
-        body = [f"if ({cond}) {{"] + ["  " + b for b in body] + ["}"]
+
+    ew = _elementwise_arrays(func, info)
+    arrays = {p.name: p for p in params if p.is_array}
+
+    def body_lines(depth: int, substitute: bool) -> str:
+        def scalarise(e):
+            if substitute and isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays:
+                return c.Name(f"nomp_{e.base.id}_i")
+            return e
+        ge = GenericEmitter(knl)
+        ge.lines = []
+        ge.stmts(map_stmts(info.pre, scalarise), depth, True, False)
+        cond = " && ".join(expr_str(map_expr(p_, scalarise)) for p_ in info.preds)
+        pad = "  " * depth
+        acc = [f"{pad}{{ const {T} nomp_v = ({T})({expr_str(map_expr(info.rhs, scalarise))}); nomp_acc = {comb('nomp_acc', 'nomp_v')}; }}"]
+        if cond:
+            acc = [f"{pad}if ({cond})", "  " + acc[0]]
+        return "\n".join(ge.lines + acc)
+
     shfl = f"nomp_o = __shfl_xor_sync(0xffffffffu, nomp_acc, nomp_s); nomp_acc = {comb('nomp_acc', 'nomp_o')};"
+    tree = f"for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}"
+    slot = 8 // info.vtype.size
+
+    if ew is not None and ew[0]:
+        used, written = ew
+        esize = arrays[used[0]].ctype.size
+        lanes = 16 // esize
+        ety = {a: cuda_type(arrays[a].ctype) for a in used}
+        align = " | ".join(f"(nomp_u64_t)({a} + nomp_lo)" for a in used)
+        vec_decl = "\n".join(f"      struct __align__(16) {{ {ety[a]} v[{lanes}]; }} nomp_{a}_v;" for a in used)
+        vec_load = "\n".join(f"      *reinterpret_cast<int4 *>(&nomp_{a}_v) = *reinterpret_cast<const int4 *>({a} + nomp_e);" for a in used)
+        vec_store = "\n".join(f"      *reinterpret_cast<int4 *>({a} + nomp_e) = *reinterpret_cast<int4 *>(&nomp_{a}_v);" for a in written)
+        lane_in = "\n".join(f"        {ety[a]} nomp_{a}_i = nomp_{a}_v.v[nomp_l];" for a in used)
+        lane_out = "\n".join(f"        nomp_{a}_v.v[nomp_l] = nomp_{a}_i;" for a in written)
+        sc_in = "\n".join(f"      {ety[a]} nomp_{a}_i = {a}[nomp_e];" for a in used)
+        sc_out = "\n".join(f"      {a}[nomp_e] = nomp_{a}_i;" for a in written)
+        loop = f"""  const long long nomp_tid = (long long)blockIdx.x * 256 + threadIdx.x, nomp_nthreads = (long long)gridDim.x * 256;
+  if (nomp_n > 0 && ((({align}) & 15u) == 0)) {{
+    const long long nomp_nvec = nomp_n / {lanes};
+    for (long long nomp_v = nomp_tid; nomp_v < nomp_nvec; nomp_v += nomp_nthreads) {{
+      const long long nomp_e = nomp_lo + nomp_v * {lanes};
+{vec_decl}
+{vec_load}
+#pragma unroll
+      for (int nomp_l = 0; nomp_l < {lanes}; nomp_l++) {{
+        const {it} {info.loop.var} = ({it})(nomp_e + nomp_l);
+{lane_in}
+{body_lines(4, True)}
+{lane_out}
+      }}
+{vec_store}
+    }}
+    for (long long nomp_e = nomp_lo + nomp_nvec * {lanes} + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
+      const {it} {info.loop.var} = ({it})nomp_e;
+{sc_in}
+{body_lines(3, True)}
+{sc_out}
+    }}
+  }} else {{
+    for (long long nomp_e = nomp_lo + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
+      const {it} {info.loop.var} = ({it})nomp_e;
+{sc_in}
+{body_lines(3, True)}
+{sc_out}
+    }}
+  }}"""
+        per_block = 256 * lanes
+    else:
+        loop = f"""  for (long long nomp_e = nomp_lo + (long long)blockIdx.x * 256 + threadIdx.x; nomp_e < nomp_hi;
+       nomp_e += (long long)gridDim.x * 256) {{
+    const {it} {info.loop.var} = ({it})nomp_e;
+{body_lines(2, False)}
+  }}"""
+        per_block = 256
+
     src = f"""{PRELUDE}
-// reduce clause on `{info.var}` (op {info.op}): single-pass schedule of libnompk reduce.cu with a generated right-hand side
+// reduce clause on `{info.var}` (op {info.op}): single-pass schedule of libnompk reduce.cu with a generated loop body
 extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_parts)}) {{
   {T} nomp_acc = {ident};
   {T} nomp_o;
   const long long nomp_lo = (long long)({lo}), nomp_hi = (long long)({hi});
-  for (long long nomp_i = nomp_lo + (long long)blockIdx.x * 256 + threadIdx.x; nomp_i < nomp_hi;
-       nomp_i += (long long)gridDim.x * 256) {{
-    const {it} {info.loop.var} = ({it})nomp_i;
-{chr(10).join(pre_lines)}
-    {(chr(10) + '    ').join(body)}
-  }}
+  const long long nomp_n = nomp_hi - nomp_lo;
+{loop}
+  // ---- block tree, then the two-level deterministic ticket finish of nompk_gridreduce.cuh -----------------------------
   __shared__ {T} nomp_warp[8];
-  __shared__ bool nomp_last;
-  for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+  __shared__ int nomp_role;
+  char *nomp_w = (char *)nomp_ws;
+  unsigned int *nomp_ticket = (unsigned int *)(nomp_w + {WS_TICKET});
+  unsigned int *nomp_gticket = (unsigned int *)(nomp_w + {WS_GROUP_TICKET});
+  {T} *nomp_l2 = ({T} *)(nomp_w + {WS_L2});
+  {T} *nomp_l1 = ({T} *)(nomp_w + {WS_L1});
+  {tree}
   if ((threadIdx.x & 31) == 0) nomp_warp[threadIdx.x >> 5] = nomp_acc;
   __syncthreads();
   if (threadIdx.x < 32) {{
     nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
-    for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+    {tree}
   }}
+  const unsigned int nomp_b = blockIdx.x, nomp_nb = gridDim.x;
+  const unsigned int nomp_g = nomp_b / {RED_GROUP}, nomp_ng = (nomp_nb + {RED_GROUP - 1}) / {RED_GROUP};
+  const unsigned int nomp_gs = (nomp_g == nomp_ng - 1) ? nomp_nb - nomp_g * {RED_GROUP} : {RED_GROUP};
   if (threadIdx.x == 0) {{
-    nomp_partials[blockIdx.x] = nomp_acc;
+    nomp_l1[(size_t)nomp_b * {slot}] = nomp_acc;
     __threadfence();
-    nomp_last = (atomicAdd(nomp_ticket, 1u) == gridDim.x - 1);
+    nomp_role = (atomicAdd(&nomp_gticket[nomp_g], 1u) == nomp_gs - 1) ? 1 : 0;
   }}
   __syncthreads();
-  if (!nomp_last) return;
+  if (nomp_role == 0) return;
+  if (threadIdx.x < 32) {{
+    __threadfence();
+    nomp_acc = threadIdx.x < nomp_gs ? __ldcg(nomp_l1 + ((size_t)nomp_g * {RED_GROUP} + threadIdx.x) * {slot}) : {ident};
+    {tree}
+    if (threadIdx.x == 0) {{
+      nomp_l2[(size_t)nomp_g * {slot}] = nomp_acc;
+      nomp_gticket[nomp_g] = 0u;
+      __threadfence();
+      nomp_role = (atomicAdd(nomp_ticket, 1u) == nomp_ng - 1) ? 2 : 0;
+    }}
+  }}
+  __syncthreads();
+  if (nomp_role != 2) return;
   __threadfence();
   nomp_acc = {ident};
-  for (unsigned int nomp_b = threadIdx.x; nomp_b < gridDim.x; nomp_b += 256) {{
-    nomp_o = __ldcg(nomp_partials + nomp_b);
+  for (unsigned int nomp_i = threadIdx.x; nomp_i < nomp_ng; nomp_i += 256) {{
+    nomp_o = __ldcg(nomp_l2 + (size_t)nomp_i * {slot});
     nomp_acc = {comb('nomp_acc', 'nomp_o')};
   }}
-  for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
-  __syncthreads();
+  {tree}
   if ((threadIdx.x & 31) == 0) nomp_warp[threadIdx.x >> 5] = nomp_acc;
   __syncthreads();
   if (threadIdx.x < 32) {{
     nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
-    for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}
+    {tree}
     if (threadIdx.x == 0) {{
       *nomp_result = nomp_acc;
       if (nomp_result_host) {{
@@ -262,10 +391,8 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     extent = c.BinOp("-", info.loop.hi, info.loop.lo) if const_int(info.loop.lo) != 0 else info.loop.hi
     try:
         ext = grid_expr_str(extent, int_params)
-        grid = f"max(1, min(({ext} + 255) / 256, {max(1, sm_count) * 8}))"
+        grid = f"max(1, min(({ext} + {per_block - 1}) / {per_block}, {RED_MAX_CTAS}))"
     except KernelError:
         grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
-    names = [p.name for p in params] + ["nomp_partials", "nomp_ticket", "nomp_result", "nomp_result_host", "nomp_seq"]
+    names = [p.name for p in params] + ["nomp_ws", "nomp_result", "nomp_result_host", "nomp_seq"]
     return src, [grid, "1", "1"], ["256", "1", "1"], names
-
-

@@ -35,9 +35,18 @@ def test_headers_and_libraries_agree():
     for sym in want_n:
         assert hasattr(n, sym), f"libnomp.so does not export {sym}"
     assert sorted(capi.NOMPK_SYMBOLS) == want_k
-    assert k.nompk_version() == 100 and k.nompk_reduce_workspace_bytes() >= 2048 * 8
+    assert k.nompk_version() == 100 and k.nompk_reduce_workspace_bytes() >= 65536 * 8
     assert [k.nompk_dtype_size(d) for d in range(6)] == [4, 4, 8, 8, 4, 8]
     assert [k.nompk_ax_supported(x) for x in (6, 7, 8, 9, 10, 12)] == [1, 0, 1, 0, 1, 1]
+
+
+def test_generated_reduce_kernels_use_the_library_workspace_layout():
+    sys.path.insert(0, str(ROOT / "libnomp_b200" / "python"))
+    from nomp_bridge import reduction as r
+    off = (C.c_size_t * 4)()
+    capi.nompk().nompk_reduce_workspace_layout(off)
+    assert list(off) == [r.WS_TICKET, r.WS_GROUP_TICKET, r.WS_L2, r.WS_L1]
+    assert capi.nompk().nompk_reduce_workspace_bytes() == r.WS_L1 + 8 * r.RED_MAX_CTAS
 
 
 def test_public_enum_values_are_the_reference_abi():
