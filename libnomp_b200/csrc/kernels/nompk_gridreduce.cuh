@@ -8,6 +8,7 @@
 //            32 folds the group's partials with one warp (lane i <- partial i, shuffle tree) into a level-2 partial;
 //   level 2: that CTA then takes the global ticket; the last one folds the <= 2048 level-2 partials (256 threads, 8
 //            each, block tree) and publishes the result.
+// Grids of at most 2048 CTAs skip level 1 (the last CTA folds all partials); a single CTA publishes directly.
 // Every fold has a fixed shape, so the result does not depend on the order in which CTAs finish.  All tickets are
 // reset by the CTA that consumes them: the workspace is ready for the next launch on the same stream.
 #pragma once
@@ -19,6 +20,7 @@ namespace nompk {
 constexpr int kRedGroup = 32;
 constexpr int kRedMaxGroups = 2048;
 constexpr int kRedMaxCtas = kRedGroup * kRedMaxGroups;              // 65536
+constexpr int kRedSingleLevel = 2048;                               // grids up to this size use one ticket level
 constexpr size_t kWsTicket = 0;                                     // unsigned int
 constexpr size_t kWsGroupTicket = 64;                               // unsigned int[2048]
 constexpr size_t kWsL2 = kWsGroupTicket + 4 * kRedMaxGroups;        // 8-byte slots[2048]
@@ -47,6 +49,41 @@ __device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result
   __shared__ T warp_part[kThreads / 32];
 
   const unsigned int b = blockIdx.x, nb = gridDim.x;
+  if (nb == 1) {  // a single CTA: nothing to combine, no atomics
+    if (threadIdx.x == 0) {
+      *result = v;
+      if (result_host) publish_to_host(result_host, v, host_seq);
+    }
+    return;
+  }
+  if (nb <= kRedSingleLevel) {
+    // Few CTAs: one ticket level is shorter (one atomic round trip less).  The last CTA folds the level-1 partials.
+    if (threadIdx.x == 0) {
+      l1[(size_t)b * kSlot] = v;
+      __threadfence();
+      role = (atomicAdd(ticket, 1u) == nb - 1) ? 2 : 0;
+    }
+    __syncthreads();
+    if (role != 2) return;
+    __threadfence();
+    T w1 = Op::identity();
+    for (unsigned int i = threadIdx.x; i < nb; i += kThreads) w1 = Op::combine(w1, __ldcg(l1 + (size_t)i * kSlot));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) w1 = Op::combine(w1, __shfl_xor_sync(0xffffffffu, w1, off));
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = w1;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      w1 = threadIdx.x < kThreads / 32 ? warp_part[threadIdx.x] : Op::identity();
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) w1 = Op::combine(w1, __shfl_xor_sync(0xffffffffu, w1, off));
+      if (threadIdx.x == 0) {
+        *result = w1;
+        if (result_host) publish_to_host(result_host, w1, host_seq);
+        *ticket = 0u;
+      }
+    }
+    return;
+  }
   const unsigned int group = b / kRedGroup, ngroups = (nb + kRedGroup - 1) / kRedGroup;
   const unsigned int gsize = (group == ngroups - 1) ? nb - group * kRedGroup : kRedGroup;
   if (threadIdx.x == 0) {

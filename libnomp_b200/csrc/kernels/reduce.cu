@@ -164,6 +164,9 @@ int launch_reduce(size_t n, const void *x_, const void *y_, void *result, void *
   const size_t per_block = vec ? (size_t)kBlock * kUnroll * L : (size_t)kBlock;
   // one tile per CTA (up to 65536 CTAs, then the CTAs stride): many small CTAs stream faster than a persistent grid
   size_t blocks = (n + per_block - 1) / per_block;
+  // up to 2^26 elements a grid of <= 2048 striding CTAs with the one-level finish is faster end to end (the second
+  // ticket level costs ~2 us); beyond that one tile per CTA wins (+3 % bandwidth at n = 2^28)
+  if (n < ((size_t)1 << 26) && blocks > (size_t)kRedSingleLevel) blocks = kRedSingleLevel;
   if (blocks > (size_t)kRedMaxCtas) blocks = kRedMaxCtas;
   if (blocks == 0) blocks = 1;
   const unsigned g = (unsigned)blocks;

@@ -153,6 +153,7 @@ _RED_IDENTITY = {"+": "0", "*": "1"}
 WS_TICKET, WS_GROUP_TICKET, WS_L2, WS_L1 = 0, 64, 64 + 4 * 2048, 64 + 4 * 2048 + 8 * 2048
 RED_GROUP, RED_MAX_GROUPS = 32, 2048
 RED_MAX_CTAS = RED_GROUP * RED_MAX_GROUPS
+RED_SINGLE_LEVEL = 2048
 
 
 def _limits(t: c.CType, hi: bool) -> str:
@@ -246,6 +247,10 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
 
     ew = _elementwise_arrays(func, info)
     arrays = {p.name: p for p in params if p.is_array}
+    if ew is not None:
+        sig_parts = [(f"{cuda_type(p.ctype)} *__restrict__ {p.name}" if p.name in written_any else
+                      f"const {cuda_type(p.ctype)} *__restrict__ {p.name}") if p.is_array else f"{cuda_type(p.ctype)} {p.name}"
+                     for p in params] + sig_parts[len(params):]
 
     def body_lines(depth: int, substitute: bool) -> str:
         def scalarise(e):
@@ -279,10 +284,17 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         lane_out = "\n".join(f"        nomp_{a}_v.v[nomp_l] = nomp_{a}_i;" for a in written)
         sc_in = "\n".join(f"      {ety[a]} nomp_{a}_i = {a}[nomp_e];" for a in used)
         sc_out = "\n".join(f"      {a}[nomp_e] = nomp_{a}_i;" for a in written)
+        U = 4   # vectors per thread and tile: a CTA owns a CONTIGUOUS tile of 256 * U vectors (DRAM locality), all loads
+        #         of the tile can be in flight before the first use (every array is __restrict__ in this mode: each
+        #         element is only touched by the thread-iteration that owns it)
         loop = f"""  const long long nomp_tid = (long long)blockIdx.x * 256 + threadIdx.x, nomp_nthreads = (long long)gridDim.x * 256;
   if (nomp_n > 0 && ((({align}) & 15u) == 0)) {{
     const long long nomp_nvec = nomp_n / {lanes};
-    for (long long nomp_v = nomp_tid; nomp_v < nomp_nvec; nomp_v += nomp_nthreads) {{
+    for (long long nomp_base = (long long)blockIdx.x * {256 * U}; nomp_base < nomp_nvec; nomp_base += (long long)gridDim.x * {256 * U}) {{
+#pragma unroll
+      for (int nomp_u = 0; nomp_u < {U}; nomp_u++) {{
+      const long long nomp_v = nomp_base + nomp_u * 256 + threadIdx.x;
+      if (nomp_v < nomp_nvec) {{
       const long long nomp_e = nomp_lo + nomp_v * {lanes};
 {vec_decl}
 {vec_load}
@@ -294,6 +306,8 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
 {lane_out}
       }}
 {vec_store}
+      }}
+      }}
     }}
     for (long long nomp_e = nomp_lo + nomp_nvec * {lanes} + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
       const {it} {info.loop.var} = ({it})nomp_e;
@@ -309,7 +323,7 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
 {sc_out}
     }}
   }}"""
-        per_block = 256 * lanes
+        per_block = 256 * lanes * U
     else:
         loop = f"""  for (long long nomp_e = nomp_lo + (long long)blockIdx.x * 256 + threadIdx.x; nomp_e < nomp_hi;
        nomp_e += (long long)gridDim.x * 256) {{
@@ -342,6 +356,40 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     {tree}
   }}
   const unsigned int nomp_b = blockIdx.x, nomp_nb = gridDim.x;
+  if (nomp_nb <= {RED_SINGLE_LEVEL}) {{   // few CTAs: one ticket level (a single CTA publishes directly)
+    if (nomp_nb > 1) {{
+      if (threadIdx.x == 0) {{
+        nomp_l1[(size_t)nomp_b * {slot}] = nomp_acc;
+        __threadfence();
+        nomp_role = (atomicAdd(nomp_ticket, 1u) == nomp_nb - 1) ? 2 : 0;
+      }}
+      __syncthreads();
+      if (nomp_role != 2) return;
+      __threadfence();
+      nomp_acc = {ident};
+      for (unsigned int nomp_i = threadIdx.x; nomp_i < nomp_nb; nomp_i += 256) {{
+        nomp_o = __ldcg(nomp_l1 + (size_t)nomp_i * {slot});
+        nomp_acc = {comb('nomp_acc', 'nomp_o')};
+      }}
+      {tree}
+      if ((threadIdx.x & 31) == 0) nomp_warp[threadIdx.x >> 5] = nomp_acc;
+      __syncthreads();
+      if (threadIdx.x < 32) {{
+        nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
+        {tree}
+      }}
+    }}
+    if (threadIdx.x == 0) {{
+      *nomp_result = nomp_acc;
+      if (nomp_result_host) {{
+        *(volatile {T} *)nomp_result_host = nomp_acc;
+        __threadfence_system();
+        *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
+      }}
+      if (nomp_nb > 1) *nomp_ticket = 0u;
+    }}
+    return;
+  }}
   const unsigned int nomp_g = nomp_b / {RED_GROUP}, nomp_ng = (nomp_nb + {RED_GROUP - 1}) / {RED_GROUP};
   const unsigned int nomp_gs = (nomp_g == nomp_ng - 1) ? nomp_nb - nomp_g * {RED_GROUP} : {RED_GROUP};
   if (threadIdx.x == 0) {{
@@ -391,7 +439,10 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     extent = c.BinOp("-", info.loop.hi, info.loop.lo) if const_int(info.loop.lo) != 0 else info.loop.hi
     try:
         ext = grid_expr_str(extent, int_params)
-        grid = f"max(1, min(({ext} + {per_block - 1}) / {per_block}, {RED_MAX_CTAS}))"
+        # one tile per CTA for large loops (two ticket levels), <= 2048 striding CTAs (one level) below 2^26 iterations;
+        # the expression language has no conditional, so: min(tiles, 2048 + (tiles / 32768) * 63488)
+        tiles = f"(({ext} + {per_block - 1}) / {per_block})"
+        grid = f"max(1, min(min({tiles}, {RED_SINGLE_LEVEL} + ({tiles} / {(1 << 26) // per_block}) * {RED_MAX_CTAS - RED_SINGLE_LEVEL}), {RED_MAX_CTAS}))"
     except KernelError:
         grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
     names = [p.name for p in params] + ["nomp_ws", "nomp_result", "nomp_result_host", "nomp_seq"]

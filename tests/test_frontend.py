@@ -254,7 +254,7 @@ def test_fused_cg_families():
            " for (int i = 0; i < N; i++) { x[i] += alpha * p[i]; r[i] -= alpha * w[i]; rr[0] += r[i] * r[i]; } }")
     desc, cuda, grid, _ = plan(upd, None, ("rr", "+"))
     assert desc["kind"] == "nvrtc" and desc["family"] == "reduce" and desc["ro"] == "p,w"
-    assert "double *x, double *r, const double *__restrict__ p" in cuda
+    assert "double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p" in cuda
     ok, log = nvrtc_compile(cuda)
     assert ok, log
     with pytest.raises(nb.KernelError):
