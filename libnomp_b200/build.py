@@ -119,6 +119,11 @@ def build_tools(force=False):
     if force or _stale(out, [src, LIB / "libnomp.so"]):
         _run(["gcc", "-O2", "-I", str(ROOT / "include"), str(src), "-o", str(out), "-L", str(LIB), "-lnomp",
               f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
+    ex = OBJ / "cg_poisson"
+    ex_src = ROOT / "examples" / "cg_poisson.c"
+    if force or _stale(ex, [ex_src, LIB / "libnomp.so"]):
+        _run(["gcc", "-O2", "-I", str(ROOT / "include"), str(ex_src), "-o", str(ex), "-L", str(LIB), "-lnomp", "-lm",
+              f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
     return out
 
 

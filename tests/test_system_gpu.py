@@ -46,6 +46,88 @@ def test_bench_contract():
     assert "family=ax" in line["config"]["kernel"]
 
 
+def _cg_reference(E_total, n, iters):
+    """The example's CG on the host with the oracle's Ax and plain numpy dots (same data generator)."""
+    import numpy as np
+    from oracle import ffi
+    n3 = n ** 3
+    N = E_total * n3
+    xt = ffi.fill_uniform_f64(N, 11, 0.0, 1.0) - 0.5
+    v = ffi.fill_uniform_f64(6 * N, 13, 0.0, 1.0).reshape(E_total, 6, n3)
+    g = 0.2 * (v - 0.5)
+    for f in (0, 3, 5):
+        g[:, f, :] = 1.0 + 0.5 * v[:, f, :]
+    g = np.ascontiguousarray(g.ravel())
+    D = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    b = ffi.ax(n, xt, g, D)
+    x, r, p = np.zeros(N), b.copy(), b.copy()
+    rr = float(r @ r)
+    out = [dict(rr0=rr)]
+    for it in range(iters):
+        w = ffi.ax(n, p, g, D)
+        pap = float(p @ w)
+        alpha = rr / pap
+        x += alpha * p
+        r -= alpha * w
+        rr_new = float(r @ r)
+        p = r + (rr_new / rr) * p
+        out.append(dict(pAp=pap, alpha=alpha, rr=rr_new))
+        rr = rr_new
+    return out
+
+
+def _run_cg(world, E, n, tmp_path):
+    exe = ROOT / "libnomp_b200" / "build" / "cg_poisson"
+    if not exe.exists():
+        pytest.skip("examples/cg_poisson was not built")
+    idfile = f"/dev/shm/nomp-test-cg-{os.getpid()}-{world}"
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
+        if world > 1:
+            env.update(NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(r), NOMP_COMM_ID_FILE=idfile)
+        procs.append(subprocess.Popen([str(exe), str(E), str(n), "400", "1e-9", "--nomp-backend", "cuda", "--nomp-device", str(r),
+                                       "--nomp-verbose", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+    outs = [p.communicate(timeout=900)[0] for p in procs]
+    for f in [idfile] + [f"{idfile}.ipc.{r}" for r in range(world)]:
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    return [[json.loads(l) for l in o.splitlines() if l.startswith("{")] for o in outs]
+
+
+def test_cg_example_matches_host_cg(tmp_path):
+    """examples/cg_poisson.c (fused Ax+dot, fused update+dot, xpay through the public API) against the same CG on the
+    host: the first iterations agree to 1e-10 relative, the solver converges, the true residual is small."""
+    E, n = 48, 8
+    lines = _run_cg(1, E, n, tmp_path)[0]
+    ref = _cg_reference(E, n, 5)
+    assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
+    for it in range(5):
+        for key in ("pAp", "alpha", "rr"):
+            assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
+    final = lines[-1]
+    assert final["iterations"] < 400 and final["true_residual_rel"] < 1e-7
+
+
+def test_cg_example_on_two_gpus(tmp_path):
+    """Two ranks, each with its own block of elements of a 2E-element mesh: every rank sees the global scalars."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    E, n = 24, 8
+    per_rank = _run_cg(2, E, n, tmp_path)
+    ref = _cg_reference(2 * E, n, 5)
+    for lines in per_rank:
+        assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
+        for it in range(5):
+            for key in ("pAp", "alpha", "rr"):
+                assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
+    assert per_rank[0][1:6] == per_rank[1][1:6], "ranks must see bit-identical reduction results"
+
+
 NCCL_WORKER = r"""
 import ctypes as C, os, sys
 import numpy as np
