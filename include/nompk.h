@@ -123,7 +123,7 @@ int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, voi
  *          D  double[n][n] row-major, D[a][l] = d phi_l / dx at node a.
  * The reference has no such operator (reference tests/sem.py:10-36 only tags loops); the canonical kernel
  * string that the bridge maps onto this entry point is in libnomp_b200/python/nomp_bridge/families.py.
- * Hand-written for n in {8, 10} (N = 7, 9); other n return NOMPK_EUNSUPPORTED and the bridge falls back to
+ * Hand-written for n in {6, 8, 10, 12} (N = 5, 7, 9, 11); other n return NOMPK_EUNSUPPORTED and the bridge falls back to
  * NVRTC.  D is staged into __constant__ memory on `stream` unless NOMPK_AX_D_CACHED is set, which asserts
  * that the previous call with the same n used identical D values. */
 #define NOMPK_AX_D_CACHED 1
