@@ -38,6 +38,14 @@ int nomp_b200_comm_uses_nvlink_kernel(void);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 /* "kind=native family=map ..." descriptor of program `id` (valid until nomp_finalize), or NULL. */
 const char *nomp_b200_prog_info(int id);
+/* On-disk JIT cache (directory $NOMP_JIT_CACHE_DIR, else $XDG_CACHE_HOME/libnomp_b200, else ~/.cache/libnomp_b200;
+ * NOMP_JIT_CACHE=0 disables it).  Counters since load: {programs served from the cache, programs built by the
+ * bridge and stored, CUBINs loaded from the cache, CUBINs compiled by NVRTC and stored}.  A transform or annotation
+ * script is part of the key by its own text only: scripts that import other user modules need NOMP_JIT_CACHE=0 (or
+ * a fresh directory) when those modules change. */
+void nomp_b200_jit_cache_stats(unsigned long long counters[4]);
+/* The hash the cache keys are made of (SHA-256, lower-case hex, NUL-terminated); exported for the tests. */
+void nomp_b200_sha256_hex(const void *data, size_t n, char hex[65]);
 
 #ifdef __cplusplus
 }

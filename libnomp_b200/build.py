@@ -35,7 +35,7 @@ NVCC_FLAGS = [
 ]
 
 KERNEL_SRCS = ["map.cu", "reduce.cu", "ax.cu", "nompk.cu"]
-LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c",
+LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c", "src/jitcache.c",
                 "backends/cuda.c"]
 
 

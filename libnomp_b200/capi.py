@@ -45,6 +45,7 @@ NOMP_SYMBOLS = [
     # extensions declared in include/nomp-b200.h
     "nomp_b200_stream", "nomp_b200_update_async", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
     "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
+    "nomp_b200_jit_cache_stats", "nomp_b200_sha256_hex",
 ]
 
 
@@ -139,8 +140,19 @@ def nomp() -> C.CDLL:
         lib.nomp_b200_prog_info.argtypes = [C.c_int]
         lib.nomp_b200_exchange_blob.restype = C.c_int
         lib.nomp_b200_exchange_blob.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
+        lib.nomp_b200_jit_cache_stats.restype = None
+        lib.nomp_b200_jit_cache_stats.argtypes = [C.POINTER(C.c_ulonglong * 4)]
+        lib.nomp_b200_sha256_hex.restype = None
+        lib.nomp_b200_sha256_hex.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
         _nomp = lib
     return _nomp
+
+
+def jit_cache_stats() -> dict:
+    """Counters of the on-disk JIT cache since the library was loaded (include/nomp-b200.h)."""
+    out = (C.c_ulonglong * 4)()
+    nomp().nomp_b200_jit_cache_stats(C.byref(out))
+    return dict(zip(("knl_hits", "knl_misses", "cubin_hits", "cubin_misses"), (int(v) for v in out)))
 
 
 _libc = C.CDLL(None)

@@ -264,14 +264,42 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
   char flag[8];
   cp->is_reduce = desc_get(source, "reduce", flag, sizeof(flag)) && flag[0] == '1';
 
-  nvrtcProgram prog;
-  check_nvrtc(nvrtcCreateProgram(&prog, source, name, 0, NULL, NULL));
   char arch[64];
   /* architecture-specific target ("a" suffix) for Hopper and newer: sm_100a on B200 */
   snprintf(arch, sizeof(arch), "--gpu-architecture=sm_%d%d%s", st->prop.major, st->prop.minor,
            st->prop.major >= 9 ? "a" : "");
   const char *options[] = {arch, "--fmad=false", "--std=c++17", "-lineinfo"};
-  nvrtcResult result = nvrtcCompileProgram(prog, 4, options);
+  const int noptions = (int)(sizeof(options) / sizeof(options[0]));
+
+  /* on-disk cache of the CUBIN (src/jitcache.c): key = source, entry name, options, NVRTC version */
+  char key[65] = "", *cubin = NULL;
+  size_t size = 0;
+  int cacheable = nomp_jit_cache_dir() != NULL, major = 0, minor = 0;
+  if (cacheable) {
+    nomp_sha256_t c;
+    char version[64];
+    nvrtcVersion(&major, &minor);
+    snprintf(version, sizeof(version), "libnomp_b200 cubin 1 nvrtc %d.%d", major, minor);
+    nomp_sha256_init(&c);
+    nomp_sha256_field(&c, version), nomp_sha256_field(&c, source), nomp_sha256_field(&c, name);
+    for (int i = 0; i < noptions; i++) nomp_sha256_field(&c, options[i]);
+    nomp_sha256_hex(&c, key);
+    if (!nomp_jit_cache_load(key, "cubin", &cubin, &size)) {
+      /* a damaged entry fails to load as a module: fall through and recompile */
+      if (size > 0 && drv.ModuleLoadData(&cp->module, cubin) == CUDA_SUCCESS &&
+          drv.ModuleGetFunction(&cp->function, cp->module, name) == CUDA_SUCCESS) {
+        free(cubin);
+        nomp_jit_cache_count(NOMP_CACHE_CUBIN_HIT);
+        return 0;
+      }
+      if (cp->module) drv.ModuleUnload(cp->module), cp->module = NULL;
+      free(cubin), cubin = NULL;
+    }
+  }
+
+  nvrtcProgram prog;
+  check_nvrtc(nvrtcCreateProgram(&prog, source, name, 0, NULL, NULL));
+  nvrtcResult result = nvrtcCompileProgram(prog, noptions, options);
   if (result != NVRTC_SUCCESS) {
     size_t log_size = 0;
     nvrtcGetProgramLogSize(prog, &log_size);
@@ -282,11 +310,11 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
     nvrtcDestroyProgram(&prog);
     return err;
   }
-  size_t size = 0;
   check_nvrtc(nvrtcGetCUBINSize(prog, &size));
-  char *cubin = nomp_calloc(char, size + 1);
+  cubin = nomp_calloc(char, size + 1);
   check_nvrtc(nvrtcGetCUBIN(prog, cubin));
   check_nvrtc(nvrtcDestroyProgram(&prog));
+  if (cacheable && !nomp_jit_cache_store(key, "cubin", cubin, size)) nomp_jit_cache_count(NOMP_CACHE_CUBIN_MISS);
   CUresult r = drv.ModuleLoadData(&cp->module, cubin);
   free(cubin);
   check_driver(r);

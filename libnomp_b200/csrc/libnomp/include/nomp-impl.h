@@ -126,6 +126,26 @@ int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_m
                         void *stream, int *published);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 
+/* on-disk JIT cache (src/jitcache.c) */
+typedef struct {
+  uint32_t h[8];
+  uint64_t len;
+  unsigned fill;
+  unsigned char buf[64];
+} nomp_sha256_t;
+void nomp_sha256_init(nomp_sha256_t *c);
+void nomp_sha256_update(nomp_sha256_t *c, const void *data, size_t n);
+void nomp_sha256_field(nomp_sha256_t *c, const char *s);
+int nomp_sha256_file(nomp_sha256_t *c, const char *path);
+int nomp_sha256_dir(nomp_sha256_t *c, const char *dir, const char *suffix);
+void nomp_sha256_hex(nomp_sha256_t *c, char hex[65]);
+const char *nomp_jit_cache_dir(void); /* NULL when the cache is off */
+void nomp_jit_cache_reset(void);
+enum { NOMP_CACHE_KNL_HIT = 0, NOMP_CACHE_KNL_MISS = 1, NOMP_CACHE_CUBIN_HIT = 2, NOMP_CACHE_CUBIN_MISS = 3 };
+void nomp_jit_cache_count(int which);
+int nomp_jit_cache_load(const char *hex, const char *ext, char **data, size_t *size);
+int nomp_jit_cache_store(const char *hex, const char *ext, const void *data, size_t size);
+
 extern const char *ERR_STR_USER_MAP_PTR_IS_INVALID;
 extern const char *ERR_STR_USER_DEVICE_IS_INVALID;
 

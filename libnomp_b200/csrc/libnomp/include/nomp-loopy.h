@@ -21,6 +21,9 @@ int nomp_py_fix_parameters(PyObject **kernel, const PyObject *dict);
 int nomp_py_get_knl_name_and_src(char **name, char **src, const PyObject *kernel, const PyObject *context);
 int nomp_py_get_grid_size(nomp_prog_t *prg, PyObject *kernel, const PyObject *context);
 int nomp_py_finalize(int interpreter);
+/* for the JIT cache key: repr() of a dict, and the source file behind an importable module (both malloc'ed) */
+int nomp_py_repr(char **out, const PyObject *obj);
+int nomp_py_module_file(char **out, const char *module);
 
 /* small dict helpers so that nomp.c and the backend need no Python API knowledge of their own */
 PyObject *nomp_py_dict_new(void);

@@ -267,6 +267,32 @@ int nomp_py_get_grid_size(nomp_prog_t *prg, PyObject *kernel, const PyObject *co
   WITH_GIL(grid_size_locked(prg, kernel, context));
 }
 
+/* ---- helpers of the on-disk JIT cache: no error is logged, a failure only means "do not cache" ---------------- */
+static int repr_locked(char **out, const PyObject *obj) {
+  PyObject *r = obj ? PyObject_Repr((PyObject *)obj) : NULL;
+  const char *s = r ? PyUnicode_AsUTF8(r) : NULL;
+  *out = s ? strdup(s) : NULL;
+  Py_XDECREF(r);
+  PyErr_Clear();
+  return *out == NULL;
+}
+
+int nomp_py_repr(char **out, const PyObject *obj) { WITH_GIL(repr_locked(out, obj)); }
+
+static int module_file_locked(char **out, const char *module) {
+  *out = NULL;
+  PyObject *util = PyImport_ImportModule("importlib.util");
+  PyObject *spec = util ? PyObject_CallMethod(util, "find_spec", "s", module) : NULL;
+  PyObject *origin = (spec && spec != Py_None) ? PyObject_GetAttrString(spec, "origin") : NULL;
+  const char *s = (origin && PyUnicode_Check(origin)) ? PyUnicode_AsUTF8(origin) : NULL;
+  if (s) *out = strdup(s);
+  Py_XDECREF(origin), Py_XDECREF(spec), Py_XDECREF(util);
+  PyErr_Clear();
+  return *out == NULL;
+}
+
+int nomp_py_module_file(char **out, const char *module) { WITH_GIL(module_file_locked(out, module)); }
+
 /* ------------------------------------------------------------------------------------------------------------ */
 PyObject *nomp_py_dict_new(void) {
   PyGILState_STATE gil = PyGILState_Ensure();

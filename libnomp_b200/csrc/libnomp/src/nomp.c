@@ -19,6 +19,7 @@
 #include "nomp-loopy.h"
 
 static nomp_backend_t nomp;
+static nomp_config_t config; /* of the last successful nomp_init() */
 static int initialized = 0;
 
 /* ============================================================================================================== */
@@ -127,6 +128,8 @@ NOMP_EXPORT int nomp_init(int argc, const char **argv) {
     release_partial_init();
     return err;
   }
+  config = cfg;
+  nomp_jit_cache_reset();
   initialized = 1;
   return 0;
 }
@@ -288,12 +291,15 @@ static nomp_prog_t *collect_args(unsigned nargs, va_list ap) {
   return prg;
 }
 
-static int apply_clauses(PyObject **knl, nomp_prog_t *prg, const char **clauses, const char **reduce_op) {
+/* with_python = 0: only the C side (validation, reduction bookkeeping), for programs served from the JIT cache */
+static int apply_clauses(PyObject **knl, nomp_prog_t *prg, const char **clauses, const char **reduce_op,
+                         int with_python) {
   *reduce_op = NULL;
   for (unsigned i = 0; clauses && clauses[i]; i += 3) {
     const char *kind = clauses[i];
     if (!strcmp(kind, "transform")) {
       const char *file = clauses[i + 1], *function = clauses[i + 2];
+      if (!with_python) continue;
       nomp_check(nomp_py_check_module(file, function));
       nomp_check(nomp_py_transform(knl, file, function, nomp.py_context));
     } else if (!strcmp(kind, "reduce")) {
@@ -319,6 +325,7 @@ static int apply_clauses(PyObject **knl, nomp_prog_t *prg, const char **clauses,
                         "Reduction operator \"%s\" is not one of \"+\", \"*\", \"min\", \"max\".", op);
       *reduce_op = op;
     } else if (!strcmp(kind, "annotate")) {
+      if (!with_python) continue;
       PyObject *annotations = nomp_py_dict_new();
       nomp_py_dict_set_str(annotations, clauses[i + 1], clauses[i + 2] ? clauses[i + 2] : "");
       int err = nomp_py_annotate(knl, nomp.py_annotate, annotations, nomp.py_context);
@@ -332,25 +339,143 @@ static int apply_clauses(PyObject **knl, nomp_prog_t *prg, const char **clauses,
   return 0;
 }
 
+/* ---- on-disk cache of what the bridge produces for one nomp_jit() (src/jitcache.c) ------------------------------ */
+/* SHA-256 of the bridge's own Python text: a new bridge version never reads entries of an old one. */
+static const char *bridge_digest(void) {
+  static char digest[65], of_dir[PATH_MAX + 1];
+  if (digest[0] && !strcmp(of_dir, config.install_dir)) return digest[0] == '-' ? NULL : digest;
+  snprintf(of_dir, sizeof(of_dir), "%s", config.install_dir);
+  nomp_sha256_t c;
+  nomp_sha256_init(&c);
+  char dir[PATH_MAX + 64];
+  snprintf(dir, sizeof(dir), "%s/python/nomp_bridge", config.install_dir);
+  int err = nomp_sha256_dir(&c, dir, ".py");
+  snprintf(dir, sizeof(dir), "%s/python/loopy", config.install_dir);
+  err |= nomp_sha256_dir(&c, dir, ".py");
+  if (err) {
+    strcpy(digest, "-");
+    return NULL;
+  }
+  nomp_sha256_hex(&c, digest);
+  return digest;
+}
+
+static int hash_script(nomp_sha256_t *c, const char *module) {
+  char *path = NULL;
+  if (module == NULL || nomp_py_module_file(&path, module)) return 1;
+  const int err = nomp_sha256_file(c, path);
+  free(path);
+  return err;
+}
+
+/* Key of a program; non-zero when it cannot be cached (cache off, a script that cannot be located, ...). */
+static int program_key(char hex[65], const nomp_prog_t *prg, const char *csrc, const char **clauses) {
+  if (nomp_jit_cache_dir() == NULL) return 1;
+  const char *bridge = bridge_digest();
+  if (bridge == NULL) return 1;
+  nomp_sha256_t c;
+  nomp_sha256_init(&c);
+  nomp_sha256_field(&c, "libnomp_b200 knl 1");
+  nomp_sha256_field(&c, bridge);
+  nomp_sha256_field(&c, csrc);
+  int annotated = 0;
+  for (unsigned i = 0; clauses && clauses[i]; i += 3) {
+    nomp_sha256_field(&c, clauses[i]), nomp_sha256_field(&c, clauses[i + 1]), nomp_sha256_field(&c, clauses[i + 2]);
+    if (!strcmp(clauses[i], "transform") && hash_script(&c, clauses[i + 1])) return 1;
+    annotated |= !strcmp(clauses[i], "annotate");
+  }
+  if (annotated && nomp.py_annotate && hash_script(&c, config.annotations_script)) return 1;
+  for (unsigned i = 0; i < prg->nargs; i++) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%zu:%d", prg->args[i].size, (int)prg->args[i].type);
+    nomp_sha256_field(&c, prg->args[i].name), nomp_sha256_field(&c, buf);
+  }
+  char *jit_values = NULL, *context = NULL;
+  int err = nomp_py_repr(&jit_values, prg->py_dict) || nomp_py_repr(&context, nomp.py_context);
+  if (!err) nomp_sha256_field(&c, jit_values), nomp_sha256_field(&c, context);
+  free(jit_values), free(context);
+  if (!err) nomp_sha256_hex(&c, hex);
+  return err;
+}
+
+#define KNL_ENTRY_MAGIC "NOMPJIT1\n"
+
+static void store_program(const char *hex, const nomp_prog_t *prg, const char *name, const char *src) {
+  size_t cap = strlen(KNL_ENTRY_MAGIC) + strlen(name) + strlen(src) + 16;
+  for (int d = 0; d < 3; d++) cap += strlen(prg->sym_global[d]) + strlen(prg->sym_local[d]);
+  char *buf = nomp_calloc(char, cap);
+  const int n = snprintf(buf, cap, KNL_ENTRY_MAGIC "%s\n%s\n%s\n%s\n%s\n%s\n%s\n%s", name, prg->sym_global[0],
+                         prg->sym_global[1], prg->sym_global[2], prg->sym_local[0], prg->sym_local[1], prg->sym_local[2], src);
+  if (n > 0 && (size_t)n < cap) nomp_jit_cache_store(hex, "knl", buf, (size_t)n);
+  free(buf);
+}
+
+/* name, six launch-size expressions (one per line), then the generated source up to the end of the file */
+static int load_program(const char *hex, nomp_prog_t *prg, char **name, char **src) {
+  char *data = NULL;
+  size_t size = 0;
+  if (nomp_jit_cache_load(hex, "knl", &data, &size)) return 1;
+  const size_t lm = strlen(KNL_ENTRY_MAGIC);
+  char *line[7], *p = data + lm;
+  int ok = size > lm && !memcmp(data, KNL_ENTRY_MAGIC, lm) && strlen(data) == size;
+  for (int i = 0; ok && i < 7; i++) {
+    char *eol = strchr(p, '\n');
+    if (!(ok = eol != NULL)) break;
+    *eol = '\0', line[i] = p, p = eol + 1;
+  }
+  ok = ok && !strncmp(p, "//!nomp ", 8);
+  if (ok) {
+    *name = strdup(line[0]), *src = strdup(p);
+    for (int d = 0; d < 3; d++) {
+      free(prg->sym_global[d]), free(prg->sym_local[d]);
+      prg->sym_global[d] = strdup(line[1 + d]), prg->sym_local[d] = strdup(line[4 + d]);
+    }
+    prg->ndim = 3;
+  }
+  free(data);
+  return !ok;
+}
+
+static void set_info(nomp_prog_t *prg, const char *src) {
+  const char *eol = strchr(src, '\n');
+  prg->info = strndup(src + 8, eol ? (size_t)(eol - src) - 8 : strlen(src) - 8);
+}
+
 static int build_program(nomp_prog_t *prg, const char *csrc, const char **clauses) {
+  const char *reduce_op = NULL;
+  char key[65], *name = NULL, *src = NULL;
+  const int cacheable = !program_key(key, prg, csrc, clauses);
+  if (cacheable && !load_program(key, prg, &name, &src)) {
+    /* served from the cache: the interpreter is not entered, user scripts do not run */
+    int err = apply_clauses(NULL, prg, clauses, &reduce_op, 0);
+    if (!err) {
+      set_info(prg, src);
+      err = nomp.knl_build(&nomp, prg, src, name);
+    }
+    free(name), free(src);
+    if (!err) nomp_jit_cache_count(NOMP_CACHE_KNL_HIT);
+    return err;
+  }
+
   PyObject *knl = NULL;
   nomp_check(nomp_py_c_to_loopy(&knl, csrc));
 
-  const char *reduce_op = NULL;
-  int err = apply_clauses(&knl, prg, clauses, &reduce_op);
+  int err = apply_clauses(&knl, prg, clauses, &reduce_op, 1);
   if (!err && prg->reduction_index >= 0)
     err = nomp_py_realize_reduction(&knl, prg->args[prg->reduction_index].name, reduce_op, nomp.py_context);
   if (!err && nomp_py_dict_size(prg->py_dict) > 0) err = nomp_py_fix_parameters(&knl, prg->py_dict);
 
-  char *name = NULL, *src = NULL;
   if (!err) err = nomp_py_get_knl_name_and_src(&name, &src, knl, nomp.py_context);
   if (!err) {
-    const char *eol = strchr(src, '\n');
-    prg->info = strndup(src + 8, eol ? (size_t)(eol - src) - 8 : strlen(src) - 8);
+    set_info(prg, src);
     err = nomp.knl_build(&nomp, prg, src, name);
   }
-  free(name), free(src);
   if (!err) err = nomp_py_get_grid_size(prg, knl, nomp.py_context);
+  if (!err && cacheable) {
+    store_program(key, prg, name, src);
+    nomp_jit_cache_count(NOMP_CACHE_KNL_MISS);
+  }
+  free(name), free(src);
   nomp_py_decref(&knl);
   return err;
 }

@@ -9,6 +9,11 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 
+# Tests exercise the transform bridge and NVRTC for real: the on-disk JIT cache is off unless a test turns it on
+# with its own directory (tests/test_jit_cache_gpu.py).
+os.environ.setdefault("NOMP_JIT_CACHE", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -150,3 +150,22 @@ def test_aux_helpers():
     assert lib.nomp_copy_env(b"NOMP_TEST_ENV_UNSET", 5) is None
     lib.nomp_max.restype = C.c_int
     assert lib.nomp_max(C.c_uint(3), C.c_int(-5), C.c_int(9), C.c_int(2)) == 9
+
+
+def test_jit_cache_hash_is_sha256():
+    """Cache keys (src/jitcache.c) are SHA-256: FIPS 180-4 test vectors and random lengths around the block edges."""
+    import hashlib
+
+    import numpy as np
+    lib = capi.nomp()
+    out = C.create_string_buffer(65)
+    lib.nomp_b200_sha256_hex(b"abc", 3, out)
+    assert out.value == b"ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    lib.nomp_b200_sha256_hex(b"", 0, out)
+    assert out.value == b"e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    rng = np.random.default_rng(5)
+    for n in (1, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1000, 70001):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        lib.nomp_b200_sha256_hex(data, n, out)
+        assert out.value.decode() == hashlib.sha256(data).hexdigest(), n
+    assert capi.jit_cache_stats() == {"knl_hits": 0, "knl_misses": 0, "cubin_hits": 0, "cubin_misses": 0}

@@ -1,6 +1,9 @@
 #!/bin/bash
 # Run the reference's own nomp-api test programs (built by `make -C oracle ref-tests` into oracle/_ref/tests)
 # against this implementation, with the flag set of reference scripts/lnrun:120-130.
+# The on-disk JIT cache is off unless the caller sets NOMP_JIT_CACHE=1 (with NOMP_JIT_CACHE_DIR): every kernel then
+# goes through the transform bridge and NVRTC, as in the reference.
+export NOMP_JIT_CACHE="${NOMP_JIT_CACHE:-0}"
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 DIR="$ROOT/oracle/_ref/tests"
 export NOMP_INSTALL_DIR="$ROOT/libnomp_b200"

@@ -2,7 +2,7 @@
 """Turn `ncu` outputs brought back in gpurun_out/ into the small text summaries kept under profiles/.
 
   summarize_ncu.py launches <launches.csv>             -> per-kernel launch counts / total time / share
-  summarize_ncu.py report <file.ncu-rep> [title]       -> key counters of the first profiled launch
+  summarize_ncu.py report <file.ncu-rep | raw.csv> [title] -> key counters of the first profiled launch
 """
 import collections
 import csv
@@ -59,7 +59,10 @@ def launches(path):
 
 
 def report(path, title=None):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     col = {h: i for i, h in enumerate(hdr)}
