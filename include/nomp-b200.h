@@ -38,6 +38,21 @@ int nomp_b200_comm_uses_nvlink_kernel(void);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 /* "kind=native family=map ..." descriptor of program `id` (valid until nomp_finalize), or NULL. */
 const char *nomp_b200_prog_info(int id);
+/* Gather-scatter (direct stiffness summation, the gs_setup / gs_op pair of Nekbone and gslib; not in the reference).
+ * ids[i] > 0 is the global number of local degree of freedom i (ids <= 0 do not take part).  After nomp_b200_gs()
+ * every element of the mapped vector holds the combination of all elements -- on this GPU and on every other rank of
+ * the communicator -- that carry the same id.  Setup and free are collective (every rank calls them, in the same
+ * order); nomp_b200_gs() is asynchronous like nomp_run(): kernels on the backend stream, partial results exchanged by
+ * stores into the peers' memory over NVLink (needs CUDA peer access between the ranks' GPUs), no host
+ * synchronisation.  `ptr` must be mapped from element 0 over at least n elements of `unit_size` bytes; `type` is
+ * NOMP_INT, NOMP_UINT or NOMP_FLOAT; `op` is "+", "*", "min" or "max".  Copies are combined in ascending local index,
+ * ranks in ascending rank order: results are deterministic and bit-identical on every rank.
+ * nomp_b200_gs_info: {n, distinct ids, groups, copies in groups, groups shared with other ranks, (group, rank) pairs,
+ * neighbour ranks, ids shared with other ranks}. */
+int nomp_b200_gs_setup(int *handle, const long long *ids, size_t n);
+int nomp_b200_gs(int handle, void *ptr, size_t unit_size, int type, const char *op);
+int nomp_b200_gs_info(int handle, size_t info[8]);
+int nomp_b200_gs_free(int handle);
 /* On-disk JIT cache (directory $NOMP_JIT_CACHE_DIR, else $XDG_CACHE_HOME/libnomp_b200, else ~/.cache/libnomp_b200;
  * NOMP_JIT_CACHE=0 disables it).  Counters since load: {programs served from the cache, programs built by the
  * bridge and stored, CUBINs loaded from the cache, CUBINs compiled by NVRTC and stored}.  A transform or annotation

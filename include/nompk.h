@@ -141,6 +141,42 @@ int nompk_ax_supported(int n);
 /* Variant selector for benchmarking/profiling (0 = default). */
 int nompk_ax_set_variant(int variant);
 
+/* Gather-scatter (direct stiffness summation; gs_setup / gs_op of Nekbone and gslib): after nompk_gs_apply every local
+ * degree of freedom v[i] holds the combination (op) of all degrees of freedom -- on this GPU and on every peer rank --
+ * whose global id equals ids[i].  ids <= 0 do not take part.  The reference has no such operator; it is the step either
+ * side of the local Ax in a spectral-element solve.
+ *
+ * Setup (all arrays are DEVICE arrays; every call synchronises `stream`):
+ *   nompk_gs_create          sorts the n ids (n < 2^32 - 1) and finds the distinct ones
+ *   nompk_gs_unique          ascending distinct ids of this rank, to be shown to the peers
+ *   nompk_gs_match_peer      once per peer rank: intersects with that peer's distinct ids (any pointer this device
+ *                            can read: a local copy or a CUDA-IPC mapping); *n_shared = number of shared ids
+ *   nompk_gs_finalize_setup  builds the groups; *xchg_bytes = size of the exchange buffer this rank must allocate
+ *                            (zero-filled; 0 when no id is shared with a peer)
+ *   nompk_gs_recv_offsets    offsets[r] / counts[r]: where rank r's segment starts in MY exchange buffer (in values)
+ *   nompk_gs_connect         peer_xchg[r] = rank r's exchange buffer as mapped into this process (own buffer at
+ *                            [rank]); send_offsets[r] = what rank r reported as ITS offsets[my rank]
+ * Single-GPU use: create -> finalize_setup(0, 1) -> apply.
+ *
+ * nompk_gs_apply: asynchronous on `stream`, two launches (one when nothing is shared with a peer).  Copies of one id
+ * are combined in ascending local index, ranks in ascending rank order: the result is deterministic and bit-identical
+ * on every rank.  Partial results travel by stores into the peers' exchange buffers over NVLink; a peer that does not
+ * arrive within 20 s makes the kernel give up (no GPU hang) and store the call number at *error_host_mapped (device
+ * address of mapped pinned host memory, may be NULL).  All ranks must call apply in the same order. */
+typedef struct nompk_gs nompk_gs_t;
+int nompk_gs_create(const long long *ids, size_t n, nompk_gs_t **gs, void *stream);
+int nompk_gs_unique(const nompk_gs_t *gs, const long long **ids, size_t *count);
+int nompk_gs_match_peer(nompk_gs_t *gs, int peer, int world, const long long *peer_ids, size_t peer_count,
+                        size_t *n_shared, void *stream);
+int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size_t *xchg_bytes, void *stream);
+int nompk_gs_recv_offsets(const nompk_gs_t *gs, size_t *offsets, size_t *counts);
+int nompk_gs_connect(nompk_gs_t *gs, void *const *peer_xchg, const size_t *send_offsets, void *stream);
+int nompk_gs_apply(nompk_gs_t *gs, nompk_red_op_t op, nompk_dtype_t dt, void *v, unsigned long long *error_host_mapped,
+                   void *stream);
+/* {n, distinct ids, groups, copies in groups, groups shared with peers, (group, peer) pairs, neighbours, shared ids} */
+int nompk_gs_stats(const nompk_gs_t *gs, size_t out[8]);
+void nompk_gs_destroy(nompk_gs_t *gs);
+
 /* Launch bookkeeping used by bench.py's "gpu_launches" field: number of kernels this library has
  * launched since load (monotonic, process-wide). */
 unsigned long long nompk_launch_count(void);

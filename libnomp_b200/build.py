@@ -34,8 +34,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"),
 ]
 
-KERNEL_SRCS = ["map.cu", "reduce.cu", "ax.cu", "nompk.cu"]
-LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c", "src/jitcache.c",
+KERNEL_SRCS = ["map.cu", "reduce.cu", "ax.cu", "gs.cu", "nompk.cu"]
+LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c", "src/jitcache.c", "src/gs.c",
                 "backends/cuda.c"]
 
 
@@ -119,11 +119,13 @@ def build_tools(force=False):
     if force or _stale(out, [src, LIB / "libnomp.so"]):
         _run(["gcc", "-O2", "-I", str(ROOT / "include"), str(src), "-o", str(out), "-L", str(LIB), "-lnomp",
               f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
-    ex = OBJ / "cg_poisson"
-    ex_src = ROOT / "examples" / "cg_poisson.c"
-    if force or _stale(ex, [ex_src, LIB / "libnomp.so"]):
-        _run(["gcc", "-O2", "-I", str(ROOT / "include"), str(ex_src), "-o", str(ex), "-L", str(LIB), "-lnomp", "-lm",
-              f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
+    common = ROOT / "examples" / "sem_common.h"
+    for name in ("cg_poisson", "poisson_box"):
+        ex = OBJ / name
+        ex_src = ROOT / "examples" / f"{name}.c"
+        if force or _stale(ex, [ex_src, common, LIB / "libnomp.so"]):
+            _run(["gcc", "-O2", "-Wall", "-I", str(ROOT / "include"), str(ex_src), "-o", str(ex), "-L", str(LIB), "-lnomp", "-lm",
+                  f"-Wl,-rpath,{LIB}", "-Wl,-rpath,$ORIGIN/../lib"])
     return out
 
 

@@ -38,6 +38,8 @@ NOMP_CUDA_FAILURE = -512
 NOMPK_SYMBOLS = [
     "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes", "nompk_reduce_workspace_layout",
     "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_dot_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
+    "nompk_gs_create", "nompk_gs_unique", "nompk_gs_match_peer", "nompk_gs_finalize_setup", "nompk_gs_recv_offsets",
+    "nompk_gs_connect", "nompk_gs_apply", "nompk_gs_stats", "nompk_gs_destroy",
 ]
 NOMP_SYMBOLS = [
     "nomp_init", "nomp_update", "nomp_jit", "nomp_run", "nomp_sync", "nomp_get_err_str", "nomp_get_err_no",
@@ -45,7 +47,8 @@ NOMP_SYMBOLS = [
     # extensions declared in include/nomp-b200.h
     "nomp_b200_stream", "nomp_b200_update_async", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
     "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
-    "nomp_b200_jit_cache_stats", "nomp_b200_sha256_hex",
+    "nomp_b200_jit_cache_stats", "nomp_b200_sha256_hex", "nomp_b200_gs_setup", "nomp_b200_gs", "nomp_b200_gs_info",
+    "nomp_b200_gs_free",
 ]
 
 
@@ -99,6 +102,19 @@ def nompk() -> C.CDLL:
         lib.nompk_ax_set_variant.restype = C.c_int
         lib.nompk_ax_set_variant.argtypes = [C.c_int]
         lib.nompk_launch_count.restype = C.c_ulonglong
+        vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+        for name, args in (("nompk_gs_create", [vp, sz, C.POINTER(vp), vp]),
+                           ("nompk_gs_unique", [vp, C.POINTER(vp), C.POINTER(sz)]),
+                           ("nompk_gs_match_peer", [vp, i, i, vp, sz, C.POINTER(sz), vp]),
+                           ("nompk_gs_finalize_setup", [vp, i, i, C.POINTER(sz), vp]),
+                           ("nompk_gs_recv_offsets", [vp, C.POINTER(sz), C.POINTER(sz)]),
+                           ("nompk_gs_connect", [vp, C.POINTER(vp), C.POINTER(sz), vp]),
+                           ("nompk_gs_apply", [vp, i, i, vp, vp, vp]),
+                           ("nompk_gs_stats", [vp, C.POINTER(sz * 8)])):
+            getattr(lib, name).restype = i
+            getattr(lib, name).argtypes = args
+        lib.nompk_gs_destroy.restype = None
+        lib.nompk_gs_destroy.argtypes = [vp]
         _nompk = lib
     return _nompk
 
@@ -140,12 +156,40 @@ def nomp() -> C.CDLL:
         lib.nomp_b200_prog_info.argtypes = [C.c_int]
         lib.nomp_b200_exchange_blob.restype = C.c_int
         lib.nomp_b200_exchange_blob.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
+        lib.nomp_b200_gs_setup.restype = C.c_int
+        lib.nomp_b200_gs_setup.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        lib.nomp_b200_gs.restype = C.c_int
+        lib.nomp_b200_gs.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_char_p]
+        lib.nomp_b200_gs_info.restype = C.c_int
+        lib.nomp_b200_gs_info.argtypes = [C.c_int, C.POINTER(C.c_size_t * 8)]
+        lib.nomp_b200_gs_free.restype = C.c_int
+        lib.nomp_b200_gs_free.argtypes = [C.c_int]
         lib.nomp_b200_jit_cache_stats.restype = None
         lib.nomp_b200_jit_cache_stats.argtypes = [C.POINTER(C.c_ulonglong * 4)]
         lib.nomp_b200_sha256_hex.restype = None
         lib.nomp_b200_sha256_hex.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
         _nomp = lib
     return _nomp
+
+
+def gs_setup(ids) -> int:
+    """nomp_b200_gs_setup for a contiguous int64 numpy array of global ids; returns the handle."""
+    handle = C.c_int(-1)
+    check(nomp().nomp_b200_gs_setup(C.byref(handle), ids.ctypes.data, ids.size))
+    return handle.value
+
+
+def gs(handle: int, vec, op: str = "+") -> None:
+    """nomp_b200_gs on a mapped numpy array."""
+    kind = NOMP_FLOAT if vec.dtype.kind == "f" else NOMP_UINT if vec.dtype.kind == "u" else NOMP_INT
+    check(nomp().nomp_b200_gs(handle, vec.ctypes.data, vec.itemsize, kind, op.encode()))
+
+
+def gs_info(handle: int) -> dict:
+    out = (C.c_size_t * 8)()
+    check(nomp().nomp_b200_gs_info(handle, C.byref(out)))
+    return dict(zip(("n", "distinct", "groups", "copies", "shared_groups", "shared_pairs", "neighbours", "shared_ids"),
+                    (int(v) for v in out)))
 
 
 def jit_cache_stats() -> dict:

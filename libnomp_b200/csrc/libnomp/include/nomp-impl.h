@@ -125,6 +125,12 @@ int nomp_comm_size(void);
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
                         void *stream, int *published);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
+/* all[r] <- rank r's `bytes`-byte record, through files "<id file>.<tag>.<r>" (small setup-time records only) */
+int nomp_comm_allgather(const char *tag, const void *mine, void *all, size_t bytes);
+int nomp_comm_barrier(void);
+
+/* gather-scatter handles (src/gs.c) */
+void nomp_gs_finalize(void);
 
 /* on-disk JIT cache (src/jitcache.c) */
 typedef struct {

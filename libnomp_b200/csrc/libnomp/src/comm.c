@@ -36,6 +36,7 @@ static struct {
 
 static ncclComm_t comm = NULL;
 static int comm_rank = 0, comm_size = 1;
+static char comm_path[PATH_MAX + 1]; /* NOMP_COMM_ID_FILE of this communicator */
 
 /* NVLink one-shot all-reduce state */
 static struct {
@@ -127,6 +128,7 @@ int nomp_comm_init(int device) {
   nomp_check(nomp_b200_exchange_blob(path, rank, &id, sizeof(id)));
   check_nccl(nccl.CommInitRank(&comm, size, id, rank));
   comm_rank = rank, comm_size = size;
+  snprintf(comm_path, sizeof(comm_path), "%s", path);
 
   /* optional NVLink one-shot path: enabled only if EVERY rank managed to map every peer (min over ranks via NCCL) */
   p2p_setup(path, rank, size);
@@ -182,6 +184,47 @@ static void p2p_setup(const char *path, int rank, int size) {
   snprintf(name, sizeof(name), "%s.ipc.%d", path, rank);
   /* every rank must agree: all-reduce the flag through NCCL-free means is overkill -- a rank that failed simply keeps
    * enabled = 0 and the others would wait for it forever, so agreement is checked with one NCCL allreduce below */
+}
+
+/* Every rank publishes its record as "<id file>.<tag>.<rank>" and reads everybody else's.  The files are removed by
+ * their writers after a barrier, so a tag can only be used once per communicator. */
+int nomp_comm_allgather(const char *tag, const void *mine, void *all, size_t bytes) {
+  if (comm_size == 1) {
+    memcpy(all, mine, bytes);
+    return 0;
+  }
+  char name[PATH_MAX + 128];
+  void *copy = malloc(bytes);
+  memcpy(copy, mine, bytes);
+  snprintf(name, sizeof(name), "%s.%s.%d", comm_path, tag, comm_rank);
+  int err = nomp_b200_exchange_blob(name, 0, copy, bytes);
+  free(copy);
+  for (int r = 0; r < comm_size && !err; r++) {
+    char *slot = (char *)all + (size_t)r * bytes;
+    if (r == comm_rank) {
+      memcpy(slot, mine, bytes);
+      continue;
+    }
+    snprintf(name, sizeof(name), "%s.%s.%d", comm_path, tag, r);
+    err = nomp_b200_exchange_blob(name, 1, slot, bytes);
+  }
+  if (!err) err = nomp_comm_barrier();
+  snprintf(name, sizeof(name), "%s.%s.%d", comm_path, tag, comm_rank);
+  unlink(name);
+  return err;
+}
+
+/* Host-level barrier: one NCCL all-reduce on the default stream, waited for. */
+int nomp_comm_barrier(void) {
+  if (comm_size == 1) return 0;
+  static int *token = NULL;
+  if (token == NULL && cudaMalloc((void **)&token, sizeof(int)) != cudaSuccess)
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "NCCL failure: no memory for the barrier token.");
+  cudaMemset(token, 0, sizeof(int));
+  check_nccl(nccl.AllReduce(token, token, 1, ncclInt32, ncclSum, comm, 0));
+  if (cudaStreamSynchronize(0) != cudaSuccess)
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "NCCL failure: barrier did not complete.");
+  return 0;
 }
 
 int nomp_comm_finalize(void) {

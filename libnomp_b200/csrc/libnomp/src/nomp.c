@@ -597,6 +597,7 @@ NOMP_EXPORT const char *nomp_b200_prog_info(int id) {
 static int finalize_impl(int interpreter) {
   if (!initialized) return NOMP_FINALIZE_FAILURE; /* raw code, no log entry (reference src/nomp.c:671) */
 
+  nomp_gs_finalize();
   nomp_py_decref(&nomp.py_annotate);
   nomp_py_decref(&nomp.py_context);
 

@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         L.oracle_fill_uniform_f64.argtypes = [vp, sz, u64, d, d, sz]
         L.oracle_fill_i64.restype = None
         L.oracle_fill_i64.argtypes = [vp, sz, u64, sz]
+        L.oracle_gs.restype = i
+        L.oracle_gs.argtypes = [i, i, vp, sz, vp, i, vp]
         L.oracle_gll_derivative.restype = i
         L.oracle_gll_derivative.argtypes = [i, vp, vp]
         _lib = L
@@ -109,3 +111,28 @@ def gll_derivative(n):
     rc = lib().oracle_gll_derivative(n, _p(D), _p(x))
     assert rc == 0
     return D, x
+
+
+def gs(op, dtype, ids, v, segments=None):
+    """In-place gather-scatter of v under the global numbering ids (int64); segments = rank boundaries or None."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    assert v.dtype == NP_DTYPES[dtype] and v.flags.c_contiguous and ids.size == v.size
+    seg = None if segments is None else np.ascontiguousarray(segments, dtype=np.uint64)
+    rc = lib().oracle_gs(op, dtype, ids.ctypes.data, v.size, v.ctypes.data, 0 if seg is None else seg.size - 1, _p(seg))
+    assert rc == 0
+    return v
+
+
+def box_ids(n, ex, ey, ez, z0=0, nz=None):
+    """Global ids (1-based, lexicographic over the (n-1)*e + 1 points per direction) of the local degrees of freedom
+    of a box of ex x ey x ez hexahedral elements with n points per direction, element-major (x fastest), for the
+    elements with z index in [z0, z0 + nz): the slab of one rank."""
+    nz = ez if nz is None else nz
+    N = n - 1
+    px, py = N * ex + 1, N * ey + 1
+    e_z, e_y, e_x = np.meshgrid(np.arange(z0, z0 + nz), np.arange(ey), np.arange(ex), indexing="ij")
+    k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    gx = (e_x.reshape(-1, 1, 1, 1) * N + i[None]).astype(np.int64)
+    gy = (e_y.reshape(-1, 1, 1, 1) * N + j[None]).astype(np.int64)
+    gz = (e_z.reshape(-1, 1, 1, 1) * N + k[None]).astype(np.int64)
+    return (1 + gx + px * (gy + py * gz)).reshape(-1)

@@ -16,6 +16,10 @@
  *   - Ax: NOT in the reference (tests/sem.py:10-36 only tags loops).  Restated from the definition in
  *     SURVEY.md 8(a-17) / include/nompk.h (Nekbone ax_e: local_grad3 -> geometric factors -> local_grad3_t).
  *     PARITY UNPINNED by the reference for this function; tests pin it with analytic properties instead.
+ *   - gather-scatter: NOT in the reference either.  Restated from the definition of gslib's gs_op as Nekbone uses
+ *     it (every copy of a global id receives the combination of all copies; ids <= 0 do not take part), with the
+ *     association order include/nompk.h documents.  PARITY UNPINNED by the reference; pinned by closed forms
+ *     (multiplicity counts of a box mesh, idempotence of min/max, conservation of the sum).
  *
  * Pinning: tests/test_oracle.py checks these functions against every closed-form golden value the
  * reference tests hold for the path (tests/nomp-api-200/205/500/600-impl.h, listed in SURVEY.md 8c).
@@ -28,6 +32,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <pthread.h>
@@ -395,4 +400,78 @@ ORACLE_API int oracle_gll_derivative(int n, double *D, double *nodes_out) {
     }
   if (nodes_out) memcpy(nodes_out, x, sizeof(double) * n);
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* gather-scatter (direct stiffness summation)                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { long long id; size_t idx; } gs_key;
+static int gs_key_cmp(const void *a, const void *b) {
+  const gs_key *x = a, *y = b;
+  if (x->id != y->id) return x->id < y->id ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+#define GS_FN(NAME, T)                                                                              \
+  static T NAME##_op(int op, T a, T b) {                                                            \
+    switch (op) {                                                                                   \
+    case R_SUM: return (T)(a + b);                                                                  \
+    case R_PROD: return (T)(a * b);                                                                 \
+    case R_MIN: return b < a ? b : a;                                                               \
+    default: return b > a ? b : a;                                                                  \
+    }                                                                                               \
+  }                                                                                                 \
+  static void NAME(int op, const gs_key *k, size_t lo, size_t hi, T *v, int nseg, const size_t *seg) { \
+    /* copies [lo, hi) of one id, ascending index: fold inside each segment (rank), then the segment \
+     * partials in segment order */                                                                 \
+    T total = 0;                                                                                    \
+    int have_total = 0;                                                                             \
+    size_t i = lo;                                                                                  \
+    for (int s = 0; s < nseg && i < hi; s++) {                                                      \
+      if (k[i].idx >= seg[s + 1]) continue;                                                         \
+      T part = v[k[i].idx];                                                                         \
+      for (i++; i < hi && k[i].idx < seg[s + 1]; i++) part = NAME##_op(op, part, v[k[i].idx]);      \
+      total = have_total ? NAME##_op(op, total, part) : part;                                       \
+      have_total = 1;                                                                               \
+    }                                                                                               \
+    for (i = lo; i < hi; i++) v[k[i].idx] = total;                                                  \
+  }
+
+GS_FN(gs_i32, int32_t)
+GS_FN(gs_u32, uint32_t)
+GS_FN(gs_i64, int64_t)
+GS_FN(gs_u64, uint64_t)
+GS_FN(gs_f32, float)
+GS_FN(gs_f64, double)
+
+/* v[i] <- op over { v[j] : ids[j] == ids[i] } for ids[i] > 0.  The n values are the concatenation of nseg
+ * segments (one per rank), seg[0] = 0 <= ... <= seg[nseg] = n; nseg = 1 is the single-GPU case. */
+ORACLE_API int oracle_gs(int op, int dtype, const long long *ids, size_t n, void *v, int nseg, const size_t *seg) {
+  const size_t one[2] = {0, n};
+  if (nseg <= 0 || seg == NULL) nseg = 1, seg = one;
+  gs_key *k = malloc((n ? n : 1) * sizeof(*k));
+  if (!k) return -1;
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++)
+    if (ids[i] > 0) k[m].id = ids[i], k[m].idx = i, m++;
+  qsort(k, m, sizeof(*k), gs_key_cmp);
+  int err = 0;
+  for (size_t lo = 0; lo < m && !err;) {
+    size_t hi = lo + 1;
+    while (hi < m && k[hi].id == k[lo].id) hi++;
+    if (hi - lo > 1) {
+      switch (dtype) {
+      case O_I32: if (op == R_SUM || op == R_PROD) gs_u32(op, k, lo, hi, v, nseg, seg); else gs_i32(op, k, lo, hi, v, nseg, seg); break;
+      case O_U32: gs_u32(op, k, lo, hi, v, nseg, seg); break;
+      case O_I64: if (op == R_SUM || op == R_PROD) gs_u64(op, k, lo, hi, v, nseg, seg); else gs_i64(op, k, lo, hi, v, nseg, seg); break;
+      case O_U64: gs_u64(op, k, lo, hi, v, nseg, seg); break;
+      case O_F32: gs_f32(op, k, lo, hi, v, nseg, seg); break;
+      case O_F64: gs_f64(op, k, lo, hi, v, nseg, seg); break;
+      default: err = -1;
+      }
+    }
+    lo = hi;
+  }
+  free(k);
+  return err;
 }

@@ -128,6 +128,113 @@ def test_cg_example_on_two_gpus(tmp_path):
     assert per_rank[0][1:6] == per_rank[1][1:6], "ranks must see bit-identical reduction results"
 
 
+def _poisson_reference(ex, ey, ez, n, iters):
+    """examples/poisson_box.c on the host: oracle Ax, oracle gather-scatter, numpy dots."""
+    import numpy as np
+    from oracle import ffi
+    D, xi = ffi.gll_derivative(n)
+    N = n - 1
+    P = np.polynomial.legendre.Legendre.basis(N)(xi)
+    wt = 2.0 / (N * (N + 1.0) * P * P)
+    hx, hy, hz = 1.0 / ex, 1.0 / ey, 1.0 / ez
+    J = hx * hy * hz / 8.0
+    ids = ffi.box_ids(n, ex, ey, ez)
+    E = ex * ey * ez
+    e = np.arange(E)
+    e_x, e_y, e_z = e % ex, (e // ex) % ey, e // (ex * ey)
+    k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    X = (e_x[:, None, None, None] + 0.5 * (xi[i] + 1.0)[None]) * hx
+    Y = (e_y[:, None, None, None] + 0.5 * (xi[j] + 1.0)[None]) * hy
+    Z = (e_z[:, None, None, None] + 0.5 * (xi[k] + 1.0)[None]) * hz
+    B = np.broadcast_to((wt[i] * wt[j] * wt[k] * J)[None], X.shape)
+    ue = (np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)).reshape(-1)
+    px, py, pz = N * ex + 1, N * ey + 1, N * ez + 1
+    gid = ids - 1
+    gx, gy, gz = gid % px, (gid // px) % py, gid // (px * py)
+    mask = ((gx > 0) & (gx < px - 1) & (gy > 0) & (gy < py - 1) & (gz > 0) & (gz < pz - 1)).astype(np.float64)
+    g = np.zeros((E, 6, n ** 3))
+    Bf = np.ascontiguousarray(B).reshape(E, -1)
+    g[:, 0], g[:, 3], g[:, 5] = Bf * 4 / hx ** 2, Bf * 4 / hy ** 2, Bf * 4 / hz ** 2
+    g = np.ascontiguousarray(g.ravel())
+    Dm = np.ascontiguousarray(D.ravel())
+    c = 1.0 / ffi.gs(0, ffi.F64, ids, np.ones(ids.size))
+    r = ffi.gs(0, ffi.F64, ids, (Bf.reshape(-1) * 3 * np.pi ** 2 * ue).copy()) * mask
+    x, p = np.zeros_like(r), r.copy()
+    rr = float((r * r * c).sum())
+    out = [dict(rr0=rr)]
+    for _ in range(iters):
+        w = ffi.ax(n, p, g, Dm)
+        pap = float(p @ w)
+        w = ffi.gs(0, ffi.F64, ids, w)
+        alpha = rr / pap
+        x += alpha * p
+        r -= alpha * (mask * w)
+        rr_new = float((r * r * c).sum())
+        p = r + (rr_new / rr) * p
+        out.append(dict(pAp=pap, alpha=alpha, rr=rr_new))
+        rr = rr_new
+    return out
+
+
+def _run_poisson(world, dims, tmp_path, extra=()):
+    exe = ROOT / "libnomp_b200" / "build" / "poisson_box"
+    if not exe.exists():
+        pytest.skip("examples/poisson_box was not built")
+    idfile = f"/dev/shm/nomp-test-poisson-{os.getpid()}-{world}"
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
+        if world > 1:
+            env.update(NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(r), NOMP_COMM_ID_FILE=idfile)
+        procs.append(subprocess.Popen([str(exe), *[str(d) for d in dims], *extra, "--nomp-backend", "cuda", "--nomp-device", str(r),
+                                       "--nomp-verbose", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+    outs = [p.communicate(timeout=900)[0] for p in procs]
+    for f in [idfile] + [f"{idfile}.ipc.{r}" for r in range(world)]:
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    return [[json.loads(l) for l in o.splitlines() if l.startswith("{")] for o in outs]
+
+
+def test_poisson_box_solves_the_pde(tmp_path):
+    """examples/poisson_box.c: CG on the assembled operator (Ax + gather-scatter + mask).  The first iterations agree
+    with the same algorithm on the host (oracle Ax, oracle gather-scatter) and the converged solution is the exact
+    sin(pi x) sin(pi y) sin(pi z) up to the spectral discretisation error."""
+    dims = (3, 4, 2, 8)
+    lines = _run_poisson(1, dims, tmp_path)[0]
+    ref = _poisson_reference(*dims, 5)
+    assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
+    for it in range(5):
+        for key in ("pAp", "alpha", "rr"):
+            assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
+    final = lines[-1]
+    assert final["iterations"] < 500 and final["residual_rel"] <= 1e-10 and final["max_error"] < 1e-6, final
+    # refinement in the polynomial degree: the error of the discrete solution falls spectrally
+    coarse = _run_poisson(1, (2, 2, 2, 6), tmp_path)[0][-1]["max_error"]
+    fine = _run_poisson(1, (2, 2, 2, 10), tmp_path)[0][-1]["max_error"]
+    assert fine < 1e-3 * coarse, (coarse, fine)
+
+
+def test_poisson_box_on_two_gpus(tmp_path):
+    """Slab partition over two ranks: same scalars as the single-rank run (the interface plane is summed through
+    NVLink peer memory), same solution."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dims = (3, 4, 4, 8)
+    one = _run_poisson(1, dims, tmp_path)[0]
+    two = _run_poisson(2, dims, tmp_path)
+    assert two[0][0]["gs_shared_with_ranks"] == (7 * 3 + 1) * (7 * 4 + 1)
+    for rank_lines in two:
+        assert abs(rank_lines[0]["rr0"] - one[0]["rr0"]) <= 1e-12 * one[0]["rr0"]
+        for it in range(5):
+            for key in ("pAp", "alpha", "rr"):
+                assert abs(rank_lines[1 + it][key] - one[1 + it][key]) <= 1e-10 * abs(one[1 + it][key]), (it, key)
+        assert rank_lines[-1]["max_error"] < 1e-6 and rank_lines[-1]["iterations"] == two[0][-1]["iterations"]
+
+
 NCCL_WORKER = r"""
 import ctypes as C, os, sys
 import numpy as np
