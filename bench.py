@@ -174,6 +174,25 @@ class ClockSampler:
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 
+def box_slab_ids(n, ex, ey, ez, z0, nz):
+    """Global ids (1-based, lexicographic over the (n-1)*e + 1 points per direction) of the degrees of freedom of the
+    element layers [z0, z0 + nz) of an ex x ey x ez box, element-major with x fastest (the layout of u and w)."""
+    import numpy as np
+    N = n - 1
+    px, py = N * ex + 1, N * ey + 1
+    pt = np.arange(n, dtype=np.int64)
+    gx = (np.arange(ex, dtype=np.int64)[:, None] * N + pt[None]).reshape(1, 1, ex, 1, 1, n)
+    gy = (np.arange(ey, dtype=np.int64)[:, None] * N + pt[None]).reshape(1, ey, 1, 1, n, 1)
+    gz = (np.arange(z0, z0 + nz, dtype=np.int64)[:, None] * N + pt[None]).reshape(nz, 1, 1, n, 1, 1)
+    out = np.empty((nz, ey, ex, n, n, n), dtype=np.int64)
+    np.multiply(gz, py, out=out)
+    out += gy
+    out *= px
+    out += gx
+    out += 1
+    return out.reshape(-1)
+
+
 def gll_derivative_matrix(n: int):
     """D[a][l] = l_l'(x_a) on the n Gauss-Lobatto-Legendre nodes (numpy; the product path does not touch oracle/)."""
     import numpy as np
@@ -542,6 +561,36 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
                                 "frac_of_peak": ndof * 88 / ms_f / 1e6 / peak, "pAp_rel_diff_vs_unfused": rel}
     except Exception as exc:
         out["cg_step_fused"] = {"error": repr(exc)}
+
+    # gather-scatter (row f): the mesh seen as a 64 x 64 x (64 / ranks) slab of a 64^3 box of elements, lexicographic
+    # global numbering; "min" so that repeated application leaves the data alone
+    try:
+        ex = ey = 64
+        nz = int(E_c.value) // (ex * ey)
+        if nz * ex * ey != int(E_c.value) or nz * world != 64:
+            raise ValueError("gather-scatter extra needs E_total = 64^3 split into whole layers")
+        ids = box_slab_ids(N_POINTS, ex, ey, 64, rank * nz, nz)
+        h = capi.gs_setup(ids)
+        del ids
+        info = capi.gs_info(h)
+        gs_call = lambda: capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))  # noqa: E731
+        ms_gs = timed(gs_call, 20)
+        alg = info["copies"] * 20 + (info["groups"] + 1) * 4
+        out["gather_scatter"] = {"what": "nomp_b200_gs(min) on this rank's slab of a 64^3-element box, N=7", "ms": ms_gs,
+                                 "groups": info["groups"], "copies": info["copies"], "ids_shared_with_other_ranks": info["shared_ids"],
+                                 "algorithmic_bytes": alg, "GB/s_per_gpu": alg / ms_gs / 1e6, "frac_of_peak": alg / ms_gs / 1e6 / peak,
+                                 "note": "algorithmic = 8 B read + 8 B written + 4 B index per shared copy, 4 B per group; the DRAM traffic is about 1.5x that (whole 64-byte lines of the vector are touched)"}
+        if "error" not in out.get("cg_step_fused", {}):
+            def cg_step_assembled():
+                capi.check(capi.run(axdot_id, wp, up, gp, Dp, E_c, s2))
+                capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))
+                capi.check(capi.run(axpy_id, wp, up, alpha, nd))
+            ms_a = timed(cg_step_assembled, 20)
+            out["cg_step_assembled"] = {"what": "Ax with p.Ap fused + gather-scatter (interface planes over NVLink) + axpy", "ms": ms_a,
+                                        "GDOF/s": ndof * world / ms_a / 1e6}
+        capi.check(lib.nomp_b200_gs_free(h))
+    except Exception as exc:
+        out["gather_scatter"] = {"error": repr(exc)}
 
     ms = timed(cg_step, 20)
     total_dof = ndof * world

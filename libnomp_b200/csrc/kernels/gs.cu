@@ -21,8 +21,6 @@
 // With one rank the second launch does not happen.
 #include <cub/cub.cuh>
 
-#include <stdlib.h>
-
 #include <vector>
 
 #include "nompk_common.cuh"
@@ -39,7 +37,6 @@ struct nompk_gs {
   std::vector<size_t> recv_off, send_off;
   bool finalized = false;
   size_t G = 0, nnz = 0, Q = 0, R = 0, total_shared = 0;
-  size_t pairs = 0;  // leading groups that are plain local pairs (two copies, not shared with a peer)
   unsigned *offsets = nullptr, *indices = nullptr;
   int *remote_slot = nullptr;
   unsigned *rgroup = nullptr, *roffsets = nullptr, *rpos = nullptr;
@@ -121,17 +118,10 @@ __global__ void classify_kernel(const long long *__restrict__ ids, const unsigne
   rcount[u] = on ? rc : 0;
 }
 
-// sort key of a group: local pairs (two copies, no peer) first, then by the position of the first copy
-__global__ void group_key_kernel(const unsigned *__restrict__ sel, const unsigned *__restrict__ run_start,
-                                 const unsigned *__restrict__ sorted_idx, const unsigned *__restrict__ count,
-                                 const unsigned *__restrict__ rcount, unsigned long long *__restrict__ key,
-                                 unsigned *__restrict__ is_pair, size_t G, int pairs_first) {
+__global__ void first_index_kernel(const unsigned *__restrict__ sel, const unsigned *__restrict__ run_start,
+                                   const unsigned *__restrict__ sorted_idx, unsigned *__restrict__ first, size_t G) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  const unsigned u = sel[g];
-  const bool pair = pairs_first && count[u] == 2 && rcount[u] == 0;
-  is_pair[g] = pair;
-  key[g] = ((unsigned long long)(pair ? 0 : 1) << 32) | sorted_idx[run_start[u]];
+  if (g < G) first[g] = sorted_idx[run_start[sel[g]]];
 }
 
 __global__ void group_sizes_kernel(const unsigned *__restrict__ order, const unsigned *__restrict__ count,
@@ -181,29 +171,19 @@ struct GsView {
   void *const *peer_xchg;
   const int *neighbours;
   size_t G, Q, values_base;  // values_base: byte offset of this call's slot in an exchange buffer
-  size_t vec_pairs;          // leading local pairs handled two per thread (even)
-  unsigned pair_blocks;      // CTAs that do so
   int n_neighbours, rank, world, slot;
   unsigned long long seq;
   unsigned long long *error_host;
 };
 
+// One group per thread.  Two other schedules were measured on a box mesh of 1.3e8 points (0.58 ms as written) and
+// dropped: plain local pairs moved to the front and handled two per thread from one 16-byte index load (0.66 ms: the
+// pairs and the edge / vertex groups of a cache line are then swept in two passes, DRAM traffic 3.5 GB instead of
+// 2.5 GB), and four groups per thread with all loads of a level issued together (0.61 ms).  The traffic is what it
+// has to be -- faces normal to the fastest index touch both 32-byte sectors of every 64-byte line, so the whole
+// vector is read and written once (ncu: 1.51 GB read, 1.01 GB written for a 1.07 GB vector) -- at 4.35 TB/s.
 template <int OP, typename T> __global__ void __launch_bounds__(kGsThreads) gs_local_kernel(T *__restrict__ v, GsView s) {
-  if (blockIdx.x < s.pair_blocks) {
-    // Local pairs (a point on the face between two elements of this rank: 85 % of the groups of a hexahedral mesh):
-    // groups 0 .. vec_pairs-1 have offsets 2g, so one 16-byte load brings the four indices of two pairs and the four
-    // values are in flight together.
-    const size_t t = (size_t)blockIdx.x * kGsThreads + threadIdx.x;
-    if (2 * t < s.vec_pairs) {
-      const uint4 ix = __ldg(reinterpret_cast<const uint4 *>(s.indices) + t);
-      const T a0 = v[ix.x], a1 = v[ix.y], b0 = v[ix.z], b1 = v[ix.w];
-      const T sa = combine<OP, T>(a0, a1), sb = combine<OP, T>(b0, b1);
-      v[ix.x] = sa, v[ix.y] = sa, v[ix.z] = sb, v[ix.w] = sb;
-    }
-  }
-  const size_t g = blockIdx.x < s.pair_blocks
-                       ? s.G
-                       : s.vec_pairs + (size_t)(blockIdx.x - s.pair_blocks) * kGsThreads + threadIdx.x;
+  const size_t g = (size_t)blockIdx.x * kGsThreads + threadIdx.x;
   if (g < s.G) {
     const unsigned b = s.offsets[g], e = s.offsets[g + 1];
     T acc = v[s.indices[b]];
@@ -292,9 +272,7 @@ template <int OP, typename T> int launch_gs(nompk_gs *gs, void *v, unsigned long
   s.partial = gs->partial, s.ticket = gs->ticket, s.recv_off = gs->d_recv_off, s.send_off = gs->d_send_off;
   s.peer_xchg = gs->d_peer_xchg, s.neighbours = gs->d_neighbours;
   s.G = gs->G, s.Q = gs->Q;
-  s.vec_pairs = gs->pairs & ~(size_t)1;
-  s.pair_blocks = (unsigned)((s.vec_pairs / 2 + kGsThreads - 1) / kGsThreads);
-  const unsigned blocks = s.pair_blocks + (unsigned)((gs->G - s.vec_pairs + kGsThreads - 1) / kGsThreads);
+  const unsigned blocks = (unsigned)((gs->G + kGsThreads - 1) / kGsThreads);
   s.slot = (int)(gs->seq & 1ull);
   s.values_base = flags_bytes(gs->world) + (size_t)s.slot * gs->total_shared * 8;
   s.n_neighbours = gs->n_neighbours, s.rank = gs->rank, s.world = gs->world;
@@ -482,8 +460,7 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
   const size_t U = gs->n_unique;
   unsigned **d_pos = nullptr;
   unsigned char *active = nullptr;
-  unsigned *iota = nullptr, *rcount = nullptr, *sel = nullptr, *nsel = nullptr, *is_pair = nullptr, *pair_scan = nullptr, *order = nullptr;
-  unsigned long long *key = nullptr, *key_sorted = nullptr;
+  unsigned *iota = nullptr, *rcount = nullptr, *sel = nullptr, *nsel = nullptr, *first = nullptr, *first_sorted = nullptr, *order = nullptr;
   unsigned *cnt = nullptr, *rcnt = nullptr, *rflag = nullptr, *rstart = nullptr, *rslot = nullptr;
   void *tmp = nullptr;
   auto body = [&]() -> int {
@@ -513,10 +490,8 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
     }
     gs->G = G;
     // order the groups by their first local copy
-    if (int e = dev_alloc(&key, G)) return e;
-    if (int e = dev_alloc(&key_sorted, G)) return e;
-    if (int e = dev_alloc(&is_pair, G)) return e;
-    if (int e = dev_alloc(&pair_scan, G + 1)) return e;
+    if (int e = dev_alloc(&first, G)) return e;
+    if (int e = dev_alloc(&first_sorted, G)) return e;
     if (int e = dev_alloc(&order, G)) return e;
     if (int e = dev_alloc(&cnt, G)) return e;
     if (int e = dev_alloc(&rcnt, G)) return e;
@@ -525,20 +500,14 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
     if (int e = dev_alloc(&rslot, G + 1)) return e;
     if (int e = dev_alloc(&gs->offsets, G + 1)) return e;
     if (int e = dev_alloc(&gs->remote_slot, G)) return e;
-    size_t nnz = 0, R = 0, Q = 0, P = 0;
-    // Experiment switch: NOMPK_GS_PAIRS_FIRST=1 moves the plain local pairs to the front, where one thread handles two
-    // of them from a single 16-byte index load.  Measured slower on a box mesh (0.66 vs 0.58 ms at 1.3e8 points): the
-    // pairs and the edge / vertex groups of one cache line are then swept in two passes instead of one.
-    const char *pf = getenv("NOMPK_GS_PAIRS_FIRST");
-    const int pairs_first = pf && pf[0] == '1';
+    size_t nnz = 0, R = 0, Q = 0;
     if (G > 0) {
-      group_key_kernel<<<blocks_for(G), 256, 0, stream>>>(sel, gs->run_start, gs->sorted_idx, gs->run_count, rcount, key, is_pair, G, pairs_first);
-      NOMPK_LAUNCH_CHECK("group_key_kernel");
-      if (int e = exclusive_sum(is_pair, pair_scan, G, &P, stream)) return e;
+      first_index_kernel<<<blocks_for(G), 256, 0, stream>>>(sel, gs->run_start, gs->sorted_idx, first, G);
+      NOMPK_LAUNCH_CHECK("first_index_kernel");
       size_t bytes = 0;
-      NOMPK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key, key_sorted, sel, order, G, 0, 33, stream));
+      NOMPK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, first, first_sorted, sel, order, G, 0, 32, stream));
       NOMPK_CUDA_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
-      NOMPK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, bytes, key, key_sorted, sel, order, G, 0, 33, stream));
+      NOMPK_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, bytes, first, first_sorted, sel, order, G, 0, 32, stream));
       group_sizes_kernel<<<blocks_for(G), 256, 0, stream>>>(order, gs->run_count, rcount, cnt, rcnt, rflag, G);
       NOMPK_LAUNCH_CHECK("group_sizes_kernel");
       if (int e = exclusive_sum(cnt, gs->offsets, G, &nnz, stream)) return e;
@@ -551,7 +520,7 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
       set_error("nompk_gs_finalize_setup: more than 2^32 shared copies");
       return NOMPK_EUNSUPPORTED;
     }
-    gs->nnz = nnz, gs->R = R, gs->Q = Q, gs->pairs = P;
+    gs->nnz = nnz, gs->R = R, gs->Q = Q;
     if (int e = dev_alloc(&gs->indices, nnz)) return e;
     if (int e = dev_alloc(&gs->rgroup, Q)) return e;
     if (int e = dev_alloc(&gs->roffsets, Q + 1)) return e;
@@ -590,7 +559,7 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
   };
   const int err = body();
   cudaStreamSynchronize(stream);
-  void *scratch[] = {d_pos, iota, active, rcount, sel, nsel, key, key_sorted, is_pair, pair_scan, order, cnt, rcnt, rflag, rstart, rslot, tmp};
+  void *scratch[] = {d_pos, iota, active, rcount, sel, nsel, first, first_sorted, order, cnt, rcnt, rflag, rstart, rslot, tmp};
   for (void *p : scratch) cudaFree(p);
   if (err) return err;
   // setup-only arrays are no longer needed
