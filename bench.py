@@ -361,7 +361,7 @@ def run_ours(args):
     # (b) pipelined: the arrays are mapped in NCHUNK element blocks; per block nomp_b200_update_async(u_c, TO),
     # nomp_run on the block, nomp_b200_update_async(w_c, FROM); one nomp_sync per step.  Both PCIe directions and the
     # kernel overlap.  The big mappings of u, w, g are released first (same host buffers, new device images).
-    NCHUNK = 8
+    NCHUNK = int(os.environ.get("NOMP_BENCH_E2E_BLOCKS", "8"))
     Ec = E // NCHUNK
     e2e_value, e2e_note = e2e_blocking, "blocking only (E per GPU not divisible into 8 blocks)"
     if Ec * NCHUNK == E and Ec > 0:

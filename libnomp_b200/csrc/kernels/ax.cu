@@ -71,6 +71,15 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// Groups whose lanes outnumber their work items (n = 10: 160 lanes, 150 items) let the surplus lanes mirror the last
+// item: same loads, same arithmetic, same stores of the same values to the same addresses -- control flow stays
+// uniform (see ax_kernel).  Where a stage reads and then overwrites one shared-memory location (S4, S7) the mirrors
+// and their original sit in the same warp; this fence orders all the reads of the warp before its writes without
+// relying on lock-step execution.  Compiles to nothing for groups without surplus lanes.
+template <bool kHasMirrors> __device__ __forceinline__ void mirror_fence() {
+  if constexpr (kHasMirrors) __syncwarp();
+}
+
 template <int GL> __device__ __forceinline__ void element_sync(int grp) {
   if constexpr (GL == 32) {
     __syncwarp();
@@ -326,6 +335,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double ey = fma(ur.y, wr.y, fma(us.y, ws.y, ut.y * wt.y));
         energy = fma(dot_weight, ex + ey, energy);
       }
+      mirror_fence<G * T < GL>();
       B1[a] = wr;
       B2[a] = ws;
       col[k] = wt;
@@ -361,7 +371,9 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       static_for(SeqN{}, [&](auto A) {
         constexpr int j = decltype(A)::value;
         const int a = L::at(q, j, p);
-        B0[a] = dot_pair<N, true, j>(in, B0[a], z7);
+        const double2 sum = dot_pair<N, true, j>(in, B0[a], z7);
+        mirror_fence<G * T < GL>();
+        B0[a] = sum;
       });
     }
     element_sync<GL>(grp);

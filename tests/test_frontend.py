@@ -400,3 +400,35 @@ def test_grid_expression_grammar_matches_the_c_evaluator():
     for bad in ["N +", "foo", "(N", "N / 0", "max(N)", "N N"]:
         out = C.c_long()
         assert lib.nomp_gridexpr_eval(bad.encode(), names, values, 3, C.byref(out)) != 0, bad
+
+
+def test_nomp_sem_annotations_give_one_block_per_element():
+    """libnomp_b200/python/nomp_sem.py honours dof_loop (the reference's tests/sem.py drops it): an operator that is
+    not the canonical Ax string -- here with a mass term added -- gets one thread block per element, the dof loops as
+    thread axes in clause order, and its per-element temporaries in shared memory between two barriers."""
+    import nomp_sem
+    src = families.AX_KERNEL_SOURCE.replace("const double *D, int E, int n)", "const double *D, const double *h, int E, int n)")
+    src = src.replace("nomp_ax(", "helmholtz(")
+    point = "e * n * n * n + k * n * n + j * n + i"
+    assert f"w[{point}] = acc;" in src
+    src = src.replace(f"w[{point}] = acc;", f"w[{point}] = acc + h[{point}] * u[{point}];")
+    k = nb.c_to_loopy(src, "cuda")
+    for key, loop in (("element_loop", "e"), ("dof_loop", "i"), ("dof_loop", "j"), ("dof_loop", "k"), ("dof_loop", "zz")):
+        k = nomp_sem.annotate(k, {key: loop}, CTX)
+    assert k.tags() == {"e": "g.0", "i": "l.0", "j": "l.1", "k": "l.2", "l": None}
+    with pytest.raises(ValueError):
+        nomp_sem.annotate(k, {"dof_loop": "l"}, CTX)
+    k = nb.fix_parameters(k, {"n": 6})
+    text = nb.get_knl_src(k, CTX)
+    header, _, cuda = text.partition("\n")
+    assert "family=generic" in header and "kind=nvrtc" in header
+    assert nb.get_grid_size(k, CTX) == (("E", "1", "1"), ("6", "6", "6"))
+    for name in ("ur", "us", "ut"):
+        assert f"__shared__ double {name}[6][6][6];" in cuda
+    assert cuda.count("__syncthreads();") == 2
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log
+    # grid_loop behaves like the reference script
+    flat = nb.c_to_loopy("void f(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] += b[i]; }")
+    flat = nomp_sem.annotate(flat, {"grid_loop": "i"}, CTX)
+    assert flat.tags() == {"i_outer": "g.0", "i_inner": "l.0"}
