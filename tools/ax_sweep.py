@@ -78,6 +78,33 @@ def main():
                      gbs=gb / med * 1e3, frac=gb / med * 1e3 / PEAK)
             lib.nompk_ax_set_variant(0)
             del u, g, w
+    if "axrobust" in which:
+        # Interleaved rounds: on a power-capped board the same kernel moves by several per cent between one timing and
+        # the next, so every variant is timed once per round, round after round, and the median over rounds is kept.
+        variants = [int(v) for v in os.environ.get("AX_VARIANTS", "0,1,7,8,11").split(",")]
+        rounds = int(os.environ.get("AX_ROUNDS", "7"))
+        for n, E in ((10, 131072), (12, 65536), (8, 262144), (6, 524288)):
+            n3 = n ** 3
+            u = torch.rand(E * n3, dtype=torch.float64, device="cuda")
+            g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
+            D = torch.rand(n * n, dtype=torch.float64, device="cuda")
+            w = torch.empty_like(u)
+            samples = {v: [] for v in variants}
+
+            def run():
+                capi.nompk_check(lib.nompk_ax_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(), 0, st))
+            for _ in range(rounds):
+                for v in variants:
+                    lib.nompk_ax_set_variant(v)
+                    samples[v].append(timeit(run, reps=10, warm=3)[0])
+            lib.nompk_ax_set_variant(0)
+            gb = E * n3 * 64 / 1e9
+            for v in variants:
+                ts = sorted(samples[v])
+                med = ts[len(ts) // 2]
+                emit(kernel="ax_interleaved", n=n, E=E, variant=v, rounds=rounds, ms=med, ms_min=ts[0], ms_max=ts[-1],
+                     gdofs=E * n3 / med / 1e6, frac=gb / med * 1e3 / PEAK)
+            del u, g, w
     if "map" in which:
         for lg in (20, 24, 26, 28):
             n = 1 << lg
