@@ -442,7 +442,10 @@ def run_ours(args):
                              f"({dt:.1f} s); stand-in for libnomp's OpenCL backend on pocl, not installable here"}
 
     allreduce_path = "nvlink-kernel" if lib.nomp_b200_comm_uses_nvlink_kernel() else ("nccl" if world > 1 else "none")
-    capi.check(lib.nomp_finalize_excluding_interpreter())
+    try:
+        capi.check(lib.nomp_finalize_excluding_interpreter())
+    except Exception as exc:  # a failure while shutting down must not cost the measured line
+        extras = dict(extras, finalize_error=repr(exc))
     if world > 1:
         dist.barrier()
         if rank == 0:   # rendezvous files of this job
@@ -563,7 +566,9 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
         out["cg_step_fused"] = {"error": repr(exc)}
 
     # gather-scatter (row f): the mesh seen as a 64 x 64 x (64 / ranks) slab of a 64^3 box of elements, lexicographic
-    # global numbering; "min" so that repeated application leaves the data alone
+    # global numbering; "min" so that repeated application leaves the data alone.  Every rank reports whether its setup
+    # worked and all ranks agree before anything collective is timed.
+    h, gs_error = None, None
     try:
         ex = ey = 64
         nz = int(E_c.value) // (ex * ey)
@@ -572,25 +577,38 @@ def run_extras(args, capi, lib, torch, dist, world, rank, stream, up, wp, gp, Dp
         ids = box_slab_ids(N_POINTS, ex, ey, 64, rank * nz, nz)
         h = capi.gs_setup(ids)
         del ids
-        info = capi.gs_info(h)
-        gs_call = lambda: capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))  # noqa: E731
-        ms_gs = timed(gs_call, 20)
-        alg = info["copies"] * 20 + (info["groups"] + 1) * 4
-        out["gather_scatter"] = {"what": "nomp_b200_gs(min) on this rank's slab of a 64^3-element box, N=7", "ms": ms_gs,
-                                 "groups": info["groups"], "copies": info["copies"], "ids_shared_with_other_ranks": info["shared_ids"],
-                                 "algorithmic_bytes": alg, "GB/s_per_gpu": alg / ms_gs / 1e6, "frac_of_peak": alg / ms_gs / 1e6 / peak,
-                                 "note": "algorithmic = 8 B read + 8 B written + 4 B index per shared copy, 4 B per group; the DRAM traffic is about 1.5x that (whole 64-byte lines of the vector are touched)"}
-        if "error" not in out.get("cg_step_fused", {}):
-            def cg_step_assembled():
-                capi.check(capi.run(axdot_id, wp, up, gp, Dp, E_c, s2))
-                capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))
-                capi.check(capi.run(axpy_id, wp, up, alpha, nd))
-            ms_a = timed(cg_step_assembled, 20)
-            out["cg_step_assembled"] = {"what": "Ax with p.Ap fused + gather-scatter (interface planes over NVLink) + axpy", "ms": ms_a,
-                                        "GDOF/s": ndof * world / ms_a / 1e6}
-        capi.check(lib.nomp_b200_gs_free(h))
     except Exception as exc:
-        out["gather_scatter"] = {"error": repr(exc)}
+        gs_error = repr(exc)
+    ok = torch.tensor([0 if gs_error else 1], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
+        try:
+            info = capi.gs_info(h)
+            gs_call = lambda: capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))  # noqa: E731
+            ms_gs = timed(gs_call, 20)
+            alg = info["copies"] * 20 + (info["groups"] + 1) * 4
+            out["gather_scatter"] = {"what": "nomp_b200_gs(min) on this rank's slab of a 64^3-element box, N=7", "ms": ms_gs,
+                                     "groups": info["groups"], "copies": info["copies"], "ids_shared_with_other_ranks": info["shared_ids"],
+                                     "algorithmic_bytes": alg, "GB/s_per_gpu": alg / ms_gs / 1e6, "frac_of_peak": alg / ms_gs / 1e6 / peak,
+                                     "note": "algorithmic = 8 B read + 8 B written + 4 B index per shared copy, 4 B per group; the DRAM traffic is about 1.5x that (whole 64-byte lines of the vector are touched)"}
+            if "error" not in out.get("cg_step_fused", {"error": 1}):
+                def cg_step_assembled():
+                    capi.check(capi.run(axdot_id, wp, up, gp, Dp, E_c, s2))
+                    capi.check(lib.nomp_b200_gs(h, wp, 8, capi.NOMP_FLOAT, b"min"))
+                    capi.check(capi.run(axpy_id, wp, up, alpha, nd))
+                ms_a = timed(cg_step_assembled, 20)
+                out["cg_step_assembled"] = {"what": "Ax with p.Ap fused + gather-scatter (interface planes over NVLink) + axpy", "ms": ms_a,
+                                            "GDOF/s": ndof * world / ms_a / 1e6}
+        except Exception as exc:
+            out["gather_scatter"] = {"error": repr(exc)}
+    else:
+        out["gather_scatter"] = {"error": gs_error or "setup failed on another rank"}
+    if h is not None:
+        try:
+            capi.check(lib.nomp_b200_gs_free(h))
+        except Exception as exc:
+            out.setdefault("gather_scatter", {})["free_error"] = repr(exc)
 
     ms = timed(cg_step, 20)
     total_dof = ndof * world

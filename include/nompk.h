@@ -155,7 +155,8 @@ int nompk_ax_set_variant(int variant);
  *                            (zero-filled; 0 when no id is shared with a peer)
  *   nompk_gs_recv_offsets    offsets[r] / counts[r]: where rank r's segment starts in MY exchange buffer (in values)
  *   nompk_gs_connect         peer_xchg[r] = rank r's exchange buffer as mapped into this process (own buffer at
- *                            [rank]); send_offsets[r] = what rank r reported as ITS offsets[my rank]
+ *                            [rank]); send_offsets[r] = what rank r reported as ITS offsets[my rank];
+ *                            peer_totals[r] = the sum of rank r's counts (the stride of the two slots in ITS buffer)
  * Single-GPU use: create -> finalize_setup(0, 1) -> apply.
  *
  * nompk_gs_apply: asynchronous on `stream`, two launches (one when nothing is shared with a peer).  Copies of one id
@@ -170,7 +171,8 @@ int nompk_gs_match_peer(nompk_gs_t *gs, int peer, int world, const long long *pe
                         size_t *n_shared, void *stream);
 int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size_t *xchg_bytes, void *stream);
 int nompk_gs_recv_offsets(const nompk_gs_t *gs, size_t *offsets, size_t *counts);
-int nompk_gs_connect(nompk_gs_t *gs, void *const *peer_xchg, const size_t *send_offsets, void *stream);
+int nompk_gs_connect(nompk_gs_t *gs, void *const *peer_xchg, const size_t *send_offsets, const size_t *peer_totals,
+                     void *stream);
 int nompk_gs_apply(nompk_gs_t *gs, nompk_red_op_t op, nompk_dtype_t dt, void *v, unsigned long long *error_host_mapped,
                    void *stream);
 /* {n, distinct ids, groups, copies in groups, groups shared with peers, (group, peer) pairs, neighbours, shared ids} */

@@ -108,7 +108,7 @@ def nompk() -> C.CDLL:
                            ("nompk_gs_match_peer", [vp, i, i, vp, sz, C.POINTER(sz), vp]),
                            ("nompk_gs_finalize_setup", [vp, i, i, C.POINTER(sz), vp]),
                            ("nompk_gs_recv_offsets", [vp, C.POINTER(sz), C.POINTER(sz)]),
-                           ("nompk_gs_connect", [vp, C.POINTER(vp), C.POINTER(sz), vp]),
+                           ("nompk_gs_connect", [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), vp]),
                            ("nompk_gs_apply", [vp, i, i, vp, vp, vp]),
                            ("nompk_gs_stats", [vp, C.POINTER(sz * 8)])):
             getattr(lib, name).restype = i

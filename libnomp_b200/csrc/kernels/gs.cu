@@ -170,7 +170,8 @@ struct GsView {
   const size_t *recv_off, *send_off;
   void *const *peer_xchg;
   const int *neighbours;
-  size_t G, Q, values_base;  // values_base: byte offset of this call's slot in an exchange buffer
+  size_t G, Q, values_base;  // values_base: byte offset of this call's slot in THIS rank's exchange buffer
+  size_t flags_bytes;        // size of the flag block in front of the values of every exchange buffer
   int n_neighbours, rank, world, slot;
   unsigned long long seq;
   unsigned long long *error_host;
@@ -197,7 +198,8 @@ template <int OP, typename T> __global__ void __launch_bounds__(kGsThreads) gs_l
       s.partial[q] = word;
       for (unsigned k = s.roffsets[q]; k < s.roffsets[q + 1]; k++) {
         const int r = s.rpeer[k];
-        char *dst = static_cast<char *>(s.peer_xchg[r]) + s.values_base + (s.send_off[r] + s.rpos[k]) * 8;
+        // the slot of this call in the PEER's buffer: its stride is the peer's number of shared ids, not ours
+        char *dst = static_cast<char *>(s.peer_xchg[r]) + s.flags_bytes + (s.send_off[s.slot * s.world + r] + s.rpos[k]) * 8;
         *reinterpret_cast<volatile unsigned long long *>(dst) = word;
       }
       __threadfence_system();
@@ -274,7 +276,8 @@ template <int OP, typename T> int launch_gs(nompk_gs *gs, void *v, unsigned long
   s.G = gs->G, s.Q = gs->Q;
   const unsigned blocks = (unsigned)((gs->G + kGsThreads - 1) / kGsThreads);
   s.slot = (int)(gs->seq & 1ull);
-  s.values_base = flags_bytes(gs->world) + (size_t)s.slot * gs->total_shared * 8;
+  s.flags_bytes = flags_bytes(gs->world);
+  s.values_base = s.flags_bytes + (size_t)s.slot * gs->total_shared * 8;
   s.n_neighbours = gs->n_neighbours, s.rank = gs->rank, s.world = gs->world;
   s.seq = gs->seq, s.error_host = error_host;
   gs_local_kernel<OP, T><<<blocks, kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
@@ -547,7 +550,7 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
     }
     gs->total_shared = off, gs->n_neighbours = (int)neighbours.size();
     if (int e = dev_alloc(&gs->d_recv_off, (size_t)world)) return e;
-    if (int e = dev_alloc(&gs->d_send_off, (size_t)world)) return e;
+    if (int e = dev_alloc(&gs->d_send_off, (size_t)2 * world)) return e;
     if (int e = dev_alloc(&gs->d_peer_xchg, (size_t)world)) return e;
     if (int e = dev_alloc(&gs->d_neighbours, (size_t)world)) return e;
     NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->d_recv_off, gs->recv_off.data(), world * sizeof(size_t), cudaMemcpyHostToDevice, stream));
@@ -582,21 +585,31 @@ extern "C" int nompk_gs_recv_offsets(const nompk_gs_t *gs, size_t *offsets, size
   return NOMPK_OK;
 }
 
-extern "C" int nompk_gs_connect(nompk_gs_t *gs, void *const *peer_xchg, const size_t *send_offsets, void *stream_) {
+extern "C" int nompk_gs_connect(nompk_gs_t *gs, void *const *peer_xchg, const size_t *send_offsets,
+                                const size_t *peer_totals, void *stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!gs || !gs->finalized || !peer_xchg || !send_offsets) {
+  if (!gs || !gs->finalized || !peer_xchg || !send_offsets || !peer_totals) {
     set_error("nompk_gs_connect: bad arguments");
     return NOMPK_EINVAL;
   }
+  // where this rank's segment starts in rank r's buffer, per slot: slot * (ids rank r shares in total) + offset
+  std::vector<size_t> table((size_t)2 * gs->world, 0);
   for (int r = 0; r < gs->world; r++) {
     if ((gs->shared[r] > 0 || r == gs->rank) && gs->Q > 0 && peer_xchg[r] == nullptr) {
       set_error("nompk_gs_connect: no exchange buffer for rank %d", r);
       return NOMPK_EINVAL;
     }
+    if (gs->shared[r] > 0 && send_offsets[r] + gs->shared[r] > peer_totals[r]) {
+      set_error("nompk_gs_connect: segment [%zu, %zu) does not fit rank %d's %zu shared ids", send_offsets[r],
+                send_offsets[r] + gs->shared[r], r, peer_totals[r]);
+      return NOMPK_EINVAL;
+    }
     gs->send_off[r] = send_offsets[r];
+    table[r] = send_offsets[r];
+    table[(size_t)gs->world + r] = peer_totals[r] + send_offsets[r];
   }
   NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->d_peer_xchg, peer_xchg, gs->world * sizeof(void *), cudaMemcpyHostToDevice, stream));
-  NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->d_send_off, gs->send_off.data(), gs->world * sizeof(size_t), cudaMemcpyHostToDevice, stream));
+  NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->d_send_off, table.data(), table.size() * sizeof(size_t), cudaMemcpyHostToDevice, stream));
   NOMPK_CUDA_TRY(cudaStreamSynchronize(stream));
   gs->connected = true;
   return NOMPK_OK;

@@ -62,7 +62,8 @@ typedef struct {
 typedef struct {
   int ok, has_buffer;
   cudaIpcMemHandle_t mem;
-  size_t offsets[64];
+  size_t total;       /* ids this rank shares with all its peers: the stride of the two slots of its buffer */
+  size_t offsets[64]; /* where each peer's segment starts inside a slot */
 } xchg_record_t;
 
 NOMP_EXPORT int nomp_b200_gs_setup(int *handle, const long long *ids, size_t n) {
@@ -125,6 +126,7 @@ NOMP_EXPORT int nomp_b200_gs_setup(int *handle, const long long *ids, size_t n) 
     memset(&xr, 0, sizeof(xr));
     xr.ok = 1;
     gs_nompk(nompk_gs_recv_offsets(h.gs, xr.offsets, counts));
+    for (int r = 0; r < size; r++) xr.total += counts[r];
     if (xchg_bytes > 0) {
       gs_cuda(cudaMalloc(&h.xchg, xchg_bytes));
       gs_cuda(cudaMemset(h.xchg, 0, xchg_bytes));
@@ -134,13 +136,13 @@ NOMP_EXPORT int nomp_b200_gs_setup(int *handle, const long long *ids, size_t n) 
     }
     snprintf(tag, sizeof(tag), "gs%u.xchg", setup);
     if ((err = nomp_comm_allgather(tag, &xr, xall, sizeof(xr)))) goto done;
-    size_t send_offsets[64] = {0};
+    size_t send_offsets[64] = {0}, peer_totals[64] = {0};
     for (int r = 0; r < size; r++) {
       if (!xall[r].ok) {
         err = nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "Gather-scatter across ranks needs CUDA IPC (rank %d has none).", r);
         goto done;
       }
-      send_offsets[r] = xall[r].offsets[rank];
+      send_offsets[r] = xall[r].offsets[rank], peer_totals[r] = xall[r].total;
       if (r == rank) h.peers[r] = h.xchg;
       else if (counts[r] > 0) {
         if (!xall[r].has_buffer) {
@@ -150,7 +152,7 @@ NOMP_EXPORT int nomp_b200_gs_setup(int *handle, const long long *ids, size_t n) 
         gs_cuda(cudaIpcOpenMemHandle(&h.peers[r], xall[r].mem, cudaIpcMemLazyEnablePeerAccess));
       }
     }
-    if (xchg_bytes > 0) gs_nompk(nompk_gs_connect(h.gs, (void *const *)h.peers, send_offsets, stream));
+    if (xchg_bytes > 0) gs_nompk(nompk_gs_connect(h.gs, (void *const *)h.peers, send_offsets, peer_totals, stream));
     if ((err = nomp_comm_barrier())) goto done;
   }
 

@@ -133,11 +133,16 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
                             D=roles["D"], w=roles["w"]), one, one)
             knl._plan = plan
             return plan
-        if n_val is not None:
-            # no tuned kernel for this n: one thread per element through the generic path
-            outer = roles["e"]
-            if knl.tags().get(outer) is None:
+        if n_val is not None and all(t is None for t in knl.tags().values()):
+            # no tuned kernel for this n and no schedule from the user: one block per element with the points as
+            # threads and ur / us / ut in shared memory (what nomp_sem.py's element_loop / dof_loop clauses give);
+            # one thread per element when the points do not fit a block
+            max_threads = int(context.get("device::max_threads_per_block", 1024) or 1024)
+            if int(n_val) ** 3 <= max_threads:
+                knl = tag_inames(knl, {roles["e"]: "g.0", roles["i"]: "l.0", roles["j"]: "l.1", roles["k"]: "l.2"})
+            else:
                 from .ir import split_iname
+                outer = roles["e"]
                 k2 = split_iname(knl, outer, 32)
                 knl = tag_inames(k2, {f"{outer}_outer": "g.0", f"{outer}_inner": "l.0"})
 

@@ -230,13 +230,18 @@ def test_ax_recognition():
         renamed = re.sub(rf"\b{old}\b", new, renamed)
     kr = nb.fix_parameters(nb.c_to_loopy(renamed), {"n": 8})
     assert "family=ax" in nb.get_knl_src(kr, CTX) and "w=out" in nb.get_knl_src(kr, CTX) and "E=nel" in nb.get_knl_src(kr, CTX)
-    # an n without a hand-written kernel falls back to one thread per element through NVRTC
+    # an n without a hand-written kernel goes through NVRTC with one block per element, the points as threads and the
+    # per-element temporaries in shared memory; one thread per element when the points do not fit a block
     k9 = nb.fix_parameters(k, {"n": 9})
     text = nb.get_knl_src(k9, CTX)
-    assert "kind=nvrtc family=generic" in text
+    assert "kind=nvrtc family=generic" in text and "__shared__ double ur[9][9][9];" in text
     ok, log = nvrtc_compile(text)
     assert ok, log
-    assert nb.get_grid_size(k9, CTX) == (("((E + 31) / 32)", "1", "1"), ("32", "1", "1"))
+    assert nb.get_grid_size(k9, CTX) == (("E", "1", "1"), ("9", "9", "9"))
+    k11 = nb.fix_parameters(k, {"n": 11})
+    assert nb.get_grid_size(k11, CTX) == (("((E + 31) / 32)", "1", "1"), ("32", "1", "1"))
+    ok, log = nvrtc_compile(nb.get_knl_src(k11, CTX))
+    assert ok, log
     # a changed loop body is not the Ax family
     other = nb.fix_parameters(nb.c_to_loopy(families.AX_KERNEL_SOURCE.replace("double acc = 0;", "double acc = 1;")), {"n": 8})
     assert "family=ax" not in nb.get_knl_src(other, CTX)

@@ -239,3 +239,96 @@ def test_gather_scatter_across_gpus(tmp_path):
             pass
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]
+
+
+class EmulatedRanks:
+    """The multi-rank protocol of nompk_gs_* with every "rank" on this one GPU: one handle, one exchange buffer and
+    one stream per rank.  The kernels of different ranks run concurrently and talk through the same flags and slots
+    they use over NVLink, so layouts and offsets for any number of ranks are testable without that many GPUs."""
+
+    def __init__(self, id_parts):
+        self.lib, self.world = capi.nompk(), len(id_parts)
+        lib, world = self.lib, self.world
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.streams = [torch.cuda.Stream() for _ in range(world)]
+        self.handles, uniq = [], []
+        for ids in id_parts:
+            d = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).cuda()
+            h = C.c_void_p()
+            capi.nompk_check(lib.nompk_gs_create(d.data_ptr(), d.numel(), C.byref(h), st))
+            ptr, cnt = C.c_void_p(), C.c_size_t()
+            capi.nompk_check(lib.nompk_gs_unique(h, C.byref(ptr), C.byref(cnt)))
+            self.handles.append(h)
+            uniq.append((ptr, cnt.value))
+        self.shared = [[0] * world for _ in range(world)]
+        for r, h in enumerate(self.handles):
+            for p in range(world):
+                if p != r:
+                    n = C.c_size_t()
+                    capi.nompk_check(lib.nompk_gs_match_peer(h, p, world, uniq[p][0], uniq[p][1], C.byref(n), st))
+                    self.shared[r][p] = n.value
+        self.buffers, offsets, totals = [], [], []
+        for r, h in enumerate(self.handles):
+            xb = C.c_size_t()
+            capi.nompk_check(lib.nompk_gs_finalize_setup(h, r, world, C.byref(xb), st))
+            self.buffers.append(torch.zeros(max(int(xb.value), 8), dtype=torch.uint8, device="cuda"))
+            off, cnt = (C.c_size_t * world)(), (C.c_size_t * world)()
+            capi.nompk_check(lib.nompk_gs_recv_offsets(h, off, cnt))
+            assert list(cnt) == self.shared[r]
+            offsets.append(list(off))
+            totals.append(sum(cnt))
+        for r, h in enumerate(self.handles):
+            peers = (C.c_void_p * world)(*[b.data_ptr() for b in self.buffers])
+            send = (C.c_size_t * world)(*[offsets[p][r] for p in range(world)])
+            tot = (C.c_size_t * world)(*totals)
+            capi.nompk_check(lib.nompk_gs_connect(h, peers, send, tot, st))
+        torch.cuda.synchronize()
+
+    def apply(self, op, dtype, parts):
+        dev = [torch.from_numpy(p).cuda() for p in parts]
+        torch.cuda.synchronize()
+        for r, h in enumerate(self.handles):
+            capi.nompk_check(self.lib.nompk_gs_apply(h, op, dtype, dev[r].data_ptr(), None,
+                                                     C.c_void_p(self.streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        return [d.cpu().numpy() for d in dev]
+
+    def close(self):
+        for h in self.handles:
+            self.lib.nompk_gs_destroy(h)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 5, 8])
+def test_multi_rank_protocol_on_one_gpu(world):
+    """Slabs of a box mesh (inner ranks have two neighbours with segments of their own in the exchange buffer) and a
+    random numbering whose ids live on any subset of the ranks; repeated calls alternate the two slots."""
+    n, ex, ey, ezr = 6, 4, 3, 2
+    ids_all = ffi.box_ids(n, ex, ey, ezr * world)
+    per = ids_all.size // world
+    seg = [r * per for r in range(world + 1)]
+    ranks = EmulatedRanks([ids_all[seg[r]:seg[r + 1]] for r in range(world)])
+    plane = (5 * ex + 1) * (5 * ey + 1)
+    for r in range(world):
+        assert sum(ranks.shared[r]) == plane * ((r > 0) + (r < world - 1))
+    for rep, (op, dtype) in enumerate([(capi.RED_SUM, capi.F64), (capi.RED_MAX, capi.I64), (capi.RED_SUM, capi.F64),
+                                       (capi.RED_MIN, capi.F32), (capi.RED_SUM, capi.F64)]):
+        full = values(dtype, ids_all.size, 60 + rep)
+        want = ffi.gs(op, dtype, ids_all, full.copy(), seg)
+        got = ranks.apply(op, dtype, [full[seg[r]:seg[r + 1]].copy() for r in range(world)])
+        for r in range(world):
+            assert np.array_equal(got[r], want[seg[r]:seg[r + 1]]), (world, rep, r)
+    ranks.close()
+
+    rng = np.random.default_rng(world)
+    m = 20000
+    ids2 = rng.integers(1, 3000, m * world).astype(np.int64)
+    ids2[rng.integers(0, ids2.size, 500)] = 0
+    seg2 = [r * m for r in range(world + 1)]
+    ranks = EmulatedRanks([ids2[seg2[r]:seg2[r + 1]] for r in range(world)])
+    for rep in range(3):
+        full = values(capi.F64, ids2.size, 80 + rep)
+        want = ffi.gs(capi.RED_SUM, capi.F64, ids2, full.copy(), seg2)
+        got = ranks.apply(capi.RED_SUM, capi.F64, [full[seg2[r]:seg2[r + 1]].copy() for r in range(world)])
+        for r in range(world):
+            assert np.array_equal(got[r], want[seg2[r]:seg2[r + 1]]), (world, rep, r)
+    ranks.close()

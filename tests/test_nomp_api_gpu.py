@@ -455,8 +455,9 @@ def test_min_max_and_product_clauses(T):
 
 # ---- Ax through the API ------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("n,expect_family", [(8, ("native", "ax")), (10, ("native", "ax")), (6, ("native", "ax")), (4, ("nvrtc", "generic")),
-                                             (5, ("nvrtc", "generic"))])
+@pytest.mark.parametrize("n,expect_family", [(8, ("native", "ax")), (10, ("native", "ax")), (6, ("native", "ax")), (12, ("native", "ax")),
+                                             (4, ("nvrtc", "generic")), (5, ("nvrtc", "generic")), (9, ("nvrtc", "generic")),
+                                             (11, ("nvrtc", "generic"))])
 def test_ax_kernel_string(n, expect_family):
     from nomp_bridge.families import AX_KERNEL_SOURCE
     E = 37
