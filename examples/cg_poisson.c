@@ -92,9 +92,13 @@ int main(int argc, const char **argv) {
   printf("{\"E_per_rank\": %d, \"n\": %d, \"dof_per_rank\": %zu, \"rr0\": %.17g}\n", E, n, N, rr0);
 
   CHECK(nomp_sync());
-  const double t0 = now_s();
+  double t0 = now_s();
   int it = 0;
   for (; it < max_iter && rr > tol * tol * rr0; it++) {
+    if (it == 1) { /* the first iteration loads every kernel (lazy module loading): time from the second one */
+      CHECK(nomp_sync());
+      t0 = now_s();
+    }
     CHECK(nomp_run(id_axdot, w, p, g, D, &E, &pap));
     const double alpha = rr / pap;
     double rr_new = 0;
@@ -119,7 +123,7 @@ int main(int argc, const char **argv) {
   CHECK(nomp_run(id_dot, p, p, &Ni, &res2));
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
          "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": 136}\n",
-         it, rr, sqrt(res2 / rr0), dt, dt / (it ? it : 1) * 1e3, it ? (double)N * it / dt / 1e9 : 0.0);
+         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0);
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

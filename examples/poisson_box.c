@@ -136,9 +136,13 @@ int main(int argc, const char **argv) {
          rank, world, ex, ey, ez, n, N, px * py * pz, info[2], info[3], info[7], setup_s, rr0);
 
   CHECK(nomp_sync());
-  const double t0 = now_s();
+  double t0 = now_s();
   int it = 0;
   for (; it < max_iter && rr > tol * tol * rr0; it++) {
+    if (it == 1) { /* the first iteration loads every kernel (lazy module loading): time from the second one */
+      CHECK(nomp_sync());
+      t0 = now_s();
+    }
     CHECK(nomp_run(id_axdot, w, p, g, D, &E, &pap));
     CHECK(nomp_b200_gs(gs, w, 8, NOMP_FLOAT, "+"));
     const double alpha = rr / pap;
@@ -152,11 +156,36 @@ int main(int argc, const char **argv) {
   CHECK(nomp_sync());
   const double dt = now_s() - t0;
 
+  /* POISSON_PHASES=1: ten more iterations with a nomp_sync() after every call, to see where an iteration's time goes
+   * (the solution is left alone: alpha = 0 for these) */
+  if (getenv("POISSON_PHASES")) {
+    double t[5] = {0, 0, 0, 0, 0}, none_alpha = 0.0, rr_tmp = 0, one = 1.0;
+    for (int rep = 0; rep < 10; rep++) {
+      double a = now_s();
+      CHECK(nomp_run(id_axdot, w, p, g, D, &E, &pap));
+      CHECK(nomp_sync());
+      double b = now_s();
+      CHECK(nomp_b200_gs(gs, w, 8, NOMP_FLOAT, "+"));
+      CHECK(nomp_sync());
+      double c2 = now_s();
+      CHECK(nomp_run(id_upd, x, r, p, w, mask, c, &none_alpha, &Ni, &rr_tmp));
+      CHECK(nomp_sync());
+      double d = now_s();
+      CHECK(nomp_run(id_dir, p, p, &zero, &Ni));
+      CHECK(nomp_sync());
+      double e2 = now_s();
+      t[0] += b - a, t[1] += c2 - b, t[2] += d - c2, t[3] += e2 - d;
+    }
+    (void)one;
+    printf("{\"phase_ms\": {\"ax_dot\": %.4f, \"gather_scatter\": %.4f, \"update_rr\": %.4f, \"direction\": %.4f}}\n",
+           t[0] * 100, t[1] * 100, t[2] * 100, t[3] * 100);
+  }
+
   double err2 = 0;
   CHECK(nomp_run(id_err, x, ue, &Ni, &err2));
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"residual_rel\": %.3e, \"max_error\": %.3e, \"seconds\": %.6f, "
          "\"ms_per_iter\": %.4f, \"GDOF_per_s_per_rank\": %.2f}\n",
-         it, rr, sqrt(rr / rr0), sqrt(err2), dt, dt / (it ? it : 1) * 1e3, it ? (double)N * it / dt / 1e9 : 0.0);
+         it, rr, sqrt(rr / rr0), sqrt(err2), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0);
   CHECK(nomp_b200_gs_free(gs));
   CHECK(nomp_finalize());
   return 0;

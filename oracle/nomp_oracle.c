@@ -19,7 +19,8 @@
  *   - gather-scatter: NOT in the reference either.  Restated from the definition of gslib's gs_op as Nekbone uses
  *     it (every copy of a global id receives the combination of all copies; ids <= 0 do not take part), with the
  *     association order include/nompk.h documents.  PARITY UNPINNED by the reference; pinned by closed forms
- *     (multiplicity counts of a box mesh, idempotence of min/max, conservation of the sum).
+ *     (multiplicity counts of a box mesh, idempotence of min/max, conservation of the sum) and by the independent
+ *     numpy restatement behind tests/golden/gs_cases.json.
  *
  * Pinning: tests/test_oracle.py checks these functions against every closed-form golden value the
  * reference tests hold for the path (tests/nomp-api-200/205/500/600-impl.h, listed in SURVEY.md 8c).

@@ -6,9 +6,9 @@ Two sources, neither of them the oracle itself:
      tests/nomp-api-200-impl.h:31-185, tests/nomp-api-205-impl.h:30-135, tests/nomp-api-500-impl.h:17-248,
      tests/nomp-api-600-impl.h:33-52; listed in SURVEY.md 8c).  The reference cannot be run here (SymEngine, loopy,
      libclang, pocl missing), so its golden vectors are these formulas, re-evaluated below for the same n and types;
-  2. for Ax, which the reference does not contain ("parity unpinned" by the reference), an independent numpy
-     restatement (einsum over the definition in include/nompk.h) on exact-integer data, plus the analytic identities
-     the tests check.
+  2. for Ax and the gather-scatter, which the reference does not contain ("parity unpinned" by the reference),
+     independent numpy restatements (einsum over the definition in include/nompk.h; bincount / ufunc.at over the
+     global ids) on exact-integer data, plus the analytic identities the tests check.
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
@@ -85,7 +85,58 @@ def ax_cases():
     return cases
 
 
+def gs_numpy(ids, v, op):
+    """Independent restatement of the gather-scatter: combine per global id with ufunc.at, then read back."""
+    ids = np.asarray(ids)
+    out = v.copy()
+    live = ids > 0
+    table_size = int(ids.max()) + 1
+    if op == "+":
+        table = np.zeros(table_size, dtype=v.dtype)
+        np.add.at(table, ids[live], v[live])
+    elif op == "*":
+        table = np.ones(table_size, dtype=v.dtype)
+        np.multiply.at(table, ids[live], v[live])
+    elif op == "min":
+        table = np.full(table_size, v.max(), dtype=v.dtype)
+        np.minimum.at(table, ids[live], v[live])
+    else:
+        table = np.full(table_size, v.min(), dtype=v.dtype)
+        np.maximum.at(table, ids[live], v[live])
+    out[live] = table[ids[live]]
+    return out
+
+
+def gs_cases():
+    """A 3 x 2 x 2 box of elements with 3 points per direction (lexicographic global numbering written out here, not
+    taken from the oracle's helper) and a random numbering with non-participating ids; integer-valued data."""
+    cases = []
+    n, ex, ey, ez = 3, 3, 2, 2
+    N = n - 1
+    px, py = N * ex + 1, N * ey + 1
+    ids = []
+    for e in range(ex * ey * ez):
+        e_x, e_y, e_z = e % ex, (e // ex) % ey, e // (ex * ey)
+        for k in range(n):
+            for j in range(n):
+                for i in range(n):
+                    ids.append(1 + (e_x * N + i) + px * ((e_y * N + j) + py * (e_z * N + k)))
+    rng = np.random.default_rng(11)
+    numberings = [("box", np.array(ids, dtype=np.int64)), ("random", rng.integers(-1, 40, 300).astype(np.int64))]
+    for name, idv in numberings:
+        for op in ("+", "*", "min", "max"):
+            for dtype in ("float64", "int64", "float32", "int32"):
+                v = rng.integers(1, 4, idv.size) if op == "*" else rng.integers(-9, 10, idv.size)
+                v = v.astype(dtype)
+                if op == "*" and name == "random":
+                    v = np.where(rng.random(idv.size) < 0.7, 1, v).astype(dtype)   # keep products small and exact
+                cases.append(dict(name=name, op=op, dtype=dtype, ids=idv.tolist(), v=v.tolist(),
+                                  want=gs_numpy(idv, v, op).tolist()))
+    return cases
+
+
 def main():
+    (HERE / "gs_cases.json").write_text(json.dumps(dict(cases=gs_cases())))
     (HERE / "map_cases.json").write_text(json.dumps(dict(types=TYPES, cases=map_cases())))
     (HERE / "reduce_cases.json").write_text(json.dumps(dict(types=TYPES, cases=reduce_cases())))
     (HERE / "ax_cases.json").write_text(json.dumps(dict(cases=ax_cases())))

@@ -102,6 +102,23 @@ def test_all_types_and_operators_on_random_numbering(dtype, op):
     gs.close()
 
 
+def test_golden_fixture():
+    """tests/golden/gs_cases.json (independent numpy restatement, exact-integer data): the GPU agrees with it too."""
+    import json
+    ops = {"+": capi.RED_SUM, "*": capi.RED_PROD, "min": capi.RED_MIN, "max": capi.RED_MAX}
+    dts = {"float64": capi.F64, "float32": capi.F32, "int64": capi.I64, "int32": capi.I32}
+    cases = json.loads((ROOT / "tests" / "golden" / "gs_cases.json").read_text())["cases"]
+    handles = {}
+    for c in cases:
+        if c["name"] not in handles:
+            handles[c["name"]] = Gs(np.array(c["ids"], dtype=np.int64))
+        d = torch.from_numpy(np.array(c["v"], dtype=c["dtype"])).cuda()
+        handles[c["name"]].apply(ops[c["op"]], dts[c["dtype"]], d)
+        assert np.array_equal(d.cpu().numpy(), np.array(c["want"], dtype=c["dtype"])), (c["name"], c["op"], c["dtype"])
+    for h in handles.values():
+        h.close()
+
+
 def test_degenerate_numberings():
     # no shared id at all: nothing to do, nothing launched
     ids = np.arange(1, 1001, dtype=np.int64)
