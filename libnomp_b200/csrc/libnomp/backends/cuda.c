@@ -136,9 +136,38 @@ typedef struct {
 } cuda_prog_t;
 
 /* ---- memory --------------------------------------------------------------------------------------------------- */
+/* Page-lock the host range of a mapping that is being copied for the SECOND time: pageable copies are staged by the
+ * driver at a fraction of the PCIe rate, and a range that moves twice usually moves every time step.  One copy is not
+ * worth the registration (about as slow as the pageable copy it would save).  Ranges below 1 MiB, ranges somebody
+ * else already pinned, and NOMP_PIN_HOST=0 leave the host memory alone. */
+#define NOMP_PIN_MIN_BYTES ((size_t)1 << 20)
+
+static void pin_host_range(nomp_mem_t *m) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char *e = getenv("NOMP_PIN_HOST");
+    enabled = !(e && e[0] == '0');
+  }
+  const size_t bytes = NOMP_MEM_BYTES(m->idx0, m->idx1, m->usize);
+  if (!enabled || m->host_registered || bytes < NOMP_PIN_MIN_BYTES) return;
+  m->host_registered = -1; /* tried: do not try again */
+  if (cudaHostRegister((char *)m->hptr + NOMP_MEM_OFFSET(m->idx0, m->usize), bytes, cudaHostRegisterDefault) == cudaSuccess)
+    m->host_registered = 1;
+  else
+    cudaGetLastError(); /* already pinned by its owner, or not registrable: copies stay pageable */
+}
+
+static void unpin_host_range(nomp_mem_t *m) {
+  if (m->host_registered == 1) {
+    if (cudaHostUnregister((char *)m->hptr + NOMP_MEM_OFFSET(m->idx0, m->usize)) != cudaSuccess) cudaGetLastError();
+  }
+  m->host_registered = 0;
+}
+
 static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direction_t op, size_t start, size_t end,
                        size_t usize) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (((op & NOMP_TO) || op == NOMP_FROM) && m != &bnd->scratch && m->transfers++ == 1) pin_host_range(m);
   if (op & NOMP_ALLOC) {
     size_t bytes = NOMP_MEM_BYTES(start, end, usize);
     check_runtime(cudaMalloc(&m->bptr, bytes ? bytes : 1));
@@ -166,6 +195,7 @@ static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direct
     check_runtime(cudaStreamSynchronize(st->stream));
   } else if (op == NOMP_FREE) {
     check_runtime(cudaStreamSynchronize(st->stream));
+    unpin_host_range(m);
     check_runtime(cudaFree(m->bptr));
     m->bptr = NULL; /* tells the core to drop the entry (reference src/nomp.c:360) */
   }
@@ -535,6 +565,7 @@ int nomp_cuda_update_async(nomp_backend_t *bnd, nomp_mem_t *m, nomp_map_directio
     check_runtime(cudaEventCreateWithFlags(&st->ev_h2d, cudaEventDisableTiming));
   }
   st->async_used = 1;
+  if (m->transfers++ == 1) pin_host_range(m);
   cudaStream_t cs = op == NOMP_TO ? st->stream_h2d : st->stream_d2h;
   check_runtime(cudaEventRecord(st->ev_compute, st->stream));
   check_runtime(cudaStreamWaitEvent(cs, st->ev_compute, 0));

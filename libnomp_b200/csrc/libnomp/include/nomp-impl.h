@@ -74,6 +74,8 @@ typedef struct {
   void *bptr;
   size_t bsize;
   unsigned long version; /* bumped whenever the device image may have changed */
+  unsigned transfers;    /* host <-> device copies of this mapping so far */
+  int host_registered;   /* the backend page-locked the host range (cudaHostRegister) and must release it */
 } nomp_mem_t;
 
 struct nomp_backend {

@@ -565,3 +565,39 @@ def test_extensions_and_launch_counter():
         for _ in range(3):
             capi.check(capi.run(kid, a.ctypes.data, b.ctypes.data, C.c_int(1000)))
     assert lib.nomp_b200_launch_count() - before == 3 and np.all(a == 4)
+
+
+def test_repeated_updates_pin_the_host_range():
+    """A mapping that is copied a second time gets its host range page-locked (cudaHostRegister) so that the copies run
+    at PCIe speed instead of through the driver's staging buffers; NOMP_FREE releases it.  Small ranges are left alone."""
+    import time
+    cudart = C.CDLL("libcudart.so.12")
+    cudart.cudaHostGetFlags.argtypes = [C.POINTER(C.c_uint), C.c_void_p]
+
+    def pinned(arr):
+        flags = C.c_uint()
+        rc = cudart.cudaHostGetFlags(C.byref(flags), arr.ctypes.data)
+        cudart.cudaGetLastError()
+        return rc == 0
+
+    a = np.random.default_rng(1).random(1 << 25)        # 256 MiB of pageable memory
+    want = a.copy()
+    times = []
+    for i in range(5):
+        t0 = time.perf_counter()
+        capi.check(capi.update(a.ctypes.data, 0, a.size, 8, capi.NOMP_TO))
+        times.append(time.perf_counter() - t0)
+        assert pinned(a) == (i >= 1), i                   # from the second copy on
+    a[:] = 0
+    capi.check(capi.update(a.ctypes.data, 0, a.size, 8, capi.NOMP_FROM))
+    assert np.array_equal(a, want)
+    capi.check(capi.update(a.ctypes.data, 0, a.size, 8, capi.NOMP_FREE))
+    assert not pinned(a)
+    gbs = [a.nbytes / t / 1e9 for t in times]
+    print("H2D GB/s per call (pageable, registering, pinned...):", [round(g, 1) for g in gbs])
+    assert max(gbs[2:]) > 0.9 * gbs[0]
+    small = np.arange(1000.0)
+    for _ in range(3):
+        capi.check(capi.update(small.ctypes.data, 0, small.size, 8, capi.NOMP_TO))
+    assert not pinned(small)
+    capi.check(capi.update(small.ctypes.data, 0, small.size, 8, capi.NOMP_FREE))
