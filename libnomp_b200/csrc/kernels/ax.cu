@@ -30,7 +30,8 @@
 #include "nompk_common.cuh"
 #include "nompk_gridreduce.cuh"
 
-// D[a][l] at nompk_ax_cD[a * n + l].  C linkage: the kernel reads it through inline PTX by symbol name.
+// D[a][l] at nompk_ax_cD[a * n + l] (constant bank 3; read with LDCU into uniform registers, see ld_D).  C linkage so
+// that the symbol has one unmangled name in cuobjdump / ncu listings.
 extern "C" {
 __constant__ double nompk_ax_cD[12 * 12];
 }

@@ -102,6 +102,49 @@ def test_all_types_and_operators_on_random_numbering(dtype, op):
     gs.close()
 
 
+def test_full_size_properties():
+    """BASELINE size (64^3 elements, N = 7: 1.34e8 points, ids built on the device): size-independent properties in
+    exact arithmetic -- multiplicities are 1/2/4/8 and sum(1/m) counts every distinct point once; the weighted sum of
+    integer data is conserved; min is idempotent and never increases a value."""
+    n, e = 8, 64
+    N = n - 1
+    px = N * e + 1
+    el = torch.arange(e ** 3, device="cuda")
+    pt = torch.arange(n ** 3, device="cuda")
+    gx = (el % e)[:, None] * N + (pt % n)[None]
+    gy = ((el // e) % e)[:, None] * N + ((pt // n) % n)[None]
+    gz = (el // (e * e))[:, None] * N + (pt // (n * n))[None]
+    ids = (1 + gx + px * (gy + px * gz)).reshape(-1).contiguous()
+    del gx, gy, gz, el, pt
+    lib = capi.nompk()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = C.c_void_p()
+    capi.nompk_check(lib.nompk_gs_create(ids.data_ptr(), ids.numel(), C.byref(h), st))
+    del ids
+    xb = C.c_size_t()
+    capi.nompk_check(lib.nompk_gs_finalize_setup(h, 0, 1, C.byref(xb), st))
+    stats = (C.c_size_t * 8)()
+    lib.nompk_gs_stats(h, C.byref(stats))
+    assert stats[0] == e ** 3 * n ** 3 and stats[1] == px ** 3
+    m = torch.ones(stats[0], dtype=torch.float64, device="cuda")
+    capi.nompk_check(lib.nompk_gs_apply(h, capi.RED_SUM, capi.F64, m.data_ptr(), None, st))
+    counts = torch.bincount(m.to(torch.int64), minlength=9)
+    assert int(counts[[0, 3, 5, 6, 7]].sum()) == 0
+    assert int(counts[8]) == 8 * (e - 1) ** 3                                   # interior vertices of the box
+    assert float((1.0 / m).sum()) == float(px ** 3)                            # dyadic terms: exact in any order
+    v = torch.randint(-8, 9, (stats[0],), device="cuda").to(torch.float64)
+    before = float((v).sum())
+    capi.nompk_check(lib.nompk_gs_apply(h, capi.RED_SUM, capi.F64, v.data_ptr(), None, st))
+    assert float((v / m).sum()) == before                                      # multiples of 1/8 below 2^40: exact
+    w = torch.randint(-1000, 1000, (stats[0],), device="cuda").to(torch.float64)
+    w0 = w.clone()
+    capi.nompk_check(lib.nompk_gs_apply(h, capi.RED_MIN, capi.F64, w.data_ptr(), None, st))
+    w1 = w.clone()
+    capi.nompk_check(lib.nompk_gs_apply(h, capi.RED_MIN, capi.F64, w.data_ptr(), None, st))
+    assert torch.equal(w, w1) and bool((w1 <= w0).all()) and bool((w1[m == 1] == w0[m == 1]).all())
+    lib.nompk_gs_destroy(h)
+
+
 def test_golden_fixture():
     """tests/golden/gs_cases.json (independent numpy restatement, exact-integer data): the GPU agrees with it too."""
     import json
