@@ -133,6 +133,7 @@ int nomp_comm_barrier(void);
 
 /* gather-scatter handles (src/gs.c) */
 void nomp_gs_finalize(void);
+int nomp_gs_check(void);
 
 /* on-disk JIT cache (src/jitcache.c) */
 typedef struct {

@@ -231,6 +231,15 @@ NOMP_EXPORT int nomp_b200_gs_free(int handle) {
   return err;
 }
 
+/* nomp_sync: the asynchronous kernels report a peer that never arrived through the mapped error word */
+int nomp_gs_check(void) {
+  for (unsigned i = 0; i < n_handles; i++)
+    if (handles[i].gs && *handles[i].err_host)
+      return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "Gather-scatter call %llu timed out waiting for a peer rank.",
+                      *handles[i].err_host);
+  return 0;
+}
+
 /* nomp_finalize: drop whatever the program did not free (collective when ranks > 1, like nomp_finalize itself) */
 void nomp_gs_finalize(void) {
   for (unsigned i = 0; i < n_handles; i++)

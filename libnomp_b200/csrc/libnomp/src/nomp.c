@@ -583,7 +583,8 @@ NOMP_EXPORT int nomp_run(int id, ...) {
 
 NOMP_EXPORT int nomp_sync(void) {
   if (!initialized) return nomp_log(NOMP_INITIALIZE_FAILURE, NOMP_ERROR, "libnomp is not initialized.");
-  return nomp.sync(&nomp);
+  nomp_check(nomp.sync(&nomp));
+  return nomp_gs_check(); /* a gather-scatter that gave up waiting for a peer rank reports it here */
 }
 
 NOMP_EXPORT const char *nomp_b200_prog_info(int id) {

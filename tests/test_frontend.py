@@ -437,3 +437,60 @@ def test_nomp_sem_annotations_give_one_block_per_element():
     flat = nb.c_to_loopy("void f(double *a, double *b, int N) { for (int i = 0; i < N; i++) a[i] += b[i]; }")
     flat = nomp_sem.annotate(flat, {"grid_loop": "i"}, CTX)
     assert flat.tags() == {"i_outer": "g.0", "i_inner": "l.0"}
+
+
+# ---- randomized fidelity of the parser + emitter --------------------------------------------------------------------------
+
+def _random_expr(rng, depth, leaves, int_ops):
+    if depth == 0 or rng.random() < 0.25:
+        return leaves[rng.integers(len(leaves))]
+    kind = rng.random()
+    a = _random_expr(rng, depth - 1, leaves, int_ops)
+    b = _random_expr(rng, depth - 1, leaves, int_ops)
+    if kind < 0.08:
+        return f"(-{a})" if not a.startswith("(-") else a
+    if kind < 0.16:
+        c = _random_expr(rng, depth - 1, leaves, int_ops)
+        return f"(({a} < {b}) ? {c} : {b})"
+    ops = ["+", "-", "*"] + (["&", "|", "^"] if int_ops else [])
+    op = ops[rng.integers(len(ops))]
+    return f"({a} {op} {b})" if rng.random() < 0.7 else f"{a} {op} {b}"
+
+
+@pytest.mark.parametrize("T", ["double", "float", "int", "unsigned", "long"])
+def test_random_expressions_survive_parsing_and_code_generation(T):
+    """Forty random right-hand sides per type (precedence with and without parentheses, unary minus, ternaries, bit
+    operations for the integer types): the generated CUDA kernel, executed on the host thread by thread, returns the
+    bits of the kernel string compiled by gcc -- through the vector skeleton (no transform) and through the generic
+    emitter (user tiling)."""
+    rng = np.random.default_rng({"double": 1, "float": 2, "int": 3, "unsigned": 4, "long": 5}[T])
+    dt = NP[T]
+    is_int = np.issubdtype(dt, np.integer)
+    cuda_t = {"long": "long long", "unsigned long": "unsigned long long"}.get(T, T)
+    n = 257
+    for case in range(40):
+        leaves = ["a[i]", "b[i]", "c[i]", "s", "t", "3", "i"] if is_int else ["a[i]", "b[i]", "c[i]", "s", "t", "0.5", "2"]
+        expr = _random_expr(rng, 3, leaves, is_int)
+        src = (f"void foo({T} *a, const {T} *b, const {T} *c, {T} s, {T} t, int N) "
+               f"{{ for (int i = 0; i < N; i++) a[i] = {expr}; }}")
+        if is_int:
+            a0 = rng.integers(0, 50, n).astype(dt)
+            b0, c0 = rng.integers(0, 50, n).astype(dt), rng.integers(0, 50, n).astype(dt)
+            sv, tv = dt(3), dt(5)
+        else:
+            a0 = rng.uniform(0.5, 1.5, n).astype(dt)
+            b0, c0 = rng.uniform(0.5, 1.5, n).astype(dt), rng.uniform(0.5, 1.5, n).astype(dt)
+            sv, tv = dt(0.75), dt(1.25)
+        ctype = {np.float64: C.c_double, np.float32: C.c_float, np.int32: C.c_int, np.uint32: C.c_uint, np.int64: C.c_longlong}[dt]
+        want = a0.copy()
+        run_kernel(src, want, b0, c0, ctype(sv), ctype(tv), n)
+        argtypes = [f"{cuda_t} *", f"const {cuda_t} *", f"const {cuda_t} *", cuda_t, cuda_t, "int"]
+        for transform in (None, tile):
+            desc, cuda, (grid, block), _ = plan(src, transform)
+            if desc["kind"] == "native":      # the draw happens to be one of libnompk's maps: covered on the GPU
+                continue
+            got = a0.copy()
+            g = (grid_eval(grid[0], {"N": n}), 1, 1)
+            emulate(cuda, "foo", g, (int(block[0]), 1, 1), argtypes,
+                    [_ptr(got), _ptr(b0), _ptr(c0), ctype(sv), ctype(tv), C.c_int(n)])
+            assert np.array_equal(got, want), (T, case, desc["family"], expr)
