@@ -102,6 +102,20 @@ int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, c
                  void *result, void *result_host_mapped, unsigned long long host_seq, void *workspace,
                  void *stream);
 
+/* nompk_reduce fused with the all-reduce of its result over `world` ranks (one GPU each): the CTA that finishes the
+ * grid-wide fold stores the value straight into every peer's exchange buffer and folds the peers' values in rank
+ * order -- the collective costs no launch of its own.  `peers` describes the exchange buffers exactly as for
+ * nompk_allreduce_scalar below (same buffers, same sequence numbering; at most 32 ranks; NULL or world <= 1 = plain
+ * nompk_reduce); result / result_host_mapped receive the all-reduced value, the host block is 24 bytes (error word). */
+typedef struct {
+  void *const *peer_xchg; /* DEVICE array of `world` pointers to the ranks' exchange buffers as mapped here */
+  int rank, world;
+  unsigned long long seq; /* number of this collective call: 1, 2, 3, ... in the same order on all ranks */
+} nompk_peers_t;
+int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y, void *result,
+                       void *result_host_mapped, unsigned long long host_seq, void *workspace,
+                       const nompk_peers_t *peers, void *stream);
+
 /* One-shot all-reduce of one scalar across `world` processes (one GPU each) over NVLink peer memory.
  * `value` (device, 8-byte aligned) holds this rank's contribution and receives the result, identical bit for bit on
  * every rank (contributions are folded in rank order).  peer_xchg is a DEVICE array of `world` pointers: entry r is
@@ -137,6 +151,10 @@ int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double
 int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, double *result,
                      double *result_host_mapped, unsigned long long host_seq, void *workspace, unsigned flags,
                      void *stream);
+/* ... and with the all-reduce of u . (A u) over the ranks fused in as well (see nompk_reduce_peers). */
+int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, double *result,
+                           double *result_host_mapped, unsigned long long host_seq, void *workspace,
+                           const nompk_peers_t *peers, unsigned flags, void *stream);
 int nompk_ax_supported(int n);
 /* Variant selector for benchmarking/profiling (0 = default). */
 int nompk_ax_set_variant(int variant);

@@ -172,6 +172,7 @@ struct AxDotArgs {
   double *result;
   double *result_host;
   unsigned long long host_seq;
+  PeerExchange px;  // all-reduce over ranks fused into the finish (world <= 1: none)
 };
 
 // kPersistent: the grid has as many CTAs as fit on the device and each strides over the elements; otherwise one CTA
@@ -406,7 +407,8 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       static __device__ __forceinline__ double identity() { return 0.0; }
       static __device__ __forceinline__ double combine(double a, double b) { return a + b; }
     };
-    grid_finish<Sum, double, (kWarps * 32 < 64 ? 64 : kWarps * 32)>(s, dot.workspace, dot.result, dot.result_host, dot.host_seq);
+    grid_finish<Sum, double, (kWarps * 32 < 64 ? 64 : kWarps * 32)>(s, dot.workspace, dot.result, dot.result_host, dot.host_seq,
+                                                                    dot.px);
   }
 }
 
@@ -505,6 +507,12 @@ extern "C" int nompk_ax_f64(int n, size_t E, const double *u, const double *g, c
 extern "C" int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                                 double *result, double *result_host_mapped, unsigned long long host_seq,
                                 void *workspace, unsigned flags, void *stream_) {
+  return nompk_ax_dot_peers_f64(n, E, u, g, D, w, result, result_host_mapped, host_seq, workspace, nullptr, flags, stream_);
+}
+
+extern "C" int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
+                                      double *result, double *result_host_mapped, unsigned long long host_seq,
+                                      void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream_) {
   using namespace nompk;
   if (!result || !workspace) {
     set_error("nompk_ax_dot_f64: NULL result/workspace");
@@ -513,6 +521,18 @@ extern "C" int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *
   AxDotArgs dot;
   dot.workspace = workspace;
   dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
+  if (peers && peers->world > 1) {
+    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0) {
+      set_error("nompk_ax_dot_peers_f64: bad peer description (rank %d of %d; at most %d ranks)", peers->rank, peers->world,
+                kMaxFusedRanks);
+      return NOMPK_EINVAL;
+    }
+    if (E == 0) {
+      set_error("nompk_ax_dot_peers_f64: every rank needs at least one element");
+      return NOMPK_EINVAL;
+    }
+    dot.px.peer_xchg = peers->peer_xchg, dot.px.rank = peers->rank, dot.px.world = peers->world, dot.px.seq = peers->seq;
+  }
   if (E == 0) {  // identity, through the same publication protocol
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NOMPK_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(double), stream));

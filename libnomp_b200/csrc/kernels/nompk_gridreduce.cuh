@@ -35,10 +35,75 @@ template <typename T> __device__ __forceinline__ void publish_to_host(T *result_
   *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 8) = seq;
 }
 
+// All-reduce over ranks fused into the finish.  Every rank owns an exchange buffer xchg[2 slots][world][16 B] =
+// {value, sequence} mapped by its peers (CUDA IPC over NVLink; reduce.cu describes the protocol and why two slots
+// suffice).  world <= 1 means "no exchange".
+struct PeerExchange {
+  void *const *peer_xchg = nullptr;
+  int rank = 0, world = 1;
+  unsigned long long seq = 0;
+};
+
+constexpr int kMaxFusedRanks = 32;  // one lane of the finishing warp per rank
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// The grid's result is in lane 0 of the calling warp (all 32 lanes call).  With peers: lane r stores it into rank r's
+// buffer, waits for rank r's value in this rank's buffer, and the values are folded in rank order (the same on
+// every rank: bit-identical results).  Then the value goes to device memory and, if asked, to the host block
+// {value, sequence, error}.  The collective costs no launch of its own: the kernel that produced the value delivers
+// it to the peers the moment its last CTA has it.
+template <typename Op, typename T>
+__device__ __forceinline__ void finish_result(T v, T *result, T *result_host, unsigned long long host_seq,
+                                              const PeerExchange &px) {
+  const int lane = threadIdx.x & 31;
+  bool timed_out = false;
+  if (px.world > 1) {
+    v = __shfl_sync(0xffffffffu, v, 0);
+    const size_t slot = (size_t)(px.seq & 1ull) * (size_t)px.world;
+    T got = Op::identity();
+    bool ok = true;
+    if (lane < px.world) {
+      char *dst = static_cast<char *>(px.peer_xchg[lane]) + (slot + (size_t)px.rank) * 16;
+      *reinterpret_cast<volatile T *>(dst) = v;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long *>(dst + 8) = px.seq;
+      const char *src = static_cast<const char *>(px.peer_xchg[px.rank]) + (slot + (size_t)lane) * 16;
+      const unsigned long long t0 = global_timer_ns();
+      while (*reinterpret_cast<const volatile unsigned long long *>(src + 8) != px.seq) {
+        if (global_timer_ns() - t0 > kPeerTimeoutNs) {  // a peer that never arrives must not hang the GPU
+          ok = false;
+          break;
+        }
+      }
+      __threadfence_system();
+      got = *reinterpret_cast<const volatile T *>(src);
+    }
+    T acc = __shfl_sync(0xffffffffu, got, 0);
+    for (int r = 1; r < px.world; r++) acc = Op::combine(acc, __shfl_sync(0xffffffffu, got, r));
+    timed_out = __any_sync(0xffffffffu, !ok);
+    v = acc;
+  }
+  if (lane == 0) {
+    *result = v;
+    if (result_host) {
+      if (timed_out)
+        *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = px.seq;
+      publish_to_host(result_host, v, host_seq);
+    }
+  }
+}
+
 // Combine functor interface: Op::identity(), Op::combine(a, b).
 // `v` must hold the CTA's partial in thread 0.  Every thread of the CTA must call; kThreads >= 64, multiple of 32.
 template <typename Op, typename T, int kThreads>
-__device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result_host, unsigned long long host_seq) {
+__device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result_host, unsigned long long host_seq,
+                                            const PeerExchange &px = PeerExchange()) {
   char *ws = static_cast<char *>(ws_);
   unsigned int *ticket = reinterpret_cast<unsigned int *>(ws + kWsTicket);
   unsigned int *group_ticket = reinterpret_cast<unsigned int *>(ws + kWsGroupTicket);
@@ -50,10 +115,7 @@ __device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result
 
   const unsigned int b = blockIdx.x, nb = gridDim.x;
   if (nb == 1) {  // a single CTA: nothing to combine, no atomics
-    if (threadIdx.x == 0) {
-      *result = v;
-      if (result_host) publish_to_host(result_host, v, host_seq);
-    }
+    if (threadIdx.x < 32) finish_result<Op, T>(v, result, result_host, host_seq, px);
     return;
   }
   if (nb <= kRedSingleLevel) {
@@ -76,11 +138,8 @@ __device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result
       w1 = threadIdx.x < kThreads / 32 ? warp_part[threadIdx.x] : Op::identity();
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) w1 = Op::combine(w1, __shfl_xor_sync(0xffffffffu, w1, off));
-      if (threadIdx.x == 0) {
-        *result = w1;
-        if (result_host) publish_to_host(result_host, w1, host_seq);
-        *ticket = 0u;
-      }
+      if (threadIdx.x == 0) *ticket = 0u;
+      finish_result<Op, T>(w1, result, result_host, host_seq, px);
     }
     return;
   }
@@ -120,11 +179,8 @@ __device__ __forceinline__ void grid_finish(T v, void *ws_, T *result, T *result
     w = threadIdx.x < kThreads / 32 ? warp_part[threadIdx.x] : Op::identity();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) w = Op::combine(w, __shfl_xor_sync(0xffffffffu, w, off));
-    if (threadIdx.x == 0) {
-      *result = w;
-      if (result_host) publish_to_host(result_host, w, host_seq);
-      *ticket = 0u;
-    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    finish_result<Op, T>(w, result, result_host, host_seq, px);
   }
 }
 

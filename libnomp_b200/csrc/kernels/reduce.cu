@@ -92,7 +92,7 @@ template <int OP, typename T> struct RedOp {
 template <int OP, bool DOT, bool VEC, typename T>
 __global__ void __launch_bounds__(kBlock)
 reduce_kernel(const T *__restrict__ x, const T *__restrict__ y, size_t n, void *__restrict__ workspace,
-              T *__restrict__ result, T *__restrict__ result_host, unsigned long long host_seq) {
+              T *__restrict__ result, T *__restrict__ result_host, unsigned long long host_seq, PeerExchange px) {
   T acc[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; u++) acc[u] = red_identity<OP, T>();
@@ -144,12 +144,12 @@ reduce_kernel(const T *__restrict__ x, const T *__restrict__ y, size_t n, void *
   for (int u = 1; u < kUnroll; u++) v = red_combine<OP, T>(v, acc[u]);
   v = block_reduce<OP, T>(v);
 
-  grid_finish<RedOp<OP, T>, T, kBlock>(v, workspace, result, result_host, host_seq);
+  grid_finish<RedOp<OP, T>, T, kBlock>(v, workspace, result, result_host, host_seq, px);
 }
 
 template <int OP, typename T>
 int launch_reduce(size_t n, const void *x_, const void *y_, void *result, void *result_host,
-                  unsigned long long host_seq, void *workspace, cudaStream_t stream) {
+                  unsigned long long host_seq, void *workspace, const PeerExchange &px, cudaStream_t stream) {
   const T *x = static_cast<const T *>(x_);
   const T *y = static_cast<const T *>(y_);
   if (!result || !workspace || (n > 0 && !x)) {
@@ -172,17 +172,18 @@ int launch_reduce(size_t n, const void *x_, const void *y_, void *result, void *
   const unsigned g = (unsigned)blocks;
 
   if (y) {
-    if (vec) reduce_kernel<OP, true, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
-    else reduce_kernel<OP, true, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
+    if (vec) reduce_kernel<OP, true, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq, px);
+    else reduce_kernel<OP, true, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq, px);
   } else {
-    if (vec) reduce_kernel<OP, false, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
-    else reduce_kernel<OP, false, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq);
+    if (vec) reduce_kernel<OP, false, true, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq, px);
+    else reduce_kernel<OP, false, false, T><<<g, kBlock, 0, stream>>>(x, y, n, workspace, res, res_h, host_seq, px);
   }
   NOMPK_LAUNCH_CHECK("reduce_kernel");
   return NOMPK_OK;
 }
 
-typedef int (*reduce_fn)(size_t, const void *, const void *, void *, void *, unsigned long long, void *, cudaStream_t);
+typedef int (*reduce_fn)(size_t, const void *, const void *, void *, void *, unsigned long long, void *,
+                         const PeerExchange &, cudaStream_t);
 
 // SUM/PROD of integers wrap, so signed == unsigned bitwise; MIN/MAX need the real type.
 template <int OP> reduce_fn pick_dtype(nompk_dtype_t dt) {
@@ -218,11 +219,6 @@ template <int OP> reduce_fn pick_dtype(nompk_dtype_t dt) {
 constexpr int kMaxRanks = 64;
 constexpr unsigned long long kAllreduceTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
 
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 template <int OP, typename T>
 __global__ void __launch_bounds__(kMaxRanks)
@@ -333,7 +329,22 @@ extern "C" void nompk_reduce_workspace_layout(size_t offsets[4]) {
 extern "C" int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y,
                             void *result, void *result_host_mapped, unsigned long long host_seq, void *workspace,
                             void *stream) {
+  return nompk_reduce_peers(op, dt, n, x, y, result, result_host_mapped, host_seq, workspace, nullptr, stream);
+}
+
+extern "C" int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y,
+                                  void *result, void *result_host_mapped, unsigned long long host_seq, void *workspace,
+                                  const nompk_peers_t *peers, void *stream) {
   using namespace nompk;
+  PeerExchange px;
+  if (peers && peers->world > 1) {
+    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0) {
+      set_error("nompk_reduce_peers: bad peer description (rank %d of %d; at most %d ranks)", peers->rank, peers->world,
+                kMaxFusedRanks);
+      return NOMPK_EINVAL;
+    }
+    px.peer_xchg = peers->peer_xchg, px.rank = peers->rank, px.world = peers->world, px.seq = peers->seq;
+  }
   reduce_fn fn = nullptr;
   switch (op) {
   case NOMPK_RED_SUM: fn = pick_dtype<NOMPK_RED_SUM>(dt); break;
@@ -346,5 +357,5 @@ extern "C" int nompk_reduce(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const
     set_error("nompk_reduce: unsupported op %d / dtype %d", (int)op, (int)dt);
     return NOMPK_EINVAL;
   }
-  return fn(n, x, y, result, result_host_mapped, host_seq, workspace, static_cast<cudaStream_t>(stream));
+  return fn(n, x, y, result, result_host_mapped, host_seq, workspace, px, static_cast<cudaStream_t>(stream));
 }

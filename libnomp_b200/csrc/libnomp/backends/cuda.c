@@ -97,6 +97,7 @@ typedef struct {
   cudaStream_t stream_h2d, stream_d2h; /* copy streams of nomp_b200_update_async (created on first use) */
   cudaEvent_t ev_compute, ev_h2d;
   int async_used;
+  int fused_allreduce; /* the reduction kernel just launched all-reduces its result itself */
   void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
   unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
@@ -420,8 +421,12 @@ static void *ptr_arg(const nomp_prog_t *prg, int idx) { return idx < 0 ? NULL : 
 static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
   cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
-  /* with several ranks the host-visible value must be the all-reduced one, so the kernel only fills the device slot */
+  /* with several ranks the host-visible value must be the all-reduced one: the native reductions all-reduce their own
+   * result over NVLink peer memory (fused = 1), the others only fill the device slot and the finish all-reduces it */
   void *result_host = nomp_comm_size() > 1 ? NULL : st->pinned_dev;
+  nompk_peers_t peers;
+  const nompk_peers_t *px = NULL;
+  st->fused_allreduce = 0;
 
   switch (cp->family) {
   case FAM_MAP: {
@@ -435,9 +440,10 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   case FAM_REDUCE: {
     long n = int_arg(prg, cp->a_n, cp->n_literal);
     if (n < 0) n = 0;
-    check_nompk(nompk_reduce((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
-                             ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_ws,
-                             st->stream));
+    if (nomp_comm_size() > 1 && nomp_comm_peers(&peers)) px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
+    check_nompk(nompk_reduce_peers((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
+                                   ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_ws, px,
+                                   st->stream));
     return 0;
   }
   case FAM_AX:
@@ -451,11 +457,16 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     const unsigned long version = dm ? dm->version : 0;
     unsigned flags = 0;
     if (dm && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
+    /* a rank without elements launches nothing: it joins through the stand-alone all-reduce kernel of the finish,
+     * which speaks the same protocol on the same buffers */
+    if (cp->family == FAM_AXDOT && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers))
+      px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
     if (cp->family == FAM_AXDOT)
-      check_nompk(nompk_ax_dot_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
-                                   (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
-                                   (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result, (double *)result_host,
-                                   ++st->host_seq, st->red_ws, flags, st->stream));
+      check_nompk(nompk_ax_dot_peers_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
+                                         (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
+                                         (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result,
+                                         (double *)result_host, ++st->host_seq, st->red_ws, px, flags,
+                                         st->stream));
     else
       check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
@@ -491,7 +502,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
  * ranks if there are several, then wait for the kernel to publish {value, sequence number} to the host. */
 int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg, int dtype, size_t size) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
-  if (nomp_comm_size() > 1) {
+  if (nomp_comm_size() > 1 && !st->fused_allreduce) {
     /* all-reduce the device scalar in place; the NVLink one-shot kernel also publishes {value, seq} to the host,
      * the NCCL fallback needs an explicit 8-byte copy */
     int published = 0;

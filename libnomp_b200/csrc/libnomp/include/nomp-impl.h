@@ -126,6 +126,7 @@ int nomp_comm_size(void);
  * *published = 1 if {value, host_seq} was also written to result_host_mapped (NVLink one-shot path). */
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
                         void *stream, int *published);
+int nomp_comm_peers(void *peers /* nompk_peers_t * */);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 /* all[r] <- rank r's `bytes`-byte record, through files "<id file>.<tag>.<r>" (small setup-time records only) */
 int nomp_comm_allgather(const char *tag, const void *mine, void *all, size_t bytes);

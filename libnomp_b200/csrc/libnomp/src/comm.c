@@ -245,6 +245,23 @@ int nomp_comm_finalize(void) {
 
 NOMP_EXPORT int nomp_b200_comm_uses_nvlink_kernel(void) { return p2p.enabled; }
 
+/* Peer description for a reduction kernel that all-reduces its own result (nompk_reduce_peers, nompk_ax_dot_peers_f64):
+ * takes the next collective sequence number.  Returns 0 when the kernels cannot do it (one rank, no peer access, more
+ * ranks than a warp has lanes, or NOMP_COMM_FUSED=0) and the caller must use nomp_comm_allreduce after the kernel. */
+int nomp_comm_peers(void *peers_) {
+  nompk_peers_t *peers = (nompk_peers_t *)peers_;
+  static int fused = -1;
+  if (fused < 0) {
+    const char *e = getenv("NOMP_COMM_FUSED");
+    fused = !(e && e[0] == '0');
+  }
+  if (comm_size == 1 || !p2p.enabled || !fused || comm_size > 32) return 0;
+  peers->peer_xchg = (void *const *)p2p.table_dev;
+  peers->rank = comm_rank, peers->world = comm_size;
+  peers->seq = ++p2p.seq;
+  return 1;
+}
+
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
                         void *stream, int *published) {
   *published = 0;

@@ -290,3 +290,88 @@ def test_ax_unsupported_n_is_reported():
     t = torch.zeros(9 ** 3 * 6, dtype=torch.float64, device="cuda")
     rc = lib.nompk_ax_f64(9, 1, t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, stream())
     assert rc == -3 and b"n = 9" in lib.nompk_last_error()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_reduction_fused_with_the_all_reduce_on_emulated_ranks(world):
+    """nompk_reduce_peers / nompk_ax_dot_peers_f64: the finishing CTA of every rank's kernel exchanges the result through
+    the peers' buffers and folds in rank order.  The ranks are emulated on this GPU (one stream, workspace and exchange
+    buffer each; the kernels run concurrently and spin on each other's flags exactly as over NVLink).  One rank may use
+    the stand-alone path (nompk_reduce + nompk_allreduce_scalar) on the same buffers: the protocols are the same."""
+    lib = capi.nompk()
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    bufs = [torch.zeros(lib.nompk_allreduce_xchg_bytes(world), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    wss = [torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ress = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    pins = [torch.zeros(3, dtype=torch.int64).pin_memory() for _ in range(world)]
+    seq = 0
+
+    def fold(op, parts):
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = {capi.RED_SUM: lambda a, b: a + b, capi.RED_PROD: lambda a, b: a * b, capi.RED_MIN: min, capi.RED_MAX: max}[op](acc, p)
+        return acc
+
+    cases = [(capi.RED_SUM, capi.F64, 100003, True), (capi.RED_SUM, capi.I64, 5000, False), (capi.RED_MAX, capi.F64, 1, False),
+             (capi.RED_SUM, capi.F64, (1 << 22) + 3, False), (capi.RED_MIN, capi.I32, 70001, False), (capi.RED_SUM, capi.F64, 0, False)]
+    # Load every stand-alone all-reduce kernel used below before anything spins: with CUDA's lazy module loading the
+    # first launch of a kernel waits for the device to drain, which a kernel spinning on a peer of the SAME process
+    # never lets happen (a hazard of this one-GPU emulation only: real ranks are separate processes).
+    solo = torch.zeros(lib.nompk_allreduce_xchg_bytes(1), dtype=torch.uint8, device="cuda")
+    solo_table = torch.tensor([solo.data_ptr()], dtype=torch.int64, device="cuda")
+    for k, (op, dtype, _, _) in enumerate(cases):
+        capi.nompk_check(lib.nompk_allreduce_scalar(op, dtype, ress[0].data_ptr(), None, 0, solo_table.data_ptr(), 0, 1, k + 1,
+                                                    stream()))
+    torch.cuda.synchronize()
+
+    for op, dtype, n, dot in cases:
+        npdt = NP[dtype]
+        seq += 1
+        xs = [ffi.fill_int_f64(n + r, 50 + r, 0, 7).astype(npdt) if dtype != capi.I64 else ffi.fill_i64(n + r, 60 + r)
+              for r in range(world)]
+        ys = [ffi.fill_int_f64(n + r, 70 + r, 0, 7).astype(npdt) if dot else None for r in range(world)]
+        txs, tys = [dev(x) for x in xs], [dev(y) if y is not None else None for y in ys]
+        local = [ffi.reduce_(op, dtype, xs[r], ys[r]) for r in range(world)]
+        with np.errstate(over="ignore"):
+            want = fold(op, [npdt(v) for v in local])
+        torch.cuda.synchronize()
+        for r in range(world):
+            st = C.c_void_p(streams[r].cuda_stream)
+            ty = tys[r].data_ptr() if tys[r] is not None else None
+            if r == world - 1 and seq % 2 == 0:      # this rank takes the two-kernel path
+                capi.nompk_check(lib.nompk_reduce(op, dtype, xs[r].size, txs[r].data_ptr(), ty, ress[r].data_ptr(), None, 0,
+                                                  wss[r].data_ptr(), st))
+                capi.nompk_check(lib.nompk_allreduce_scalar(op, dtype, ress[r].data_ptr(), pins[r].data_ptr(), 1000 + seq,
+                                                            table.data_ptr(), r, world, seq, st))
+            else:
+                peers = capi.NompkPeers(table.data_ptr(), r, world, seq)
+                capi.nompk_check(lib.nompk_reduce_peers(op, dtype, xs[r].size, txs[r].data_ptr(), ty, ress[r].data_ptr(),
+                                                        pins[r].data_ptr(), 1000 + seq, wss[r].data_ptr(), C.byref(peers), st))
+        torch.cuda.synchronize()
+        for r in range(world):
+            got = ress[r].cpu().numpy().view(npdt)[0]
+            assert got.tobytes() == np.array([want], dtype=npdt).tobytes()[: got.nbytes], (op, dtype, n, r, got, want)
+            assert pins[r].numpy().view(npdt)[0].tobytes() == got.tobytes() and pins[r][1].item() == 1000 + seq
+            assert pins[r][2].item() == 0            # nobody timed out
+
+    # Ax fused with p.Ap fused with the all-reduce
+    n, D = 8, ffi.fill_int_f64(64, 23, -2, 2)
+    tD = dev(D)
+    us = [ffi.fill_int_f64((3 + r) * 512, 21 + r, -4, 4) for r in range(world)]
+    gs_ = [ffi.fill_int_f64((3 + r) * 6 * 512, 31 + r, 0, 3) for r in range(world)]
+    tus, tgs = [dev(u) for u in us], [dev(g) for g in gs_]
+    tws = [torch.empty_like(t) for t in tus]
+    fres = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+    seq += 1
+    torch.cuda.synchronize()
+    for r in range(world):
+        peers = capi.NompkPeers(table.data_ptr(), r, world, seq)
+        capi.nompk_check(lib.nompk_ax_dot_peers_f64(n, 3 + r, tus[r].data_ptr(), tgs[r].data_ptr(), tD.data_ptr(), tws[r].data_ptr(),
+                                                    fres[r].data_ptr(), None, 0, wss[r].data_ptr(), C.byref(peers), 0,
+                                                    C.c_void_p(streams[r].cuda_stream)))
+    torch.cuda.synchronize()
+    parts = [float(us[r] @ ffi.ax(n, us[r], gs_[r], D)) for r in range(world)]
+    for r in range(world):
+        assert np.array_equal(host(tws[r], np.float64), ffi.ax(n, us[r], gs_[r], D))
+        assert fres[r].item() == fold(capi.RED_SUM, parts)
