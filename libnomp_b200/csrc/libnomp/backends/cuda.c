@@ -98,6 +98,9 @@ typedef struct {
   cudaEvent_t ev_compute, ev_h2d;
   int async_used;
   int fused_allreduce; /* the reduction kernel just launched all-reduces its result itself */
+  void *nv_peers;      /* peer description handed to a generated reduction kernel (by address, cuLaunchKernel) */
+  int nv_rank, nv_world;
+  unsigned long long nv_cseq;
   void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
   unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
@@ -120,6 +123,10 @@ typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT } family_t;
 #define SLOT_RESULT (-4)
 #define SLOT_RESULT_HOST (-5)
 #define SLOT_SEQ (-6)
+#define SLOT_PEERS (-7)  /* fused all-reduce of a generated reduction: exchange-buffer table, rank, world, call number */
+#define SLOT_RANK (-8)
+#define SLOT_WORLD (-9)
+#define SLOT_CSEQ (-10)
 
 typedef struct {
   family_t family;
@@ -127,7 +134,8 @@ typedef struct {
   CUmodule module;
   CUfunction function;
   int nparams;
-  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 5]; /* index into prg->args, or SLOT_* */
+  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 9]; /* index into prg->args, or SLOT_* */
+  int has_peers;                                  /* the kernel takes the peer description (SLOT_PEERS ...) */
   int is_reduce;
   /* native */
   int op, dtype, ax_n;
@@ -282,13 +290,17 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
     else if (!strcmp(tok, "nomp_result")) slot = SLOT_RESULT;
     else if (!strcmp(tok, "nomp_result_host")) slot = SLOT_RESULT_HOST;
     else if (!strcmp(tok, "nomp_seq")) slot = SLOT_SEQ;
+    else if (!strcmp(tok, "nomp_peers")) slot = SLOT_PEERS, cp->has_peers = 1;
+    else if (!strcmp(tok, "nomp_rank")) slot = SLOT_RANK;
+    else if (!strcmp(tok, "nomp_world")) slot = SLOT_WORLD;
+    else if (!strcmp(tok, "nomp_cseq")) slot = SLOT_CSEQ;
     else {
       slot = arg_index(prg, tok);
       if (slot == SLOT_NONE)
         return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
                         "Kernel argument \"%s\" was not declared in nomp_jit().", tok);
     }
-    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 5)
+    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 9)
       return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Too many kernel arguments.");
     cp->param_slot[cp->nparams++] = slot;
   }
@@ -475,15 +487,24 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     return 0;
   }
   case FAM_NVRTC: {
+    st->nv_peers = NULL, st->nv_rank = 0, st->nv_world = 1, st->nv_cseq = 0;
+    if (cp->is_reduce && cp->has_peers && nomp_comm_size() > 1 && nomp_comm_peers(&peers)) {
+      st->nv_peers = (void *)peers.peer_xchg, st->nv_rank = peers.rank, st->nv_world = peers.world, st->nv_cseq = peers.seq;
+      st->fused_allreduce = 1, result_host = st->pinned_dev;
+    }
     st->red_result_host = result_host;
     if (cp->is_reduce) ++st->host_seq;
-    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 5];
+    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 9];
     for (int i = 0; i < cp->nparams; i++) {
       int s = cp->param_slot[i];
       if (s == SLOT_WS) vargs[i] = &st->red_ws;
       else if (s == SLOT_RESULT) vargs[i] = &st->red_result;
       else if (s == SLOT_RESULT_HOST) vargs[i] = &st->red_result_host;
       else if (s == SLOT_SEQ) vargs[i] = &st->host_seq;
+      else if (s == SLOT_PEERS) vargs[i] = &st->nv_peers;
+      else if (s == SLOT_RANK) vargs[i] = &st->nv_rank;
+      else if (s == SLOT_WORLD) vargs[i] = &st->nv_world;
+      else if (s == SLOT_CSEQ) vargs[i] = &st->nv_cseq;
       else if (prg->args[s].type == NOMP_PTR) vargs[i] = &prg->args[s].ptr; /* device pointer by value */
       else vargs[i] = prg->args[s].ptr;                                       /* the caller's scalar */
     }

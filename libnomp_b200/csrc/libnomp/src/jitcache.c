@@ -13,7 +13,8 @@
  *
  * Directory: $NOMP_JIT_CACHE_DIR, else $XDG_CACHE_HOME/libnomp_b200, else $HOME/.cache/libnomp_b200.  NOMP_JIT_CACHE=0
  * turns the cache off.  Entries are written to a temporary name and rename()d, so concurrent processes (one per GPU)
- * never see a partial file; a corrupt or truncated entry is treated as a miss and overwritten.
+ * never see a partial file, and carry a SHA-256 trailer of their content: a corrupt or truncated entry is a miss and
+ * is overwritten.
  */
 #include <dirent.h>
 #include <errno.h>
@@ -137,6 +138,18 @@ void nomp_jit_cache_count(int which) { stats[which & 3]++; }
 NOMP_EXPORT void nomp_b200_jit_cache_stats(unsigned long long out[4]) { memcpy(out, stats, sizeof(stats)); }
 
 /* ---- entries -------------------------------------------------------------------------------------------------- */
+/* Every entry ends with the SHA-256 (64 hex characters) of what precedes it.  A truncated or damaged file -- a crashed
+ * writer, a full disk -- must never reach the CUDA driver: cuModuleLoadData trusts the ELF headers of the image it is
+ * given and reads wherever they point. */
+#define TRAILER 64
+
+static void digest_of(const void *data, size_t n, char hex[65]) {
+  nomp_sha256_t c;
+  nomp_sha256_init(&c);
+  nomp_sha256_update(&c, data, n);
+  nomp_sha256_hex(&c, hex);
+}
+
 int nomp_jit_cache_load(const char *hex, const char *ext, char **data, size_t *size) {
   const char *dir = nomp_jit_cache_dir();
   if (!dir) return 1;
@@ -146,13 +159,17 @@ int nomp_jit_cache_load(const char *hex, const char *ext, char **data, size_t *s
   if (!fp) return 1;
   int err = 1;
   long n = -1;
-  if (!fseek(fp, 0, SEEK_END) && (n = ftell(fp)) >= 0 && !fseek(fp, 0, SEEK_SET)) {
+  if (!fseek(fp, 0, SEEK_END) && (n = ftell(fp)) >= TRAILER && !fseek(fp, 0, SEEK_SET)) {
     char *buf = nomp_calloc(char, (size_t)n + 1);
+    char want[65];
     if (fread(buf, 1, (size_t)n, fp) == (size_t)n) {
-      *data = buf, *size = (size_t)n, err = 0;
-    } else {
-      free(buf);
+      digest_of(buf, (size_t)n - TRAILER, want);
+      if (!memcmp(want, buf + n - TRAILER, TRAILER)) {
+        buf[n - TRAILER] = '\0';
+        *data = buf, *size = (size_t)n - TRAILER, err = 0;
+      }
     }
+    if (err) free(buf);
   }
   fclose(fp);
   return err;
@@ -166,7 +183,9 @@ int nomp_jit_cache_store(const char *hex, const char *ext, const void *data, siz
   snprintf(tmp, sizeof(tmp), "%s.%ld.tmp", path, (long)getpid());
   FILE *fp = fopen(tmp, "wb");
   if (!fp) return 1;
-  const int ok = fwrite(data, 1, size, fp) == size;
+  char trailer[65];
+  digest_of(data, size, trailer);
+  const int ok = fwrite(data, 1, size, fp) == size && fwrite(trailer, 1, TRAILER, fp) == TRAILER;
   if (fclose(fp) || !ok || rename(tmp, path)) {
     unlink(tmp);
     return 1;

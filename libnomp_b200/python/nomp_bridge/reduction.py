@@ -212,8 +212,9 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
     optional conditions and elementwise updates in front of the accumulation.  One tile of 256 threads per CTA (up to
     65536 CTAs, then the CTAs stride), 128-bit loads/stores when every array is elementwise and 16-byte aligned, and
     the two-level deterministic ticket finish of nompk_gridreduce.cuh.
-    Returns (source, grid exprs, block exprs, kernel parameter names); the trailing four parameters
-    (workspace, result, result_host, seq) are supplied by the backend."""
+    Returns (source, grid exprs, block exprs, kernel parameter names); the trailing eight parameters (workspace,
+    result, result_host, seq, and the peer description of the fused all-reduce: exchange-buffer table, rank, world,
+    collective call number) are supplied by the backend."""
     from .emit_cuda import GenericEmitter
     from .ir import map_expr, map_stmts
     T = cuda_type(info.vtype)
@@ -231,7 +232,8 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         else:
             sig_parts.append(f"{cuda_type(t)} {prm.name}")
     sig_parts += ["void *__restrict__ nomp_ws", f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host",
-                  "unsigned long long nomp_seq"]
+                  "unsigned long long nomp_seq", "void *const *__restrict__ nomp_peers", "int nomp_rank", "int nomp_world",
+                  "unsigned long long nomp_cseq"]
     int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}
     it = cuda_type(info.loop.vtype)
     lo, hi = expr_str(info.loop.lo), expr_str(info.loop.hi)
@@ -333,6 +335,54 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         per_block = 256
 
     src = f"""{PRELUDE}
+// Publication of the grid's result by the first warp of the finishing CTA (text twin of finish_result in
+// csrc/kernels/nompk_gridreduce.cuh).  With nomp_world > 1 the all-reduce over the ranks happens right here: lane r
+// stores the value into rank r's exchange buffer ({{value, call number}} per rank and slot, mapped over NVLink), waits
+// for rank r's value in this rank's buffer, and the values are folded in rank order.
+__device__ __forceinline__ void nomp_finish({T} nomp_v, {T} *nomp_result, {T} *nomp_result_host, unsigned long long nomp_seq,
+                                            void *const *nomp_peers, int nomp_rank, int nomp_world,
+                                            unsigned long long nomp_cseq) {{
+  const int nomp_lane = threadIdx.x & 31;
+  bool nomp_late = false;
+  if (nomp_world > 1) {{
+    nomp_v = __shfl_sync(0xffffffffu, nomp_v, 0);
+    const size_t nomp_slot = (size_t)(nomp_cseq & 1ull) * (size_t)nomp_world;
+    {T} nomp_got = {ident};
+    bool nomp_ok = true;
+    if (nomp_lane < nomp_world) {{
+      char *nomp_dst = (char *)nomp_peers[nomp_lane] + (nomp_slot + (size_t)nomp_rank) * 16;
+      *(volatile {T} *)nomp_dst = nomp_v;
+      __threadfence_system();
+      *(volatile unsigned long long *)(nomp_dst + 8) = nomp_cseq;
+      const char *nomp_src = (const char *)nomp_peers[nomp_rank] + (nomp_slot + (size_t)nomp_lane) * 16;
+      unsigned long long nomp_t0, nomp_t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(nomp_t0));
+      while (*(const volatile unsigned long long *)(nomp_src + 8) != nomp_cseq) {{
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(nomp_t1));
+        if (nomp_t1 - nomp_t0 > 20000000000ull) {{ nomp_ok = false; break; }}   // a rank that never arrives: give up after 20 s
+      }}
+      __threadfence_system();
+      nomp_got = *(const volatile {T} *)nomp_src;
+    }}
+    {T} nomp_acc = __shfl_sync(0xffffffffu, nomp_got, 0);
+    for (int nomp_r = 1; nomp_r < nomp_world; nomp_r++) {{
+      const {T} nomp_o = __shfl_sync(0xffffffffu, nomp_got, nomp_r);
+      nomp_acc = {comb('nomp_acc', 'nomp_o')};
+    }}
+    nomp_late = __any_sync(0xffffffffu, !nomp_ok);
+    nomp_v = nomp_acc;
+  }}
+  if (nomp_lane == 0) {{
+    *nomp_result = nomp_v;
+    if (nomp_result_host) {{
+      if (nomp_late) *(volatile unsigned long long *)((char *)nomp_result_host + 16) = nomp_cseq;
+      *(volatile {T} *)nomp_result_host = nomp_v;
+      __threadfence_system();
+      *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
+    }}
+  }}
+}}
+
 // reduce clause on `{info.var}` (op {info.op}): single-pass schedule of libnompk reduce.cu with a generated loop body
 extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_parts)}) {{
   {T} nomp_acc = {ident};
@@ -379,15 +429,8 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
         {tree}
       }}
     }}
-    if (threadIdx.x == 0) {{
-      *nomp_result = nomp_acc;
-      if (nomp_result_host) {{
-        *(volatile {T} *)nomp_result_host = nomp_acc;
-        __threadfence_system();
-        *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
-      }}
-      if (nomp_nb > 1) *nomp_ticket = 0u;
-    }}
+    if (threadIdx.x == 0 && nomp_nb > 1) *nomp_ticket = 0u;
+    if (threadIdx.x < 32) nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq);
     return;
   }}
   const unsigned int nomp_g = nomp_b / {RED_GROUP}, nomp_ng = (nomp_nb + {RED_GROUP - 1}) / {RED_GROUP};
@@ -424,15 +467,8 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
   if (threadIdx.x < 32) {{
     nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
     {tree}
-    if (threadIdx.x == 0) {{
-      *nomp_result = nomp_acc;
-      if (nomp_result_host) {{
-        *(volatile {T} *)nomp_result_host = nomp_acc;
-        __threadfence_system();
-        *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
-      }}
-      *nomp_ticket = 0u;
-    }}
+    if (threadIdx.x == 0) *nomp_ticket = 0u;
+    nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq);
   }}
 }}
 """
@@ -445,5 +481,6 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
         grid = f"max(1, min(min({tiles}, {RED_SINGLE_LEVEL} + ({tiles} / {(1 << 26) // per_block}) * {RED_MAX_CTAS - RED_SINGLE_LEVEL}), {RED_MAX_CTAS}))"
     except KernelError:
         grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
-    names = [p.name for p in params] + ["nomp_ws", "nomp_result", "nomp_result_host", "nomp_seq"]
+    names = [p.name for p in params] + ["nomp_ws", "nomp_result", "nomp_result_host", "nomp_seq", "nomp_peers", "nomp_rank",
+                                        "nomp_world", "nomp_cseq"]
     return src, [grid, "1", "1"], ["256", "1", "1"], names

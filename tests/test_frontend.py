@@ -207,7 +207,7 @@ def test_reduce_recognition_and_errors():
     for body in ("s[0] += 1;", "s[0] += i;", "if (a[i] > 0) s[0] += 1;", "s[0] += a[i] * a[i] + 1;"):
         desc, cuda, grid, _ = plan(f"void f(double *a, int N, double *s) {{ for (int i = 0; i < N; i++) {{ {body} }} }}", None, ("s", "+"))
         assert desc["kind"] == "nvrtc" and desc["family"] == "reduce" and desc["out"] == "s"
-        assert desc["params"].endswith("nomp_ws,nomp_result,nomp_result_host,nomp_seq")
+        assert desc["params"].endswith("nomp_ws,nomp_result,nomp_result_host,nomp_seq,nomp_peers,nomp_rank,nomp_world,nomp_cseq")
         ok, log = nvrtc_compile(cuda)
         assert ok, log
     with pytest.raises(nb.KernelError):   # two loops

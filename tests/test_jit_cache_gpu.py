@@ -168,11 +168,20 @@ def test_damaged_entries_are_rebuilt_and_failures_are_not_cached(cache):
     assert np.all(a == 13.0) and d["knl_misses"] == 1 and d["cubin_misses"] == 1
     for p in (cache / "jit").iterdir():
         data = p.read_bytes()
-        p.write_bytes(data[: len(data) // 2] if p.suffix == ".cubin" else b"NOMPJIT1\ngarbage")
+        if p.suffix == ".cubin":     # truncated, and (second variant below) one flipped byte in the middle
+            p.write_bytes(data[: len(data) // 2])
+        else:
+            p.write_bytes(b"NOMPJIT1\ngarbage")
     a, d = session(cache, body)
     assert np.all(a == 13.0) and d == {"knl_hits": 0, "knl_misses": 1, "cubin_hits": 0, "cubin_misses": 1}
     a, d = session(cache, body)
     assert np.all(a == 13.0) and d["knl_hits"] == 1 and d["cubin_hits"] == 1
+    for p in (cache / "jit").iterdir():            # same length, one byte changed: the checksum trailer catches it
+        data = bytearray(p.read_bytes())
+        data[len(data) // 3] ^= 0x5A
+        p.write_bytes(bytes(data))
+    a, d = session(cache, body)
+    assert np.all(a == 13.0) and d == {"knl_hits": 0, "knl_misses": 1, "cubin_hits": 0, "cubin_misses": 1}
 
     def failing():
         err, _ = capi.jit(SQ, capi.clauses(("transform", TR, "raises")), vec)
