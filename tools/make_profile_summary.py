@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""Turn what tools/profile_round.sh brought back (gpurun_out/<tag>/) into the files kept under profiles/:
+
+    python tools/make_profile_summary.py gpurun_out/r01c r01
+
+writes profiles/<round>_ncu_summary.md, profiles/ncu_traffic.json, profiles/<round>_bench_n1.json,
+profiles/<round>_bench_reference.json and profiles/<round>_launches_head.csv.
+"""
+import json
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+src = Path(sys.argv[1])
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
+prof = ROOT / "profiles"
+
+CAPTURES = [
+    ("ax8", "ax 8 262144 0 5", "Ax N=7, E=262144 (the headline workload)", 262144 * 512 * 64),
+    ("ax10", "ax 10 131072 0 5", "Ax N=9", 131072 * 1000 * 64),
+    ("ax12", "ax 12 65536 0 5", "Ax N=11", 65536 * 1728 * 64),
+    ("ax6", "ax 6 524288 0 5", "Ax N=5", 524288 * 216 * 64),
+    ("axdot8", "axdot 8 262144 0 5", "Ax N=7 fused with p.Ap", 262144 * 512 * 64),
+    ("dot", "reduce 1 268435456 0 5", "fp64 dot product, n = 2^28", 2 ** 28 * 16),
+    ("add", "map 0 268435456 0 5", "fp64 a += b, n = 2^28", 2 ** 28 * 24),
+    ("gs", "(tools/gs_bench.py 8 64 64 64 3 --no-warmup)", "gather-scatter, 64^3 elements, N=7: 1.34e8 points", 76705272 * 20 + 33006394 * 4),
+]
+
+
+def summarize(kind, path, title=None):
+    args = ["python", str(ROOT / "tools" / "summarize_ncu.py"), kind, str(path)] + ([title] if title else [])
+    return subprocess.run(args, capture_output=True, text=True).stdout
+
+
+def counter(text, name):
+    m = re.search(r"\| " + re.escape(name) + r" \| ([0-9.,]+) \| (\w+)", text)
+    if not m:
+        return None
+    return float(m.group(1).replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1.0, "us": 1e-3}[m.group(2)]
+
+
+out = [f"""# Round {rnd[1:].lstrip('0') or '0'} -- ncu evidence (B200, sm_100a)
+
+Captured on one B200 with `gpurun -- 'bash tools/profile_round.sh <tag>'` (the script holds every command) and turned
+into this file by `tools/make_profile_summary.py`.  Numbers printed by a run under ncu are never bench values; the bench
+lines of the same box and build are `profiles/{rnd}_bench_n1.json` (`python bench.py --steps 20 --warmup 3`, CUDA events)
+and `profiles/{rnd}_bench_reference.json` (`--impl reference`).  The `.ncu-rep` files (23 MB each with sources) stay on
+the box; kept here is the raw counter page of each capture (`ncu -i x.ncu-rep --page raw --csv`), summarised below by
+`tools/summarize_ncu.py`.
+
+## 1. Launch list of `python bench.py --steps 20 --warmup 3 --no-cpu-baseline`
+
+`ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline`
+(first 800 launches of the process: fill, the Ax warm-up (>= 0.3 s of launches) and the 20 timed launches, then the e2e
+leg -- 8 blocks of 32768 elements per step, which is why the average Ax launch in the table is shorter than the
+headline's 1.3 ms -- then the extras)
+
+""", summarize("launches", src / "launches.csv"), """
+The timed region of the headline number holds launches of the production `ax_kernel<8, ...>` only (template arguments:
+n, elements per group, warps per group, groups per CTA, geometric slabs in flight, L2 prefetch distance, streaming
+loads, min CTAs/SM, fused dot, persistent): its share of the step is 100 %, `gpu_launches = steps` in the bench line.
+
+## 2. `ncu --set full --clock-control none --import-source on`, one launch each
+
+| capture | command (`python tools/run_kernel_once.py ...`) | kernel |
+|---|---|---|
+"""]
+for name, cmd, what, _ in CAPTURES:
+    if (src / f"{name}.raw.csv").exists():
+        out.append(f"| {name} | `{cmd}` | {what} |\n")
+out.append("\n")
+traffic = {}
+for name, _, what, alg in CAPTURES:
+    f = src / f"{name}.raw.csv"
+    if not f.exists():
+        continue
+    text = summarize("report", f, f"{name} ({what})")
+    out.append(text)
+    rd, wr, ms = counter(text, "dram__bytes_read.sum"), counter(text, "dram__bytes_write.sum"), counter(text, "gpu__time_duration.sum")
+    traffic[name] = dict(read_bytes=int(rd), write_bytes=int(wr), ms=ms, algorithmic_bytes=alg)
+out.append("## 3. DRAM traffic against algorithmic bytes\n\n| capture | ms under ncu | DRAM read GB | DRAM write GB | algorithmic GB | traffic / algorithmic |\n|---|---:|---:|---:|---:|---:|\n")
+for name, t in traffic.items():
+    alg = t["algorithmic_bytes"]
+    ratio = f"{(t['read_bytes'] + t['write_bytes']) / alg:.3f}" if alg else "see DESIGN 5.4"
+    out.append(f"| {name} | {t['ms']:.3f} | {t['read_bytes'] / 1e9:.3f} | {t['write_bytes'] / 1e9:.3f} | "
+               f"{(alg or 0) / 1e9:.3f} | {ratio} |\n")
+out.append("""
+Reading: the Ax kernels move 1.00-1.03x their algorithmic bytes (nothing is read twice); issue slots are about a third
+busy and the fp64 pipe about 35 %, the n = 8 kernel waits on HBM (long scoreboard), n = 10 / 12 have 9-10 resident warps
+per SM (two CTAs of 5 warps at 168 registers) to cover the same latency and lose 15-25 %; dot / add move exactly their
+operands; the gather-scatter reads and writes the whole vector once (both 32-byte sectors of every 64-byte line hold a
+point of a face normal to the fastest index) plus its index arrays.
+""")
+(prof / f"{rnd}_ncu_summary.md").write_text("".join(out))
+
+ax = {}
+for name, key in (("ax8", "n8_E262144"), ("ax10", "n10_E131072"), ("ax12", "n12_E65536"), ("ax6", "n6_E524288"), ("axdot8", "dot_n8_E262144")):
+    if name in traffic:
+        t = traffic[name]
+        ax[key] = dict(read_bytes=t["read_bytes"], write_bytes=t["write_bytes"], algorithmic_bytes=t["algorithmic_bytes"], capture=name)
+doc = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of "
+                   "tools/profile_round.sh (profiles/%s_ncu_summary.md); bench.py copies the matching entry into roofline.traffic" % rnd,
+       "ax_kernel": ax}
+for name, key in (("dot", "reduce_kernel_dot_f64_n2^28"), ("add", "map_vec_kernel_add_f64_n2^28"), ("gs", "gs_local_kernel_box64_n8")):
+    if name in traffic:
+        t = traffic[name]
+        doc[key] = dict(read_bytes=t["read_bytes"], write_bytes=t["write_bytes"], algorithmic_bytes=t["algorithmic_bytes"])
+(prof / "ncu_traffic.json").write_text(json.dumps(doc, indent=1) + "\n")
+for a, b in (("bench_n1.json", f"{rnd}_bench_n1.json"), ("bench_reference.json", f"{rnd}_bench_reference.json")):
+    if (src / a).exists() and (src / a).stat().st_size > 0:
+        shutil.copy(src / a, prof / b)
+if (src / "launches.csv").exists():
+    (prof / f"{rnd}_launches_head.csv").write_text("".join(open(src / "launches.csv").readlines()[:40]))
+print("wrote", prof / f"{rnd}_ncu_summary.md", "and", prof / "ncu_traffic.json")
