@@ -37,6 +37,7 @@ struct nompk_gs {
   std::vector<size_t> recv_off, send_off;
   bool finalized = false;
   size_t G = 0, nnz = 0, Q = 0, R = 0, total_shared = 0;
+  unsigned remote_ctas = 0;  // CTAs of gs_local_kernel (kGsThreads consecutive groups each) that hold a shared group
   unsigned *offsets = nullptr, *indices = nullptr;
   int *remote_slot = nullptr;
   unsigned *rgroup = nullptr, *roffsets = nullptr, *rpos = nullptr;
@@ -159,6 +160,12 @@ __global__ void fill_kernel(const unsigned *__restrict__ order, const unsigned *
   }
 }
 
+// blk[b] = 1 if CTA b of gs_local_kernel (groups b * threads .. ) holds a group shared with a peer
+__global__ void mark_remote_ctas_kernel(const int *__restrict__ remote_slot, size_t G, int threads, unsigned *__restrict__ blk) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G && remote_slot[g] >= 0) blk[g / threads] = 1u;
+}
+
 // ---- apply ----------------------------------------------------------------------------------------------------
 struct GsView {
   const unsigned *offsets, *indices;
@@ -171,6 +178,7 @@ struct GsView {
   void *const *peer_xchg;
   const int *neighbours;
   size_t G, Q, values_base;  // values_base: byte offset of this call's slot in THIS rank's exchange buffer
+  unsigned remote_ctas;      // how many CTAs of gs_local_kernel hold shared groups (they take the ticket)
   size_t flags_bytes;        // size of the flag block in front of the values of every exchange buffer
   int n_neighbours, rank, world, slot;
   unsigned long long seq;
@@ -185,6 +193,7 @@ struct GsView {
 // vector is read and written once (ncu: 1.51 GB read, 1.01 GB written for a 1.07 GB vector) -- at 4.35 TB/s.
 template <int OP, typename T> __global__ void __launch_bounds__(kGsThreads) gs_local_kernel(T *__restrict__ v, GsView s) {
   const size_t g = (size_t)blockIdx.x * kGsThreads + threadIdx.x;
+  bool remote_here = false;
   if (g < s.G) {
     const unsigned b = s.offsets[g], e = s.offsets[g + 1];
     T acc = v[s.indices[b]];
@@ -203,15 +212,18 @@ template <int OP, typename T> __global__ void __launch_bounds__(kGsThreads) gs_l
         *reinterpret_cast<volatile unsigned long long *>(dst) = word;
       }
       __threadfence_system();
+      remote_here = true;
     }
   }
   if (s.Q == 0) return;
-  // this rank's values are complete on every neighbour once all CTAs have passed here: the last one raises the flags
-  __syncthreads();
+  // This rank's values are complete on every neighbour once all CTAs that hold shared groups have passed here; the
+  // last of THEM raises the flags.  (One ticket per CTA of the whole grid would serialise 10^4 - 10^5 atomics on one
+  // address: tens of microseconds for a kernel of a few hundred.)
+  if (!__syncthreads_or(remote_here)) return;
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned t = atomicAdd(s.ticket, 1u);
-    if (t == gridDim.x - 1) {
+    if (t == s.remote_ctas - 1) {
       *s.ticket = 0;
       __threadfence_system();
       for (int i = 0; i < s.n_neighbours; i++) {
@@ -273,7 +285,7 @@ template <int OP, typename T> int launch_gs(nompk_gs *gs, void *v, unsigned long
   s.rgroup = gs->rgroup, s.roffsets = gs->roffsets, s.rpos = gs->rpos, s.rpeer = gs->rpeer;
   s.partial = gs->partial, s.ticket = gs->ticket, s.recv_off = gs->d_recv_off, s.send_off = gs->d_send_off;
   s.peer_xchg = gs->d_peer_xchg, s.neighbours = gs->d_neighbours;
-  s.G = gs->G, s.Q = gs->Q;
+  s.G = gs->G, s.Q = gs->Q, s.remote_ctas = gs->remote_ctas;
   const unsigned blocks = (unsigned)((gs->G + kGsThreads - 1) / kGsThreads);
   s.slot = (int)(gs->seq & 1ull);
   s.flags_bytes = flags_bytes(gs->world);
@@ -537,6 +549,22 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
                                                       rcnt, rstart, rslot, d_pos, world, gs->indices, gs->remote_slot,
                                                       gs->rgroup, gs->roffsets, gs->rpeer, gs->rpos, G);
       NOMPK_LAUNCH_CHECK("fill_kernel");
+    }
+    if (Q > 0) {
+      const size_t nblk = (G + kGsThreads - 1) / kGsThreads;
+      unsigned *blk = nullptr, *blk_scan = nullptr;
+      if (int e = dev_alloc(&blk, nblk)) return e;
+      if (int e = dev_alloc(&blk_scan, nblk + 1)) {
+        cudaFree(blk);
+        return e;
+      }
+      size_t count = 0;
+      cudaMemsetAsync(blk, 0, nblk * sizeof(unsigned), stream);
+      mark_remote_ctas_kernel<<<blocks_for(G), 256, 0, stream>>>(gs->remote_slot, G, kGsThreads, blk);
+      const int e = exclusive_sum(blk, blk_scan, nblk, &count, stream);
+      cudaFree(blk), cudaFree(blk_scan);
+      if (e) return e;
+      gs->remote_ctas = (unsigned)count;
     }
     const unsigned r32 = (unsigned)R;
     NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->roffsets + Q, &r32, sizeof(unsigned), cudaMemcpyHostToDevice, stream));
