@@ -77,6 +77,41 @@ def _worker(rank, world, port, tmp, results):
     pieces = [torch.zeros((ehi - elo) * n3, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(pieces, w_local)
     assert np.array_equal(torch.cat(pieces).numpy(), ffi.ax(nn, u, g, D))
+
+    # 4. slab-partitioned gather-scatter, the algorithm of gs.cu on the host: fold the local copies of every id, exchange
+    #    the partials of the ids both ranks hold (the interface plane, in ascending id order -- the list S(me, peer)),
+    #    fold them in rank order, write back.  Must equal the oracle's rank-segmented fold of the whole mesh bit for bit.
+    import bench
+    n_pts, ex, ey, ez = 4, 3, 2, 2 * world
+    nz = ez // world
+    ids_full = ffi.box_ids(n_pts, ex, ey, ez)
+    ids = bench.box_slab_ids(n_pts, ex, ey, ez, rank * nz, nz)
+    per = ids_full.size // world
+    assert np.array_equal(ids, ids_full[rank * per:(rank + 1) * per])
+    v_full = ffi.fill_uniform_f64(ids_full.size, 31, 0.5, 1.5)
+    local = ffi.gs(0, ffi.F64, ids, v_full[rank * per:(rank + 1) * per].copy())
+    uniq = torch.from_numpy(np.unique(ids))
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([uniq.numel()]))
+    padded = torch.zeros(int(max(t.item() for t in sizes)), dtype=torch.int64)
+    padded[:uniq.numel()] = uniq
+    everyone = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(everyone, padded)
+    peer = 1 - rank
+    shared = np.intersect1d(uniq.numpy(), everyone[peer][:int(sizes[peer].item())].numpy())   # ascending: S(me, peer)
+    assert shared.size == (3 * ex + 1) * (3 * ey + 1)                                        # one plane of points
+    first = {int(i): k for k, i in reversed(list(enumerate(ids)))}
+    mine = torch.tensor([local[first[int(i)]] for i in shared], dtype=torch.float64)
+    partials = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(partials, mine)
+    total = partials[0] + partials[1]                                                        # rank order
+    out = local.copy()
+    where = {int(i): k for k, i in enumerate(shared)}
+    for k, i in enumerate(ids):
+        if int(i) in where:
+            out[k] = total[where[int(i)]].item()
+    want = ffi.gs(0, ffi.F64, ids_full, v_full.copy(), [r * per for r in range(world + 1)])
+    assert np.array_equal(out, want[rank * per:(rank + 1) * per])
     results[rank] = 1
     dist.destroy_process_group()
 
