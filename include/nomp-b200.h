@@ -59,6 +59,12 @@ int nomp_b200_gs_free(int handle);
  * script is part of the key by its own text only: scripts that import other user modules need NOMP_JIT_CACHE=0 (or
  * a fresh directory) when those modules change. */
 void nomp_b200_jit_cache_stats(unsigned long long counters[4]);
+/* The entry store behind the cache, for diagnostics and tests: the directory in use (NULL when the cache is off;
+ * re-reads the environment), and raw put / get of one entry "<hex>.<ext>".  get returns 1 when there is no intact entry
+ * (missing, truncated, or its checksum trailer does not match). */
+const char *nomp_b200_jit_cache_dir(void);
+int nomp_b200_jit_cache_put(const char *hex, const char *ext, const void *data, size_t size);
+int nomp_b200_jit_cache_get(const char *hex, const char *ext, void *buf, size_t cap, size_t *size);
 /* The hash the cache keys are made of (SHA-256, lower-case hex, NUL-terminated); exported for the tests. */
 void nomp_b200_sha256_hex(const void *data, size_t n, char hex[65]);
 

@@ -49,7 +49,7 @@ NOMP_SYMBOLS = [
     "nomp_b200_stream", "nomp_b200_update_async", "nomp_b200_device_ptr", "nomp_b200_launch_count", "nomp_b200_comm_rank",
     "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
     "nomp_b200_jit_cache_stats", "nomp_b200_sha256_hex", "nomp_b200_gs_setup", "nomp_b200_gs", "nomp_b200_gs_info",
-    "nomp_b200_gs_free",
+    "nomp_b200_gs_free", "nomp_b200_jit_cache_dir", "nomp_b200_jit_cache_put", "nomp_b200_jit_cache_get",
 ]
 
 
@@ -179,6 +179,11 @@ def nomp() -> C.CDLL:
         lib.nomp_b200_gs_free.argtypes = [C.c_int]
         lib.nomp_b200_jit_cache_stats.restype = None
         lib.nomp_b200_jit_cache_stats.argtypes = [C.POINTER(C.c_ulonglong * 4)]
+        lib.nomp_b200_jit_cache_dir.restype = C.c_char_p
+        lib.nomp_b200_jit_cache_put.restype = C.c_int
+        lib.nomp_b200_jit_cache_put.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        lib.nomp_b200_jit_cache_get.restype = C.c_int
+        lib.nomp_b200_jit_cache_get.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.nomp_b200_sha256_hex.restype = None
         lib.nomp_b200_sha256_hex.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
         _nomp = lib

@@ -234,3 +234,24 @@ int nomp_sha256_dir(nomp_sha256_t *c, const char *dir, const char *suffix) {
   free(names);
   return err || n == 0;
 }
+
+/* ---- diagnostics (include/nomp-b200.h): the entry store as seen from outside, used by the CPU tests ----------------- */
+NOMP_EXPORT const char *nomp_b200_jit_cache_dir(void) {
+  nomp_jit_cache_reset(); /* re-read the environment, as nomp_init does */
+  return nomp_jit_cache_dir();
+}
+
+NOMP_EXPORT int nomp_b200_jit_cache_put(const char *hex, const char *ext, const void *data, size_t size) {
+  return nomp_jit_cache_store(hex, ext, data, size);
+}
+
+/* 0 and *size = length of the entry (copied to buf if it fits in cap); 1 if there is no intact entry */
+NOMP_EXPORT int nomp_b200_jit_cache_get(const char *hex, const char *ext, void *buf, size_t cap, size_t *size) {
+  char *data = NULL;
+  size_t n = 0;
+  if (nomp_jit_cache_load(hex, ext, &data, &n)) return 1;
+  if (buf && n <= cap) memcpy(buf, data, n);
+  if (size) *size = n;
+  free(data);
+  return 0;
+}

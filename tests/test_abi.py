@@ -169,3 +169,47 @@ def test_jit_cache_hash_is_sha256():
         lib.nomp_b200_sha256_hex(data, n, out)
         assert out.value.decode() == hashlib.sha256(data).hexdigest(), n
     assert capi.jit_cache_stats() == {"knl_hits": 0, "knl_misses": 0, "cubin_hits": 0, "cubin_misses": 0}
+
+
+def test_jit_cache_entry_store(tmp_path, monkeypatch):
+    """src/jitcache.c without a device: directory selection, atomic put, get, and the checksum trailer that keeps a
+    truncated or damaged entry away from the CUDA driver."""
+    import hashlib
+    lib = capi.nomp()
+    monkeypatch.setenv("NOMP_JIT_CACHE", "1")
+    monkeypatch.setenv("NOMP_JIT_CACHE_DIR", str(tmp_path / "a" / "b"))
+    assert lib.nomp_b200_jit_cache_dir() == str(tmp_path / "a" / "b").encode() and (tmp_path / "a" / "b").is_dir()
+    monkeypatch.delenv("NOMP_JIT_CACHE_DIR")
+    monkeypatch.setenv("XDG_CACHE_HOME", str(tmp_path / "xdg"))
+    assert lib.nomp_b200_jit_cache_dir() == str(tmp_path / "xdg" / "libnomp_b200").encode()
+    monkeypatch.delenv("XDG_CACHE_HOME")
+    monkeypatch.setenv("HOME", str(tmp_path / "home"))
+    assert lib.nomp_b200_jit_cache_dir() == str(tmp_path / "home" / ".cache" / "libnomp_b200").encode()
+    monkeypatch.setenv("NOMP_JIT_CACHE", "0")
+    assert lib.nomp_b200_jit_cache_dir() is None
+    assert lib.nomp_b200_jit_cache_put(b"00", b"knl", b"x", 1) != 0
+    monkeypatch.setenv("NOMP_JIT_CACHE", "1")
+    monkeypatch.setenv("NOMP_JIT_CACHE_DIR", str(tmp_path / "jit"))
+    assert lib.nomp_b200_jit_cache_dir() == str(tmp_path / "jit").encode()
+
+    payload = bytes(range(256)) * 33 + b"tail"
+    key = hashlib.sha256(b"key").hexdigest().encode()
+    n = C.c_size_t()
+    buf = C.create_string_buffer(len(payload))
+    assert lib.nomp_b200_jit_cache_get(key, b"cubin", buf, len(payload), C.byref(n)) == 1           # nothing there yet
+    assert lib.nomp_b200_jit_cache_put(key, b"cubin", payload, len(payload)) == 0
+    files = sorted(p.name for p in (tmp_path / "jit").iterdir())
+    assert files == [key.decode() + ".cubin"]                                                      # no temporary left
+    raw = (tmp_path / "jit" / files[0]).read_bytes()
+    assert raw[:-64] == payload and raw[-64:] == hashlib.sha256(payload).hexdigest().encode()
+    assert lib.nomp_b200_jit_cache_get(key, b"cubin", buf, len(payload), C.byref(n)) == 0
+    assert n.value == len(payload) and buf.raw == payload
+    assert lib.nomp_b200_jit_cache_get(key, b"knl", buf, len(payload), C.byref(n)) == 1             # other kind, other file
+    entry = tmp_path / "jit" / files[0]
+    for damaged in (raw[: len(raw) // 2], raw[:-1], raw[:100] + bytes([raw[100] ^ 1]) + raw[101:], b"", raw + b"x"):
+        entry.write_bytes(damaged)
+        assert lib.nomp_b200_jit_cache_get(key, b"cubin", buf, len(payload), C.byref(n)) == 1, len(damaged)
+    assert lib.nomp_b200_jit_cache_put(key, b"cubin", payload, len(payload)) == 0                   # rewritten
+    assert lib.nomp_b200_jit_cache_get(key, b"cubin", buf, len(payload), C.byref(n)) == 0 and buf.raw == payload
+    assert lib.nomp_b200_jit_cache_put(key, b"knl", b"", 0) == 0                                    # empty payloads are fine
+    assert lib.nomp_b200_jit_cache_get(key, b"knl", buf, len(payload), C.byref(n)) == 0 and n.value == 0
