@@ -494,3 +494,69 @@ def test_random_expressions_survive_parsing_and_code_generation(T):
             emulate(cuda, "foo", g, (int(block[0]), 1, 1), argtypes,
                     [_ptr(got), _ptr(b0), _ptr(c0), ctype(sv), ctype(tv), C.c_int(n)])
             assert np.array_equal(got, want), (T, case, desc["family"], expr)
+
+
+# ---- the accepted kernel language, feature by feature ----------------------------------------------------
+
+def _tile_first(knl, ctx):
+    i = sorted(knl.default_entrypoint.all_inames())[0]
+    knl = lp.split_iname(knl, i, 64)
+    return lp.tag_inames(knl, {f"{i}_outer": "g.0", f"{i}_inner": "l.0"})
+
+
+LANGUAGE_CASES = {
+ "char_short_bool": ("void f(char *a, short *b, unsigned char *c, int N) { for (int i = 0; i < N; i++) { a[i] = a[i] + 1; b[i] = b[i] * 2; c[i] = !c[i]; } }",
+     [("char *", np.int8), ("short *", np.int16), ("unsigned char *", np.uint8)]),
+ "le_loop": ("void f(int *a, int N) { for (int i = 0; i <= N - 1; i++) a[i] = i % 7 + (i >> 1) - (i / 3); }", [("int *", np.int32)]),
+ "div_assign": ("void f(double *a, int N) { for (int i = 0; i < N; i++) a[i] /= 4; }", [("double *", np.float64)]),
+ "nested_2d_decl": ("void f(double *a, int N) { for (int i = 0; i < N; i++) { double t[2][3]; for (int j = 0; j < 2; j++) for (int k = 0; k < 3; k++) t[j][k] = a[i] * j + k; a[i] = t[1][2] - t[0][1]; } }", [("double *", np.float64)]),
+ "if_else_chain": ("void f(int *a, int N) { for (int i = 0; i < N; i++) { if (a[i] > 10) a[i] = 1; else if (a[i] > 5) a[i] = 2; else a[i] = 3; } }", [("int *", np.int32)]),
+ "logical": ("void f(int *a, int N) { for (int i = 0; i < N; i++) a[i] = (a[i] > 3 && a[i] < 9) || a[i] == 12; }", [("int *", np.int32)]),
+ "bitops": ("void f(unsigned *a, int N) { for (int i = 0; i < N; i++) a[i] = (~a[i] & 255) | (a[i] << 3) ^ (a[i] >> 2); }", [("unsigned *", np.uint32)]),
+ "float_literals": ("void f(float *a, int N) { for (int i = 0; i < N; i++) a[i] = a[i] * 0.5f + 1.5e-1f - .25f; }", [("float *", np.float32)]),
+ "casts": ("void f(double *a, int N) { for (int i = 0; i < N; i++) a[i] = (double)((int)a[i] / 2) + (float)i; }", [("double *", np.float64)]),
+ "while_like_break": ("void f(int *a, int N) { for (int i = 0; i < N; i++) { int s = 0; for (int j = 0; j < 100; j++) { if (j > a[i]) break; if (j % 2) continue; s += j; } a[i] = s; } }", [("int *", np.int32)]),
+ "long_unsigned_long": ("void f(long *a, unsigned long *b, int N) { for (int i = 0; i < N; i++) { a[i] = a[i] * 3 - b[i]; b[i] = b[i] + a[i]; } }", [("long long *", np.int64), ("unsigned long long *", np.uint64)]),
+ "math_calls": ("void f(double *a, int N) { for (int i = 0; i < N; i++) a[i] = sqrt(a[i]) + fabs(a[i] - 3.0) + fmin(a[i], 2.0); }", [("double *", np.float64)]),
+ "scalar_decl_no_init": ("void f(double *a, int N) { for (int i = 0; i < N; i++) { double t; t = a[i]; t *= t; a[i] = t; } }", [("double *", np.float64)]),
+ "hoisted_bound": ("void f(int *a, int *b, int N) { for (int i = 0; i < N; i++) { int s = 0; for (int j = b[i]; j < b[i + 1]; j++) s += j; a[i] = s; } }", [("int *", np.int32), ("int *", np.int32)]),
+ "array_param_syntax": ("void f(double a[], const double b[], int N) { for (int i = 0; i < N; i++) a[i] += b[i] * b[i]; }", [("double *", np.float64), ("const double *", np.float64)]),
+ "uint_loop_var": ("void f(int *a, unsigned N) { for (unsigned i = 0; i < N; i++) a[i] = i * 2; }", [("int *", np.int32)]),
+ "pre_increment": ("void f(int *a, int N) { for (int i = 0; i < N; ++i) a[i] = i; }", [("int *", np.int32)]),
+ "step_plus_equal": ("void f(int *a, int N) { for (int i = 0; i < N; i += 1) a[i] = i; }", [("int *", np.int32)]),
+ "comments": ("void f(int *a, int N) { /* block */ for (int i = 0; i < N; i++) { // line\n a[i] = i; } }", [("int *", np.int32)]),
+ "modulo_neg": ("void f(int *a, int N) { for (int i = 0; i < N; i++) a[i] = (a[i] - 20) % 7 + (a[i] - 20) / 3; }", [("int *", np.int32)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LANGUAGE_CASES))
+def test_kernel_language_feature(name):
+    """One kernel per language feature (narrow integer types, <= loops, /=, N-D temporaries, else-if chains, logical and
+    bit operators, float literals, casts, break / continue, math calls, data-dependent inner bounds, array-syntax
+    parameters, unsigned loop variables, ++i and i += 1, comments, signed % and /): the generated CUDA -- with and
+    without a user tiling -- executed on the host returns the bits of the kernel string compiled by gcc."""
+    src, arrs = LANGUAGE_CASES[name]
+    n = 100
+    rng = np.random.default_rng(1)
+    data = []
+    for _, dt in arrs:
+        if np.issubdtype(dt, np.floating):
+            data.append(rng.uniform(1, 9, n + 1).astype(dt))
+        elif "b[i + 1]" in src and len(data) == 1:
+            data.append(np.sort(rng.integers(0, 30, n + 1)).astype(dt))
+        else:
+            data.append(rng.integers(0, 20, n + 1).astype(dt))
+    unsigned_n = "unsigned N" in src
+    want = [d.copy() for d in data]
+    run_kernel(src, *want, (C.c_uint(n) if unsigned_n else n))
+    for transform in (None, _tile_first):
+        desc, cuda, (grid, block), _ = plan(src, transform)
+        assert desc["kind"] == "nvrtc", desc
+        ok, log = nvrtc_compile(cuda)
+        assert ok, log
+        got = [d.copy() for d in data]
+        emulate(cuda, "f", (grid_eval(grid[0], {"N": n}), 1, 1), (int(block[0]), 1, 1),
+                [a[0] for a in arrs] + ["unsigned" if unsigned_n else "int"],
+                [C.c_void_p(x.ctypes.data) for x in got] + [C.c_uint(n) if unsigned_n else C.c_int(n)])
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (name, desc["family"])
