@@ -560,3 +560,46 @@ def test_kernel_language_feature(name):
                 [C.c_void_p(x.ctypes.data) for x in got] + [C.c_uint(n) if unsigned_n else C.c_int(n)])
         for a, b in zip(got, want):
             assert np.array_equal(a, b), (name, desc["family"])
+
+
+def test_mutated_kernel_strings_fail_cleanly():
+    """1500 random token-level mutations of four kernels (delete / insert / replace): the bridge either accepts the
+    result or raises its own syntax / kernel error -- never anything else, never slowly (libnomp turns the exception
+    into NOMP_LOOPY_CONVERSION_FAILURE with the message; a stray IndexError or a hang would be a bug of ours)."""
+    import random
+    import re
+    import time
+    seeds = ["void f(double *a, const double *b, int N) { for (int i = 0; i < N; i++) a[i] += b[i] * 2; }",
+             "void g(int *a, int N, int *s) { for (int i = 0; i < N; i++) { if (a[i] > 3) s[0] += a[i]; else continue; } }",
+             "void h(double *a, int n, int m) { for (int i = 0; i < n; i++) { double t[m]; for (int j = 0; j < m; j++) "
+             "t[j] = a[i * m + j]; for (int j = 0; j < m; j++) a[i * m + j] = t[m - 1 - j]; } }",
+             families.AX_KERNEL_SOURCE]
+    tok = re.compile(r"[A-Za-z_]\w*|\d+\.?\d*|==|!=|<=|>=|&&|\|\||<<|>>|\+=|-=|\*=|\+\+|--|\S")
+    extra = ["(", ")", "{", "}", "[", "]", ";", ",", "for", "if", "else", "int", "double", "*", "+", "-", "=", "0", "x",
+             "?", ":", "<", "++"]
+    rng = random.Random(5)
+    allowed = (nb.KernelError, cparse.CSyntaxError)
+    accepted = 0
+    for _ in range(1500):
+        toks = tok.findall(rng.choice(seeds))
+        for _ in range(rng.randint(1, 4)):
+            op, pos = rng.random(), rng.randrange(len(toks))
+            if op < 0.4:
+                del toks[pos]
+            elif op < 0.8:
+                toks.insert(pos, rng.choice(extra))
+            else:
+                toks[pos] = rng.choice(extra)
+        text = " ".join(toks)
+        t0 = time.perf_counter()
+        try:
+            k = nb.c_to_loopy(text, "cuda")
+            if rng.random() < 0.5:
+                k = nb.fix_parameters(k, {"n": 4, "m": 3})
+            nb.get_knl_src(k, CTX)
+            nb.get_grid_size(k, CTX)
+            accepted += 1
+        except allowed:
+            pass
+        assert time.perf_counter() - t0 < 2.0, text
+    assert 0 < accepted < 300
