@@ -5,6 +5,10 @@ nvrtc_compile(): compile a kernel for sm_100a with NVRTC (the same call sequence
 emulate():       run a generated kernel on the host by compiling it with g++ against a tiny shim that turns
                  blockIdx / threadIdx into loop variables (threads of a block run one after the other, so only
                  kernels whose threads do not exchange data through __shared__ memory mid-kernel are meaningful).
+emulate_cooperative(): the same with one coroutine per thread and real __syncthreads / warp-shuffle / atomic-ticket
+                 semantics, for the kernels whose threads do cooperate: the single-pass reduction skeleton (block tree,
+                 one- and two-level ticket finish, publication) and the one-block-per-element kernels with temporaries
+                 in shared memory.
 """
 from __future__ import annotations
 
@@ -91,3 +95,156 @@ extern "C" void nomp_emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned 
     fn = lib.nomp_emu_launch
     fn.restype = None
     fn(*[C.c_uint(v) for v in (*grid, *block)], *args)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Cooperative emulation: kernels whose threads DO exchange data (shared memory + __syncthreads, warp shuffles, atomic
+# tickets across blocks) run on the host with one coroutine (ucontext) per thread of a block.  A thread runs until it
+# reaches a barrier or a shuffle, the scheduler releases a barrier when every live thread of the block (or of the
+# warp) has arrived, blocks run one after the other.  Faithful for race-free kernels; a deadlock aborts.
+# ----------------------------------------------------------------------------------------------------------------------
+_COOP_SHIM = r"""
+#include <cstdint>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ucontext.h>
+struct nomp_emu_dim3 { unsigned x, y, z; };
+struct nomp_emu_thread { ucontext_t ctx; nomp_emu_dim3 tid; int state, warp, lane; char *stack; };
+enum { EMU_READY = 0, EMU_BLOCK_BARRIER = 1, EMU_WARP_BARRIER = 2, EMU_DONE = 3 };
+static nomp_emu_dim3 blockIdx, blockDim, gridDim;
+static nomp_emu_thread *nomp_emu_cur;
+static ucontext_t nomp_emu_sched;
+static unsigned long long nomp_emu_xchg[64][32];
+#define threadIdx (nomp_emu_cur->tid)
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __shared__ static
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+struct alignas(16) int4 { int x, y, z, w; };
+static void nomp_emu_yield(int state) {
+  nomp_emu_thread *t = nomp_emu_cur;
+  t->state = state;
+  swapcontext(&t->ctx, &nomp_emu_sched);
+}
+static inline void __syncthreads() { nomp_emu_yield(EMU_BLOCK_BARRIER); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { nomp_emu_yield(EMU_WARP_BARRIER); }
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T, typename U> static inline T atomicAdd(T *p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T> static inline T nomp_emu_exchange(T v, int from_lane) {
+  nomp_emu_thread *t = nomp_emu_cur;
+  unsigned long long w = 0;
+  memcpy(&w, &v, sizeof(T));
+  nomp_emu_xchg[t->warp][t->lane] = w;
+  nomp_emu_yield(EMU_WARP_BARRIER);                 // everybody has written
+  const unsigned long long o = nomp_emu_xchg[t->warp][from_lane & 31];
+  nomp_emu_yield(EMU_WARP_BARRIER);                 // everybody has read: the slots may be reused
+  T r;
+  memcpy(&r, &o, sizeof(T));
+  return r;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int mask) { return nomp_emu_exchange(v, nomp_emu_cur->lane ^ mask); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int lane) { return nomp_emu_exchange(v, lane); }
+static inline int __any_sync(unsigned, int pred) {
+  int any = 0;
+  for (int l = 0; l < 32; l++) any |= nomp_emu_exchange<int>(pred != 0, l);
+  return any;
+}
+"""
+
+_COOP_DRIVER = r"""
+static void nomp_emu_entry() {
+  NOMP_EMU_CALL;
+  nomp_emu_cur->state = EMU_DONE;
+  swapcontext(&nomp_emu_cur->ctx, &nomp_emu_sched);
+}
+extern "C" int nomp_emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz NOMP_EMU_PARAMS) {
+  NOMP_EMU_STORE
+  gridDim = {gx, gy, gz}; blockDim = {bx, by, bz};
+  const unsigned nt = bx * by * bz;
+  const size_t stack_bytes = 512 * 1024;
+  nomp_emu_thread *th = (nomp_emu_thread *)calloc(nt, sizeof(nomp_emu_thread));
+  for (unsigned i = 0; i < nt; i++) th[i].stack = (char *)malloc(stack_bytes);
+  int rc = 0;
+  for (unsigned Z = 0; Z < gz && !rc; Z++) for (unsigned Y = 0; Y < gy && !rc; Y++) for (unsigned X = 0; X < gx && !rc; X++) {
+    blockIdx = {X, Y, Z};
+    for (unsigned i = 0; i < nt; i++) {
+      nomp_emu_thread *t = &th[i];
+      t->tid = {i % bx, (i / bx) % by, i / (bx * by)};
+      t->state = EMU_READY, t->warp = (int)(i / 32), t->lane = (int)(i % 32);
+      getcontext(&t->ctx);
+      t->ctx.uc_stack.ss_sp = t->stack, t->ctx.uc_stack.ss_size = stack_bytes, t->ctx.uc_link = &nomp_emu_sched;
+      makecontext(&t->ctx, nomp_emu_entry, 0);
+    }
+    for (;;) {
+      bool progressed = false;
+      unsigned live = 0, at_block = 0;
+      for (unsigned i = 0; i < nt; i++) {
+        if (th[i].state == EMU_READY) {
+          nomp_emu_cur = &th[i];
+          swapcontext(&nomp_emu_sched, &th[i].ctx);
+          progressed = true;
+        }
+      }
+      for (unsigned w = 0; w * 32 < nt; w++) {          // warp barriers
+        unsigned alive = 0, waiting = 0;
+        for (unsigned i = w * 32; i < nt && i < (w + 1) * 32; i++) {
+          alive += th[i].state != EMU_DONE;
+          waiting += th[i].state == EMU_WARP_BARRIER;
+        }
+        if (waiting && waiting == alive) {
+          for (unsigned i = w * 32; i < nt && i < (w + 1) * 32; i++)
+            if (th[i].state == EMU_WARP_BARRIER) th[i].state = EMU_READY;
+          progressed = true;
+        }
+      }
+      for (unsigned i = 0; i < nt; i++) live += th[i].state != EMU_DONE, at_block += th[i].state == EMU_BLOCK_BARRIER;
+      if (live == 0) break;
+      if (at_block == live) {
+        for (unsigned i = 0; i < nt; i++) if (th[i].state == EMU_BLOCK_BARRIER) th[i].state = EMU_READY;
+        progressed = true;
+      }
+      if (!progressed) { fprintf(stderr, "nomp emulation: deadlock in block (%u, %u, %u)\n", X, Y, Z); rc = 1; break; }
+    }
+  }
+  for (unsigned i = 0; i < nt; i++) free(th[i].stack);
+  free(th);
+  return rc;
+}
+"""
+
+
+def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args):
+    """Run a generated kernel on the host with real barrier / shuffle / ticket semantics (see above)."""
+    key = hashlib.sha256(("coop" + src + kernel + repr(argtypes)).encode()).hexdigest()[:16]
+    so = _DIR / f"c{key}.so"
+    if not so.exists():
+        body = re.sub(r'extern "C"\s*', "", src)
+        # the only inline PTX the bridge emits reads the global timer (time-out of the peer exchange): no peers here
+        body = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = 0;", body)
+        params = "".join(f", {t} a{i}" for i, t in enumerate(argtypes))
+        decls = "\n".join(f"static {t.replace('const ', '')} nomp_emu_a{i};" for i, t in enumerate(argtypes))
+        store = " ".join(f"nomp_emu_a{i} = ({t.replace('const ', '')})a{i};" for i, t in enumerate(argtypes))
+        call = f"{kernel}(" + ", ".join(f"nomp_emu_a{i}" for i in range(len(argtypes))) + ")"
+        driver = (_COOP_DRIVER.replace("NOMP_EMU_CALL", call).replace("NOMP_EMU_PARAMS", params)
+                  .replace("NOMP_EMU_STORE", store))
+        cpp = _DIR / f"c{key}.cpp"
+        cpp.write_text(_COOP_SHIM + body + "\n" + decls + "\n" + driver)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(so), str(cpp)],
+                       check=True)
+    lib = C.CDLL(str(so))
+    fn = lib.nomp_emu_launch
+    fn.restype = C.c_int
+    rc = fn(*[C.c_uint(v) for v in (*grid, *block)], *args)
+    assert rc == 0, "the emulated kernel deadlocked"

@@ -603,3 +603,117 @@ def test_mutated_kernel_strings_fail_cleanly():
             pass
         assert time.perf_counter() - t0 < 2.0, text
     assert 0 < accepted < 300
+
+
+# ---- kernels whose threads cooperate, executed on the host (tests/cuda_emulation.py: emulate_cooperative) -------------------
+
+REDUCE_TAIL = ["void *", "{T} *", "{T} *", "unsigned long long", "void **", "int", "int", "unsigned long long"]
+
+
+def _run_reduce_skeleton(src, var, op, T, arrays, scalars, n, grid_override=None):
+    """Generated reduction kernel on the host with real barriers, shuffles and block tickets.  Returns (result,
+    result as published to the 'host' block, sequence number, workspace ticket words after the run)."""
+    from tests.cuda_emulation import emulate_cooperative
+    desc, cuda, (grid, block), _ = plan(src, reduce=(var, op))
+    assert desc["kind"] == "nvrtc" and desc["family"] == "reduce", desc
+    name = src.split("(")[0].split()[-1]
+    cuda_t = {"long": "long long", "unsigned long": "unsigned long long"}.get(T, T)
+    dt = NP[T]
+    ws = np.zeros(548928 // 8 + 8, dtype=np.uint64)      # nompk_reduce_workspace_bytes()
+    res, pub = np.zeros(1, dtype=dt), np.zeros(24, dtype=np.uint8)
+    params = desc["params"].split(",")[:-8]
+    types, args = [], []
+    for prm in params:
+        if prm in arrays:
+            a, ct = arrays[prm]
+            types.append(ct)
+            args.append(C.c_void_p(a.ctypes.data))
+        else:
+            ct, val = scalars[prm]
+            types.append(ct)
+            args.append(val)
+    types += [t.format(T=cuda_t) for t in REDUCE_TAIL]
+    args += [C.c_void_p(ws.ctypes.data), C.c_void_p(res.ctypes.data), C.c_void_p(pub.ctypes.data), C.c_ulonglong(41),
+             C.c_void_p(0), C.c_int(0), C.c_int(1), C.c_ulonglong(0)]
+    g = grid_override or grid_eval(grid[0], {"N": n})
+    emulate_cooperative(cuda, name, (g, 1, 1), (256, 1, 1), types, args)
+    return res[0], pub[:dt().nbytes].view(dt)[0], int(pub[8:16].view(np.uint64)[0]), ws[:2].copy()
+
+
+@pytest.mark.parametrize("T", ["double", "long", "int", "float"])
+@pytest.mark.parametrize("grid", [None, 1, 37, 2500])
+def test_reduce_skeleton_runs_on_the_host(T, grid):
+    """Sum with a condition and a non-trivial right-hand side, through the generated single-pass reduction: every
+    grid shape of the finish (one CTA, one ticket level, two ticket levels) gives the serial loop's value on exact
+    data, publishes it with its sequence number and leaves the tickets at zero."""
+    dt = NP[T]
+    n = 30011
+    a = (np.arange(n) * 7 % 13).astype(dt)
+    b = (np.arange(n) * 5 % 11).astype(dt)
+    src = f"void red({T} *a, {T} *b, int N, {T} *s) {{ for (int i = 0; i < N; i++) if (a[i] > 2) s[0] += a[i] * b[i] + 1; }}"
+    cuda_t = {"long": "long long"}.get(T, T)
+    got, pub, seq, tickets = _run_reduce_skeleton(src, "s", "+", T, {"a": (a, f"{cuda_t} *"), "b": (b, f"{cuda_t} *")},
+                                                  {"N": ("int", C.c_int(n))}, n, grid)
+    want = np.zeros(1, dtype=dt)
+    run_kernel(src, a, b, n, want)
+    assert got == want[0] == pub and seq == 41 and not tickets.any()
+
+
+def test_min_max_and_fused_update_skeletons_run_on_the_host():
+    n = 5003
+    rng = np.random.default_rng(3)
+    a = rng.integers(-1000, 1000, n).astype(np.float64)
+    for op, body, fn in (("min", "m[0] = (a[i] * 2 < m[0]) ? a[i] * 2 : m[0];", np.min),
+                         ("max", "m[0] = (a[i] * 2 > m[0]) ? a[i] * 2 : m[0];", np.max)):
+        src = f"void mm(const double *a, int N, double *m) {{ for (int i = 0; i < N; i++) {body} }}"
+        got, pub, _, _ = _run_reduce_skeleton(src, "m", op, "double", {"a": (a, "const double *")}, {"N": ("int", C.c_int(n))}, n)
+        assert got == fn(2 * a) == pub
+    # the fused CG update: elementwise writes in front of the accumulation, vectorised path (all arrays 16-byte aligned)
+    src = ("void upd(double *x, double *r, const double *p, const double *w, double alpha, int N, double *rr) {"
+           " for (int i = 0; i < N; i++) { x[i] += alpha * p[i]; r[i] -= alpha * w[i]; rr[0] += r[i] * r[i]; } }")
+    x, r = rng.integers(-4, 5, n).astype(np.float64), rng.integers(-4, 5, n).astype(np.float64)
+    p, w = rng.integers(-4, 5, n).astype(np.float64), rng.integers(-4, 5, n).astype(np.float64)
+    xw, rw, want = x.copy(), r.copy(), np.zeros(1)
+    run_kernel(src, xw, rw, p, w, 0.5, n, want)
+    got, _, _, _ = _run_reduce_skeleton(src, "rr", "+", "double",
+                                        {"x": (x, "double *"), "r": (r, "double *"), "p": (p, "const double *"), "w": (w, "const double *")},
+                                        {"alpha": ("double", C.c_double(0.5)), "N": ("int", C.c_int(n))}, n)
+    assert got == want[0] and np.array_equal(x, xw) and np.array_equal(r, rw)
+
+
+def test_annotated_element_kernel_runs_on_the_host():
+    """The one-block-per-element schedule of nomp_sem.py (shared-memory temporaries between barriers) for an operator
+    that is not a hand-written family, executed with one coroutine per thread: bitwise the kernel string run by gcc."""
+    import nomp_sem
+    from tests.cuda_emulation import emulate_cooperative
+    from oracle import ffi
+    point = "e * n * n * n + k * n * n + j * n + i"
+    src = families.AX_KERNEL_SOURCE.replace("const double *D, int E, int n)", "const double *D, const double *h, int E, int n)")
+    src = src.replace("nomp_ax(", "helmholtz(").replace(f"w[{point}] = acc;", f"w[{point}] = acc + h[{point}] * u[{point}];")
+    n, E = 4, 5
+    k = nb.c_to_loopy(src, "cuda")
+    for key, loop in (("element_loop", "e"), ("dof_loop", "i"), ("dof_loop", "j"), ("dof_loop", "k")):
+        k = nomp_sem.annotate(k, {key: loop}, CTX)
+    k = nb.fix_parameters(k, {"n": n})
+    header, _, cuda = nb.get_knl_src(k, CTX).partition("\n")
+    u = ffi.fill_uniform_f64(E * n ** 3, 1, -1.0, 1.0)
+    g = ffi.fill_uniform_f64(E * 6 * n ** 3, 2, 0.5, 1.5)
+    h = ffi.fill_uniform_f64(E * n ** 3, 3, 0.0, 2.0)
+    D = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    want, got = np.zeros_like(u), np.zeros_like(u)
+    run_kernel(src, want, u, g, D, h, E, n)
+    ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    emulate_cooperative(cuda, "helmholtz", (E, 1, 1), (n, n, n),
+                        ["double *", "const double *", "const double *", "const double *", "const double *", "int"],
+                        [ptr(got), ptr(u), ptr(g), ptr(D), ptr(h), C.c_int(E)])
+    assert np.array_equal(got, want)
+    # the Ax kernel string itself at a size without a hand-written kernel takes the same schedule
+    k5 = nb.fix_parameters(nb.c_to_loopy(families.AX_KERNEL_SOURCE, "cuda"), {"n": 5})
+    _, _, cuda5 = nb.get_knl_src(k5, CTX).partition("\n")
+    u5 = ffi.fill_int_f64(3 * 125, 5, -4, 4)
+    g5 = ffi.fill_int_f64(3 * 6 * 125, 6, 0, 3)
+    D5 = ffi.fill_int_f64(25, 7, -2, 2)
+    w5 = np.zeros_like(u5)
+    emulate_cooperative(cuda5, "nomp_ax", (3, 1, 1), (5, 5, 5), ["double *", "const double *", "const double *", "const double *", "int"],
+                        [ptr(w5), ptr(u5), ptr(g5), ptr(D5), C.c_int(3)])
+    assert np.array_equal(w5, ffi.ax(5, u5, g5, D5))
