@@ -133,9 +133,16 @@ static void nomp_emu_yield(int state) {
 }
 static inline void __syncthreads() { nomp_emu_yield(EMU_BLOCK_BARRIER); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { nomp_emu_yield(EMU_WARP_BARRIER); }
-static inline void __threadfence() {}
+#include <atomic>
+#include <time.h>
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned long long nomp_emu_now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
@@ -225,14 +232,16 @@ extern "C" int nomp_emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned b
 """
 
 
-def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args):
-    """Run a generated kernel on the host with real barrier / shuffle / ticket semantics (see above)."""
-    key = hashlib.sha256(("coop" + src + kernel + repr(argtypes)).encode()).hexdigest()[:16]
+def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args, instance: int = 0):
+    """Run a generated kernel on the host with real barrier / shuffle / ticket semantics (see above).  Different
+    `instance` numbers give separate copies of the library (own globals), so several "ranks" can run at the same time
+    in different Python threads and talk through host memory the way GPUs talk through peer memory."""
+    key = hashlib.sha256((f"coop{instance}" + src + kernel + repr(argtypes)).encode()).hexdigest()[:16]
     so = _DIR / f"c{key}.so"
     if not so.exists():
         body = re.sub(r'extern "C"\s*', "", src)
-        # the only inline PTX the bridge emits reads the global timer (time-out of the peer exchange): no peers here
-        body = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = 0;", body)
+        # the only inline PTX the bridge emits reads the global timer (time-out of the peer exchange)
+        body = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", body)
         params = "".join(f", {t} a{i}" for i, t in enumerate(argtypes))
         decls = "\n".join(f"static {t.replace('const ', '')} nomp_emu_a{i};" for i, t in enumerate(argtypes))
         store = " ".join(f"nomp_emu_a{i} = ({t.replace('const ', '')})a{i};" for i, t in enumerate(argtypes))

@@ -717,3 +717,51 @@ def test_annotated_element_kernel_runs_on_the_host():
     emulate_cooperative(cuda5, "nomp_ax", (3, 1, 1), (5, 5, 5), ["double *", "const double *", "const double *", "const double *", "int"],
                         [ptr(w5), ptr(u5), ptr(g5), ptr(D5), C.c_int(3)])
     assert np.array_equal(w5, ffi.ax(5, u5, g5, D5))
+
+
+def test_generated_reduction_all_reduces_between_two_host_ranks():
+    """nomp_finish with nomp_world = 2: two copies of the emulated kernel run at the same time in two threads, each with
+    its own workspace and exchange buffer ("peer memory" = host memory both can see).  Both end with the fold of the two
+    partial sums in rank order, publish it, and the next call uses the other slot."""
+    import threading
+    from tests.cuda_emulation import emulate_cooperative
+    src = "void red(const double *a, const double *b, int N, double *s) { for (int i = 0; i < N; i++) if (a[i] > 2) s[0] += a[i] * b[i] + 1; }"
+    desc, cuda, (grid, block), _ = plan(src, reduce=("s", "+"))
+    world, n = 2, 20011
+    xchg = [np.zeros(2 * world * 2, dtype=np.uint64) for _ in range(world)]              # [2 slots][world]{value, seq}
+    table = np.array([x.ctypes.data for x in xchg], dtype=np.uint64)
+    data = [((np.arange(n + 5 * r) * (7 + r) % 13).astype(np.float64), (np.arange(n + 5 * r) * 5 % 11).astype(np.float64))
+            for r in range(world)]
+    parts = []
+    for a, b in data:
+        w = np.zeros(1)
+        run_kernel(src, a, b, a.size, w)
+        parts.append(w[0])
+    types = ["const double *", "const double *", "int", "void *", "double *", "double *", "unsigned long long", "void **", "int",
+             "int", "unsigned long long"]
+    ws = [np.zeros(548928 // 8 + 8, dtype=np.uint64) for _ in range(world)]
+    res, pub = [np.zeros(1) for _ in range(world)], [np.zeros(3, dtype=np.uint64) for _ in range(world)]
+    for call in (1, 2, 3):
+        errors = []
+
+        def rank_main(r):
+            try:
+                a, b = data[r]
+                ptr = lambda v: C.c_void_p(v.ctypes.data)  # noqa: E731
+                emulate_cooperative(cuda, "red", (grid_eval(grid[0], {"N": a.size}), 1, 1), (256, 1, 1), types,
+                                    [ptr(a), ptr(b), C.c_int(a.size), ptr(ws[r]), ptr(res[r]), ptr(pub[r]), C.c_ulonglong(100 + call),
+                                     ptr(table), C.c_int(r), C.c_int(world), C.c_ulonglong(call)], instance=r)
+            except Exception as exc:   # pragma: no cover
+                errors.append(exc)
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert not errors and not any(t.is_alive() for t in threads)
+        for r in range(world):
+            assert res[r][0] == parts[0] + parts[1] == pub[r].view(np.float64)[0]
+            assert pub[r][1] == 100 + call and pub[r][2] == 0                              # published, nobody was late
+        slot = (call & 1) * world
+        assert all(int(xchg[r][2 * (slot + q) + 1]) == call for r in range(world) for q in range(world))
