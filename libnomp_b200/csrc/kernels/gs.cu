@@ -15,8 +15,8 @@
 //
 // apply = two launches.  gs_local_kernel folds the local copies of each group in ascending index order; local-only
 // groups are written back at once; for shared groups the partial is kept and stored straight into the peers'
-// exchange buffers (P2P stores over NVLink, no staging copy, no NCCL), and the last CTA to finish raises this rank's
-// flag on every neighbour.  gs_remote_kernel waits for the neighbours' flags, folds own and received partials in
+// exchange buffers (P2P stores over NVLink, no staging copy, no NCCL), and the last of the CTAs that hold shared groups
+// raises this rank's flag on every neighbour.  gs_remote_kernel waits for the neighbours' flags, folds own and received partials in
 // ascending RANK order (same order on every rank: bit-identical results everywhere) and writes the copies back.
 // With one rank the second launch does not happen.
 #include <cub/cub.cuh>
