@@ -765,3 +765,43 @@ def test_generated_reduction_all_reduces_between_two_host_ranks():
             assert pub[r][1] == 100 + call and pub[r][2] == 0                              # published, nobody was late
         slot = (call & 1) * world
         assert all(int(xchg[r][2 * (slot + q) + 1]) == call for r in range(world) for q in range(world))
+
+
+@pytest.mark.parametrize("T,op", [("long", "+"), ("int", "+"), ("unsigned", "+"), ("double", "+"), ("int", "*"), ("long", "min"),
+                                  ("double", "max")])
+def test_random_reductions_run_on_the_host(T, op):
+    """Ten random right-hand sides per (type, operator), some under a random condition, through the generated
+    single-pass reduction executed on the host; integer-valued data, so the grid-wide fold has the serial loop's bits."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{T} {op}".encode()))       # a fixed seed per case (str hashes are salted)
+    dt = NP[T]
+    is_int = np.issubdtype(dt, np.integer)
+    cuda_t = {"long": "long long"}.get(T, T)
+    n = 4099
+    for case in range(10):
+        leaves = ["a[i]", "b[i]", "3", "i"] if is_int else ["a[i]", "b[i]", "2", "0.5"]
+        expr = _random_expr(rng, 2, leaves, is_int and op == "+")
+        cond = f"if ({_random_expr(rng, 1, ['a[i]', 'b[i]', '4'], False)} > 3) " if rng.random() < 0.5 else ""
+        if op == "+":
+            stmt = f"{cond}s[0] += {expr};"
+        elif op == "*":
+            expr = "(a[i] & 1) + 1"                                   # factors 1 and 2 only: 2^k stays exact for a while
+            stmt = f"if (i < 25) s[0] *= {expr};"
+        else:
+            cmp_ = "<" if op == "min" else ">"
+            stmt = f"{cond}s[0] = (({expr}) {cmp_} s[0]) ? ({expr}) : s[0];"
+        src = f"void red(const {T} *a, const {T} *b, int N, {T} *s) {{ for (int i = 0; i < N; i++) {stmt} }}"
+        a = rng.integers(0, 9, n).astype(dt)
+        b = rng.integers(0, 9, n).astype(dt)
+        want = np.array([{"+": 0, "*": 1}.get(op, 0)], dtype=dt)
+        if op == "min":
+            want[0] = np.iinfo(dt).max if is_int else np.inf
+        if op == "max":
+            want[0] = np.iinfo(dt).min if is_int else -np.inf
+        run_kernel(src, a, b, n, want)
+        desc = plan(src, reduce=("s", op))[0]
+        if desc["kind"] == "native":
+            continue
+        got, pub, _, tickets = _run_reduce_skeleton(src, "s", op, T, {"a": (a, f"const {cuda_t} *"), "b": (b, f"const {cuda_t} *")},
+                                                    {"N": ("int", C.c_int(n))}, n, grid_override=int(rng.integers(1, 40)))
+        assert got == want[0] == pub and not tickets.any(), (T, op, case, stmt)
