@@ -213,3 +213,24 @@ def test_jit_cache_entry_store(tmp_path, monkeypatch):
     assert lib.nomp_b200_jit_cache_get(key, b"cubin", buf, len(payload), C.byref(n)) == 0 and buf.raw == payload
     assert lib.nomp_b200_jit_cache_put(key, b"knl", b"", 0) == 0                                    # empty payloads are fine
     assert lib.nomp_b200_jit_cache_get(key, b"knl", buf, len(payload), C.byref(n)) == 0 and n.value == 0
+
+
+def test_public_headers_compile_as_c99_and_cxx17(tmp_path):
+    """Every header under include/ is self-contained, pedantic C99 and valid C++ (extern "C" guards)."""
+    headers = sorted(p.name for p in (ROOT / "include").glob("*.h"))
+    assert {"nomp.h", "nomp-aux.h", "nomp-mem.h", "nomp-b200.h", "nompk.h"} <= set(headers)
+    body = "".join(f'#include "{h}"\n' for h in headers) + "int main(void) { return 0; }\n"
+    for name, cmd in (("t.c", ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror"]),
+                      ("t.cpp", ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror"])):
+        src = tmp_path / name
+        src.write_text(body)
+        r = subprocess.run(cmd + ["-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / (name + ".o"))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    # each header alone, too (no hidden dependency on include order)
+    for h in headers:
+        src = tmp_path / "one.c"
+        src.write_text(f'#include "{h}"\nint main(void) {{ return 0; }}\n')
+        r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o",
+                            str(tmp_path / "one.o")], capture_output=True, text=True)
+        assert r.returncode == 0, (h, r.stderr)
