@@ -176,7 +176,7 @@ static void nomp_emu_entry() {
   nomp_emu_cur->state = EMU_DONE;
   swapcontext(&nomp_emu_cur->ctx, &nomp_emu_sched);
 }
-extern "C" int nomp_emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz NOMP_EMU_PARAMS) {
+extern "C" __attribute__((visibility("default"))) int nomp_emu_launch(unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz NOMP_EMU_PARAMS) {
   NOMP_EMU_STORE
   gridDim = {gx, gy, gz}; blockDim = {bx, by, bz};
   const unsigned nt = bx * by * bz;
@@ -250,8 +250,10 @@ def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args, inst
                   .replace("NOMP_EMU_STORE", store))
         cpp = _DIR / f"c{key}.cpp"
         cpp.write_text(_COOP_SHIM + body + "\n" + decls + "\n" + driver)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", str(so), str(cpp)],
-                       check=True)
+        # -fno-gnu-unique: static locals of templates (__shared__ arrays of templated device code) must stay private to
+        # each copy of the library, or two emulated ranks in one process would share their "shared memory"
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fno-gnu-unique",
+                        "-fvisibility=hidden", "-o", str(so), str(cpp)], check=True)
     lib = C.CDLL(str(so))
     fn = lib.nomp_emu_launch
     fn.restype = C.c_int
