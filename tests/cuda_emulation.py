@@ -111,7 +111,7 @@ _COOP_SHIM = r"""
 #include <cstring>
 #include <ucontext.h>
 struct nomp_emu_dim3 { unsigned x, y, z; };
-struct nomp_emu_thread { ucontext_t ctx; nomp_emu_dim3 tid; int state, warp, lane; char *stack; };
+struct nomp_emu_thread { ucontext_t ctx; nomp_emu_dim3 tid; int state, warp, lane; unsigned or_calls; char *stack; };
 enum { EMU_READY = 0, EMU_BLOCK_BARRIER = 1, EMU_WARP_BARRIER = 2, EMU_DONE = 3 };
 static nomp_emu_dim3 blockIdx, blockDim, gridDim;
 static nomp_emu_thread *nomp_emu_cur;
@@ -133,6 +133,16 @@ static void nomp_emu_yield(int state) {
 }
 static inline void __syncthreads() { nomp_emu_yield(EMU_BLOCK_BARRIER); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { nomp_emu_yield(EMU_WARP_BARRIER); }
+static int nomp_emu_or[2];
+static inline int __syncthreads_or(int pred) {
+  const int k = (int)(nomp_emu_cur->or_calls++ & 1u);
+  nomp_emu_or[k] |= pred != 0;
+  nomp_emu_yield(EMU_BLOCK_BARRIER);      // everybody has contributed
+  const int r = nomp_emu_or[k];
+  nomp_emu_or[k ^ 1] = 0;                 // the other accumulator is idle between these two barriers
+  nomp_emu_yield(EMU_BLOCK_BARRIER);
+  return r;
+}
 #include <atomic>
 #include <time.h>
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -186,10 +196,11 @@ extern "C" __attribute__((visibility("default"))) int nomp_emu_launch(unsigned g
   int rc = 0;
   for (unsigned Z = 0; Z < gz && !rc; Z++) for (unsigned Y = 0; Y < gy && !rc; Y++) for (unsigned X = 0; X < gx && !rc; X++) {
     blockIdx = {X, Y, Z};
+    nomp_emu_or[0] = nomp_emu_or[1] = 0;
     for (unsigned i = 0; i < nt; i++) {
       nomp_emu_thread *t = &th[i];
       t->tid = {i % bx, (i / bx) % by, i / (bx * by)};
-      t->state = EMU_READY, t->warp = (int)(i / 32), t->lane = (int)(i % 32);
+      t->state = EMU_READY, t->warp = (int)(i / 32), t->lane = (int)(i % 32), t->or_calls = 0;
       getcontext(&t->ctx);
       t->ctx.uc_stack.ss_sp = t->stack, t->ctx.uc_stack.ss_size = stack_bytes, t->ctx.uc_link = &nomp_emu_sched;
       makecontext(&t->ctx, nomp_emu_entry, 0);

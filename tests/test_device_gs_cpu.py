@@ -1,0 +1,208 @@
+"""The two device kernels of the gather-scatter (libnomp_b200/csrc/kernels/gs.cu: gs_local_kernel, gs_remote_kernel)
+compiled for the HOST -- their text is cut out of gs.cu unchanged -- and executed with the cooperative emulator, one
+thread per rank and host memory as "peer memory".  The index structures the CUDA setup builds with CUB are rebuilt here
+with numpy from their documented meaning, so this checks the protocol between the ranks (segments and slot strides in
+the peers' buffers, flags, the ticket among the CTAs that hold shared groups, the rank-ordered fold) against the oracle
+without a GPU; the setup itself is covered by the GPU tests."""
+import ctypes as C
+import re
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ffi
+from tests import cuda_emulation as emu
+
+ROOT = Path(__file__).resolve().parent.parent
+GS_CU = ROOT / "libnomp_b200" / "csrc" / "kernels" / "gs.cu"
+
+PRELUDE = r"""
+enum { NOMPK_RED_SUM = 0, NOMPK_RED_PROD = 1, NOMPK_RED_MIN = 2, NOMPK_RED_MAX = 3 };
+template <typename T> static inline T op_add(T a, T b) { return a + b; }
+template <typename T> static inline T op_mul(T a, T b) { return a * b; }
+constexpr int kGsThreads = 256;
+constexpr unsigned long long kGsTimeoutNs = 20ull * 1000 * 1000 * 1000;
+static inline unsigned long long timer_ns() { return nomp_emu_now_ns(); }
+"""
+WRAPPERS = r"""
+static void local_sum_f64(double *v, GsView s) { gs_local_kernel<NOMPK_RED_SUM, double>(v, s); }
+static void remote_sum_f64(double *v, GsView s) { gs_remote_kernel<NOMPK_RED_SUM, double>(v, s); }
+static void local_max_i64(long long *v, GsView s) { gs_local_kernel<NOMPK_RED_MAX, long long>(v, s); }
+static void remote_max_i64(long long *v, GsView s) { gs_remote_kernel<NOMPK_RED_MAX, long long>(v, s); }
+"""
+
+
+def device_source():
+    text = GS_CU.read_text()
+    combine = re.search(r"template <int OP, typename T> __device__ __forceinline__ T combine\(T a, T b\) \{.*?\n\}\n", text, re.S)
+    a = text.index("struct GsView {")
+    b = text.index("template <int OP, typename T> int launch_gs(")
+    assert combine and a < b
+    return PRELUDE + combine.group(0) + text[a:b] + WRAPPERS
+
+
+class GsView(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("indices", C.c_void_p), ("remote_slot", C.c_void_p), ("rgroup", C.c_void_p),
+                ("roffsets", C.c_void_p), ("rpos", C.c_void_p), ("rpeer", C.c_void_p), ("partial", C.c_void_p),
+                ("ticket", C.c_void_p), ("recv_off", C.c_void_p), ("send_off", C.c_void_p), ("peer_xchg", C.c_void_p),
+                ("neighbours", C.c_void_p), ("G", C.c_size_t), ("Q", C.c_size_t), ("values_base", C.c_size_t),
+                ("remote_ctas", C.c_uint), ("flags_bytes", C.c_size_t), ("n_neighbours", C.c_int), ("rank", C.c_int),
+                ("world", C.c_int), ("slot", C.c_int), ("seq", C.c_ulonglong), ("error_host", C.c_void_p)]
+
+
+def flags_bytes(world):
+    return (2 * world * 8 + 255) // 256 * 256
+
+
+class Rank:
+    """What nompk_gs_create / match_peer / finalize_setup / connect produce for one rank, built with numpy."""
+
+    def __init__(self, rank, id_parts):
+        world = len(id_parts)
+        ids = id_parts[rank]
+        self.rank, self.world = rank, world
+        uniq, counts = np.unique(ids[ids > 0], return_counts=True)
+        order = np.argsort(ids, kind="stable")            # copies of an id in ascending local index
+        sorted_ids = ids[order]
+        starts = np.searchsorted(sorted_ids, uniq)
+        self.shared = []                                  # per peer: ascending ids both ranks hold = S(me, peer)
+        for r in range(world):
+            other = np.unique(id_parts[r][id_parts[r] > 0])
+            self.shared.append(np.intersect1d(uniq, other) if r != rank else np.zeros(0, dtype=np.int64))
+        npeers = np.zeros(uniq.size, dtype=np.int64)
+        for r in range(world):
+            npeers += np.isin(uniq, self.shared[r])
+        active = (counts >= 2) | (npeers > 0)
+        act = np.flatnonzero(active)
+        first_idx = order[starts[act]]
+        act = act[np.argsort(first_idx, kind="stable")]   # groups ordered by their first local copy
+        offsets, indices, remote_slot, rgroup, roffsets, rpeer, rpos = [0], [], [], [], [0], [], []
+        for g, u in enumerate(act):
+            idx = order[starts[u]:starts[u] + counts[u]]
+            indices += idx.tolist()
+            offsets.append(len(indices))
+            if npeers[u] == 0:
+                remote_slot.append(-1)
+                continue
+            remote_slot.append(len(rgroup))
+            rgroup.append(g)
+            for r in range(world):
+                if r != rank:
+                    pos = np.searchsorted(self.shared[r], uniq[u])
+                    if pos < self.shared[r].size and self.shared[r][pos] == uniq[u]:
+                        rpeer.append(r)
+                        rpos.append(int(pos))
+            roffsets.append(len(rpeer))
+        u32, i32 = (lambda a: np.array(a, dtype=np.uint32)), (lambda a: np.array(a, dtype=np.int32))
+        self.offsets, self.indices, self.remote_slot = u32(offsets), u32(indices + [0]), i32(remote_slot + [0])
+        self.rgroup, self.roffsets, self.rpeer, self.rpos = u32(rgroup + [0]), u32(roffsets), i32(rpeer + [0]), u32(rpos + [0])
+        self.G, self.Q = len(remote_slot), len(rgroup)
+        self.counts = [int(s.size) for s in self.shared]
+        self.recv_off = np.concatenate([[0], np.cumsum(self.counts)[:-1]]).astype(np.uint64)
+        self.total = int(sum(self.counts))
+        self.neighbours = i32([r for r in range(world) if self.counts[r] > 0] + [0])
+        self.n_neighbours = sum(1 for c in self.counts if c > 0)
+        blocks = {g // 256 for g, q in enumerate(remote_slot) if q >= 0}
+        self.remote_ctas = len(blocks)
+        self.partial = np.zeros(max(self.Q, 1), dtype=np.uint64)
+        self.ticket = np.zeros(2, dtype=np.uint32)
+        self.xchg = np.zeros((flags_bytes(world) + 2 * self.total * 8) // 8 + 1, dtype=np.uint64)
+        self.error = np.zeros(1, dtype=np.uint64)
+        self.seq = 0
+
+    def connect(self, ranks):
+        world = self.world
+        self.table = np.array([r.xchg.ctypes.data for r in ranks], dtype=np.uint64)
+        send = np.zeros(2 * world, dtype=np.uint64)
+        for r in range(world):
+            send[r] = ranks[r].recv_off[self.rank]
+            send[world + r] = ranks[r].total + int(ranks[r].recv_off[self.rank])
+        self.send_off = send
+
+    def view(self):
+        self.seq += 1
+        slot = self.seq & 1
+        p = lambda a: a.ctypes.data  # noqa: E731
+        return GsView(p(self.offsets), p(self.indices), p(self.remote_slot), p(self.rgroup), p(self.roffsets), p(self.rpos),
+                      p(self.rpeer), p(self.partial), p(self.ticket), p(self.recv_off), p(self.send_off), p(self.table),
+                      p(self.neighbours), self.G, self.Q, flags_bytes(self.world) + slot * self.total * 8, self.remote_ctas,
+                      flags_bytes(self.world), self.n_neighbours, self.rank, self.world, slot, self.seq, p(self.error))
+
+
+def apply(ranks, parts, kind):
+    T = {"sum_f64": "double", "max_i64": "long long"}[kind]
+    src = device_source()
+    errors = []
+
+    def main(r):
+        try:
+            rk = ranks[r]
+            if rk.G == 0:
+                return
+            view = rk.view()
+            v = C.c_void_p(parts[r].ctypes.data)
+            emu.emulate_cooperative(src, f"local_{kind}", ((rk.G + 255) // 256, 1, 1), (256, 1, 1), [f"{T} *", "GsView"], [v, view],
+                                    instance=20 + r)
+            if rk.Q:
+                emu.emulate_cooperative(src, f"remote_{kind}", ((rk.Q + 255) // 256, 1, 1), (256, 1, 1), [f"{T} *", "GsView"],
+                                        [v, view], instance=20 + r)
+        except BaseException as exc:   # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=main, args=(r,)) for r in range(len(ranks))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors and not any(t.is_alive() for t in threads), errors
+    assert all(int(r.error[0]) == 0 and int(r.ticket[0]) == 0 for r in ranks)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_gs_kernels_between_host_ranks(world):
+    n, ex, ey, ezr = 4, 3, 2, 2
+    ids_all = ffi.box_ids(n, ex, ey, ezr * world)
+    per = ids_all.size // world
+    seg = [r * per for r in range(world + 1)]
+    id_parts = [ids_all[seg[r]:seg[r + 1]].copy() for r in range(world)]
+    ranks = [Rank(r, id_parts) for r in range(world)]
+    for r in ranks:
+        r.connect(ranks)
+    plane = (3 * ex + 1) * (3 * ey + 1)
+    assert [rk.total for rk in ranks] == [plane * ((r > 0) + (r < world - 1)) for r in range(world)]
+    rng = np.random.default_rng(world)
+    for call in range(3):                      # consecutive calls alternate the two slots of the exchange buffers
+        full = rng.uniform(0.5, 1.5, ids_all.size)
+        want = ffi.gs(0, ffi.F64, ids_all, full.copy(), seg)
+        parts = [full[seg[r]:seg[r + 1]].copy() for r in range(world)]
+        apply(ranks, parts, "sum_f64")
+        for r in range(world):
+            assert np.array_equal(parts[r], want[seg[r]:seg[r + 1]]), (world, call, r)
+    full = rng.integers(-1000, 1000, ids_all.size).astype(np.int64)
+    want = ffi.gs(3, ffi.I64, ids_all, full.copy(), seg)
+    parts = [full[seg[r]:seg[r + 1]].copy() for r in range(world)]
+    apply(ranks, parts, "max_i64")
+    for r in range(world):
+        assert np.array_equal(parts[r], want[seg[r]:seg[r + 1]])
+
+
+def test_gs_kernels_with_ids_on_every_rank():
+    """A numbering in which an id may live on any subset of three ranks, with ids <= 0 that do not take part: segments
+    of different sizes per peer, groups shared with two peers at once."""
+    world, m = 3, 4000
+    rng = np.random.default_rng(9)
+    ids = rng.integers(-1, 900, m * world).astype(np.int64)
+    seg = [r * m for r in range(world + 1)]
+    id_parts = [ids[seg[r]:seg[r + 1]].copy() for r in range(world)]
+    ranks = [Rank(r, id_parts) for r in range(world)]
+    for r in ranks:
+        r.connect(ranks)
+    for call in range(2):
+        full = rng.uniform(0.5, 1.5, ids.size)
+        want = ffi.gs(0, ffi.F64, ids, full.copy(), seg)
+        parts = [full[seg[r]:seg[r + 1]].copy() for r in range(world)]
+        apply(ranks, parts, "sum_f64")
+        for r in range(world):
+            assert np.array_equal(parts[r], want[seg[r]:seg[r + 1]]), (call, r)
