@@ -389,7 +389,9 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       o.y = wacc[k].y + rs.y;
       we[k * SLAB2] = o;
     }
-    // No barrier needed here: the next iteration's S0 writes exactly the B0 chunks this lane just read.
+    // No group barrier needed here: the next iteration's S0 writes exactly the B0 chunks this lane just read.  Its
+    // mirrors read the same chunks, though, and must have done so before anybody overwrites them.
+    mirror_fence<G * T < GL>();
   }
 
   if constexpr (kDot) {

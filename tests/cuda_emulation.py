@@ -111,8 +111,8 @@ _COOP_SHIM = r"""
 #include <cstring>
 #include <ucontext.h>
 struct nomp_emu_dim3 { unsigned x, y, z; };
-struct nomp_emu_thread { ucontext_t ctx; nomp_emu_dim3 tid; int state, warp, lane; unsigned or_calls; char *stack; };
-enum { EMU_READY = 0, EMU_BLOCK_BARRIER = 1, EMU_WARP_BARRIER = 2, EMU_DONE = 3 };
+struct nomp_emu_thread { ucontext_t ctx; nomp_emu_dim3 tid; int state, warp, lane, bar_id, bar_count; unsigned or_calls; char *stack; };
+enum { EMU_READY = 0, EMU_BLOCK_BARRIER = 1, EMU_WARP_BARRIER = 2, EMU_DONE = 3, EMU_NAMED_BARRIER = 4 };
 static nomp_emu_dim3 blockIdx, blockDim, gridDim;
 static nomp_emu_thread *nomp_emu_cur;
 static ucontext_t nomp_emu_sched;
@@ -133,6 +133,13 @@ static void nomp_emu_yield(int state) {
 }
 static inline void __syncthreads() { nomp_emu_yield(EMU_BLOCK_BARRIER); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { nomp_emu_yield(EMU_WARP_BARRIER); }
+// PTX "bar.sync id, count": the first `count` threads that arrive at barrier `id` release each other
+static inline void nomp_emu_named_barrier(int id, int count) {
+  nomp_emu_cur->bar_id = id, nomp_emu_cur->bar_count = count;
+  nomp_emu_yield(EMU_NAMED_BARRIER);
+}
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
 static int nomp_emu_or[2];
 static inline int __syncthreads_or(int pred) {
   const int k = (int)(nomp_emu_cur->or_calls++ & 1u);
@@ -224,6 +231,16 @@ extern "C" __attribute__((visibility("default"))) int nomp_emu_launch(unsigned g
         if (waiting && waiting == alive) {
           for (unsigned i = w * 32; i < nt && i < (w + 1) * 32; i++)
             if (th[i].state == EMU_WARP_BARRIER) th[i].state = EMU_READY;
+          progressed = true;
+        }
+      }
+      for (int id = 0; id < 16; id++) {                 // named barriers
+        unsigned waiting = 0, count = 0;
+        for (unsigned i = 0; i < nt; i++)
+          if (th[i].state == EMU_NAMED_BARRIER && th[i].bar_id == id) waiting++, count = (unsigned)th[i].bar_count;
+        if (waiting && waiting >= count) {
+          for (unsigned i = 0; i < nt; i++)
+            if (th[i].state == EMU_NAMED_BARRIER && th[i].bar_id == id) th[i].state = EMU_READY;
           progressed = true;
         }
       }

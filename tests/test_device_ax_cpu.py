@@ -1,0 +1,86 @@
+"""The hand-written Ax kernel (libnomp_b200/csrc/kernels/ax.cu: ax_kernel, every element-group shape, with and without
+the fused p.Ap) compiled for the HOST from its own text and executed with the cooperative emulator: one coroutine per
+thread, __syncwarp / named barriers / shuffles / block tickets with their real semantics.  Only the four lines of inline
+PTX are swapped (streaming load -> plain load, L2 prefetches -> nothing, bar.sync -> the emulator's named barrier) and
+dynamic shared memory becomes a static array.  Checks the kernel's arithmetic and its shared-memory choreography
+(mirrored lanes, stage barriers, element groups of several warps, partial last groups) against the oracle bit for bit
+without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ffi
+from tests import cuda_emulation as emu
+
+ROOT = Path(__file__).resolve().parent.parent
+KERNELS = ROOT / "libnomp_b200" / "csrc" / "kernels"
+
+# <n, elements per group, warps per group, groups per CTA>, as in ax.cu: Shape<N>
+SHAPES = {6: (7, 4, 1), 8: (1, 1, 4), 10: (3, 5, 1), 12: (2, 5, 1)}
+
+
+def device_source():
+    finish = (KERNELS / "nompk_gridreduce.cuh").read_text().replace('#include "nompk_common.cuh"', "").replace("#pragma once", "")
+    finish = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", finish)
+    text = (KERNELS / "ax.cu").read_text()
+    a, b = text.index("extern \"C\" {\n__constant__"), text.index("int g_variant = 0;")
+    body = text[a:b] + "}  // namespace\n}  // namespace nompk\n"
+    body, n = re.subn(r'extern "C" \{\n__constant__ double nompk_ax_cD\[12 \* 12\];\n\}', "static double nompk_ax_cD[12 * 12];", body)
+    assert n == 1
+    swaps = [(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.v2\.f64[^;]*;"[^;]*;', "r = *p;"),
+             (r'asm volatile\("cp\.async\.bulk\.prefetch\.L2\.global[^;]*;"[^;]*;', ";"),
+             (r'asm volatile\("prefetch\.global\.L2[^;]*;"[^;]*;', ";"),
+             (r'asm volatile\("bar\.sync %0, %1;"[^;]*;', "nomp_emu_named_barrier(grp + 1, GL);")]
+    for pattern, repl in swaps:
+        body, n = re.subn(pattern, repl, body)
+        assert n == 1, pattern
+    body, n = re.subn(r"extern __shared__ double2 smem\[\];", "static double2 smem[1 << 16];", body)
+    assert n == 1
+    wrappers = ["#include <utility>\n#include <type_traits>\n#define __constant__ static\n", finish, body,
+                ]
+    for n_, (G, W, GPC) in SHAPES.items():
+        for dot in (0, 1):
+            wrappers.append(
+                f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
+                f" double *res, unsigned long long stride) {{\n"
+                f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
+                f"  __syncthreads();\n"
+                f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
+                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, 2, 4, false, 1, {'true' if dot else 'false'}, true, >(u, g, w, E, d, stride);\n}}\n"
+                .replace("true, >", "true>"))
+    return "".join(wrappers)
+
+
+def run_ax(n, E, u, g, D, dot, blocks):
+    G, W, GPC = SHAPES[n]
+    src = device_source()
+    ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    w = np.full(E * n ** 3, np.nan)
+    ws = np.zeros(548928 // 8 + 8, dtype=np.uint64)
+    res = np.zeros(1)
+    emu.emulate_cooperative(src, f"ax{n}_{dot}", (blocks, 1, 1), (GPC * W * 32, 1, 1),
+                            ["const double *", "const double *", "const double *", "double *", "unsigned long long", "void *", "double *",
+                             "unsigned long long"],
+                            [ptr(u), ptr(g), ptr(D), ptr(w), C.c_ulonglong(E), ptr(ws), ptr(res), C.c_ulonglong(blocks * GPC * G)], instance=40)
+    return w, res[0], ws
+
+
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+@pytest.mark.parametrize("dot", [0, 1])
+def test_ax_kernel_on_the_host(n, dot):
+    """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
+    size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""
+    G, W, GPC = SHAPES[n]
+    per_cta = G * GPC
+    for E, blocks in ((2 * per_cta + 1, 2), (per_cta + max(1, per_cta // 2), 2), (1, 1)):
+        u = ffi.fill_int_f64(E * n ** 3, 5 + n, -4, 4)
+        g = ffi.fill_int_f64(E * 6 * n ** 3, 6 + n, 0, 3)
+        D = ffi.fill_int_f64(n * n, 7 + n, -2, 2)
+        w, pap, ws = run_ax(n, E, u, g, D, dot, blocks)
+        want = ffi.ax(n, u, g, D)
+        assert np.array_equal(w, want), (n, E, blocks, int((w != want).sum()))
+        if dot:
+            assert pap == float(u @ want) and not ws[: (64 + 4 * 2048) // 8].any()
