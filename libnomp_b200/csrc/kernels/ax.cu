@@ -178,8 +178,13 @@ struct AxDotArgs {
 // kPersistent: the grid has as many CTAs as fit on the device and each strides over the elements; otherwise one CTA
 // per GPC*G elements (the hardware scheduler streams the CTAs) and `pf_stride` = elements of all resident CTAs is only
 // the distance of the L2 prefetch (what will be scheduled next on SOME SM).
+//
+// kTwoBuf (experimental, not the default anywhere yet): two shared buffers per element instead of three.  us is computed
+// first (B0 -> B2); after a barrier ur replaces u IN PLACE in B0 (a lane reads its two i-lines whole before it writes
+// them), wr then replaces ur in place and D_r^T wr replaces wr in place.  One barrier more per element, a third less
+// shared memory: at n = 10 / 12 a third CTA fits an SM once the register budget allows it.
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent>
+          bool kPersistent, bool kTwoBuf = false>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
           size_t pf_stride) {
@@ -205,9 +210,10 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   // i-line items: rows r0 = 2t and r0 + 1 (same k, adjacent j).
   const int rk = (2 * tt) / N, rj = (2 * tt) % N;
 
-  double2 *B0 = smem + (size_t)(grp * G + el) * 3 * L::kChunks;
-  double2 *B1 = B0 + L::kChunks;
-  double2 *B2 = B1 + L::kChunks;
+  constexpr int kBufs = kTwoBuf ? 2 : 3;
+  double2 *B0 = smem + (size_t)(grp * G + el) * kBufs * L::kChunks;
+  double2 *B1 = kTwoBuf ? B0 : B0 + L::kChunks;   // ur, then wr
+  double2 *B2 = B0 + (kBufs - 1) * L::kChunks;    // us, then ws
 
   constexpr int EPB = GPC * G;  // elements per CTA and iteration
   const size_t estride = kPersistent ? (size_t)gridDim.x * EPB : pf_stride;
@@ -270,30 +276,59 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     }
     element_sync<GL>(grp);
 
-    // ---- S2: ur = D_r u on two i-lines -> B1 ----------------------------------------------------------
-    {
-      double2 v0[NP], v1[NP];
+    if constexpr (kTwoBuf) {
+      // ---- S3 first: us = D_s u on a j-line pair (p, k = q): B0 -> B2 -----------------------------------
+      {
+        double2 in[N];
 #pragma unroll
-      for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
-      static_for(SeqNP{}, [&](auto C) {
-        constexpr int c = decltype(C)::value;
-        double2 o0, o1;
-        dot_rows<N, false, c>(v0, v1, o0, o1, z2);
-        B1[L::at(rk, rj, c)] = o0;
-        B1[L::at(rk, rj + 1, c)] = o1;
-      });
-    }
-    // ---- S3: us = D_s u on a j-line pair (p, k = q) -> B2 ---------------------------------------------
-    {
-      double2 in[N];
+        for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
+        static_for(SeqN{}, [&](auto A) {
+          constexpr int j = decltype(A)::value;
+          B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
+        });
+      }
+      element_sync<GL>(grp);  // nobody reads u from B0 any more
+      // ---- S2: ur = D_r u on two i-lines, in place in B0 ---------------------------------------------------
+      {
+        double2 v0[NP], v1[NP];
 #pragma unroll
-      for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
-      static_for(SeqN{}, [&](auto A) {
-        constexpr int j = decltype(A)::value;
-        B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
-      });
+        for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
+        mirror_fence<G * T < GL>();  // the mirrors of a lane have read the same two lines
+        static_for(SeqNP{}, [&](auto C) {
+          constexpr int c = decltype(C)::value;
+          double2 o0, o1;
+          dot_rows<N, false, c>(v0, v1, o0, o1, z2);
+          B0[L::at(rk, rj, c)] = o0;
+          B0[L::at(rk, rj + 1, c)] = o1;
+        });
+      }
+      element_sync<GL>(grp);
+    } else {
+      // ---- S2: ur = D_r u on two i-lines -> B1 ----------------------------------------------------------
+      {
+        double2 v0[NP], v1[NP];
+  #pragma unroll
+        for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
+        static_for(SeqNP{}, [&](auto C) {
+          constexpr int c = decltype(C)::value;
+          double2 o0, o1;
+          dot_rows<N, false, c>(v0, v1, o0, o1, z2);
+          B1[L::at(rk, rj, c)] = o0;
+          B1[L::at(rk, rj + 1, c)] = o1;
+        });
+      }
+      // ---- S3: us = D_s u on a j-line pair (p, k = q) -> B2 ---------------------------------------------
+      {
+        double2 in[N];
+  #pragma unroll
+        for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
+        static_for(SeqN{}, [&](auto A) {
+          constexpr int j = decltype(A)::value;
+          B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
+        });
+      }
+      element_sync<GL>(grp);
     }
-    element_sync<GL>(grp);
 
     // ---- S4: geometric factors at the k-column (p, j = q); wr -> B1, ws -> B2, wt -> registers ---------
 #pragma unroll
@@ -355,6 +390,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       double2 v0[NP], v1[NP];
 #pragma unroll
       for (int c = 0; c < NP; c++) v0[c] = B1[L::at(rk, rj, c)], v1[c] = B1[L::at(rk, rj + 1, c)];
+      if constexpr (kTwoBuf) mirror_fence<G * T < GL>();  // B1 is B0: in place, mirrors must have read first
       static_for(SeqNP{}, [&](auto C) {
         constexpr int c = decltype(C)::value;
         double2 o0, o1;
@@ -416,12 +452,13 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 
 int g_variant = 0;
 
-template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true>
+template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
+          bool TWOBUF = false>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
-  const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
+  const size_t smem = (size_t)kElems * (TWOBUF ? 2 : 3) * L::kChunks * sizeof(double2);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
@@ -466,7 +503,9 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
     if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
     else if constexpr (N == 6) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, false>(E, u, g, w, s);
     else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
-    else return launch_ax<N, G, W, GPC, 3, 6, false, MB168>(E, u, g, w, s);
+    // n = 10: two shared buffers per element and three CTAs per SM (128 registers, 16 bytes of spill): 80.2-80.3 GDOF/s
+    // against 75.8-76.4 for the three-buffer kernel in two interleaved sweeps (profiles/r01_kernel_sweeps.jsonl)
+    else return launch_ax<N, G, W, GPC, 2, 4, false, MB168 + 1, false, true, true>(E, u, g, w, s);
   case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
   case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
   case 3: return launch_ax<N, G, W, GPC, 2, 2, false, MB128>(E, u, g, w, s);
@@ -483,6 +522,9 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 15: return launch_ax<N, G, W, GPC, 2, 4, false, MB128, false, false>(E, u, g, w, s);
   case 16: return launch_ax<N, G, W, GPC, 2, 0, false, MB168, false, false>(E, u, g, w, s);
   case 17: return launch_ax<N, G, W, GPC, 2, 8, false, MB168, false, false>(E, u, g, w, s);
+  // experimental two-buffer variants (see ax_kernel): 168 registers / 2 CTAs, and 3 CTAs per SM where the registers fit
+  case 21: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true>(E, u, g, w, s);
+  case 22: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }
