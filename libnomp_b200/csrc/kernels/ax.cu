@@ -525,6 +525,7 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   // experimental two-buffer variants (see ax_kernel): 168 registers / 2 CTAs, and 3 CTAs per SM where the registers fit
   case 21: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true>(E, u, g, w, s);
   case 22: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
+  case 23: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);  // one slab in flight
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }

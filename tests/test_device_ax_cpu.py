@@ -42,15 +42,15 @@ def device_source():
     wrappers = ["#include <utility>\n#include <type_traits>\n#define __constant__ static\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
-        for dot in (0, 1, 2):          # 2 = the experimental two-buffer variant (no dot)
+        for dot in (0, 1, 2, 3):       # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
                 f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
-                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, 2, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
-                f" {'true' if dot == 2 else 'false'}>(u, g, w, E, d, stride);\n}}\n")
+                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
+                f" {'true' if dot >= 2 else 'false'}>(u, g, w, E, d, stride);\n}}\n")
     return "".join(wrappers)
 
 
@@ -69,7 +69,7 @@ def run_ax(n, E, u, g, D, dot, blocks):
 
 
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
-@pytest.mark.parametrize("dot", [0, 1, 2])
+@pytest.mark.parametrize("dot", [0, 1, 2, 3])
 def test_ax_kernel_on_the_host(n, dot):
     """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
     size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""

@@ -81,7 +81,7 @@ def main():
     if "axrobust" in which:
         # Interleaved rounds: on a power-capped board the same kernel moves by several per cent between one timing and
         # the next, so every variant is timed once per round, round after round, and the median over rounds is kept.
-        variants = [int(v) for v in os.environ.get("AX_VARIANTS", "0,1,7,8,11,21,22").split(",")]
+        variants = [int(v) for v in os.environ.get("AX_VARIANTS", "0,1,7,8,11,21,22,23").split(",")]
         rounds = int(os.environ.get("AX_ROUNDS", "7"))
         for n, E in ((10, 131072), (12, 65536), (8, 262144), (6, 524288)):
             n3 = n ** 3
