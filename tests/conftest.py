@@ -18,6 +18,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """A fresh clone has no built libraries (they are git-ignored): build them once, in-tree, before the first test
+    (what `python -m libnomp_b200.build` / __graft_entry__.build() do; a couple of minutes, nvcc cross-compiles without a
+    GPU).  Nothing is built when they are already there; a failed build leaves the tests to fail loudly."""
+    lib = ROOT / "libnomp_b200" / "lib"
+    if (lib / "libnompk.so").exists() and (lib / "libnomp.so").exists():
+        return
+    try:
+        from libnomp_b200 import build
+        print("\n[tests] building libnompk.so / libnomp.so (first run in this tree) ...", flush=True)
+        build.build_all()
+    except Exception as exc:  # pragma: no cover
+        print(f"[tests] build failed: {exc}", flush=True)
+
+
 def _has_gpu():
     try:
         import torch
