@@ -166,6 +166,7 @@ static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); re
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T, typename U> static inline T atomicAdd(T *p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T, typename U> static inline T atomicExch(T *p, U v) { T old = *p; *p = (T)v; return old; }
 template <typename T> static inline T nomp_emu_exchange(T v, int from_lane) {
   nomp_emu_thread *t = nomp_emu_cur;
   unsigned long long w = 0;

@@ -122,3 +122,53 @@ def test_finish_fused_with_the_all_reduce_between_host_ranks(world, blocks):
         for r in range(world):
             assert states[r]["res"][0] == want == states[r]["pub"].view(np.float64)[0]
             assert states[r]["pub"][1] == 100 + call and states[r]["pub"][2] == 0
+
+
+def allreduce_source():
+    """The stand-alone one-shot all-reduce kernel of reduce.cu (used when a reduction could not fuse the exchange)."""
+    text = (ROOT / "libnomp_b200" / "csrc" / "kernels" / "reduce.cu").read_text()
+    a = text.index("template <int OP, typename T> __device__ __forceinline__ T red_identity()")
+    b = text.index("// acc <- acc (op) f(x, y)")
+    c = text.index("constexpr int kMaxRanks = 64;")
+    d = text.index("template <int OP, typename T>\nint launch_allreduce(")
+    body = ("#include <cfloat>\n#include <climits>\nenum { NOMPK_RED_SUM, NOMPK_RED_PROD, NOMPK_RED_MIN, NOMPK_RED_MAX };\n"
+            + device_source().replace(KERNEL, "") + "namespace nompk {\ntemplate <typename T> struct Limits;\n"
+            "template <> struct Limits<double> { static double lo() { return -INFINITY; } static double hi() { return INFINITY; } };\n"
+            + text[a:b] + text[c:d] + "}\n")
+    body += ("static void allreduce_sum_f64(double *value, double *host, unsigned long long host_seq, void **peers, int rank, int world,"
+             " unsigned long long seq) { nompk::allreduce_scalar_kernel<NOMPK_RED_SUM, double>(value, host, host_seq, peers, rank, world, seq); }\n")
+    return body
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_stand_alone_all_reduce_kernel_between_host_ranks(world):
+    xchg = [np.zeros(2 * world * 2, dtype=np.uint64) for _ in range(world)]
+    table = np.array([b.ctypes.data for b in xchg], dtype=np.uint64)
+    values = [np.array([1000.5 + 3 * r]) for r in range(world)]
+    pubs = [np.zeros(3, dtype=np.uint64) for _ in range(world)]
+    src = allreduce_source()
+    for call in (1, 2):
+        contributions = [float(v[0]) for v in values]
+        errors = []
+
+        def rank_main(r):
+            try:
+                ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+                emu.emulate_cooperative(src, "allreduce_sum_f64", (1, 1, 1), (64, 1, 1),
+                                        ["double *", "double *", "unsigned long long", "void **", "int", "int", "unsigned long long"],
+                                        [ptr(values[r]), ptr(pubs[r]), C.c_ulonglong(50 + call), ptr(table), C.c_int(r), C.c_int(world),
+                                         C.c_ulonglong(call)], instance=30 + r)
+            except BaseException as exc:   # pragma: no cover
+                errors.append(exc)
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert not errors and not any(t.is_alive() for t in threads), errors
+        want = contributions[0]
+        for c_ in contributions[1:]:
+            want = want + c_
+        for r in range(world):
+            assert values[r][0] == want == pubs[r].view(np.float64)[0] and pubs[r][1] == 50 + call and pubs[r][2] == 0
