@@ -206,3 +206,113 @@ def test_gs_kernels_with_ids_on_every_rank():
         apply(ranks, parts, "sum_f64")
         for r in range(world):
             assert np.array_equal(parts[r], want[seg[r]:seg[r + 1]]), (call, r)
+
+
+# ---- the setup kernels: CUB's sort / run-length / scan / select are played by numpy, the library's own kernels run ----------
+
+SETUP_KERNELS = {
+    "iota_kernel": ["unsigned *", "size_t"],
+    "match_kernel": ["const long long *", "size_t", "const long long *", "size_t", "unsigned *"],
+    "position_kernel": ["const unsigned *", "unsigned *", "size_t"],
+    "classify_kernel": ["const long long *", "const unsigned *", "unsigned **", "int", "size_t", "unsigned char *", "unsigned *"],
+    "first_index_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "unsigned *", "size_t"],
+    "group_sizes_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "unsigned *", "unsigned *", "unsigned *", "size_t"],
+    "fill_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *",
+                    "const unsigned *", "const unsigned *", "unsigned **", "int", "unsigned *", "int *", "unsigned *", "unsigned *", "int *",
+                    "unsigned *", "size_t"],
+    "mark_remote_ctas_kernel": ["const int *", "size_t", "int", "unsigned *"],
+}
+
+
+def setup_source():
+    text = GS_CU.read_text()
+    a, b = text.index("// ---- setup kernels"), text.index("// ---- apply")
+    return "#include <cstddef>\n" + text[a:b]
+
+
+def launch(name, n_threads, *args):
+    cargs = []
+    for t, a in zip(SETUP_KERNELS[name], args):
+        if isinstance(a, np.ndarray):
+            cargs.append(C.c_void_p(a.ctypes.data))
+        elif t == "int":
+            cargs.append(C.c_int(a))
+        else:
+            cargs.append(C.c_size_t(a))
+    emu.emulate_cooperative(setup_source(), name, (max(1, (n_threads + 255) // 256), 1, 1), (256, 1, 1), SETUP_KERNELS[name], cargs,
+                            instance=60)
+
+
+def excl(a):
+    return np.concatenate([[0], np.cumsum(a)]).astype(np.uint32)
+
+
+def device_setup(rank, id_parts):
+    """nompk_gs_create / match_peer / finalize_setup step by step, as gs.cu orders them."""
+    world, ids = len(id_parts), id_parts[rank]
+    n = ids.size
+    vals = np.zeros(n, dtype=np.uint32)
+    launch("iota_kernel", n, vals, n)
+    assert np.array_equal(vals, np.arange(n))
+    order = np.argsort(ids, kind="stable")                               # cub::DeviceRadixSort::SortPairs (stable)
+    keys, sorted_idx = ids[order], vals[order]
+    uniq, counts = np.unique(keys, return_counts=True)                    # cub::DeviceRunLengthEncode::Encode
+    uniq, counts = uniq.astype(np.int64), counts.astype(np.uint32)
+    run_start = excl(counts)                                             # cub::DeviceScan::ExclusiveSum
+    U = uniq.size
+    peer_pos, shared = [None] * world, [0] * world
+    for r in range(world):
+        if r == rank:
+            continue
+        other = np.unique(id_parts[r]).astype(np.int64)
+        found, pos = np.zeros(U, dtype=np.uint32), None
+        launch("match_kernel", U, uniq, U, other, other.size, found)
+        pos = excl(found)
+        shared[r] = int(pos[U])
+        launch("position_kernel", U, found, pos, U)
+        peer_pos[r] = pos if shared[r] else None
+    table = np.array([p.ctypes.data if p is not None else 0 for p in peer_pos], dtype=np.uint64)
+    active, rcount = np.zeros(U, dtype=np.uint8), np.zeros(U, dtype=np.uint32)
+    launch("classify_kernel", U, uniq, counts, table, world, U, active, rcount)
+    sel = np.flatnonzero(active).astype(np.uint32)                        # cub::DeviceSelect::Flagged
+    G = sel.size
+    first = np.zeros(max(G, 1), dtype=np.uint32)
+    launch("first_index_kernel", G, sel, run_start, sorted_idx, first, G)
+    order_g = sel[np.argsort(first[:G], kind="stable")]                  # SortPairs(first, sel)
+    cnt, rcnt, rflag = (np.zeros(max(G, 1), dtype=np.uint32) for _ in range(3))
+    launch("group_sizes_kernel", G, order_g, counts, rcount, cnt, rcnt, rflag, G)
+    offsets, rstart, rslot = excl(cnt[:G]), excl(rcnt[:G]), excl(rflag[:G])
+    nnz, R, Q = int(offsets[G]), int(rstart[G]), int(rslot[G])
+    indices, remote_slot = np.zeros(nnz + 1, dtype=np.uint32), np.zeros(G + 1, dtype=np.int32)
+    rgroup, roffsets = np.zeros(Q + 1, dtype=np.uint32), np.zeros(Q + 1, dtype=np.uint32)
+    rpeer, rpos = np.zeros(R + 1, dtype=np.int32), np.zeros(R + 1, dtype=np.uint32)
+    launch("fill_kernel", G, order_g, run_start, counts, sorted_idx, offsets, rcnt, rstart, rslot, table, world, indices, remote_slot,
+           rgroup, roffsets, rpeer, rpos, G)
+    roffsets[Q] = R
+    blk = np.zeros((G + 255) // 256 + 1, dtype=np.uint32)
+    launch("mark_remote_ctas_kernel", G, remote_slot, G, 256, blk)
+    return dict(G=G, Q=Q, offsets=offsets, indices=indices[:nnz], remote_slot=remote_slot[:G], rgroup=rgroup[:Q], roffsets=roffsets,
+                rpeer=rpeer[:R], rpos=rpos[:R], shared=shared, remote_ctas=int(blk.sum()))
+
+
+@pytest.mark.parametrize("kind", ["slabs", "random"])
+def test_setup_kernels_build_the_documented_structures(kind):
+    """The library's setup kernels (with numpy standing in for CUB) produce, for every rank, exactly the groups, CSR
+    arrays, peer positions and remote-CTA count that the `Rank` class above derives from their documented meaning --
+    so the protocol tests above and the real setup talk about the same structures."""
+    world = 3
+    if kind == "slabs":
+        ids_all = ffi.box_ids(4, 3, 2, 2 * world)
+        per = ids_all.size // world
+        id_parts = [ids_all[r * per:(r + 1) * per].copy() for r in range(world)]
+    else:
+        rng = np.random.default_rng(4)
+        id_parts = [rng.integers(-1, 700, 3000).astype(np.int64) for _ in range(world)]
+    for rank in range(world):
+        got, want = device_setup(rank, id_parts), Rank(rank, id_parts)
+        assert got["G"] == want.G and got["Q"] == want.Q and got["shared"] == want.counts
+        assert got["remote_ctas"] == want.remote_ctas
+        for name in ("offsets", "roffsets"):
+            assert np.array_equal(got[name], getattr(want, name)), (rank, name)
+        for name in ("indices", "remote_slot", "rgroup", "rpeer", "rpos"):
+            assert np.array_equal(got[name], getattr(want, name)[:got[name].size]), (rank, name)
