@@ -34,7 +34,11 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"),
 ]
 
-KERNEL_SRCS = ["map.cu", "reduce.cu", "ax.cu", "gs.cu", "nompk.cu"]
+# (source, object name, extra flags).  ax.cu is compiled once per supported n (-DNOMPK_AX_N=<n>: the kernels of that n, in
+# parallel -- a single unit with every n and variant takes 7 minutes) and once without the macro (its C ABI).
+KERNEL_UNITS = [("map.cu", "map.cu.o", []), ("reduce.cu", "reduce.cu.o", []), ("gs.cu", "gs.cu.o", []),
+                ("nompk.cu", "nompk.cu.o", []), ("ax.cu", "ax.cu.o", [])] + \
+               [("ax.cu", f"ax_n{n}.cu.o", [f"-DNOMPK_AX_N={n}"]) for n in (12, 10, 8, 6)]
 LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c", "src/jitcache.c", "src/gs.c",
                 "backends/cuda.c"]
 
@@ -58,17 +62,17 @@ def build_kernels(force=False):
     src_dir = PKG / "csrc" / "kernels"
     LIB.mkdir(exist_ok=True)
     OBJ.mkdir(exist_ok=True)
-    headers = [src_dir / "nompk_common.cuh", ROOT / "include" / "nompk.h"]
+    headers = [*src_dir.glob("*.cuh"), ROOT / "include" / "nompk.h"]
     out = LIB / "libnompk.so"
     jobs = []
-    for s in KERNEL_SRCS:
-        o = OBJ / (s + ".o")
+    for s, oname, extra in KERNEL_UNITS:
+        o = OBJ / oname
         if force or _stale(o, [src_dir / s, *headers]):
-            jobs.append([NVCC, *NVCC_FLAGS, "-c", str(src_dir / s), "-o", str(o)])
+            jobs.append([NVCC, *NVCC_FLAGS, *extra, "-c", str(src_dir / s), "-o", str(o)])
     if jobs:
-        with cf.ThreadPoolExecutor(max_workers=len(jobs)) as ex:
-            list(ex.map(_run, jobs))
-    objs = [str(OBJ / (s + ".o")) for s in KERNEL_SRCS]
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(_run, sorted(jobs, key=lambda j: "-DNOMPK_AX_N" not in " ".join(j))))   # the long ones first
+    objs = [str(OBJ / oname) for _, oname, _ in KERNEL_UNITS]
     if force or jobs or _stale(out, objs):
         _run([NVCC, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xlinker", f"-rpath,{CUDA_HOME}/lib64", *objs, "-o", str(out)])

@@ -24,20 +24,54 @@
 //     the buffer layout (slab stride + XOR swizzle, tools/check_banks.py) makes all three access patterns
 //     bank-conflict-free for n = 8.
 //   * FP64 FMA on the CUDA cores; tensor cores are not used (the kernel is HBM-bound).
+//
+// Build: this file is compiled once per supported n with -DNOMPK_AX_N=<n> (the kernels of that n, its own copy of D
+// in constant memory and the entry point nompk_ax_run_n<n>; the four units compile in parallel) and once without the
+// macro (the C ABI of include/nompk.h, which validates the operands and forwards to the unit of n).
 #include <type_traits>
 #include <utility>
 
 #include "nompk_common.cuh"
 #include "nompk_gridreduce.cuh"
 
-// D[a][l] at nompk_ax_cD[a * n + l] (constant bank 3; read with LDCU into uniform registers, see ld_D).  C linkage so
-// that the symbol has one unmangled name in cuobjdump / ncu listings.
-extern "C" {
-__constant__ double nompk_ax_cD[12 * 12];
-}
+#ifndef NOMPK_AX_N
+#define NOMPK_AX_N 0
+#endif
 
 namespace nompk {
 namespace {
+
+// What the fused p.Ap finish needs (see ax_kernel: kDot); handed from the C ABI unit to the unit of n by pointer.
+struct AxDotArgs {
+  void *workspace;
+  double *result;
+  double *result_host;
+  unsigned long long host_seq;
+  PeerExchange px;  // all-reduce over ranks fused into the finish (world <= 1: none)
+};
+
+}  // namespace
+}  // namespace nompk
+
+// One entry point per n: stages D (unless NOMPK_AX_D_CACHED), picks the variant, launches.  `dot` is an AxDotArgs or NULL.
+#define NOMPK_AX_RUN_DECL(n)                                                                                            \
+  extern "C" __attribute__((visibility("hidden"))) int nompk_ax_run_n##n(int variant, size_t E, const double *u,       \
+                                                                         const double *g, const double *D, double *w,  \
+                                                                         unsigned flags, cudaStream_t stream,          \
+                                                                         const void *dot)
+NOMPK_AX_RUN_DECL(6);
+NOMPK_AX_RUN_DECL(8);
+NOMPK_AX_RUN_DECL(10);
+NOMPK_AX_RUN_DECL(12);
+
+#if NOMPK_AX_N != 0
+
+namespace nompk {
+namespace {
+
+// D[a][l] at nompk_ax_cD[a * n + l] (constant bank 3; read with LDCU into uniform registers, see ld_D); one copy per
+// compiled n.
+__constant__ double nompk_ax_cD[12 * 12];
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -167,14 +201,6 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // space gradient of u and (wr, ws, wt) = G (ur, us, ut), u . A u = sum over points of ur wr + us ws + ut wt, and all six
 // values are in registers in the geometric stage.  Finished like libnompk's reductions: block tree, one partial per
 // CTA, atomic ticket, the last CTA folds the partials in CTA order (deterministic) and publishes the scalar.
-struct AxDotArgs {
-  void *workspace;
-  double *result;
-  double *result_host;
-  unsigned long long host_seq;
-  PeerExchange px;  // all-reduce over ranks fused into the finish (world <= 1: none)
-};
-
 // kPersistent: the grid has as many CTAs as fit on the device and each strides over the elements; otherwise one CTA
 // per GPC*G elements (the hardware scheduler streams the CTAs) and `pf_stride` = elements of all resident CTAs is only
 // the distance of the L2 prefetch (what will be scheduled next on SOME SM).
@@ -450,8 +476,6 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   }
 }
 
-int g_variant = 0;
-
 template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
           bool TWOBUF = false>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
@@ -534,6 +558,26 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
 }  // namespace
 }  // namespace nompk
 
+#define NOMPK_AX_RUN_DEFINE_(n) NOMPK_AX_RUN_DECL(n)
+#define NOMPK_AX_RUN_DEFINE(n) NOMPK_AX_RUN_DEFINE_(n)
+NOMPK_AX_RUN_DEFINE(NOMPK_AX_N) {
+  using namespace nompk;
+  constexpr int n = NOMPK_AX_N;
+  if (!(flags & NOMPK_AX_D_CACHED)) {
+    NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (dot) return dispatch_ax_dot<n>(E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
+  return dispatch_ax<n>(variant, E, u, g, w, stream);
+}
+
+#else  // NOMPK_AX_N == 0: the C ABI
+
+namespace nompk {
+namespace {
+int g_variant = 0;
+}
+}  // namespace nompk
+
 extern "C" int nompk_ax_supported(int n) { return n == 8 || n == 10 || n == 6 || n == 12; }
 
 extern "C" int nompk_ax_set_variant(int variant) {
@@ -608,23 +652,13 @@ static int ax_common(int n, size_t E, const double *u, const double *g, const do
     set_error("nompk_ax_f64: u, g and w must be 16-byte aligned");
     return NOMPK_EINVAL;
   }
-  if (!(flags & NOMPK_AX_D_CACHED)) {
-    NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
-  }
-  if (dot) {
-    switch (n) {
-    case 6: return dispatch_ax_dot<6>(E, u, g, w, stream, *dot);
-    case 8: return dispatch_ax_dot<8>(E, u, g, w, stream, *dot);
-    case 10: return dispatch_ax_dot<10>(E, u, g, w, stream, *dot);
-    case 12: return dispatch_ax_dot<12>(E, u, g, w, stream, *dot);
-    }
-    return NOMPK_EUNSUPPORTED;
-  }
   switch (n) {
-  case 6: return dispatch_ax<6>(g_variant, E, u, g, w, stream);
-  case 8: return dispatch_ax<8>(g_variant, E, u, g, w, stream);
-  case 10: return dispatch_ax<10>(g_variant, E, u, g, w, stream);
-  case 12: return dispatch_ax<12>(g_variant, E, u, g, w, stream);
+  case 6: return nompk_ax_run_n6(g_variant, E, u, g, D, w, flags, stream, dot);
+  case 8: return nompk_ax_run_n8(g_variant, E, u, g, D, w, flags, stream, dot);
+  case 10: return nompk_ax_run_n10(g_variant, E, u, g, D, w, flags, stream, dot);
+  case 12: return nompk_ax_run_n12(g_variant, E, u, g, D, w, flags, stream, dot);
   }
   return NOMPK_EUNSUPPORTED;
 }
+
+#endif  // NOMPK_AX_N

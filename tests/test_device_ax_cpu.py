@@ -26,9 +26,11 @@ def device_source():
     finish = (KERNELS / "nompk_gridreduce.cuh").read_text().replace('#include "nompk_common.cuh"', "").replace("#pragma once", "")
     finish = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", finish)
     text = (KERNELS / "ax.cu").read_text()
-    a, b = text.index("extern \"C\" {\n__constant__"), text.index("int g_variant = 0;")
-    body = text[a:b] + "}  // namespace\n}  // namespace nompk\n"
-    body, n = re.subn(r'extern "C" \{\n__constant__ double nompk_ax_cD\[12 \* 12\];\n\}', "static double nompk_ax_cD[12 * 12];", body)
+    # the AxDotArgs structure, then everything the per-n units compile up to the host-side launcher
+    s0, s1 = text.index("namespace nompk {\nnamespace {\n\n// What the fused p.Ap finish needs"), text.index("// One entry point per n:")
+    a, b = text.index("#if NOMPK_AX_N != 0\n") + len("#if NOMPK_AX_N != 0\n"), text.index("template <int N, int G, int W, int GPC, int GA, int PF")
+    body = text[s0:s1] + text[a:b] + "}  // namespace\n}  // namespace nompk\n"
+    body, n = re.subn(r'__constant__ double nompk_ax_cD\[12 \* 12\];', "double nompk_ax_cD[12 * 12];", body)
     assert n == 1
     swaps = [(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.v2\.f64[^;]*;"[^;]*;', "r = *p;"),
              (r'asm volatile\("cp\.async\.bulk\.prefetch\.L2\.global[^;]*;"[^;]*;', ";"),
@@ -46,7 +48,7 @@ def device_source():
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
-                f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
+                f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk::nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
                 f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
