@@ -222,7 +222,7 @@ int nomp_sha256_dir(nomp_sha256_t *c, const char *dir, const char *suffix) {
     names[n++] = strdup(e->d_name);
   }
   closedir(d);
-  qsort(names, n, sizeof(*names), by_name);
+  if (n) qsort(names, n, sizeof(*names), by_name);
   int err = 0;
   for (size_t i = 0; i < n; i++) {
     char path[PATH_MAX + 300];
