@@ -34,6 +34,9 @@ def pytest_sessionstart(session):
 
 
 def _has_gpu():
+    # tests/test_hostdev_cpu.py re-runs API tests in a child pytest whose "device" is the CUDA test double (tests/hostdev)
+    if os.environ.get("NOMP_HOSTDEV_ACTIVE") == "1":
+        return True
     try:
         import torch
         return torch.cuda.is_available()

@@ -288,3 +288,41 @@ def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args, inst
     fn.restype = C.c_int
     rc = fn(*[C.c_uint(v) for v in (*grid, *block)], *args)
     assert rc == 0, "the emulated kernel deadlocked"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The same emulation behind a driver-style launch (tests/hostdev): the kernel's arguments arrive as `void **params`, one
+# pointer per parameter in declaration order, as cuLaunchKernel passes them.
+# ----------------------------------------------------------------------------------------------------------------------
+_KERNEL_HEAD = re.compile(r'extern\s+"C"\s+__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(([^)]*)\)')
+
+
+def kernel_signature(src: str):
+    """(name, [parameter types]) of the single `extern "C" __global__` function in generated CUDA source."""
+    heads = _KERNEL_HEAD.findall(src)
+    assert len(heads) == 1, f"expected one kernel, found {[h[0] for h in heads]}"
+    name, params = heads[0]
+    types = []
+    for prm in (x.strip() for x in params.split(",") if x.strip()):
+        m = re.match(r"(.*?)(\w+)\s*$", prm, re.S)
+        types.append(m.group(1).replace("__restrict__", "").strip())
+    return name, types
+
+
+def build_param_launcher(src: str, out: Path):
+    """Compile generated CUDA source for the host into `out` (a shared object) that exports
+    nomp_emu_launch(gx, gy, gz, bx, by, bz, void **params) and nomp_hostdev_kernel_name."""
+    name, types = kernel_signature(src)
+    body = re.sub(r'extern "C"\s*', "", src)
+    body = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", body)
+    plain = [t.replace("const ", "") for t in types]
+    decls = "\n".join(f"static {t} nomp_emu_a{i};" for i, t in enumerate(plain))
+    store = " ".join(f"nomp_emu_a{i} = *({t} *)nomp_emu_p[{i}];" for i, t in enumerate(plain))
+    call = f"{name}(" + ", ".join(f"nomp_emu_a{i}" for i in range(len(types))) + ")"
+    driver = (_COOP_DRIVER.replace("NOMP_EMU_CALL", call).replace("NOMP_EMU_PARAMS", ", void **nomp_emu_p")
+              .replace("NOMP_EMU_STORE", store))
+    tail = f'\nextern "C" __attribute__((visibility("default"))) const char *nomp_hostdev_kernel_name = "{name}";\n'
+    cpp = Path(str(out) + ".cpp")
+    cpp.write_text(_COOP_SHIM + body + "\n" + decls + "\n" + driver + tail)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fno-gnu-unique",
+                    "-fvisibility=hidden", "-o", str(out), str(cpp)], check=True)

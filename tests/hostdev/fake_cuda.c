@@ -1,0 +1,327 @@
+/* TEST DOUBLE -- not part of the product, never linked into it, never shipped.
+ *
+ * A stand-in for the CUDA runtime, NVRTC and the five driver entry points libnomp.so uses, so that the RUNTIME of
+ * libnomp_b200 (src/nomp.c, src/loopy.c, src/reduction.c, backends/cuda.c: mappings, argument marshalling, the jit
+ * bridge, launch-size expressions, the reduce finish, error paths) can be exercised by the CPU test tier.  It plays the
+ * part pocl plays in the reference's CI ("testing without a GPU" = its OpenCL backend on a CPU OpenCL platform,
+ * reference .github/workflows/ci.yml:60-77): the product is unchanged and unaware of it -- tests/test_hostdev_cpu.py
+ * LD_PRELOADs this library into the reference's own nomp-api test programs (oracle/_ref/tests), nothing else does.
+ * Without the preload, on a machine without a GPU, nomp_init() fails with NOMP_CUDA_FAILURE as it must.
+ *
+ *   "device" memory   = host memory (cudaMalloc -> posix_memalign, copies -> memmove); streams run at once.
+ *   NVRTC             = tests/hostdev/compile_kernel.py: the generated CUDA source is compiled with g++ against the
+ *                       cooperative emulator of tests/cuda_emulation.py (one coroutine per thread, real barriers,
+ *                       shuffles, tickets); the "CUBIN" is the path of the resulting shared object.
+ *   driver            = cuModuleLoadData -> dlopen, cuLaunchKernel -> the object's launcher (grid, block, void **params).
+ *   libnompk launches = cudaLaunchKernel fails (there is no device code to run here); tests/hostdev/fake_nompk.c
+ *                       interposes the C ABI of include/nompk.h instead.
+ */
+#define _GNU_SOURCE
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* ---- runtime: devices ------------------------------------------------------------------------------------------------ */
+static int n_devices(void) {
+  const char *e = getenv("NOMP_HOSTDEV_DEVICES");
+  return e ? atoi(e) : 1;
+}
+
+EXPORT cudaError_t cudaGetDeviceCount(int *count) {
+  *count = n_devices();
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaSetDevice(int device) { return device >= 0 && device < n_devices() ? cudaSuccess : cudaErrorInvalidDevice; }
+EXPORT cudaError_t cudaGetDevice(int *device) {
+  *device = 0;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaDriverGetVersion(int *v) {
+  *v = 12090;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaGetDeviceProperties(struct cudaDeviceProp *prop, int device) {
+  (void)device;
+  memset(prop, 0, sizeof(*prop));
+  snprintf(prop->name, sizeof(prop->name), "hostdev (CUDA runtime test double)");
+  prop->major = 10, prop->minor = 0; /* the bridge is told sm_100, as on a B200 */
+  prop->maxThreadsPerBlock = 1024;
+  prop->multiProcessorCount = 148;
+  prop->warpSize = 32;
+  prop->sharedMemPerBlock = 48 * 1024;
+  prop->totalGlobalMem = (size_t)1 << 34;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaDeviceGetAttribute(int *value, enum cudaDeviceAttr attr, int device) {
+  (void)device;
+  *value = attr == cudaDevAttrMultiProcessorCount ? 148 : 0;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+EXPORT cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+EXPORT cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
+EXPORT const char *cudaGetErrorName(cudaError_t e) {
+  switch (e) {
+  case cudaSuccess: return "cudaSuccess";
+  case cudaErrorInvalidDevice: return "cudaErrorInvalidDevice";
+  case cudaErrorMemoryAllocation: return "cudaErrorMemoryAllocation";
+  case cudaErrorNotSupported: return "cudaErrorNotSupported";
+  case cudaErrorInvalidDeviceFunction: return "cudaErrorInvalidDeviceFunction";
+  default: return "cudaErrorUnknown";
+  }
+}
+EXPORT const char *cudaGetErrorString(cudaError_t e) { return cudaGetErrorName(e); }
+
+/* ---- runtime: memory ------------------------------------------------------------------------------------------------- */
+EXPORT cudaError_t cudaMalloc(void **p, size_t bytes) {
+  if (posix_memalign(p, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;
+  memset(*p, 0xA5, bytes); /* fresh device memory is not zero */
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaFree(void *p) {
+  free(p);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned flags) {
+  (void)flags;
+  return posix_memalign(p, 256, bytes ? bytes : 1) ? cudaErrorMemoryAllocation : cudaSuccess;
+}
+EXPORT cudaError_t cudaFreeHost(void *p) {
+  free(p);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned flags) {
+  (void)flags;
+  *dev = host;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaHostRegister(void *p, size_t bytes, unsigned flags) {
+  (void)p, (void)bytes, (void)flags;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaHostUnregister(void *p) {
+  (void)p;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, enum cudaMemcpyKind kind) {
+  (void)kind;
+  memmove(dst, src, bytes);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, enum cudaMemcpyKind kind, cudaStream_t s) {
+  (void)s;
+  return cudaMemcpy(dst, src, bytes, kind);
+}
+EXPORT cudaError_t cudaMemset(void *p, int value, size_t bytes) {
+  memset(p, value, bytes);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaMemsetAsync(void *p, int value, size_t bytes, cudaStream_t s) {
+  (void)s;
+  return cudaMemset(p, value, bytes);
+}
+EXPORT cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  (void)h, (void)p;
+  return cudaErrorNotSupported;
+}
+EXPORT cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags) {
+  (void)p, (void)h, (void)flags;
+  return cudaErrorNotSupported;
+}
+EXPORT cudaError_t cudaIpcCloseMemHandle(void *p) {
+  (void)p;
+  return cudaErrorNotSupported;
+}
+
+/* ---- runtime: streams and events (everything has completed by the time a call returns) ---------------------------------- */
+EXPORT cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned flags) {
+  (void)flags;
+  *s = (cudaStream_t)calloc(1, 8);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  free(s);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+  (void)s;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaStreamQuery(cudaStream_t s) {
+  (void)s;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags) {
+  (void)s, (void)e, (void)flags;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags) {
+  (void)flags;
+  *e = (cudaEvent_t)calloc(1, 8);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaEventDestroy(cudaEvent_t e) {
+  free(e);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+  (void)e, (void)s;
+  return cudaSuccess;
+}
+
+/* ---- runtime: launches of compiled device code cannot run here -------------------------------------------------------------- */
+EXPORT cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t s) {
+  (void)func, (void)grid, (void)block, (void)args, (void)smem, (void)s;
+  fprintf(stderr, "hostdev: cudaLaunchKernel of compiled device code (libnompk) -- there is no GPU behind this test double\n");
+  return cudaErrorInvalidDeviceFunction;
+}
+EXPORT cudaError_t cudaMemcpyToSymbolAsync(const void *symbol, const void *src, size_t bytes, size_t offset,
+                                          enum cudaMemcpyKind kind, cudaStream_t s) {
+  (void)symbol, (void)src, (void)bytes, (void)offset, (void)kind, (void)s;
+  return cudaErrorInvalidDeviceFunction;
+}
+
+/* ---- NVRTC -------------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  char *src, *name, *log, *image;
+} fake_prog_t;
+
+EXPORT nvrtcResult nvrtcVersion(int *major, int *minor) {
+  *major = 12, *minor = 9;
+  return NVRTC_SUCCESS;
+}
+EXPORT const char *nvrtcGetErrorString(nvrtcResult r) { return r == NVRTC_SUCCESS ? "NVRTC_SUCCESS" : "NVRTC_ERROR_COMPILATION"; }
+EXPORT nvrtcResult nvrtcCreateProgram(nvrtcProgram *prog, const char *src, const char *name, int nh, const char *const *h,
+                                      const char *const *in) {
+  (void)nh, (void)h, (void)in;
+  fake_prog_t *p = calloc(1, sizeof(*p));
+  p->src = strdup(src), p->name = strdup(name ? name : "kernel");
+  *prog = (nvrtcProgram)p;
+  return NVRTC_SUCCESS;
+}
+EXPORT nvrtcResult nvrtcDestroyProgram(nvrtcProgram *prog) {
+  fake_prog_t *p = (fake_prog_t *)*prog;
+  if (p) free(p->src), free(p->name), free(p->log), free(p->image), free(p);
+  *prog = NULL;
+  return NVRTC_SUCCESS;
+}
+
+static char *read_file(const char *path) {
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return strdup("");
+  char *buf = calloc(1, 1 << 16);
+  size_t n = fread(buf, 1, (1 << 16) - 1, fp);
+  buf[n] = '\0';
+  fclose(fp);
+  return buf;
+}
+
+EXPORT nvrtcResult nvrtcCompileProgram(nvrtcProgram prog, int nopt, const char *const *opt) {
+  (void)nopt, (void)opt;
+  fake_prog_t *p = (fake_prog_t *)prog;
+  const char *dir = getenv("NOMP_HOSTDEV_DIR"), *py = getenv("NOMP_HOSTDEV_PYTHON"), *helper = getenv("NOMP_HOSTDEV_COMPILER");
+  if (!dir || !py || !helper) {
+    p->log = strdup("hostdev: NOMP_HOSTDEV_DIR / NOMP_HOSTDEV_PYTHON / NOMP_HOSTDEV_COMPILER are not set");
+    return NVRTC_ERROR_COMPILATION;
+  }
+  static unsigned serial = 0;
+  char base[1024], cmd[8 * 1024];
+  snprintf(base, sizeof(base), "%s/k%ld_%u", dir, (long)getpid(), serial++);
+  snprintf(cmd, sizeof(cmd), "%s.cu", base);
+  FILE *fp = fopen(cmd, "w");
+  if (!fp) {
+    p->log = strdup("hostdev: cannot write the kernel source");
+    return NVRTC_ERROR_COMPILATION;
+  }
+  fputs(p->src, fp);
+  fclose(fp);
+  /* the embedded interpreter's environment must not leak into the helper */
+  snprintf(cmd, sizeof(cmd), "env -u PYTHONHOME -u PYTHONPATH '%s' '%s' '%s.cu' '%s.so' > '%s.log' 2>&1", py, helper, base, base, base);
+  const int rc = system(cmd);
+  snprintf(cmd, sizeof(cmd), "%s.log", base);
+  p->log = read_file(cmd);
+  if (rc != 0) return NVRTC_ERROR_COMPILATION;
+  p->image = malloc(strlen(base) + 16);
+  sprintf(p->image, "HOSTDEV:%s.so", base);
+  return NVRTC_SUCCESS;
+}
+EXPORT nvrtcResult nvrtcGetProgramLogSize(nvrtcProgram prog, size_t *size) {
+  fake_prog_t *p = (fake_prog_t *)prog;
+  *size = (p->log ? strlen(p->log) : 0) + 1;
+  return NVRTC_SUCCESS;
+}
+EXPORT nvrtcResult nvrtcGetProgramLog(nvrtcProgram prog, char *log) {
+  fake_prog_t *p = (fake_prog_t *)prog;
+  strcpy(log, p->log ? p->log : "");
+  return NVRTC_SUCCESS;
+}
+EXPORT nvrtcResult nvrtcGetCUBINSize(nvrtcProgram prog, size_t *size) {
+  fake_prog_t *p = (fake_prog_t *)prog;
+  if (!p->image) return NVRTC_ERROR_INVALID_PROGRAM;
+  *size = strlen(p->image) + 1;
+  return NVRTC_SUCCESS;
+}
+EXPORT nvrtcResult nvrtcGetCUBIN(nvrtcProgram prog, char *cubin) {
+  fake_prog_t *p = (fake_prog_t *)prog;
+  if (!p->image) return NVRTC_ERROR_INVALID_PROGRAM;
+  strcpy(cubin, p->image);
+  return NVRTC_SUCCESS;
+}
+
+/* ---- driver entry points ----------------------------------------------------------------------------------------------------------- */
+typedef int (*hostdev_launch_t)(unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void **);
+
+static CUresult fake_cuModuleLoadData(CUmodule *module, const void *image) {
+  if (strncmp((const char *)image, "HOSTDEV:", 8)) return CUDA_ERROR_INVALID_IMAGE;
+  void *h = dlopen((const char *)image + 8, RTLD_NOW | RTLD_LOCAL);
+  if (!h) {
+    fprintf(stderr, "hostdev: %s\n", dlerror());
+    return CUDA_ERROR_INVALID_IMAGE;
+  }
+  *module = (CUmodule)h;
+  return CUDA_SUCCESS;
+}
+static CUresult fake_cuModuleGetFunction(CUfunction *f, CUmodule module, const char *name) {
+  const char *const *have = (const char *const *)dlsym((void *)module, "nomp_hostdev_kernel_name");
+  void *launch = dlsym((void *)module, "nomp_emu_launch");
+  if (!have || !launch || strcmp(*have, name)) return CUDA_ERROR_NOT_FOUND;
+  *f = (CUfunction)launch;
+  return CUDA_SUCCESS;
+}
+static CUresult fake_cuModuleUnload(CUmodule module) { return dlclose((void *)module) ? CUDA_ERROR_INVALID_HANDLE : CUDA_SUCCESS; }
+static CUresult fake_cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                    unsigned smem, CUstream s, void **params, void **extra) {
+  (void)smem, (void)s, (void)extra;
+  if (bx * by * bz > 1024 || bx * by * bz == 0) return CUDA_ERROR_INVALID_VALUE;
+  return ((hostdev_launch_t)f)(gx, gy, gz, bx, by, bz, params) ? CUDA_ERROR_LAUNCH_FAILED : CUDA_SUCCESS;
+}
+static CUresult fake_cuGetErrorName(CUresult r, const char **name) {
+  *name = r == CUDA_SUCCESS             ? "CUDA_SUCCESS"
+          : r == CUDA_ERROR_INVALID_IMAGE ? "CUDA_ERROR_INVALID_IMAGE"
+          : r == CUDA_ERROR_NOT_FOUND     ? "CUDA_ERROR_NOT_FOUND"
+          : r == CUDA_ERROR_LAUNCH_FAILED ? "CUDA_ERROR_LAUNCH_FAILED"
+          : r == CUDA_ERROR_INVALID_VALUE ? "CUDA_ERROR_INVALID_VALUE"
+                                          : "CUDA_ERROR_UNKNOWN";
+  return CUDA_SUCCESS;
+}
+
+EXPORT cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long flags,
+                                          enum cudaDriverEntryPointQueryResult *status) {
+  (void)flags;
+  *fn = !strcmp(symbol, "cuModuleLoadData")      ? (void *)fake_cuModuleLoadData
+        : !strcmp(symbol, "cuModuleGetFunction") ? (void *)fake_cuModuleGetFunction
+        : !strcmp(symbol, "cuModuleUnload")      ? (void *)fake_cuModuleUnload
+        : !strcmp(symbol, "cuLaunchKernel")      ? (void *)fake_cuLaunchKernel
+        : !strcmp(symbol, "cuGetErrorName")      ? (void *)fake_cuGetErrorName
+                                                 : NULL;
+  if (status) *status = *fn ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return cudaSuccess;
+}

@@ -1,0 +1,133 @@
+"""The RUNTIME of libnomp_b200 on the CPU tier: the reference's own nomp-api test programs (compiled unmodified against
+our libnomp.so, oracle/_ref/tests) run against a TEST DOUBLE of the CUDA runtime (tests/hostdev: device memory = host
+memory, "NVRTC" = g++ + the cooperative emulator, native-family calls answered by the oracle), LD_PRELOADed into the
+test programs only.  This is the part pocl plays in the reference's CI (reference .github/workflows/ci.yml:60-77).
+
+What it covers without a GPU: nomp_init / finalize cycles and argument parsing, the mapping table (sub-ranges, re-typing,
+error paths), the jit bridge inside the embedded interpreter (user transform scripts, clauses, error strings from the
+right files), argument marshalling by name, launch-size expressions, the generic emitter's kernels for every language
+feature the reference tests use, the reduce skeleton with its publication protocol, the reduce finish, the on-disk JIT
+cache.  The product is unchanged and has no CPU path: without the preload the same program fails in nomp_init().
+"""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_TESTS = ROOT / "oracle" / "_ref" / "tests"
+HOSTDEV = ROOT / "tests" / "hostdev"
+CUDA_HOME = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
+
+PROGRAMS = ["nomp-api-000", "nomp-api-020", "nomp-api-021", "nomp-api-050", "nomp-api-100", "nomp-api-150", "nomp-api-200",
+            "nomp-api-205", "nomp-api-220", "nomp-api-225", "nomp-api-240", "nomp-api-300", "nomp-api-350", "nomp-api-400",
+            "nomp-api-500", "nomp-api-600"]
+
+
+@pytest.fixture(scope="module")
+def double(tmp_path_factory):
+    if not (REF_TESTS / "nomp-api-000").exists():
+        pytest.skip("reference test programs were not built (needs /root/reference at build time)")
+    if not (CUDA_HOME / "include" / "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not found")
+    from libnomp_b200 import build as b
+    from oracle import ffi
+    b.build_kernels(), b.build_libnomp()
+    ffi.lib()
+    out = HOSTDEV / "_build"
+    out.mkdir(exist_ok=True)
+    so = out / "libhostdev.so"
+    srcs = [HOSTDEV / "fake_cuda.c", HOSTDEV / "fake_nompk.c"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["gcc", "-O1", "-g", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(CUDA_HOME / "include"),
+                        "-I", str(ROOT / "include"), "-o", str(so), *map(str, srcs), "-ldl"], check=True)
+    for f in REF_TESTS.glob("*.pyc.bin"):       # the reference's transform scripts travel byte-compiled (oracle/Makefile)
+        shutil.copyfile(f, f.with_suffix(""))
+    work = tmp_path_factory.mktemp("hostdev")
+    env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"), NOMP_JIT_CACHE="0", NOMP_HOSTDEV_DIR=str(work),
+               NOMP_HOSTDEV_PYTHON=sys.executable, NOMP_HOSTDEV_COMPILER=str(HOSTDEV / "compile_kernel.py"),
+               NOMP_HOSTDEV_ORACLE=str(ROOT / "oracle" / "libnomp_oracle.so"))
+    for k in ("NOMP_BACKEND", "NOMP_DEVICE", "NOMP_PLATFORM", "NOMP_VERBOSE", "NOMP_COMM_SIZE", "NOMP_COMM_RANK"):
+        env.pop(k, None)
+    return so, env
+
+
+def run_program(name, env, preload=None, timeout=900):
+    e = dict(env)
+    if preload is not None:
+        e["LD_PRELOAD"] = str(preload)
+    args = [str(REF_TESTS / name), "--nomp-backend", "cuda", "--nomp-device", "0", "--nomp-platform", "0", "--nomp-install-dir",
+            e["NOMP_INSTALL_DIR"], "--nomp-verbose", "1", "--nomp-annotations-script", "sem"]      # reference scripts/lnrun:120-130
+    return subprocess.run(args, cwd=REF_TESTS, env=e, capture_output=True, text=True, timeout=timeout)
+
+
+def test_reference_suite_passes_on_the_cuda_test_double(double):
+    """All 16 programs of the reference's suite, unmodified, through our runtime: every one exits 0 and prints no
+    failed case."""
+    so, env = double
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        results = dict(zip(PROGRAMS, ex.map(lambda p: run_program(p, env, so), PROGRAMS)))
+    bad = {p: (r.returncode, (r.stdout + r.stderr)[-1500:]) for p, r in results.items() if r.returncode != 0 or "Failed" in r.stdout}
+    assert not bad, bad
+    assert sum(r.stdout.count("Passed") for r in results.values()) >= 66       # test functions (each covers six types)
+
+
+def test_without_the_double_there_is_no_cpu_path(double):
+    """The same program without the preload, on a machine without a GPU: nomp_init() reports a CUDA failure."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("this machine has a GPU")
+    except ImportError:
+        pass
+    _, env = double
+    r = run_program("nomp-api-000", env)
+    assert r.returncode != 0
+    assert "CUDA runtime failure" in r.stderr + r.stdout
+
+
+def test_jit_cache_serves_a_second_process(double, tmp_path):
+    """On-disk JIT cache end to end (src/jitcache.c): the second process finds every program of the first one on disk --
+    bridge output and "CUBIN" -- and gives the same results."""
+    so, env = double
+    env = dict(env, NOMP_JIT_CACHE="1", NOMP_JIT_CACHE_DIR=str(tmp_path / "cache"))
+    first = run_program("nomp-api-225", env, so)
+    assert first.returncode == 0, first.stdout + first.stderr
+    entries = sorted(p.name for p in (tmp_path / "cache").iterdir())
+    assert any(n.endswith(".knl") for n in entries) and any(n.endswith(".cubin") for n in entries)
+    kernels_before = len(list(Path(env["NOMP_HOSTDEV_DIR"]).glob("*.cu")))
+    second = run_program("nomp-api-225", env, so)
+    assert second.returncode == 0 and "Failed" not in second.stdout, second.stdout + second.stderr
+    assert len(list(Path(env["NOMP_HOSTDEV_DIR"]).glob("*.cu"))) == kernels_before      # nothing was compiled again
+    assert sorted(p.name for p in (tmp_path / "cache").iterdir()) == entries
+
+
+# API-level tests of the GPU tier whose sizes the emulator finishes in seconds; the rest need the real device
+# (2^25-element reductions, 256 MiB transfers, throughput floors, direct libnompk calls on torch tensors, NCCL / IPC).
+API_TESTS = ["tests/test_nomp_api_gpu.py", "tests/test_jit_cache_gpu.py", "tests/test_sem_annotations_gpu.py",
+             "tests/test_system_gpu.py::test_cg_example_matches_host_cg"]      # examples/cg_poisson.c against a host CG
+TOO_BIG = ["tests/test_nomp_api_gpu.py::test_reduce_large_sizes", "tests/test_nomp_api_gpu.py::test_repeated_updates_pin_the_host_range",
+           "tests/test_sem_annotations_gpu.py::test_annotated_operator_throughput"]
+
+
+def test_api_level_gpu_tests_run_on_the_cuda_test_double(double):
+    """The ctypes tests of the public API (`-m gpu` tier) in a child pytest whose libnomp.so sees the test double: update
+    semantics and errors, sub-range mappings, jit and run error paths, every kernel-language feature against the kernel
+    string compiled by gcc, reduce clauses of six types with +, *, min, max, the Ax and fused CG kernel strings (native
+    calls answered by the oracle: marshalling only), asynchronous updates, the JIT cache, SEM annotations, and the CG example program against a host CG."""
+    so, env = double
+    env = dict(env, LD_PRELOAD=str(so), NOMP_HOSTDEV_ACTIVE="1")
+    cmd = [sys.executable, "-m", "pytest", *API_TESTS, "-m", "gpu", "-q", "-p", "no:cacheprovider", "--timeout", "600",
+           "-n", str(min(6, os.cpu_count() or 1))]
+    for t in TOO_BIG:
+        cmd += ["--deselect", t]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
+    tail = "\n".join(r.stdout.splitlines()[-40:])
+    assert r.returncode == 0, tail + r.stderr[-2000:]
+    import re
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 71 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
