@@ -26,6 +26,14 @@ void *nomp_b200_stream(void);
 int nomp_b200_update_async(void *ptr, size_t start_index, size_t end_index, size_t unit_size, int op);
 /* Device address that kernels receive for host pointer `hptr` (the address of host element 0), or NULL. */
 void *nomp_b200_device_ptr(void *hptr);
+/* Device-resident reduction results (off by default; returns the previous setting, a negative argument only queries).
+ * While on, a reduce clause whose variable is a MAPPED host address (nomp_update) leaves its result -- all-reduced over
+ * the ranks -- in the device copy of that variable, and nomp_run() returns without waiting for it: the host copy is
+ * not touched until nomp_update(NOMP_FROM).  Kernels read such scalars from device memory as `alpha[0]` (pointer
+ * arguments; the map and reduce skeletons keep their vectorised schedules for loop-invariant reads), so a whole
+ * iteration of a solver can be enqueued without a host round trip.  A reduction variable that is not mapped behaves as
+ * in the reference (result on the host when nomp_run returns, reference tests/nomp-api-500-impl.h:29-34). */
+int nomp_b200_device_reductions(int enable);
 /* Kernels launched by this runtime since load: NVRTC-built kernels + libnompk launches. */
 unsigned long long nomp_b200_launch_count(void);
 /* Rank / size of the NCCL communicator (0 / 1 when single-process). */

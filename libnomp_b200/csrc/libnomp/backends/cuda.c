@@ -107,6 +107,7 @@ typedef struct {
   void *red_ws;        /* reduction workspace of libnompk inside the core's scratch buffer */
   void *red_result;    /* device slot of the reduced scalar, right after the workspace */
   void *red_result_host;
+  void *red_result_arg; /* where this launch stores its result: red_result, or the mapped reduction variable */
   /* D staging cache of the Ax family */
   const void *ax_D;
   unsigned long ax_D_version;
@@ -439,6 +440,9 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   nompk_peers_t peers;
   const nompk_peers_t *px = NULL;
   st->fused_allreduce = 0;
+  /* nomp_b200_device_reductions: the result goes to the device copy of the (mapped) reduction variable instead of the
+   * backend's slot; the kernels are the same, only the address differs */
+  st->red_result_arg = prg->reduction_dev ? prg->reduction_dev : st->red_result;
 
   switch (cp->family) {
   case FAM_MAP: {
@@ -454,7 +458,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     if (n < 0) n = 0;
     if (nomp_comm_size() > 1 && nomp_comm_peers(&peers)) px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
     check_nompk(nompk_reduce_peers((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
-                                   ptr_arg(prg, cp->a_y), st->red_result, result_host, ++st->host_seq, st->red_ws, px,
+                                   ptr_arg(prg, cp->a_y), st->red_result_arg, result_host, ++st->host_seq, st->red_ws, px,
                                    st->stream));
     return 0;
   }
@@ -476,7 +480,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     if (cp->family == FAM_AXDOT)
       check_nompk(nompk_ax_dot_peers_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                          (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
-                                         (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result,
+                                         (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result_arg,
                                          (double *)result_host, ++st->host_seq, st->red_ws, px, flags,
                                          st->stream));
     else
@@ -498,7 +502,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     for (int i = 0; i < cp->nparams; i++) {
       int s = cp->param_slot[i];
       if (s == SLOT_WS) vargs[i] = &st->red_ws;
-      else if (s == SLOT_RESULT) vargs[i] = &st->red_result;
+      else if (s == SLOT_RESULT) vargs[i] = &st->red_result_arg;
       else if (s == SLOT_RESULT_HOST) vargs[i] = &st->red_result_host;
       else if (s == SLOT_SEQ) vargs[i] = &st->host_seq;
       else if (s == SLOT_PEERS) vargs[i] = &st->nv_peers;
@@ -523,6 +527,15 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
  * ranks if there are several, then wait for the kernel to publish {value, sequence number} to the host. */
 int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg, int dtype, size_t size) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (prg->reduction_dev) {
+    /* the result stays on the device (nomp_b200_device_reductions): all-reduce it in place if the kernel has not done
+     * so itself, and return without waiting -- the next kernel on the stream reads it from device memory */
+    int published = 0;
+    if (nomp_comm_size() > 1 && !st->fused_allreduce)
+      nomp_check(nomp_comm_allreduce(prg->reduction_dev, dtype, (int)prg->reduction_op, st->pinned_dev, st->host_seq,
+                                     st->stream, &published));
+    return 0;
+  }
   if (nomp_comm_size() > 1 && !st->fused_allreduce) {
     /* all-reduce the device scalar in place; the NVLink one-shot kernel also publishes {value, seq} to the host,
      * the NCCL fallback needs an explicit 8-byte copy */

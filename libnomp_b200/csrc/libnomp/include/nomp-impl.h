@@ -63,6 +63,8 @@ typedef struct {
   nomp_arg_type_t reduction_type;
   int reduction_size;
   void *reduction_ptr;
+  void *reduction_dev; /* device copy of the reduction variable when its result stays on the device
+                          (nomp_b200_device_reductions), else NULL */
   PyObject *py_dict; /* JIT-fixed arguments: name -> value */
   char *info;        /* descriptor line of the generated kernel (nomp_b200_prog_info) */
 } nomp_prog_t;

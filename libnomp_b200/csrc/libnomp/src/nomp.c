@@ -21,6 +21,7 @@
 static nomp_backend_t nomp;
 static nomp_config_t config; /* of the last successful nomp_init() */
 static int initialized = 0;
+static int device_reductions = 0; /* nomp_b200_device_reductions(): reduce results stay in mapped variables */
 
 /* ============================================================================================================== */
 /* configuration                                                                                                  */
@@ -131,6 +132,7 @@ NOMP_EXPORT int nomp_init(int argc, const char **argv) {
   config = cfg;
   nomp_jit_cache_reset();
   initialized = 1;
+  device_reductions = 0;
   return 0;
 }
 
@@ -232,6 +234,14 @@ NOMP_EXPORT int nomp_b200_update_async(void *ptr, size_t idx0, size_t idx1, size
     return nomp_log(NOMP_USER_MAP_OP_IS_INVALID, NOMP_ERROR,
                     "nomp_b200_update_async can only be called on a range which is already on the device.");
   return nomp_cuda_update_async(&nomp, &node->m, op, idx0, idx1, unit_size);
+}
+
+/* include/nomp-b200.h: leave the result of a reduce clause in the device copy of its variable when that variable is
+ * mapped, and do not wait for it.  Off by default: the reference writes the host variable before nomp_run returns. */
+NOMP_EXPORT int nomp_b200_device_reductions(int enable) {
+  const int before = device_reductions;
+  if (enable >= 0) device_reductions = enable != 0;
+  return before;
 }
 
 NOMP_EXPORT void *nomp_b200_device_ptr(void *hptr) {
@@ -553,15 +563,16 @@ NOMP_EXPORT int nomp_run(int id, ...) {
       nomp_mem_t *m = nomp_lookup_mem(p);
       if (m == NULL) {
         if (prg->reduction_index == (int)i) { /* the accumulator is an unmapped host address */
-          prg->reduction_ptr = p, args[i].ptr = NULL;
+          prg->reduction_ptr = p, prg->reduction_dev = NULL, args[i].ptr = NULL;
           break;
         }
         va_end(ap);
         return nomp_log(NOMP_USER_MAP_PTR_IS_INVALID, NOMP_ERROR, ERR_STR_USER_MAP_PTR_IS_INVALID, p);
       }
-      if (prg->reduction_index == (int)i) prg->reduction_ptr = p;
       args[i].mem = m;
       args[i].ptr = (char *)m->bptr - m->idx0 * m->usize; /* device address of host element 0 */
+      if (prg->reduction_index == (int)i)
+        prg->reduction_ptr = p, prg->reduction_dev = device_reductions ? args[i].ptr : NULL;
       break;
     }
     default: break; /* NOMP_FLOAT: the pointer to the scalar is passed through */

@@ -157,6 +157,33 @@ def _is_elem(e: c.Node, arrays: Dict[str, c.Param], var: str) -> Optional[str]:
     return None
 
 
+def invariant_arrays(stmts, exprs, arrays: Dict[str, c.Param]) -> set:
+    """Pointer parameters that the loop only READS, and only at constant subscripts (`alpha[0]`): scalars that live in
+    device memory -- the result a reduce clause left there, a coefficient computed by an earlier kernel.  The skeletons
+    keep such reads as they are (one cached load per thread) instead of giving up their vectorised schedule."""
+    kinds: Dict[str, set] = {}
+    written = set()
+
+    def visit(e):
+        if isinstance(e, c.Subscript) and isinstance(e.base, c.Name) and e.base.id in arrays:
+            kinds.setdefault(e.base.id, set()).add(len(e.index) == 1 and const_int(e.index[0]) is not None)
+        return e
+
+    for n in walk(stmts):
+        if isinstance(n, c.Assign):
+            map_expr(n.target, visit)
+            map_expr(n.value, visit)
+            if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name):
+                written.add(n.target.base.id)
+        elif isinstance(n, c.Decl):
+            map_expr(n.init, visit)
+        elif isinstance(n, c.If):
+            map_expr(n.cond, visit)
+    for e in exprs:
+        map_expr(e, visit)
+    return {a for a, k in kinds.items() if k == {True} and a not in written}
+
+
 def _terms(e: c.Node) -> Optional[List[List[c.Node]]]:
     """Flatten e into a sum of products (no parenthesised sums inside products). None if not of that shape."""
     if isinstance(e, c.BinOp) and e.op == "+":
@@ -310,10 +337,13 @@ def match_map_skeleton(func: c.Function) -> Optional[c.For]:
     sizes = set()
     ok = True
     written_scalars = set()
+    invariant = invariant_arrays(loop.body, [], arrays)
 
     def check_expr(e):
         nonlocal ok
         if isinstance(e, c.Subscript):
+            if isinstance(e.base, c.Name) and e.base.id in invariant:
+                return e
             a = _is_elem(e, arrays, loop.var)
             if a is None:
                 ok = False
@@ -360,6 +390,8 @@ def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, Lis
     func = knl.func
     params = _params(func)
     arrays = {k: p for k, p in params.items() if p.is_array}
+    invariant = invariant_arrays(loop.body, [], arrays)
+    arrays = {k: p for k, p in arrays.items() if k not in invariant}    # `alpha[0]` stays a plain read
     used, written = [], []
 
     def note(e):

@@ -173,6 +173,8 @@ def _elementwise_arrays(func: c.Function, info: "ReductionInfo"):
     from .ir import map_expr
     params = _params(func)
     arrays = {k: p for k, p in params.items() if p.is_array and k != info.var}
+    invariant = _fam().invariant_arrays(info.pre, list(info.preds) + [info.rhs], arrays)
+    arrays = {k: p for k, p in arrays.items() if k not in invariant}    # `alpha[0]`: a scalar in device memory
     used, written, ok = [], [], [True]
 
     def visit(e):
@@ -249,6 +251,8 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
 
     ew = _elementwise_arrays(func, info)
     arrays = {p.name: p for p in params if p.is_array}
+    if ew is not None:    # loop-invariant reads keep their subscript
+        arrays = {k: p for k, p in arrays.items() if k in ew[0]}
     if ew is not None:
         sig_parts = [(f"{cuda_type(p.ctype)} *__restrict__ {p.name}" if p.name in written_any else
                       f"const {cuda_type(p.ctype)} *__restrict__ {p.name}") if p.is_array else f"{cuda_type(p.ctype)} {p.name}"

@@ -1,0 +1,167 @@
+"""Device-resident reduction results (include/nomp-b200.h: nomp_b200_device_reductions) and kernels that read their
+scalars from device memory: a conjugate-gradient iteration enqueued without a single host round trip.
+
+State: verified on the CUDA test double of the CPU tier (tests/test_hostdev_cpu.py runs this file there); the first run
+on the B200 is pending (the feature was written after the round's GPU budget was spent), so on a real device the tests
+skip instead of gating the tier on code that has never seen one.  Remove `first_gpu_run_pending` once it has passed.
+"""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "libnomp_b200" / "python"))
+
+from libnomp_b200 import capi  # noqa: E402
+from nomp_bridge.families import AX_DOT_KERNEL_SOURCE  # noqa: E402
+from oracle import ffi  # noqa: E402
+
+first_gpu_run_pending = pytest.mark.skipif(os.environ.get("NOMP_HOSTDEV_ACTIVE") != "1" and os.environ.get("NOMP_RUN_PENDING") != "1",
+                                           reason="verified on the CUDA test double; first B200 run pending (set NOMP_RUN_PENDING=1)")
+pytestmark = [pytest.mark.gpu, first_gpu_run_pending]
+
+P, I, F = capi.NOMP_PTR, capi.NOMP_INT, capi.NOMP_FLOAT
+
+
+@pytest.fixture(scope="module", autouse=True)
+def runtime():
+    capi.check(capi.init(backend="cuda", device=0, verbose=0))
+    yield capi.nomp()
+    assert capi.nomp().nomp_finalize_excluding_interpreter() == 0
+
+
+def jit(src, clauses, args):
+    err, kid = capi.jit(src, clauses, args)
+    capi.check(err)
+    return kid
+
+
+def to_device(*arrays):
+    for a in arrays:
+        capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_TO))
+
+
+def from_device(*arrays):
+    for a in arrays:
+        capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_FROM))
+
+
+def free(*arrays):
+    for a in arrays:
+        capi.check(capi.update(a.ctypes.data, 0, a.size, a.itemsize, capi.NOMP_FREE))
+
+
+def test_mapped_reduction_variable_keeps_its_result_on_the_device():
+    lib = capi.nomp()
+    n = 10007
+    a = ffi.fill_int_f64(n, 3, 0, 7)
+    s, t = np.array([-1.0]), np.array([-2.0])
+    to_device(a, s)
+    kid = jit("void sum(const double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }",
+              capi.clauses(("reduce", "s", "+")), [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    # default: the reference's semantics even for a mapped variable -- the host copy holds the sum when nomp_run returns
+    assert lib.nomp_b200_device_reductions(-1) == 0
+    capi.check(capi.run(kid, a.ctypes.data, C.c_int(n), s.ctypes.data))
+    assert s[0] == a.sum()
+    # on: the host copy is left alone, the device copy holds the result
+    assert lib.nomp_b200_device_reductions(1) == 0 and lib.nomp_b200_device_reductions(-1) == 1
+    s[0] = -1.0
+    capi.check(capi.run(kid, a.ctypes.data, C.c_int(n), s.ctypes.data))
+    assert s[0] == -1.0
+    from_device(s)
+    assert s[0] == a.sum()
+    # a variable that is not mapped still gets its value on the host at once, and later waits are not confused by the
+    # launches that did not wait (sequence numbers)
+    capi.check(capi.run(kid, a.ctypes.data, C.c_int(n), t.ctypes.data))
+    assert t[0] == a.sum()
+    # integer type, generated reduction (condition -> skeleton), 4-byte result next to other data
+    b = (np.arange(n) % 11).astype(np.int32)
+    cnt = np.array([7, -5, 9], dtype=np.int32)
+    to_device(b, cnt)
+    kid2 = jit("void count(const int *b, int N, int *c) { for (int i = 0; i < N; i++) if (b[i] > 4) c[0] += b[i]; }",
+               capi.clauses(("reduce", "c", "+")), [("b", 4, P), ("N", 4, I), ("c", 4, I)])
+    capi.check(capi.run(kid2, b.ctypes.data, C.c_int(n), cnt.ctypes.data))
+    assert list(cnt) == [7, -5, 9]
+    from_device(cnt)
+    assert list(cnt) == [int(b[b > 4].sum()), -5, 9]
+    assert lib.nomp_b200_device_reductions(0) == 1
+    free(a, s, b, cnt)
+
+
+def test_cg_iterations_without_host_round_trips():
+    """CG on the local Poisson operator with every scalar in device memory: per iteration Ax + p.Ap (native), alpha,
+    the fused update + r.r (reduce skeleton reading alpha[0]), beta, the new direction (map skeleton reading beta[0]) --
+    six launches, no host wait; the host looks at the residual after the last iteration.  Against the same CG on the
+    host (oracle Ax, numpy dots)."""
+    lib = capi.nomp()
+    n, E, iters = 8, 6, 5
+    n3 = n ** 3
+    N = E * n3
+    xt = ffi.fill_uniform_f64(N, 11, 0.0, 1.0) - 0.5
+    v = ffi.fill_uniform_f64(6 * N, 13, 0.0, 1.0).reshape(E, 6, n3)
+    g = 0.2 * (v - 0.5)
+    for f in (0, 3, 5):
+        g[:, f, :] = 1.0 + 0.5 * v[:, f, :]
+    g = np.ascontiguousarray(g.ravel())
+    D = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    b = ffi.ax(n, xt, g, D)
+    # host CG
+    x, r, p = np.zeros(N), b.copy(), b.copy()
+    rr = float(r @ r)
+    hist = []
+    for _ in range(iters):
+        w = ffi.ax(n, p, g, D)
+        pap = float(p @ w)
+        alpha = rr / pap
+        x += alpha * p
+        r -= alpha * w
+        rr_new = float(r @ r)
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+        hist.append((pap, alpha, rr))
+    # device CG
+    dx, dr, dp, dw = np.zeros(N), b.copy(), b.copy(), np.zeros(N)
+    sc = {k: np.zeros(1) for k in ("pap", "alpha", "beta", "rr", "rr_new")}
+    sc["rr"][0] = float(b @ b)
+    trace = np.zeros(3 * iters)
+    to_device(dx, dr, dp, dw, g, D, trace, *sc.values())
+    k_ax = jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")),
+               [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | capi.NOMP_JIT, C.c_int(n)), ("pap", 8, F)])
+    k_alpha = jit("void cg_alpha(double *alpha, const double *rr, const double *pap, double *trace, int it) {"
+                  " for (int i = 0; i < 1; i++) { alpha[i] = rr[i] / pap[i]; trace[3 * it] = pap[i]; trace[3 * it + 1] = alpha[i]; } }",
+                  capi.clauses(), [("alpha", 8, P), ("rr", 8, P), ("pap", 8, P), ("trace", 8, P), ("it", 4, I)])
+    k_upd = jit("void cg_update(double *x, double *r, const double *p, const double *w, const double *alpha, int N, double *rr_new) {"
+                " for (int i = 0; i < N; i++) { x[i] += alpha[0] * p[i]; r[i] -= alpha[0] * w[i]; rr_new[0] += r[i] * r[i]; } }",
+                capi.clauses(("reduce", "rr_new", "+")),
+                [("x", 8, P), ("r", 8, P), ("p", 8, P), ("w", 8, P), ("alpha", 8, P), ("N", 4, I), ("rr_new", 8, F)])
+    k_beta = jit("void cg_beta(double *beta, double *rr, const double *rr_new, double *trace, int it) {"
+                 " for (int i = 0; i < 1; i++) { beta[i] = rr_new[i] / rr[i]; rr[i] = rr_new[i]; trace[3 * it + 2] = rr_new[i]; } }",
+                 capi.clauses(), [("beta", 8, P), ("rr", 8, P), ("rr_new", 8, P), ("trace", 8, P), ("it", 4, I)])
+    k_dir = jit("void cg_direction(double *p, const double *r, const double *beta, int N) {"
+                " for (int i = 0; i < N; i++) p[i] = r[i] + beta[0] * p[i]; }",
+                capi.clauses(), [("p", 8, P), ("r", 8, P), ("beta", 8, P), ("N", 4, I)])
+    info = lambda k: lib.nomp_b200_prog_info(k).decode()  # noqa: E731
+    assert "family=axdot" in info(k_ax) and "family=reduce" in info(k_upd) and "family=map" in info(k_dir)
+    lib.nomp_b200_device_reductions(1)
+    launches = lib.nomp_b200_launch_count()
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    for it in range(iters):
+        capi.check(capi.run(k_ax, ptr(dw), ptr(dp), ptr(g), ptr(D), C.c_int(E), ptr(sc["pap"])))
+        capi.check(capi.run(k_alpha, ptr(sc["alpha"]), ptr(sc["rr"]), ptr(sc["pap"]), ptr(trace), C.c_int(it)))
+        capi.check(capi.run(k_upd, ptr(dx), ptr(dr), ptr(dp), ptr(dw), ptr(sc["alpha"]), C.c_int(N), ptr(sc["rr_new"])))
+        capi.check(capi.run(k_beta, ptr(sc["beta"]), ptr(sc["rr"]), ptr(sc["rr_new"]), ptr(trace), C.c_int(it)))
+        capi.check(capi.run(k_dir, ptr(dp), ptr(dr), ptr(sc["beta"]), C.c_int(N)))
+    assert lib.nomp_b200_launch_count() - launches == 5 * iters
+    assert sc["pap"][0] == 0.0 and sc["rr_new"][0] == 0.0            # nothing came back to the host on its own
+    lib.nomp_b200_device_reductions(0)
+    from_device(dx, trace, sc["rr"])
+    for it, (pap, alpha, rr_it) in enumerate(hist):
+        for got, want in zip(trace[3 * it: 3 * it + 3], (pap, alpha, rr_it)):
+            assert abs(got - want) <= 1e-10 * abs(want), (it, got, want)
+    assert sc["rr"][0] == trace[-1]
+    assert np.max(np.abs(dx - x)) <= 1e-9 * np.max(np.abs(x))
+    free(dx, dr, dp, dw, g, D, trace, *sc.values())

@@ -805,3 +805,48 @@ def test_random_reductions_run_on_the_host(T, op):
         got, pub, _, tickets = _run_reduce_skeleton(src, "s", op, T, {"a": (a, f"const {cuda_t} *"), "b": (b, f"const {cuda_t} *")},
                                                     {"N": ("int", C.c_int(n))}, n, grid_override=int(rng.integers(1, 40)))
         assert got == want[0] == pub and not tickets.any(), (T, op, case, stmt)
+
+
+# ---- scalars that live in device memory ---------------------------------------------------------------------------------
+
+def test_loop_invariant_reads_keep_the_vector_schedules():
+    """`alpha[0]` -- a scalar in device memory (the result a reduce clause left there, a coefficient a previous kernel
+    computed) -- read at a constant subscript of an array the loop never writes: the map and reduce skeletons keep their
+    128-bit schedules and leave the read as it is.  Bitwise the kernel string compiled by gcc."""
+    from tests.cuda_emulation import emulate_cooperative
+    rng = np.random.default_rng(5)
+    n = 4099
+    # map skeleton: p = r + beta[1] * p, x += alpha[0] * q
+    src = ("void dir(double *p, double *x, const double *r, const double *q, const double *coef, int N) {"
+           " for (int i = 0; i < N; i++) { p[i] = r[i] + coef[1] * p[i]; x[i] += coef[0] * q[i]; } }")
+    desc, cuda, (grid, block), _ = plan(src)
+    assert (desc["kind"], desc["family"]) == ("nvrtc", "map"), desc
+    assert "coef[1]" in cuda and "coef[0]" in cuda and "nomp_coef" not in cuda and "int4" in cuda
+    p, x, r, q = (rng.integers(-4, 5, n).astype(np.float64) for _ in range(4))
+    coef = np.array([0.5, -0.25])
+    pw, xw = p.copy(), x.copy()
+    run_kernel(src, pw, xw, r, q, coef, n)
+    emulate(cuda, "dir", (grid_eval(grid[0], {"N": n}), 1, 1), (256, 1, 1),
+            ["double *", "double *", "const double *", "const double *", "const double *", "int"],
+            [_ptr(p), _ptr(x), _ptr(r), _ptr(q), _ptr(coef), C.c_int(n)])
+    assert np.array_equal(p, pw) and np.array_equal(x, xw)
+    # an array that is also written, or read at i as well, is not a scalar: no vector schedule through this rule
+    for bad in ("void k(double *a, double *s, int N) { for (int i = 0; i < N; i++) { a[i] += s[0]; s[0] = a[i]; } }",
+                "void k(double *a, const double *s, int N) { for (int i = 0; i < N; i++) a[i] += s[0] + s[i + 1]; }"):
+        assert plan(bad)[0]["family"] == "generic"
+    # reduce skeleton: the fused CG update with alpha in device memory
+    src = ("void upd(double *x, double *r, const double *p, const double *w, const double *alpha, int N, double *rr) {"
+           " for (int i = 0; i < N; i++) { x[i] += alpha[0] * p[i]; r[i] -= alpha[0] * w[i]; rr[0] += r[i] * r[i]; } }")
+    desc, cuda, _, _ = plan(src, reduce=("rr", "+"))
+    assert "alpha[0]" in cuda and "nomp_alpha" not in cuda and "int4" in cuda
+    x, r, p, w = (rng.integers(-4, 5, n).astype(np.float64) for _ in range(4))
+    alpha = np.array([0.5])
+    xw, rw, want = x.copy(), r.copy(), np.zeros(1)
+    run_kernel(src, xw, rw, p, w, alpha, n, want)
+    got, _, _, _ = _run_reduce_skeleton(src, "rr", "+", "double",
+                                        {"x": (x, "double *"), "r": (r, "double *"), "p": (p, "const double *"),
+                                         "w": (w, "const double *"), "alpha": (alpha, "const double *")},
+                                        {"N": ("int", C.c_int(n))}, n)
+    assert got == want[0] and np.array_equal(x, xw) and np.array_equal(r, rw)
+    ok, log = nvrtc_compile(cuda)
+    assert ok, log

@@ -110,7 +110,8 @@ def test_jit_cache_serves_a_second_process(double, tmp_path):
 # (2^25-element reductions, 256 MiB transfers, throughput floors, direct libnompk calls on torch tensors, NCCL / IPC).
 API_TESTS = ["tests/test_nomp_api_gpu.py", "tests/test_jit_cache_gpu.py", "tests/test_sem_annotations_gpu.py",
              "tests/test_system_gpu.py::test_cg_example_matches_host_cg",      # examples/cg_poisson.c against a host CG
-             "tests/test_system_gpu.py::test_smoke_entry_point"]                # the call sequence of __graft_entry__.smoke()
+             "tests/test_system_gpu.py::test_smoke_entry_point",                # the call sequence of __graft_entry__.smoke()
+             "tests/test_device_scalars_gpu.py"]                                # reduce results and scalars that stay on the device
 TOO_BIG = ["tests/test_nomp_api_gpu.py::test_reduce_large_sizes", "tests/test_nomp_api_gpu.py::test_repeated_updates_pin_the_host_range",
            "tests/test_sem_annotations_gpu.py::test_annotated_operator_throughput"]
 
@@ -131,7 +132,7 @@ def test_api_level_gpu_tests_run_on_the_cuda_test_double(double):
     assert r.returncode == 0, tail + r.stderr[-2000:]
     import re
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 72 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+    assert m and int(m.group(1)) >= 74 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
 
 
 def test_runtime_is_clean_under_address_and_undefined_behaviour_sanitizers(double):
