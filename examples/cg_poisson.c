@@ -8,11 +8,18 @@
  * With NOMP_COMM_SIZE > 1 every rank owns E elements of a larger mesh; the two dot products are all-reduced by the
  * runtime, nothing else changes (the local operator needs no halo exchange).
  *
- *   usage: cg_poisson [E [n [max_iter [tol]]]]  + the usual --nomp-* flags     (prints one JSON object per line)
+ *   usage: cg_poisson [E [n [max_iter [tol [host|device [check_every]]]]]]  + the usual --nomp-* flags
+ *          (prints one JSON object per line)
+ *
+ * "device" keeps every scalar of the iteration in device memory (include/nomp-b200.h: nomp_b200_device_reductions):
+ * the two dot products leave their results in mapped variables, alpha and beta are computed by one-iteration kernels,
+ * the updates read them as alpha[0] / beta[0] -- five launches per iteration and no host round trip; the host fetches
+ * the residual every `check_every` iterations (default 10) to test for convergence.
  */
 #define _POSIX_C_SOURCE 200809L
 #define _DEFAULT_SOURCE
 #include "sem_common.h"
+#include "nomp-b200.h"
 
 /* counter-based generator shared with the tests (splitmix64) */
 static double uniform(unsigned long long seed, unsigned long long i) {
@@ -31,8 +38,21 @@ static const char *XPAY_SRC =
 static const char *DOT_SRC =
     "void cg_dot(const double *a, const double *b, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i] * b[i]; }\n";
 
+/* the same iteration with its scalars in device memory */
+static const char *ALPHA_SRC =
+    "void cg_alpha(double *alpha, const double *rr, const double *pap, double *trace, int slot) {\n"
+    "  for (int i = 0; i < 1; i++) { alpha[i] = rr[i] / pap[i]; trace[3 * slot] = pap[i]; trace[3 * slot + 1] = alpha[i]; }\n}\n";
+static const char *UPDATE_DEV_SRC =
+    "void cg_update_d(double *x, double *r, const double *p, const double *w, const double *alpha, int N, double *rr_new) {\n"
+    "  for (int i = 0; i < N; i++) { x[i] += alpha[0] * p[i]; r[i] -= alpha[0] * w[i]; rr_new[0] += r[i] * r[i]; }\n}\n";
+static const char *BETA_SRC =
+    "void cg_beta(double *beta, double *rr, const double *rr_new, double *trace, int slot) {\n"
+    "  for (int i = 0; i < 1; i++) { beta[i] = rr_new[i] / rr[i]; rr[i] = rr_new[i]; trace[3 * slot + 2] = rr_new[i]; }\n}\n";
+static const char *XPAY_DEV_SRC =
+    "void cg_direction_d(double *p, const double *r, const double *beta, int N) { for (int i = 0; i < N; i++) p[i] = r[i] + beta[0] * p[i]; }\n";
+
 int main(int argc, const char **argv) {
-  int E = 1024, n = 8, max_iter = 200;
+  int E = 1024, n = 8, max_iter = 200, device_scalars = 0, check_every = 10;
   double tol = 1e-10;
   int pos = 0;
   for (int i = 1; i < argc; i++) {
@@ -41,6 +61,8 @@ int main(int argc, const char **argv) {
     else if (pos == 1) n = atoi(argv[i]);
     else if (pos == 2) max_iter = atoi(argv[i]);
     else if (pos == 3) tol = atof(argv[i]);
+    else if (pos == 4) device_scalars = !strcmp(argv[i], "device");
+    else if (pos == 5) check_every = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
     pos++;
   }
   CHECK(nomp_init(argc, argv));
@@ -91,10 +113,54 @@ int main(int argc, const char **argv) {
   rr0 = rr;
   printf("{\"E_per_rank\": %d, \"n\": %d, \"dof_per_rank\": %zu, \"rr0\": %.17g}\n", E, n, N, rr0);
 
+  /* scalars of the device-resident variant: one mapped double each; trace = {pAp, alpha, rr} of the first iterations */
+  double *pap_d = calloc(1, 8), *alpha_d = calloc(1, 8), *beta_d = calloc(1, 8), *rr_d = calloc(1, 8), *rrn_d = calloc(1, 8);
+  double *trace = calloc(18, 8);
+  double *scalars[] = {pap_d, alpha_d, beta_d, rr_d, rrn_d};
+  int id_alpha = -1, id_updd = -1, id_beta = -1, id_dird = -1;
+  if (device_scalars) {
+    const char *red_rrn[4] = {"reduce", "rr_new", "+", NULL};
+    rr_d[0] = rr;
+    for (int a = 0; a < 5; a++) CHECK(nomp_update(scalars[a], 0, 1, 8, NOMP_TO));
+    CHECK(nomp_update(trace, 0, 18, 8, NOMP_TO));
+    CHECK(nomp_jit(&id_alpha, ALPHA_SRC, none, 5, "alpha", sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "pap",
+                   sizeof(double), NOMP_PTR, "trace", sizeof(double), NOMP_PTR, "slot", sizeof(int), NOMP_INT));
+    CHECK(nomp_jit(&id_updd, UPDATE_DEV_SRC, red_rrn, 7, "x", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "p",
+                   sizeof(double), NOMP_PTR, "w", sizeof(double), NOMP_PTR, "alpha", sizeof(double), NOMP_PTR, "N", sizeof(int),
+                   NOMP_INT, "rr_new", sizeof(double), NOMP_FLOAT));
+    CHECK(nomp_jit(&id_beta, BETA_SRC, none, 5, "beta", sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "rr_new",
+                   sizeof(double), NOMP_PTR, "trace", sizeof(double), NOMP_PTR, "slot", sizeof(int), NOMP_INT));
+    CHECK(nomp_jit(&id_dird, XPAY_DEV_SRC, none, 4, "p", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "beta",
+                   sizeof(double), NOMP_PTR, "N", sizeof(int), NOMP_INT));
+    nomp_b200_device_reductions(1);
+  }
+
   CHECK(nomp_sync());
   double t0 = now_s();
   int it = 0;
-  for (; it < max_iter && rr > tol * tol * rr0; it++) {
+  for (; device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
+    if (it == 1) {
+      CHECK(nomp_sync());
+      t0 = now_s();
+    }
+    const int slot = it < 5 ? it : 5; /* iterations beyond the fifth share a scratch slot of the trace */
+    CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
+    CHECK(nomp_run(id_alpha, alpha_d, rr_d, pap_d, trace, &slot));
+    CHECK(nomp_run(id_updd, x, r, p, w, alpha_d, &Ni, rrn_d));
+    CHECK(nomp_run(id_beta, beta_d, rr_d, rrn_d, trace, &slot));
+    CHECK(nomp_run(id_dird, p, r, beta_d, &Ni));
+    if ((it + 1) % check_every == 0 || it + 1 == max_iter) { /* the only host round trip */
+      CHECK(nomp_update(rr_d, 0, 1, 8, NOMP_FROM));
+      rr = rr_d[0];
+    }
+  }
+  if (device_scalars) {
+    nomp_b200_device_reductions(0);
+    CHECK(nomp_update(trace, 0, 18, 8, NOMP_FROM));
+    for (int i = 0; i < 5 && i < it; i++)
+      printf("{\"iter\": %d, \"pAp\": %.17g, \"alpha\": %.17g, \"rr\": %.17g}\n", i, trace[3 * i], trace[3 * i + 1], trace[3 * i + 2]);
+  }
+  for (; !device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
     if (it == 1) { /* the first iteration loads every kernel (lazy module loading): time from the second one */
       CHECK(nomp_sync());
       t0 = now_s();
@@ -122,8 +188,9 @@ int main(int argc, const char **argv) {
   CHECK(nomp_run(id_axpy, p, w, &minus_one, &Ni)); /* p = b - A x */
   CHECK(nomp_run(id_dot, p, p, &Ni, &res2));
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
-         "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": 136}\n",
-         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0);
+         "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": 136, \"scalars\": \"%s\"}\n",
+         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0,
+         device_scalars ? "device" : "host");
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

@@ -165,3 +165,25 @@ def test_cg_iterations_without_host_round_trips():
     assert sc["rr"][0] == trace[-1]
     assert np.max(np.abs(dx - x)) <= 1e-9 * np.max(np.abs(x))
     free(dx, dr, dp, dw, g, D, trace, *sc.values())
+
+
+def test_cg_example_gives_the_same_iterates_with_device_scalars():
+    """examples/cg_poisson.c, "host" against "device": the same kernels on the same data in the same order -- the
+    iterates agree to the last bit, and so do the iteration counts when the check interval divides them."""
+    import json
+    import subprocess
+    exe = ROOT / "libnomp_b200" / "build" / "cg_poisson"
+    if not exe.exists():
+        pytest.skip("examples/cg_poisson was not built")
+    env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
+    runs = {}
+    for mode in ("host", "device"):
+        r = subprocess.run([str(exe), "6", "8", "400", "1e-9", mode, "1", "--nomp-backend", "cuda", "--nomp-device", "0",
+                            "--nomp-verbose", "1"], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[mode] = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
+    host, dev = runs["host"], runs["device"]
+    assert host[0] == dev[0] and host[1:6] == dev[1:6]
+    assert dev[-1]["scalars"] == "device" and host[-1]["scalars"] == "host"
+    assert dev[-1]["iterations"] == host[-1]["iterations"] and dev[-1]["rr_final"] == host[-1]["rr_final"]
+    assert dev[-1]["true_residual_rel"] < 1e-7
