@@ -265,9 +265,20 @@ def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args, inst
     """Run a generated kernel on the host with real barrier / shuffle / ticket semantics (see above).  Different
     `instance` numbers give separate copies of the library (own globals), so several "ranks" can run at the same time
     in different Python threads and talk through host memory the way GPUs talk through peer memory."""
+    so = cooperative_library(src, kernel, argtypes, instance)
+    lib = C.CDLL(str(so))
+    fn = lib.nomp_emu_launch
+    fn.restype = C.c_int
+    rc = fn(*[C.c_uint(v) for v in (*grid, *block)], *args)
+    assert rc == 0, "the emulated kernel deadlocked"
+
+
+def cooperative_library(src: str, kernel: str, argtypes, instance: int = 0, out: Path = None) -> Path:
+    """The shared object behind emulate_cooperative(): exports
+    int nomp_emu_launch(gx, gy, gz, bx, by, bz, <one argument per entry of argtypes>)."""
     key = hashlib.sha256((f"coop{instance}" + src + kernel + repr(argtypes)).encode()).hexdigest()[:16]
-    so = _DIR / f"c{key}.so"
-    if not so.exists():
+    so = Path(out) if out is not None else _DIR / f"c{key}.so"
+    if out is not None or not so.exists():
         body = re.sub(r'extern "C"\s*', "", src)
         # the only inline PTX the bridge emits reads the global timer (time-out of the peer exchange)
         body = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", body)
@@ -283,11 +294,7 @@ def emulate_cooperative(src: str, kernel: str, grid, block, argtypes, args, inst
         # each copy of the library, or two emulated ranks in one process would share their "shared memory"
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fno-gnu-unique",
                         "-fvisibility=hidden", "-o", str(so), str(cpp)], check=True)
-    lib = C.CDLL(str(so))
-    fn = lib.nomp_emu_launch
-    fn.restype = C.c_int
-    rc = fn(*[C.c_uint(v) for v in (*grid, *block)], *args)
-    assert rc == 0, "the emulated kernel deadlocked"
+    return so
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -15,16 +15,21 @@
  *   driver            = cuModuleLoadData -> dlopen, cuLaunchKernel -> the object's launcher (grid, block, void **params).
  *   libnompk launches = cudaLaunchKernel fails (there is no device code to run here); tests/hostdev/fake_nompk.c
  *                       interposes the C ABI of include/nompk.h instead.
+ *   several ranks     = NOMP_HOSTDEV_SHARED=1: allocations are POSIX shared-memory objects and the cudaIpc* calls map
+ *                       them into the peer processes; tests/hostdev/fake_nccl.c stands in for libnccl.so.2.
  */
 #define _GNU_SOURCE
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nvrtc.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #define EXPORT __attribute__((visibility("default")))
@@ -74,6 +79,7 @@ EXPORT const char *cudaGetErrorName(cudaError_t e) {
   case cudaErrorInvalidDevice: return "cudaErrorInvalidDevice";
   case cudaErrorMemoryAllocation: return "cudaErrorMemoryAllocation";
   case cudaErrorNotSupported: return "cudaErrorNotSupported";
+  case cudaErrorInvalidValue: return "cudaErrorInvalidValue";
   case cudaErrorInvalidDeviceFunction: return "cudaErrorInvalidDeviceFunction";
   default: return "cudaErrorUnknown";
   }
@@ -81,14 +87,79 @@ EXPORT const char *cudaGetErrorName(cudaError_t e) {
 EXPORT const char *cudaGetErrorString(cudaError_t e) { return cudaGetErrorName(e); }
 
 /* ---- runtime: memory ------------------------------------------------------------------------------------------------- */
+/* With NOMP_HOSTDEV_SHARED=1 (multi-rank tests: one process per rank) every "device" allocation is a POSIX shared-memory
+ * object, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map it into a peer process -- host memory standing in
+ * for NVLink peer memory.  The handle carries the object's name and size. */
+typedef struct {
+  void *ptr;
+  size_t bytes;
+  char name[48];
+  int foreign; /* mapped through cudaIpcOpenMemHandle */
+} shared_alloc_t;
+static shared_alloc_t shared_allocs[4096];
+static int n_shared_allocs = 0;
+
+static int shared_mode(void) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("NOMP_HOSTDEV_SHARED");
+    mode = e && e[0] == '1';
+  }
+  return mode;
+}
+
+static shared_alloc_t *find_shared(const void *p) {
+  for (int i = 0; i < n_shared_allocs; i++)
+    if (shared_allocs[i].ptr == p) return &shared_allocs[i];
+  return NULL;
+}
+
+static void *map_shared(const char *name, size_t bytes, int create) {
+  const int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+  if (fd < 0) return NULL;
+  if (create && ftruncate(fd, (off_t)bytes) != 0) {
+    close(fd);
+    shm_unlink(name);
+    return NULL;
+  }
+  void *p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  return p == MAP_FAILED ? NULL : p;
+}
+
 EXPORT cudaError_t cudaMalloc(void **p, size_t bytes) {
-  if (posix_memalign(p, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;
+  if (bytes == 0) bytes = 1;
+  if (shared_mode()) {
+    static unsigned serial = 0;
+    if (n_shared_allocs == 4096) return cudaErrorMemoryAllocation;
+    shared_alloc_t *a = &shared_allocs[n_shared_allocs];
+    snprintf(a->name, sizeof(a->name), "/nomp-hostdev-%ld-%u", (long)getpid(), serial++);
+    a->bytes = (bytes + 4095) & ~(size_t)4095;
+    a->ptr = map_shared(a->name, a->bytes, 1);
+    a->foreign = 0;
+    if (!a->ptr) return cudaErrorMemoryAllocation;
+    n_shared_allocs++;
+    *p = a->ptr;
+  } else if (posix_memalign(p, 256, bytes)) {
+    return cudaErrorMemoryAllocation;
+  }
   memset(*p, 0xA5, bytes); /* fresh device memory is not zero */
   return cudaSuccess;
 }
 EXPORT cudaError_t cudaFree(void *p) {
-  free(p);
+  shared_alloc_t *a = p ? find_shared(p) : NULL;
+  if (a) {
+    munmap(a->ptr, a->bytes);
+    if (!a->foreign) shm_unlink(a->name);
+    *a = shared_allocs[--n_shared_allocs];
+  } else if (!shared_mode()) {
+    free(p);
+  }
   return cudaSuccess;
+}
+__attribute__((destructor)) static void unlink_shared(void) { /* a rank that exits without freeing must not leave objects behind */
+  for (int i = 0; i < n_shared_allocs; i++)
+    if (!shared_allocs[i].foreign) shm_unlink(shared_allocs[i].name);
 }
 EXPORT cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned flags) {
   (void)flags;
@@ -129,16 +200,31 @@ EXPORT cudaError_t cudaMemsetAsync(void *p, int value, size_t bytes, cudaStream_
   return cudaMemset(p, value, bytes);
 }
 EXPORT cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
-  (void)h, (void)p;
-  return cudaErrorNotSupported;
+  shared_alloc_t *a = find_shared(p);
+  if (!a || a->foreign) return cudaErrorNotSupported;
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &a->bytes, sizeof(size_t));
+  memcpy(h->reserved + sizeof(size_t), a->name, sizeof(a->name));
+  return cudaSuccess;
 }
 EXPORT cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags) {
-  (void)p, (void)h, (void)flags;
-  return cudaErrorNotSupported;
+  (void)flags;
+  if (!shared_mode() || n_shared_allocs == 4096) return cudaErrorNotSupported;
+  shared_alloc_t *a = &shared_allocs[n_shared_allocs];
+  memcpy(&a->bytes, h.reserved, sizeof(size_t));
+  memcpy(a->name, h.reserved + sizeof(size_t), sizeof(a->name));
+  a->name[sizeof(a->name) - 1] = '\0';
+  a->ptr = map_shared(a->name, a->bytes, 0);
+  a->foreign = 1;
+  if (!a->ptr) return cudaErrorInvalidValue;
+  n_shared_allocs++;
+  *p = a->ptr;
+  return cudaSuccess;
 }
 EXPORT cudaError_t cudaIpcCloseMemHandle(void *p) {
-  (void)p;
-  return cudaErrorNotSupported;
+  shared_alloc_t *a = find_shared(p);
+  if (!a || !a->foreign) return cudaErrorInvalidValue;
+  return cudaFree(p);
 }
 
 /* ---- runtime: streams and events (everything has completed by the time a call returns) ---------------------------------- */

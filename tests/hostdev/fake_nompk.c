@@ -48,6 +48,37 @@ EXPORT int nompk_map(nompk_map_op_t op, nompk_dtype_t dt, size_t n, void *y, con
   return f((int)op, (int)dt, n, y, x, z, alpha_host, beta_host) ? NOMPK_EINVAL : NOMPK_OK;
 }
 
+/* The exchange between ranks: the product's own finish_result (nompk_gridreduce.cuh) on the emulator, one warp
+ * (tests/hostdev/build_devicecode.py).  `value` is this rank's contribution; result / result_host receive the fold. */
+static int finish_with_peers(int op, int dt, const void *value, void *result, void *result_host, unsigned long long host_seq,
+                             void *const *peer_xchg, int rank, int world, unsigned long long cseq) {
+  static int (*launch)(unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, int, int, const void *, void *, void *,
+                       unsigned long long, void *const *, int, int, unsigned long long) = NULL;
+  if (!launch) {
+    const char *path = getenv("NOMP_HOSTDEV_DEVICECODE");
+    void *lib = path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : NULL;
+    if (lib) *(void **)&launch = dlsym(lib, "nomp_emu_launch");
+    if (!launch) {
+      fprintf(stderr, "hostdev: NOMP_HOSTDEV_DEVICECODE does not name the device-code library\n");
+      abort();
+    }
+  }
+  return launch(1, 1, 1, 32, 1, 1, op, dt, value, result, result_host, host_seq, peer_xchg, rank, world, cseq) ? NOMPK_ECUDA : NOMPK_OK;
+}
+
+EXPORT size_t nompk_allreduce_xchg_bytes(int world) { return (size_t)2 * (size_t)world * 16; } /* as reduce.cu */
+
+/* Stand-alone all-reduce of a device scalar, in place: the same protocol on the same buffers (reduce.cu). */
+EXPORT int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
+                                  unsigned long long host_seq, void *const *peer_xchg, int rank, int world,
+                                  unsigned long long seq, void *stream) {
+  (void)stream;
+  unsigned long long mine = 0;
+  memcpy(&mine, value, 8);
+  calls++;
+  return finish_with_peers((int)op, (int)dt, &mine, value, result_host_mapped, host_seq, peer_xchg, rank, world, seq);
+}
+
 static void publish(const void *value, void *result, void *result_host_mapped, unsigned long long host_seq) {
   memcpy(result, value, 8);
   if (result_host_mapped) {
@@ -61,11 +92,13 @@ EXPORT int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, con
                               void *result_host_mapped, unsigned long long host_seq, void *workspace,
                               const nompk_peers_t *peers, void *stream) {
   (void)workspace, (void)stream;
-  if (peers && peers->world > 1) return NOMPK_EUNSUPPORTED; /* one rank only */
   int (*f)(int, int, size_t, const void *, const void *, void *) = oracle_sym("oracle_reduce");
   unsigned long long value = 0;
   if (f((int)op, (int)dt, n, x, y, &value)) return NOMPK_EINVAL;
   calls++;
+  if (peers && peers->world > 1)
+    return finish_with_peers((int)op, (int)dt, &value, result, result_host_mapped, host_seq, peers->peer_xchg, peers->rank,
+                             peers->world, peers->seq);
   publish(&value, result, result_host_mapped, host_seq);
   return NOMPK_OK;
 }
@@ -82,10 +115,12 @@ EXPORT int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double
                                   double *result, double *result_host_mapped, unsigned long long host_seq,
                                   void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream) {
   (void)workspace;
-  if (peers && peers->world > 1) return NOMPK_EUNSUPPORTED;
   if (nompk_ax_f64(n, E, u, g, D, w, flags, stream)) return NOMPK_EINVAL;
   double s = 0.0;
   for (size_t i = 0; i < E * (size_t)n * n * n; i++) s += u[i] * w[i];
+  if (peers && peers->world > 1)
+    return finish_with_peers(NOMPK_RED_SUM, NOMPK_F64, &s, result, result_host_mapped, host_seq, peers->peer_xchg, peers->rank,
+                             peers->world, peers->seq);
   publish(&s, result, result_host_mapped, host_seq);
   return NOMPK_OK;
 }

@@ -44,13 +44,24 @@ def double(tmp_path_factory):
     srcs = [HOSTDEV / "fake_cuda.c", HOSTDEV / "fake_nompk.c"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["gcc", "-O1", "-g", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(CUDA_HOME / "include"),
-                        "-I", str(ROOT / "include"), "-o", str(so), *map(str, srcs), "-ldl"], check=True)
+                        "-I", str(ROOT / "include"), "-o", str(so), *map(str, srcs), "-ldl", "-lrt"], check=True)
+    # multi-rank pieces: an NCCL double (found by the dlopen of src/comm.c through LD_LIBRARY_PATH) and the product's
+    # rank-exchange device code compiled for the host (tests/hostdev/build_devicecode.py)
+    nccl = out / "libnccl.so.2"
+    if not nccl.exists() or (HOSTDEV / "fake_nccl.c").stat().st_mtime > nccl.stat().st_mtime:
+        subprocess.run(["gcc", "-O1", "-g", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(CUDA_HOME / "include"),
+                        "-o", str(nccl), str(HOSTDEV / "fake_nccl.c")], check=True)
+    dev = out / "libhostdev_devicecode.so"
+    dev_deps = [HOSTDEV / "build_devicecode.py", ROOT / "tests" / "cuda_emulation.py",
+                ROOT / "libnomp_b200" / "csrc" / "kernels" / "nompk_gridreduce.cuh"]
+    if not dev.exists() or any(d.stat().st_mtime > dev.stat().st_mtime for d in dev_deps):
+        subprocess.run([sys.executable, str(HOSTDEV / "build_devicecode.py"), str(dev)], check=True)
     for f in REF_TESTS.glob("*.pyc.bin"):       # the reference's transform scripts travel byte-compiled (oracle/Makefile)
         shutil.copyfile(f, f.with_suffix(""))
     work = tmp_path_factory.mktemp("hostdev")
     env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"), NOMP_JIT_CACHE="0", NOMP_HOSTDEV_DIR=str(work),
                NOMP_HOSTDEV_PYTHON=sys.executable, NOMP_HOSTDEV_COMPILER=str(HOSTDEV / "compile_kernel.py"),
-               NOMP_HOSTDEV_ORACLE=str(ROOT / "oracle" / "libnomp_oracle.so"))
+               NOMP_HOSTDEV_ORACLE=str(ROOT / "oracle" / "libnomp_oracle.so"), NOMP_HOSTDEV_DEVICECODE=str(dev))
     for k in ("NOMP_BACKEND", "NOMP_DEVICE", "NOMP_PLATFORM", "NOMP_VERBOSE", "NOMP_COMM_SIZE", "NOMP_COMM_RANK"):
         env.pop(k, None)
     return so, env
@@ -175,3 +186,67 @@ def test_runtime_is_clean_under_address_and_undefined_behaviour_sanitizers(doubl
     # the sanitized library really was the one in use
     r = subprocess.run(["ldd", str(REF_TESTS / "nomp-api-000")], env=env, capture_output=True, text=True)
     assert str(lib) in r.stdout
+
+
+
+# ---- several ranks: one process per rank, shared memory standing in for NVLink peer memory -------------------------------
+
+def run_ranks(world, args, env, so, extra=None, timeout=600):
+    """`world` processes of examples/cg_poisson.c on the test double: NCCL double through LD_LIBRARY_PATH, "device" memory
+    in POSIX shared memory so that CUDA IPC handles work between the processes.  Returns the JSON lines of every rank."""
+    import json
+    exe = ROOT / "libnomp_b200" / "build" / "cg_poisson"
+    if not exe.exists():
+        pytest.skip("examples/cg_poisson was not built")
+    work = Path(env["NOMP_HOSTDEV_DIR"])
+    idfile = work / f"id-{os.getpid()}-{len(list(work.glob('id-*')))}"
+    procs = []
+    for r in range(world):
+        e = dict(env, LD_PRELOAD=str(so), LD_LIBRARY_PATH=str(so.parent), NOMP_HOSTDEV_SHARED="1", NOMP_HOSTDEV_DEVICES=str(world),
+                 NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(r), NOMP_COMM_ID_FILE=str(idfile), **(extra or {}))
+        procs.append(subprocess.Popen([str(exe), *map(str, args), "--nomp-backend", "cuda", "--nomp-device", str(r), "--nomp-verbose", "1"],
+                                      env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode in (0, 2), o[-3000:]         # 2 = not converged within max_iter, not an error here
+    return [[json.loads(line) for line in o.splitlines() if line.startswith("{")] for o in outs]
+
+
+@pytest.mark.parametrize("path", ["fused", "standalone", "nccl"])
+@pytest.mark.parametrize("scalars", ["host", "device"])
+def test_two_ranks_of_the_cg_example(double, path, scalars):
+    """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
+    agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
+    stand-alone kernel after it, ncclAllReduce), each with the scalars on the host and in device memory
+    (nomp_b200_device_reductions).  The exchange itself is the product's finish_result on the emulator (native families)
+    and the generated nomp_finish text (reduce skeleton), talking to each other across two processes.  Against a host CG
+    on the 2E-element mesh; the ranks must see the same bits."""
+    from tests.test_system_gpu import _cg_reference
+    so, env = double
+    extra = {"fused": {}, "standalone": {"NOMP_COMM_FUSED": "0"}, "nccl": {"NOMP_COMM_ALLREDUCE": "nccl"}}[path]
+    E, n = 3, 8
+    per_rank = run_ranks(2, [E, n, 12, "1e-30", scalars, 4], env, so, extra)
+    ref = _cg_reference(2 * E, n, 5)
+    for lines in per_rank:
+        assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
+        for it in range(5):
+            for key in ("pAp", "alpha", "rr"):
+                assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
+        assert lines[-1]["iterations"] == 12 and lines[-1]["scalars"] == scalars
+    assert per_rank[0][1:] and [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[0]] == \
+        [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[1]]
+    assert not list(Path("/dev/shm").glob("nomp-hostdev-*")), "a rank left shared-memory objects behind"
+
+
+def test_four_ranks_mixing_host_and_device_results(double):
+    """Four ranks, fused path, scalars in device memory with the residual fetched every third iteration."""
+    from tests.test_system_gpu import _cg_reference
+    so, env = double
+    E, n = 2, 8
+    per_rank = run_ranks(4, [E, n, 9, "1e-30", "device", 3], env, so)
+    ref = _cg_reference(4 * E, n, 5)
+    for lines in per_rank:
+        for it in range(5):
+            for key in ("pAp", "alpha", "rr"):
+                assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
+    assert len({json_line["rr_final"] for json_line in (lines[-1] for lines in per_rank)}) == 1
