@@ -485,6 +485,38 @@ def test_ax_kernel_string(n, expect_family):
     assert np.array_equal(w, 4 * ffi.ax(n, u, g, D / 2))
 
 
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_closed_form_on_a_sheared_element(n):
+    """The hand-written Ax kernels against an analytic known answer (tests/ax_closed_form.py: harmonic polynomial on a
+    sheared element with a full constant metric -- boundary fluxes, zero inside), the real GLL matrix, several copies of
+    the element so that every lane group of the kernel sees it; also with the fused p.Ap, whose closed form is the sum of
+    u times the answer."""
+    from nomp_bridge.families import AX_DOT_KERNEL_SOURCE, AX_KERNEL_SOURCE
+    from tests.ax_closed_form import sheared_element
+    Dm, x = ffi.gll_derivative(n)
+    u1, g1, want1, interior1 = sheared_element(n, x)
+    E = 23
+    u, g, want, interior = np.tile(u1, E), np.tile(g1, E), np.tile(want1, E), np.tile(interior1, E)
+    D = np.ascontiguousarray(Dm.ravel())
+    w = np.full_like(u, np.nan)
+    pap = C.c_double(-1.0)
+    args = [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | JIT, C.c_int(n))]
+    kid = jit(AX_KERNEL_SOURCE, capi.clauses(), args)
+    kdot = jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")), args + [("pap", 8, F)])
+    assert family(kid) == ("native", "ax") and family(kdot) == ("native", "axdot")
+    scale = np.abs(want).max()
+    with Mapped(u, g, D, w, out=(w,)):
+        capi.check(capi.run(kid, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E)))
+        capi.check(capi.update(w.ctypes.data, 0, w.size, 8, capi.NOMP_FROM))
+        assert np.abs(w - want).max() <= 1e-11 * scale
+        assert np.abs(w[interior]).max() <= 1e-11 * scale
+        w[:] = np.nan
+        capi.check(capi.update(w.ctypes.data, 0, w.size, 8, capi.NOMP_TO))
+        capi.check(capi.run(kdot, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E), pap))
+    assert np.abs(w - want).max() <= 1e-11 * scale
+    assert abs(pap.value - float(u @ want)) <= 1e-10 * abs(float(u @ want))
+
+
 def test_fused_cg_kernels():
     """Row (f): Ax fused with p.Ap through the canonical Ax+dot kernel string, and the fused CG update
     x += a p; r -= a w; rr = r.r through the reduce skeleton (elementwise writes in front of the accumulation)."""
