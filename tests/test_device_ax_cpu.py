@@ -86,3 +86,24 @@ def test_ax_kernel_on_the_host(n, dot):
         assert np.array_equal(w, want), (n, E, blocks, int((w != want).sum()))
         if dot == 1:
             assert pap == float(u @ want) and not ws[: (64 + 4 * 2048) // 8].any()
+
+
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_kernel_text_against_the_analytic_known_answer(n):
+    """The kernel's own text on the emulator against tests/ax_closed_form.py (harmonic polynomial on a sheared element:
+    boundary fluxes, zero inside) with the real GLL matrix -- real-valued data, FMA contraction and all; the fused p.Ap
+    equals u . (A u)."""
+    from tests.ax_closed_form import sheared_element
+    G, W, GPC = SHAPES[n]
+    Dm, x = ffi.gll_derivative(n)
+    u1, g1, want1, interior1 = sheared_element(n, x)
+    E = G * GPC + 1                                   # one full group and a partial one
+    u, g, want, interior = np.tile(u1, E), np.tile(g1, E), np.tile(want1, E), np.tile(interior1, E)
+    D = np.ascontiguousarray(Dm.ravel())
+    scale = np.abs(want).max()
+    for dot in (0, 1):
+        w, pap, _ = run_ax(n, E, u, g, D, dot, 2)
+        assert np.abs(w - want).max() <= 1e-11 * scale, (n, dot)
+        assert np.abs(w[interior]).max() <= 1e-11 * scale
+        if dot:
+            assert abs(pap - float(u @ want)) <= 1e-10 * abs(float(u @ want))
