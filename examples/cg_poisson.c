@@ -8,13 +8,16 @@
  * With NOMP_COMM_SIZE > 1 every rank owns E elements of a larger mesh; the two dot products are all-reduced by the
  * runtime, nothing else changes (the local operator needs no halo exchange).
  *
- *   usage: cg_poisson [E [n [max_iter [tol [host|device [check_every]]]]]]  + the usual --nomp-* flags
+ *   usage: cg_poisson [E [n [max_iter [tol [host|device|device3 [check_every]]]]]]  + the usual --nomp-* flags
  *          (prints one JSON object per line)
  *
  * "device" keeps every scalar of the iteration in device memory (include/nomp-b200.h: nomp_b200_device_reductions):
  * the two dot products leave their results in mapped variables, alpha and beta are computed by one-iteration kernels,
  * the updates read them as alpha[0] / beta[0] -- five launches per iteration and no host round trip; the host fetches
  * the residual every `check_every` iterations (default 10) to test for convergence.
+ * "device3" folds alpha and beta into their consumers (x[i] += (rr[0] / pap[0]) * p[i], ...) and swaps the roles of the
+ * two residual scalars on the host instead of copying one to the other: three launches per iteration, the same number as
+ * "host", and still no round trip (it prints no per-iteration trace).
  */
 #define _POSIX_C_SOURCE 200809L
 #define _DEFAULT_SOURCE
@@ -51,6 +54,14 @@ static const char *BETA_SRC =
 static const char *XPAY_DEV_SRC =
     "void cg_direction_d(double *p, const double *r, const double *beta, int N) { for (int i = 0; i < N; i++) p[i] = r[i] + beta[0] * p[i]; }\n";
 
+static const char *UPDATE_DEV3_SRC =
+    "void cg_update_3(double *x, double *r, const double *p, const double *w, const double *rr, const double *pap, int N,\n"
+    "                 double *rr_new) {\n"
+    "  for (int i = 0; i < N; i++) { x[i] += (rr[0] / pap[0]) * p[i]; r[i] -= (rr[0] / pap[0]) * w[i]; rr_new[0] += r[i] * r[i]; }\n}\n";
+static const char *XPAY_DEV3_SRC =
+    "void cg_direction_3(double *p, const double *r, const double *rr_new, const double *rr, int N) {\n"
+    "  for (int i = 0; i < N; i++) p[i] = r[i] + (rr_new[0] / rr[0]) * p[i];\n}\n";
+
 int main(int argc, const char **argv) {
   int E = 1024, n = 8, max_iter = 200, device_scalars = 0, check_every = 10;
   double tol = 1e-10;
@@ -61,7 +72,7 @@ int main(int argc, const char **argv) {
     else if (pos == 1) n = atoi(argv[i]);
     else if (pos == 2) max_iter = atoi(argv[i]);
     else if (pos == 3) tol = atof(argv[i]);
-    else if (pos == 4) device_scalars = !strcmp(argv[i], "device");
+    else if (pos == 4) device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : 0;
     else if (pos == 5) check_every = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
     pos++;
   }
@@ -117,7 +128,7 @@ int main(int argc, const char **argv) {
   double *pap_d = calloc(1, 8), *alpha_d = calloc(1, 8), *beta_d = calloc(1, 8), *rr_d = calloc(1, 8), *rrn_d = calloc(1, 8);
   double *trace = calloc(18, 8);
   double *scalars[] = {pap_d, alpha_d, beta_d, rr_d, rrn_d};
-  int id_alpha = -1, id_updd = -1, id_beta = -1, id_dird = -1;
+  int id_alpha = -1, id_updd = -1, id_beta = -1, id_dird = -1, id_upd3 = -1, id_dir3 = -1;
   if (device_scalars) {
     const char *red_rrn[4] = {"reduce", "rr_new", "+", NULL};
     rr_d[0] = rr;
@@ -132,6 +143,11 @@ int main(int argc, const char **argv) {
                    sizeof(double), NOMP_PTR, "trace", sizeof(double), NOMP_PTR, "slot", sizeof(int), NOMP_INT));
     CHECK(nomp_jit(&id_dird, XPAY_DEV_SRC, none, 4, "p", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "beta",
                    sizeof(double), NOMP_PTR, "N", sizeof(int), NOMP_INT));
+    CHECK(nomp_jit(&id_upd3, UPDATE_DEV3_SRC, red_rrn, 8, "x", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "p",
+                   sizeof(double), NOMP_PTR, "w", sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "pap", sizeof(double),
+                   NOMP_PTR, "N", sizeof(int), NOMP_INT, "rr_new", sizeof(double), NOMP_FLOAT));
+    CHECK(nomp_jit(&id_dir3, XPAY_DEV3_SRC, none, 5, "p", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "rr_new",
+                   sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "N", sizeof(int), NOMP_INT));
     nomp_b200_device_reductions(1);
   }
 
@@ -145,10 +161,17 @@ int main(int argc, const char **argv) {
     }
     const int slot = it < 5 ? it : 5; /* iterations beyond the fifth share a scratch slot of the trace */
     CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
-    CHECK(nomp_run(id_alpha, alpha_d, rr_d, pap_d, trace, &slot));
-    CHECK(nomp_run(id_updd, x, r, p, w, alpha_d, &Ni, rrn_d));
-    CHECK(nomp_run(id_beta, beta_d, rr_d, rrn_d, trace, &slot));
-    CHECK(nomp_run(id_dird, p, r, beta_d, &Ni));
+    if (device_scalars == 3) {
+      CHECK(nomp_run(id_upd3, x, r, p, w, rr_d, pap_d, &Ni, rrn_d));
+      CHECK(nomp_run(id_dir3, p, r, rrn_d, rr_d, &Ni));
+      double *swap = rr_d; /* the new residual becomes the current one: a host-side change of names, no copy */
+      rr_d = rrn_d, rrn_d = swap;
+    } else {
+      CHECK(nomp_run(id_alpha, alpha_d, rr_d, pap_d, trace, &slot));
+      CHECK(nomp_run(id_updd, x, r, p, w, alpha_d, &Ni, rrn_d));
+      CHECK(nomp_run(id_beta, beta_d, rr_d, rrn_d, trace, &slot));
+      CHECK(nomp_run(id_dird, p, r, beta_d, &Ni));
+    }
     if ((it + 1) % check_every == 0 || it + 1 == max_iter) { /* the only host round trip */
       CHECK(nomp_update(rr_d, 0, 1, 8, NOMP_FROM));
       rr = rr_d[0];
@@ -157,7 +180,7 @@ int main(int argc, const char **argv) {
   if (device_scalars) {
     nomp_b200_device_reductions(0);
     CHECK(nomp_update(trace, 0, 18, 8, NOMP_FROM));
-    for (int i = 0; i < 5 && i < it; i++)
+    for (int i = 0; device_scalars == 1 && i < 5 && i < it; i++)
       printf("{\"iter\": %d, \"pAp\": %.17g, \"alpha\": %.17g, \"rr\": %.17g}\n", i, trace[3 * i], trace[3 * i + 1], trace[3 * i + 2]);
   }
   for (; !device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
@@ -190,7 +213,7 @@ int main(int argc, const char **argv) {
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
          "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": 136, \"scalars\": \"%s\"}\n",
          it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0,
-         device_scalars ? "device" : "host");
+         device_scalars == 3 ? "device3" : device_scalars ? "device" : "host");
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

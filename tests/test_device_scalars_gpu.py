@@ -177,7 +177,7 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
         pytest.skip("examples/cg_poisson was not built")
     env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
     runs = {}
-    for mode in ("host", "device"):
+    for mode in ("host", "device", "device3"):
         r = subprocess.run([str(exe), "6", "8", "400", "1e-9", mode, "1", "--nomp-backend", "cuda", "--nomp-device", "0",
                             "--nomp-verbose", "1"], env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -187,3 +187,7 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
     assert dev[-1]["scalars"] == "device" and host[-1]["scalars"] == "host"
     assert dev[-1]["iterations"] == host[-1]["iterations"] and dev[-1]["rr_final"] == host[-1]["rr_final"]
     assert dev[-1]["true_residual_rel"] < 1e-7
+    # three launches per iteration (alpha and beta folded into their consumers, the residual scalars swapped by name)
+    dev3 = runs["device3"]
+    assert dev3[-1]["scalars"] == "device3" and dev3[0] == host[0]
+    assert dev3[-1]["iterations"] == host[-1]["iterations"] and dev3[-1]["rr_final"] == host[-1]["rr_final"]

@@ -217,7 +217,7 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
 
 
 @pytest.mark.parametrize("path", ["fused", "standalone", "nccl"])
-@pytest.mark.parametrize("scalars", ["host", "device"])
+@pytest.mark.parametrize("scalars", ["host", "device", "device3"])
 def test_two_ranks_of_the_cg_example(double, path, scalars):
     """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
     agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
@@ -231,12 +231,14 @@ def test_two_ranks_of_the_cg_example(double, path, scalars):
     E, n = 3, 8
     per_rank = run_ranks(2, [E, n, 12, "1e-30", scalars, 4], env, so, extra)
     ref = _cg_reference(2 * E, n, 5)
+    ref_final = _cg_reference(2 * E, n, 12)[-1]["rr"]
     for lines in per_rank:
         assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
-        for it in range(5):
+        for it in range(5 if scalars != "device3" else 0):        # "device3" prints no per-iteration trace
             for key in ("pAp", "alpha", "rr"):
                 assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
         assert lines[-1]["iterations"] == 12 and lines[-1]["scalars"] == scalars
+        assert abs(lines[-1]["rr_final"] - ref_final) <= 1e-9 * ref_final
     assert per_rank[0][1:] and [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[0]] == \
         [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[1]]
     assert not list(Path("/dev/shm").glob("nomp-hostdev-*")), "a rank left shared-memory objects behind"
