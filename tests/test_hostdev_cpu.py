@@ -216,8 +216,8 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
     return [[json.loads(line) for line in o.splitlines() if line.startswith("{")] for o in outs]
 
 
-@pytest.mark.parametrize("path", ["fused", "standalone", "nccl"])
-@pytest.mark.parametrize("scalars", ["host", "device", "device3"])
+@pytest.mark.parametrize("path,scalars", [("fused", "host"), ("fused", "device"), ("fused", "device3"), ("standalone", "host"),
+                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3")])
 def test_two_ranks_of_the_cg_example(double, path, scalars):
     """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
     agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
