@@ -34,6 +34,18 @@ void *nomp_b200_device_ptr(void *hptr);
  * iteration of a solver can be enqueued without a host round trip.  A reduction variable that is not mapped behaves as
  * in the reference (result on the host when nomp_run returns, reference tests/nomp-api-500-impl.h:29-34). */
 int nomp_b200_device_reductions(int enable);
+/* CUDA graphs of nomp_run sequences.  Between graph_begin and graph_end every nomp_run is RECORDED on the backend stream
+ * instead of executed (run the sequence once before capturing it: kernels load lazily, on their first launch); graph_launch replays the recording, asynchronously like nomp_run.  Integer
+ * and floating-point arguments are frozen with the values they have during capture, pointers as the device addresses of
+ * their mappings (which must outlive the graph) -- so what changes from one replay to the next lives in device memory:
+ * reduction results (nomp_b200_device_reductions must be on for captured reduce clauses) and scalars read as alpha[0].
+ * While capturing, nomp_update / nomp_sync / nomp_b200_update_async and reduce clauses that deliver to the host are
+ * refused (NOMP_USER_INPUT_IS_INVALID); reduce clauses on more than one rank are refused as well (the call number of the
+ * fused all-reduce would be frozen).  Up to 64 graphs; nomp_finalize releases them. */
+int nomp_b200_graph_begin(void);
+int nomp_b200_graph_end(int *graph);
+int nomp_b200_graph_launch(int graph);
+int nomp_b200_graph_free(int graph);
 /* Kernels launched by this runtime since load: NVRTC-built kernels + libnompk launches. */
 unsigned long long nomp_b200_launch_count(void);
 /* Rank / size of the NCCL communicator (0 / 1 when single-process). */

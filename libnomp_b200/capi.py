@@ -50,7 +50,7 @@ NOMP_SYMBOLS = [
     "nomp_b200_comm_size", "nomp_b200_comm_uses_nvlink_kernel", "nomp_b200_prog_info", "nomp_b200_exchange_blob",
     "nomp_b200_jit_cache_stats", "nomp_b200_sha256_hex", "nomp_b200_gs_setup", "nomp_b200_gs", "nomp_b200_gs_info",
     "nomp_b200_gs_free", "nomp_b200_jit_cache_dir", "nomp_b200_jit_cache_put", "nomp_b200_jit_cache_get",
-    "nomp_b200_device_reductions",
+    "nomp_b200_device_reductions", "nomp_b200_graph_begin", "nomp_b200_graph_end", "nomp_b200_graph_launch", "nomp_b200_graph_free",
 ]
 
 

@@ -90,6 +90,8 @@ static int resolve_driver(void) {
 
 /* ---- backend state ------------------------------------------------------------------------------------------ */
 
+#define NOMP_MAX_GRAPHS 64
+
 typedef struct {
   int device;
   struct cudaDeviceProp prop;
@@ -113,6 +115,9 @@ typedef struct {
   unsigned long ax_D_version;
   int ax_n;
   unsigned long long nvrtc_launches;
+  /* CUDA graphs of nomp_run sequences (nomp_b200_graph_*) */
+  int capturing;
+  cudaGraphExec_t graphs[NOMP_MAX_GRAPHS];
 } cuda_state_t;
 
 static cuda_state_t *g_state = NULL; /* for the nomp_b200_* accessors */
@@ -174,9 +179,16 @@ static void unpin_host_range(nomp_mem_t *m) {
   m->host_registered = 0;
 }
 
+/* While a graph is being captured (nomp_b200_graph_begin) the backend stream records work instead of executing it:
+ * anything that would wait for the stream, or that is not stream-ordered, is refused. */
+static int capture_forbids(const char *what) {
+  return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "%s is not allowed while a graph is being captured.", what);
+}
+
 static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direction_t op, size_t start, size_t end,
                        size_t usize) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (st->capturing) return capture_forbids("nomp_update");
   if (((op & NOMP_TO) || op == NOMP_FROM) && m != &bnd->scratch && m->transfers++ == 1) pin_host_range(m);
   if (op & NOMP_ALLOC) {
     size_t bytes = NOMP_MEM_BYTES(start, end, usize);
@@ -443,6 +455,13 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   /* nomp_b200_device_reductions: the result goes to the device copy of the (mapped) reduction variable instead of the
    * backend's slot; the kernels are the same, only the address differs */
   st->red_result_arg = prg->reduction_dev ? prg->reduction_dev : st->red_result;
+  if (st->capturing && cp->is_reduce) {
+    /* a captured reduction cannot hand its result to the host (nomp_run would have to wait for a stream that is only
+     * recording), and the collective call number of the fused all-reduce would be frozen into the graph */
+    if (!prg->reduction_dev)
+      return capture_forbids("A reduce clause whose variable is not device-resident (nomp_b200_device_reductions)");
+    if (nomp_comm_size() > 1) return capture_forbids("A reduce clause on more than one rank");
+  }
 
   switch (cp->family) {
   case FAM_MAP: {
@@ -472,7 +491,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     const nomp_mem_t *dm = (const nomp_mem_t *)prg->args[cp->a_D].mem;
     const unsigned long version = dm ? dm->version : 0;
     unsigned flags = 0;
-    if (dm && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
+    /* (while a graph is being captured the copy is recorded with the launch and the cache state is left alone) */
+    if (dm && !st->capturing && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
     /* a rank without elements launches nothing: it joins through the stand-alone all-reduce kernel of the finish,
      * which speaks the same protocol on the same buffers */
     if (cp->family == FAM_AXDOT && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers))
@@ -487,7 +507,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
       check_nompk(nompk_ax_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
                                (double *)ptr_arg(prg, cp->a_w), flags, st->stream));
-    st->ax_D = D, st->ax_n = cp->ax_n, st->ax_D_version = version;
+    if (!st->capturing) st->ax_D = D, st->ax_n = cp->ax_n, st->ax_D_version = version;
+    else st->ax_D = NULL; /* a replay overwrites the staged copy at a time this cache cannot know */
     return 0;
   }
   case FAM_NVRTC: {
@@ -587,6 +608,7 @@ static int cuda_knl_free(nomp_prog_t *prg) {
 
 static int cuda_sync(nomp_backend_t *bnd) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (st->capturing) return capture_forbids("nomp_sync");
   check_runtime(cudaStreamSynchronize(st->stream));
   if (st->async_used) {
     check_runtime(cudaStreamSynchronize(st->stream_h2d));
@@ -603,6 +625,7 @@ static int cuda_sync(nomp_backend_t *bnd) {
 int nomp_cuda_update_async(nomp_backend_t *bnd, nomp_mem_t *m, nomp_map_direction_t op, size_t start, size_t end,
                            size_t usize) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
+  if (st->capturing) return capture_forbids("nomp_b200_update_async");
   if (!st->stream_h2d) {
     check_runtime(cudaStreamCreateWithFlags(&st->stream_h2d, cudaStreamNonBlocking));
     check_runtime(cudaStreamCreateWithFlags(&st->stream_d2h, cudaStreamNonBlocking));
@@ -632,6 +655,8 @@ static int cuda_finalize(nomp_backend_t *bnd) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
   if (st == NULL) return 0;
   nomp_comm_finalize();
+  for (int i = 0; i < NOMP_MAX_GRAPHS; i++)
+    if (st->graphs[i]) cudaGraphExecDestroy(st->graphs[i]);
   if (st->stream) {
     cudaStreamSynchronize(st->stream);
     cudaStreamDestroy(st->stream);
@@ -709,4 +734,58 @@ NOMP_EXPORT void *nomp_b200_stream(void) { return g_state ? (void *)g_state->str
 
 NOMP_EXPORT unsigned long long nomp_b200_launch_count(void) {
   return nompk_launch_count() + (g_state ? g_state->nvrtc_launches : 0);
+}
+
+/* ---- CUDA graphs of nomp_run sequences (include/nomp-b200.h) ---------------------------------------------------------- */
+/* Between graph_begin and graph_end the backend stream captures: every nomp_run records its launches
+ * (cuLaunchKernel and the runtime launches of libnompk alike) instead of executing them.  Scalar arguments are frozen
+ * into the graph with the values they have during capture; pointers are frozen as device addresses, so the mappings
+ * must outlive the graph.  What varies between replays therefore lives in device memory: reduction results
+ * (nomp_b200_device_reductions) and the scalars kernels read as alpha[0]. */
+NOMP_EXPORT int nomp_b200_graph_begin(void) {
+  cuda_state_t *st = g_state;
+  if (!st) return nomp_log(NOMP_INITIALIZE_FAILURE, NOMP_ERROR, "libnomp is not initialized.");
+  if (st->capturing) return capture_forbids("nomp_b200_graph_begin");
+  check_runtime(cudaStreamSynchronize(st->stream));
+  check_runtime(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeRelaxed));
+  st->capturing = 1;
+  return 0;
+}
+
+NOMP_EXPORT int nomp_b200_graph_end(int *graph) {
+  cuda_state_t *st = g_state;
+  if (!st || !st->capturing || !graph)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "nomp_b200_graph_end without nomp_b200_graph_begin.");
+  st->capturing = 0;
+  cudaGraph_t g = NULL;
+  check_runtime(cudaStreamEndCapture(st->stream, &g));
+  int slot = -1;
+  for (int i = 0; i < NOMP_MAX_GRAPHS && slot < 0; i++)
+    if (!st->graphs[i]) slot = i;
+  cudaError_t e = slot < 0 ? cudaErrorMemoryAllocation : cudaGraphInstantiate(&st->graphs[slot], g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    if (slot >= 0) st->graphs[slot] = NULL;
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "graph", slot < 0 ? "too many graphs" : cudaGetErrorName(e));
+  }
+  *graph = slot;
+  return 0;
+}
+
+NOMP_EXPORT int nomp_b200_graph_launch(int graph) {
+  cuda_state_t *st = g_state;
+  if (!st || graph < 0 || graph >= NOMP_MAX_GRAPHS || !st->graphs[graph] || st->capturing)
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Graph id %d passed to nomp_b200_graph_launch is not valid.", graph);
+  check_runtime(cudaGraphLaunch(st->graphs[graph], st->stream));
+  return 0;
+}
+
+NOMP_EXPORT int nomp_b200_graph_free(int graph) {
+  cuda_state_t *st = g_state;
+  if (!st || graph < 0 || graph >= NOMP_MAX_GRAPHS || !st->graphs[graph])
+    return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Graph id %d passed to nomp_b200_graph_free is not valid.", graph);
+  check_runtime(cudaStreamSynchronize(st->stream));
+  check_runtime(cudaGraphExecDestroy(st->graphs[graph]));
+  st->graphs[graph] = NULL;
+  return 0;
 }

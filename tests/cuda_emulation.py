@@ -328,7 +328,10 @@ def build_param_launcher(src: str, out: Path):
     call = f"{name}(" + ", ".join(f"nomp_emu_a{i}" for i in range(len(types))) + ")"
     driver = (_COOP_DRIVER.replace("NOMP_EMU_CALL", call).replace("NOMP_EMU_PARAMS", ", void **nomp_emu_p")
               .replace("NOMP_EMU_STORE", store))
-    tail = f'\nextern "C" __attribute__((visibility("default"))) const char *nomp_hostdev_kernel_name = "{name}";\n'
+    sizes = ", ".join(f"sizeof({t})" for t in plain) or "0"
+    tail = (f'\nextern "C" __attribute__((visibility("default"))) const char *nomp_hostdev_kernel_name = "{name}";\n'
+            f'extern "C" __attribute__((visibility("default"))) const int nomp_hostdev_param_count = {len(plain)};\n'
+            f'extern "C" __attribute__((visibility("default"))) const size_t nomp_hostdev_param_sizes[] = {{{sizes}}};\n')
     cpp = Path(str(out) + ".cpp")
     cpp.write_text(_COOP_SHIM + body + "\n" + decls + "\n" + driver + tail)
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fno-gnu-unique",

@@ -70,7 +70,7 @@ EXPORT cudaError_t cudaDeviceGetAttribute(int *value, enum cudaDeviceAttr attr, 
   *value = attr == cudaDevAttrMultiProcessorCount ? 148 : 0;
   return cudaSuccess;
 }
-EXPORT cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+EXPORT cudaError_t cudaDeviceSynchronize(void);
 EXPORT cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 EXPORT cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
 EXPORT const char *cudaGetErrorName(cudaError_t e) {
@@ -81,6 +81,8 @@ EXPORT const char *cudaGetErrorName(cudaError_t e) {
   case cudaErrorNotSupported: return "cudaErrorNotSupported";
   case cudaErrorInvalidValue: return "cudaErrorInvalidValue";
   case cudaErrorInvalidDeviceFunction: return "cudaErrorInvalidDeviceFunction";
+  case cudaErrorStreamCaptureUnsupported: return "cudaErrorStreamCaptureUnsupported";
+  case cudaErrorLaunchFailure: return "cudaErrorLaunchFailure";
   default: return "cudaErrorUnknown";
   }
 }
@@ -227,6 +229,80 @@ EXPORT cudaError_t cudaIpcCloseMemHandle(void *p) {
   return cudaFree(p);
 }
 
+/* ---- stream capture and graphs: launches are recorded (arguments copied, as CUDA copies kernel parameters) and replayed ---- */
+typedef struct {
+  int (*fn)(void *blob);
+  void *blob;
+} recorded_t;
+typedef struct {
+  recorded_t *items;
+  int n, cap;
+} recording_t;
+static recording_t *capturing = NULL;
+
+/* used by fake_nompk.c and by cuLaunchKernel below: 1 = recorded (do not execute now) */
+__attribute__((visibility("default"))) int nomp_hostdev_record(int (*fn)(void *), const void *blob, size_t bytes) {
+  if (!capturing) return 0;
+  if (capturing->n == capturing->cap) {
+    capturing->cap = capturing->cap ? 2 * capturing->cap : 16;
+    capturing->items = realloc(capturing->items, sizeof(recorded_t) * (size_t)capturing->cap);
+  }
+  void *copy = malloc(bytes);
+  memcpy(copy, blob, bytes);
+  capturing->items[capturing->n].fn = fn, capturing->items[capturing->n].blob = copy;
+  capturing->n++;
+  return 1;
+}
+
+EXPORT cudaError_t cudaStreamBeginCapture(cudaStream_t s, enum cudaStreamCaptureMode mode) {
+  (void)s, (void)mode;
+  if (capturing) return cudaErrorInvalidValue;
+  capturing = calloc(1, sizeof(*capturing));
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t *graph) {
+  (void)s;
+  if (!capturing) return cudaErrorInvalidValue;
+  *graph = (cudaGraph_t)capturing;
+  capturing = NULL;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaGraphInstantiate(cudaGraphExec_t *exec, cudaGraph_t graph, unsigned long long flags) {
+  (void)flags;
+  recording_t *src = (recording_t *)graph, *dst = calloc(1, sizeof(*dst));
+  dst->n = dst->cap = src->n;
+  dst->items = malloc(sizeof(recorded_t) * (size_t)(src->n ? src->n : 1));
+  memcpy(dst->items, src->items, sizeof(recorded_t) * (size_t)src->n); /* the blobs are shared: freed with the exec */
+  *exec = (cudaGraphExec_t)dst;
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaGraphDestroy(cudaGraph_t graph) {
+  recording_t *r = (recording_t *)graph;
+  free(r->items);
+  free(r);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec) {
+  recording_t *r = (recording_t *)exec;
+  for (int i = 0; i < r->n; i++) free(r->items[i].blob);
+  free(r->items);
+  free(r);
+  return cudaSuccess;
+}
+EXPORT cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t s) {
+  (void)s;
+  recording_t *r = (recording_t *)exec;
+  if (capturing) return cudaErrorInvalidValue;
+  for (int i = 0; i < r->n; i++)
+    if (r->items[i].fn(r->items[i].blob)) return cudaErrorLaunchFailure;
+  return cudaSuccess;
+}
+/* everything that waits for, or is ordered outside, a capturing stream is an error in CUDA: make it one here too */
+#define REFUSE_WHILE_CAPTURING()                                                                                      \
+  do {                                                                                                                 \
+    if (capturing) return cudaErrorStreamCaptureUnsupported;                                                          \
+  } while (0)
+
 /* ---- runtime: streams and events (everything has completed by the time a call returns) ---------------------------------- */
 EXPORT cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned flags) {
   (void)flags;
@@ -239,10 +315,12 @@ EXPORT cudaError_t cudaStreamDestroy(cudaStream_t s) {
 }
 EXPORT cudaError_t cudaStreamSynchronize(cudaStream_t s) {
   (void)s;
+  REFUSE_WHILE_CAPTURING();
   return cudaSuccess;
 }
 EXPORT cudaError_t cudaStreamQuery(cudaStream_t s) {
   (void)s;
+  REFUSE_WHILE_CAPTURING();
   return cudaSuccess;
 }
 EXPORT cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags) {
@@ -273,6 +351,11 @@ EXPORT cudaError_t cudaMemcpyToSymbolAsync(const void *symbol, const void *src, 
                                           enum cudaMemcpyKind kind, cudaStream_t s) {
   (void)symbol, (void)src, (void)bytes, (void)offset, (void)kind, (void)s;
   return cudaErrorInvalidDeviceFunction;
+}
+
+EXPORT cudaError_t cudaDeviceSynchronize(void) {
+  REFUSE_WHILE_CAPTURING();
+  return cudaSuccess;
 }
 
 /* ---- NVRTC -------------------------------------------------------------------------------------------------------------------- */
@@ -383,10 +466,49 @@ static CUresult fake_cuModuleGetFunction(CUfunction *f, CUmodule module, const c
   return CUDA_SUCCESS;
 }
 static CUresult fake_cuModuleUnload(CUmodule module) { return dlclose((void *)module) ? CUDA_ERROR_INVALID_HANDLE : CUDA_SUCCESS; }
+/* a launch as a graph node: the function, its dimensions and a COPY of every parameter (sizes from the compiled object) */
+typedef struct {
+  hostdev_launch_t launch;
+  unsigned dims[6];
+  int nparams;
+  size_t offset[80];
+  unsigned char data[80 * 16];
+} launch_node_t;
+
+static int replay_launch(void *blob) {
+  launch_node_t *n = (launch_node_t *)blob;
+  void *params[80];
+  for (int i = 0; i < n->nparams; i++) params[i] = n->data + n->offset[i];
+  return n->launch(n->dims[0], n->dims[1], n->dims[2], n->dims[3], n->dims[4], n->dims[5], params);
+}
+
 static CUresult fake_cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                                     unsigned smem, CUstream s, void **params, void **extra) {
   (void)smem, (void)s, (void)extra;
   if (bx * by * bz > 1024 || bx * by * bz == 0) return CUDA_ERROR_INVALID_VALUE;
+  if (capturing) {
+    Dl_info info;
+    if (!dladdr((void *)f, &info)) return CUDA_ERROR_INVALID_HANDLE;
+    void *lib = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD);
+    const int *count = lib ? (const int *)dlsym(lib, "nomp_hostdev_param_count") : NULL;
+    const size_t *sizes = lib ? (const size_t *)dlsym(lib, "nomp_hostdev_param_sizes") : NULL;
+    if (!count || !sizes || *count > 80) return CUDA_ERROR_INVALID_HANDLE;
+    launch_node_t node;
+    memset(&node, 0, sizeof(node));
+    node.launch = (hostdev_launch_t)f, node.nparams = *count;
+    const unsigned dims[6] = {gx, gy, gz, bx, by, bz};
+    memcpy(node.dims, dims, sizeof(dims));
+    size_t off = 0;
+    for (int i = 0; i < *count; i++) {
+      if (sizes[i] > 16) return CUDA_ERROR_INVALID_VALUE;
+      node.offset[i] = off;
+      memcpy(node.data + off, params[i], sizes[i]);
+      off += 16;
+    }
+    if (lib) dlclose(lib);
+    nomp_hostdev_record(replay_launch, &node, sizeof(node));
+    return CUDA_SUCCESS;
+  }
   return ((hostdev_launch_t)f)(gx, gy, gz, bx, by, bz, params) ? CUDA_ERROR_LAUNCH_FAILED : CUDA_SUCCESS;
 }
 static CUresult fake_cuGetErrorName(CUresult r, const char **name) {

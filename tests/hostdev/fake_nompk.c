@@ -40,13 +40,38 @@ static void *oracle_sym(const char *name) {
 
 EXPORT unsigned long long nompk_launch_count(void) { return calls; }
 
+/* While the CUDA double captures a stream (fake_cuda.c), a call is recorded with COPIES of its by-value arguments -- host
+ * scalars included, as a real launch copies its kernel parameters -- and runs when the graph is launched. */
+int nomp_hostdev_record(int (*fn)(void *), const void *blob, size_t bytes);
+
+typedef struct {
+  int op, dt;
+  size_t n;
+  void *y;
+  const void *x, *z;
+  unsigned long long alpha, beta;
+  int has_alpha, has_beta;
+} map_call_t;
+
+static int run_map(void *blob) {
+  map_call_t *c = (map_call_t *)blob;
+  int (*f)(int, int, size_t, void *, const void *, const void *, const void *, const void *) = oracle_sym("oracle_map");
+  return f(c->op, c->dt, c->n, c->y, c->x, c->z, c->has_alpha ? &c->alpha : NULL, c->has_beta ? &c->beta : NULL);
+}
+
 EXPORT int nompk_map(nompk_map_op_t op, nompk_dtype_t dt, size_t n, void *y, const void *x, const void *z,
                      const void *alpha_host, const void *beta_host, void *stream) {
   (void)stream;
-  int (*f)(int, int, size_t, void *, const void *, const void *, const void *, const void *) = oracle_sym("oracle_map");
+  map_call_t c = {(int)op, (int)dt, n, y, x, z, 0, 0, alpha_host != NULL, beta_host != NULL};
+  const size_t w = nompk_dtype_size(dt);
+  if (alpha_host) memcpy(&c.alpha, alpha_host, w);
+  if (beta_host) memcpy(&c.beta, beta_host, w);
   calls++;
-  return f((int)op, (int)dt, n, y, x, z, alpha_host, beta_host) ? NOMPK_EINVAL : NOMPK_OK;
+  if (nomp_hostdev_record(run_map, &c, sizeof(c))) return NOMPK_OK;
+  return run_map(&c) ? NOMPK_EINVAL : NOMPK_OK;
 }
+
+EXPORT size_t nompk_dtype_size(nompk_dtype_t dt) { return dt == NOMPK_I64 || dt == NOMPK_U64 || dt == NOMPK_F64 ? 8 : 4; }
 
 /* The exchange between ranks: the product's own finish_result (nompk_gridreduce.cuh) on the emulator, one warp
  * (tests/hostdev/build_devicecode.py).  `value` is this rank's contribution; result / result_host receive the fold. */
@@ -88,39 +113,76 @@ static void publish(const void *value, void *result, void *result_host_mapped, u
   }
 }
 
+typedef struct {
+  int op, dt, n_ax; /* n_ax != 0: the Ax + dot call */
+  size_t n;
+  const void *x, *y, *g, *D;
+  void *w, *result, *result_host;
+  unsigned long long host_seq;
+  nompk_peers_t peers;
+} reduce_call_t;
+
+static int run_reduce(void *blob) {
+  reduce_call_t *c = (reduce_call_t *)blob;
+  unsigned long long value = 0;
+  if (c->n_ax) {
+    int (*ax)(int, size_t, const double *, const double *, const double *, double *) = oracle_sym("oracle_ax_f64");
+    if (ax(c->n_ax, c->n, c->x, c->g, c->D, c->w)) return NOMPK_EINVAL;
+    double s = 0.0;
+    const double *u = c->x, *w = c->w;
+    for (size_t i = 0; i < c->n * (size_t)c->n_ax * c->n_ax * c->n_ax; i++) s += u[i] * w[i];
+    memcpy(&value, &s, 8);
+  } else {
+    int (*f)(int, int, size_t, const void *, const void *, void *) = oracle_sym("oracle_reduce");
+    if (f(c->op, c->dt, c->n, c->x, c->y, &value)) return NOMPK_EINVAL;
+  }
+  if (c->peers.world > 1)
+    return finish_with_peers(c->op, c->dt, &value, c->result, c->result_host, c->host_seq, c->peers.peer_xchg, c->peers.rank,
+                             c->peers.world, c->peers.seq);
+  publish(&value, c->result, c->result_host, c->host_seq);
+  return NOMPK_OK;
+}
+
 EXPORT int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y, void *result,
                               void *result_host_mapped, unsigned long long host_seq, void *workspace,
                               const nompk_peers_t *peers, void *stream) {
   (void)workspace, (void)stream;
-  int (*f)(int, int, size_t, const void *, const void *, void *) = oracle_sym("oracle_reduce");
-  unsigned long long value = 0;
-  if (f((int)op, (int)dt, n, x, y, &value)) return NOMPK_EINVAL;
+  reduce_call_t c = {(int)op, (int)dt, 0, n, x, y, NULL, NULL, NULL, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}};
+  if (peers && peers->world > 1) c.peers = *peers;
   calls++;
-  if (peers && peers->world > 1)
-    return finish_with_peers((int)op, (int)dt, &value, result, result_host_mapped, host_seq, peers->peer_xchg, peers->rank,
-                             peers->world, peers->seq);
-  publish(&value, result, result_host_mapped, host_seq);
-  return NOMPK_OK;
+  if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
+  return run_reduce(&c);
+}
+
+typedef struct {
+  int n;
+  size_t E;
+  const double *u, *g, *D;
+  double *w;
+} ax_call_t;
+
+static int run_ax(void *blob) {
+  ax_call_t *c = (ax_call_t *)blob;
+  int (*f)(int, size_t, const double *, const double *, const double *, double *) = oracle_sym("oracle_ax_f64");
+  return f(c->n, c->E, c->u, c->g, c->D, c->w) ? NOMPK_EINVAL : NOMPK_OK;
 }
 
 EXPORT int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
                         void *stream) {
   (void)flags, (void)stream;
-  int (*f)(int, size_t, const double *, const double *, const double *, double *) = oracle_sym("oracle_ax_f64");
+  ax_call_t c = {n, E, u, g, D, w};
   calls++;
-  return f(n, E, u, g, D, w) ? NOMPK_EINVAL : NOMPK_OK;
+  if (nomp_hostdev_record(run_ax, &c, sizeof(c))) return NOMPK_OK;
+  return run_ax(&c);
 }
 
 EXPORT int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                                   double *result, double *result_host_mapped, unsigned long long host_seq,
                                   void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream) {
-  (void)workspace;
-  if (nompk_ax_f64(n, E, u, g, D, w, flags, stream)) return NOMPK_EINVAL;
-  double s = 0.0;
-  for (size_t i = 0; i < E * (size_t)n * n * n; i++) s += u[i] * w[i];
-  if (peers && peers->world > 1)
-    return finish_with_peers(NOMPK_RED_SUM, NOMPK_F64, &s, result, result_host_mapped, host_seq, peers->peer_xchg, peers->rank,
-                             peers->world, peers->seq);
-  publish(&s, result, result_host_mapped, host_seq);
-  return NOMPK_OK;
+  (void)workspace, (void)flags, (void)stream;
+  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}};
+  if (peers && peers->world > 1) c.peers = *peers;
+  calls++;
+  if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
+  return run_reduce(&c);
 }

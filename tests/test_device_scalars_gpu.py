@@ -191,3 +191,79 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
     dev3 = runs["device3"]
     assert dev3[-1]["scalars"] == "device3" and dev3[0] == host[0]
     assert dev3[-1]["iterations"] == host[-1]["iterations"] and dev3[-1]["rr_final"] == host[-1]["rr_final"]
+
+
+def test_cg_iterations_replayed_from_a_cuda_graph():
+    """nomp_b200_graph_*: two CG iterations in the three-launch form (the residual scalars swap names every iteration,
+    so two iterations make one period) are captured once and replayed; the iterates equal those of the same launches
+    issued one by one, bit for bit.  What a capturing stream cannot do is refused."""
+    lib = capi.nomp()
+    n, E, periods = 8, 5, 3
+    N = E * n ** 3
+    xt = ffi.fill_uniform_f64(N, 21, 0.0, 1.0) - 0.5
+    v = ffi.fill_uniform_f64(6 * N, 23, 0.0, 1.0).reshape(E, 6, n ** 3)
+    g = 0.2 * (v - 0.5)
+    for f in (0, 3, 5):
+        g[:, f, :] = 1.0 + 0.5 * v[:, f, :]
+    g = np.ascontiguousarray(g.ravel())
+    D = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    b = ffi.ax(n, xt, g, D)
+    args_ax = [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | capi.NOMP_JIT, C.c_int(n)), ("pap", 8, F)]
+    k_ax = jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")), args_ax)
+    k_upd = jit("void cg_update_3(double *x, double *r, const double *p, const double *w, const double *rr, const double *pap, int N,"
+                " double *rr_new) { for (int i = 0; i < N; i++) { x[i] += (rr[0] / pap[0]) * p[i]; r[i] -= (rr[0] / pap[0]) * w[i];"
+                " rr_new[0] += r[i] * r[i]; } }", capi.clauses(("reduce", "rr_new", "+")),
+                [("x", 8, P), ("r", 8, P), ("p", 8, P), ("w", 8, P), ("rr", 8, P), ("pap", 8, P), ("N", 4, I), ("rr_new", 8, F)])
+    k_dir = jit("void cg_direction_3(double *p, const double *r, const double *rr_new, const double *rr, int N) {"
+                " for (int i = 0; i < N; i++) p[i] = r[i] + (rr_new[0] / rr[0]) * p[i]; }", capi.clauses(),
+                [("p", 8, P), ("r", 8, P), ("rr_new", 8, P), ("rr", 8, P), ("N", 4, I)])
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+
+    def solve(use_graph):
+        x, r, p, w = np.zeros(N), b.copy(), b.copy(), np.zeros(N)
+        pap, rr, rrn = np.zeros(1), np.array([float(b @ b)]), np.zeros(1)
+        state = (x, r, p, w, pap, rr, rrn)
+        to_device(*state)
+
+        def iteration(cur, new):
+            capi.check(capi.run(k_ax, ptr(w), ptr(p), ptr(g), ptr(D), C.c_int(E), ptr(pap)))
+            capi.check(capi.run(k_upd, ptr(x), ptr(r), ptr(p), ptr(w), ptr(cur), ptr(pap), C.c_int(N), ptr(new)))
+            capi.check(capi.run(k_dir, ptr(p), ptr(r), ptr(new), ptr(cur), C.c_int(N)))
+
+        def period():
+            iteration(rr, rrn)
+            iteration(rrn, rr)
+
+        lib.nomp_b200_device_reductions(1)
+        period()                                   # also loads every kernel before anything is captured
+        if use_graph:
+            graph = C.c_int(-1)
+            capi.check(lib.nomp_b200_graph_begin())
+            period()
+            # a capturing stream cannot be waited for, and a reduction cannot deliver to the host
+            assert capi.err_info(lib.nomp_sync())[0] == capi.NOMP_USER_INPUT_IS_INVALID
+            assert capi.err_info(capi.update(ptr(x), 0, N, 8, capi.NOMP_FROM))[0] == capi.NOMP_USER_INPUT_IS_INVALID
+            host_scalar = C.c_double(0.0)
+            assert capi.err_info(capi.run(k_ax, ptr(w), ptr(p), ptr(g), ptr(D), C.c_int(E), host_scalar))[0] == capi.NOMP_USER_INPUT_IS_INVALID
+            capi.check(lib.nomp_b200_graph_end(C.byref(graph)))
+            assert graph.value >= 0
+            for _ in range(periods):               # the capture itself executed nothing: `periods` replays do the work
+                capi.check(lib.nomp_b200_graph_launch(graph.value))
+            capi.check(lib.nomp_sync())
+            capi.check(lib.nomp_b200_graph_free(graph.value))
+            assert capi.err_info(lib.nomp_b200_graph_launch(graph.value))[0] == capi.NOMP_USER_INPUT_IS_INVALID
+        else:
+            for _ in range(periods):
+                period()
+        lib.nomp_b200_device_reductions(0)
+        from_device(x, rr)
+        out = x.copy(), rr[0]
+        free(*state)
+        return out
+
+    to_device(g, D)
+    x_plain, rr_plain = solve(False)
+    x_graph, rr_graph = solve(True)
+    free(g, D)
+    assert rr_graph == rr_plain and np.array_equal(x_graph, x_plain)
+    assert rr_plain < 1e-2 * float(b @ b)            # and the iteration does reduce the residual

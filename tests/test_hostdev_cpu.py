@@ -190,7 +190,7 @@ def test_api_level_gpu_tests_run_on_the_cuda_test_double(double):
     assert r.returncode == 0, tail + r.stderr[-2000:]
     import re
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 79 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+    assert m and int(m.group(1)) >= 80 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
 
 
 # ---- several ranks: one process per rank, shared memory standing in for NVLink peer memory -------------------------------
