@@ -155,6 +155,18 @@ int nompk_ax_dot_f64(int n, size_t E, const double *u, const double *g, const do
 int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, double *result,
                            double *result_host_mapped, unsigned long long host_seq, void *workspace,
                            const nompk_peers_t *peers, unsigned flags, void *stream);
+/* The first kernel of a conjugate-gradient iteration in one launch: the direction update in front of the operator,
+ *   p <- r + beta p   (in place; multiply, then add -- the roundings of nompk_map(NOMPK_MAP_XPAY)),
+ *   w <- A p,   result <- p . w   (energy form, all-reduced over `peers` like nompk_ax_dot_peers_f64),
+ * 80 algorithmic B/DOF instead of 24 (map) + 64 (Ax) and one launch less.  beta is the host value, or beta_dev[0] from
+ * device memory when beta_dev != NULL (a scalar that a previous kernel left there).  p and r: double[E][n][n][n], 16-byte
+ * aligned.  The lane that loads a pair of p for the operator is the one that updates it; nothing else reads p.
+ * Not in the reference (it has no Ax); written after the last GPU run of round 1: verified on the host emulator
+ * (bitwise against the stand-alone sequence), to be run and timed on the B200. */
+int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double *r, double beta, const double *beta_dev,
+                                const double *g, const double *D, double *w, double *result, double *result_host_mapped,
+                                unsigned long long host_seq, void *workspace, const nompk_peers_t *peers, unsigned flags,
+                                void *stream);
 int nompk_ax_supported(int n);
 /* Variant selector for benchmarking/profiling (0 = default). */
 int nompk_ax_set_variant(int variant);

@@ -50,15 +50,23 @@ struct AxDotArgs {
   PeerExchange px;  // all-reduce over ranks fused into the finish (world <= 1: none)
 };
 
+// p <- r + beta p in front of the operator (see ax_kernel: kXpay).  beta_dev != NULL: beta is read from device memory.
+struct AxXpayArgs {
+  const double *r = nullptr;
+  double *p = nullptr;
+  const double *beta_dev = nullptr;
+  double beta = 0.0;
+};
+
 }  // namespace
 }  // namespace nompk
 
-// One entry point per n: stages D (unless NOMPK_AX_D_CACHED), picks the variant, launches.  `dot` is an AxDotArgs or NULL.
+// One entry point per n: stages D (unless NOMPK_AX_D_CACHED), picks the variant, launches.  `dot` is an AxDotArgs or NULL, `xpay` an AxXpayArgs or NULL (needs dot).
 #define NOMPK_AX_RUN_DECL(n)                                                                                            \
   extern "C" __attribute__((visibility("hidden"))) int nompk_ax_run_n##n(int variant, size_t E, const double *u,       \
                                                                          const double *g, const double *D, double *w,  \
                                                                          unsigned flags, cudaStream_t stream,          \
-                                                                         const void *dot)
+                                                                         const void *dot, const void *xpay)
 NOMPK_AX_RUN_DECL(6);
 NOMPK_AX_RUN_DECL(8);
 NOMPK_AX_RUN_DECL(10);
@@ -209,11 +217,21 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // first (B0 -> B2); after a barrier ur replaces u IN PLACE in B0 (a lane reads its two i-lines whole before it writes
 // them), wr then replaces ur in place and D_r^T wr replaces wr in place.  One barrier more per element, a third less
 // shared memory: at n = 10 / 12 a third CTA fits an SM once the register budget allows it.
+//
+// kXpay: the direction update of conjugate gradients, p <- r + beta p, in front of the operator: the lane that loads its
+// k-column pair of p for S0 loads the same pair of r, forms the new p in registers (multiply, then add: the roundings of
+// the stand-alone map kernel), stores it and carries on with it as u.  One pass over p and r less per CG iteration
+// (80 instead of 24 + 64 B/DOF) and one launch less.  p is read and written through the same non-const pointer by the
+// one lane that owns the pair; nobody else touches it.
+// (The xpay arguments are a trailing kernel parameter that is an empty structure for every other instantiation, so the
+// kernels without it keep their parameter layout -- and their SASS.)
+struct AxNoXpay {};
+
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent, bool kTwoBuf = false>
+          bool kPersistent, bool kTwoBuf = false, bool kXpay = false>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
-          size_t pf_stride) {
+          size_t pf_stride, std::conditional_t<kXpay, AxXpayArgs, AxNoXpay> xp) {
   using L = Layout<N>;
   using SeqN = std::make_integer_sequence<int, N>;
   using SeqNP = std::make_integer_sequence<int, N / 2>;
@@ -253,6 +271,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     size_t e = eb + grp * G + el;
     // lanes that only mirror another work item / element must not contribute to the dot product
     const double dot_weight = (gid < G * T && e < E) ? 1.0 : 0.0;
+    const bool e_valid = e < E;  // kXpay: an element that only mirrors the last one must not store (see S0)
     e = e < E ? e : E - 1;
     const double2 *ue = reinterpret_cast<const double2 *>(u + e * N3) + q * NP + p;
     const double2 *ge = reinterpret_cast<const double2 *>(g + e * 6 * N3) + q * NP + p;
@@ -280,8 +299,30 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     // ---- S0: u k-column pair -> registers and B0 -----------------------------------------------------
     double2 col[N];  // u column, later ut, later wt
     double2 gq[kGeoAhead][6];
+    if constexpr (kXpay) {
+      const double beta = xp.beta_dev ? xp.beta_dev[0] : xp.beta;
+      const double2 *re = reinterpret_cast<const double2 *>(xp.r + e * N3) + q * NP + p;
+      double2 *pe = reinterpret_cast<double2 *>(xp.p + e * N3) + q * NP + p;
+      // The update is in place and therefore not idempotent, unlike everything else mirrored lanes repeat.  Surplus
+      // lanes of a group sit in the warp of the lane they mirror: all of them have read the old p before anybody stores
+      // the new one (fence), and then store the same values.  A whole ELEMENT that mirrors the last one (partial last
+      // group) may read a half-updated p: it stores nothing, here and in S8, and its dot weight is zero.
 #pragma unroll
-    for (int k = 0; k < N; k++) col[k] = kStreamLoads ? ldg2_stream(ue + k * SLAB2) : ldg2(ue + k * SLAB2);
+      for (int k = 0; k < N; k++) col[k] = pe[k * SLAB2];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const double2 rk = ldg2(re + k * SLAB2);
+        col[k].x = __dadd_rn(rk.x, __dmul_rn(beta, col[k].x));
+        col[k].y = __dadd_rn(rk.y, __dmul_rn(beta, col[k].y));
+      }
+      mirror_fence<G * T < GL>();
+#pragma unroll
+      for (int k = 0; k < N; k++)
+        if (e_valid) pe[k * SLAB2] = col[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; k++) col[k] = kStreamLoads ? ldg2_stream(ue + k * SLAB2) : ldg2(ue + k * SLAB2);
+    }
     // first slabs of geometric factors: in flight during S1..S3
 #pragma unroll
     for (int a = 0; a < kGeoAhead; a++)
@@ -449,7 +490,11 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       double2 o;
       o.x = wacc[k].x + rs.x;
       o.y = wacc[k].y + rs.y;
-      we[k * SLAB2] = o;
+      if constexpr (kXpay) {
+        if (e_valid) we[k * SLAB2] = o;
+      } else {
+        we[k * SLAB2] = o;
+      }
     }
     // No group barrier needed here: the next iteration's S0 writes exactly the B0 chunks this lane just read.  Its
     // mirrors read the same chunks, though, and must have done so before anybody overwrites them.
@@ -494,8 +539,30 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
   size_t blocks = (E + kElems - 1) / kElems;
   const size_t cap = (size_t)sm_count() * blocks_per_sm;
   if (PERSISTENT && blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E, dot, cap * kElems);
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(u, g, w, E, dot, cap * kElems, AxNoXpay());
   NOMPK_LAUNCH_CHECK("ax_kernel");
+  return NOMPK_OK;
+}
+
+template <int N, int G, int W, int GPC, int GA, int PF, int MB>
+int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream, AxDotArgs dot, AxXpayArgs xp) {
+  using L = Layout<N>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true>;
+  constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
+  const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  if (!configured) {
+    NOMPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NOMPK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    configured = true;
+  }
+  size_t blocks = (E + kElems - 1) / kElems;
+  const size_t cap = (size_t)sm_count() * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(xp.p, g, w, E, dot, cap * kElems, xp);
+  NOMPK_LAUNCH_CHECK("ax_kernel (xpay)");
   return NOMPK_OK;
 }
 
@@ -513,6 +580,15 @@ template <int N> int dispatch_ax_dot(size_t E, const double *u, const double *g,
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
   if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
   else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true>(E, u, g, w, s, dot);
+}
+
+// p <- r + beta p fused in front (the shapes of dispatch_ax_dot).
+template <int N> int dispatch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t s, AxDotArgs dot, AxXpayArgs xp) {
+  constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
+  constexpr int kThreads = GPC * W * 32;
+  constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  if constexpr (N == 8 || N == 12) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168>(E, g, w, s, dot, xp);   // n = 12: no spills this way
+  else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168>(E, g, w, s, dot, xp);
 }
 
 template <int N> int dispatch_ax(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
@@ -566,6 +642,8 @@ NOMPK_AX_RUN_DEFINE(NOMPK_AX_N) {
   if (!(flags & NOMPK_AX_D_CACHED)) {
     NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
   }
+  if (dot && xpay)
+    return dispatch_ax_xpay_dot<n>(E, g, w, stream, *static_cast<const AxDotArgs *>(dot), *static_cast<const AxXpayArgs *>(xpay));
   if (dot) return dispatch_ax_dot<n>(E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
   return dispatch_ax<n>(variant, E, u, g, w, stream);
 }
@@ -586,7 +664,7 @@ extern "C" int nompk_ax_set_variant(int variant) {
 }
 
 static int ax_common(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
-                     cudaStream_t stream, const nompk::AxDotArgs *dot);
+                     cudaStream_t stream, const nompk::AxDotArgs *dot, const nompk::AxXpayArgs *xpay = nullptr);
 
 extern "C" int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                             unsigned flags, void *stream_) {
@@ -636,8 +714,36 @@ extern "C" int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const do
   return ax_common(n, E, u, g, D, w, flags, static_cast<cudaStream_t>(stream_), &dot);
 }
 
+extern "C" int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double *r, double beta, const double *beta_dev,
+                                           const double *g, const double *D, double *w, double *result,
+                                           double *result_host_mapped, unsigned long long host_seq, void *workspace,
+                                           const nompk_peers_t *peers, unsigned flags, void *stream_) {
+  using namespace nompk;
+  if (!result || !workspace || !r || !is_aligned16(r)) {
+    set_error("nompk_ax_xpay_dot_peers_f64: NULL result / workspace / r, or r not 16-byte aligned");
+    return NOMPK_EINVAL;
+  }
+  AxDotArgs dot;
+  dot.workspace = workspace;
+  dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
+  if (peers && peers->world > 1) {
+    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0 ||
+        E == 0) {
+      set_error("nompk_ax_xpay_dot_peers_f64: bad peer description (rank %d of %d), or a rank without elements", peers->rank,
+                peers->world);
+      return NOMPK_EINVAL;
+    }
+    dot.px.peer_xchg = peers->peer_xchg, dot.px.rank = peers->rank, dot.px.world = peers->world, dot.px.seq = peers->seq;
+  }
+  if (E == 0)  // nothing to update; the dot product is the identity, through the same publication protocol
+    return nompk_ax_dot_peers_f64(n, 0, p, g, D, w, result, result_host_mapped, host_seq, workspace, nullptr, flags, stream_);
+  AxXpayArgs xp;
+  xp.r = r, xp.p = p, xp.beta_dev = beta_dev, xp.beta = beta;
+  return ax_common(n, E, p, g, D, w, flags, static_cast<cudaStream_t>(stream_), &dot, &xp);
+}
+
 static int ax_common(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
-                     cudaStream_t stream, const nompk::AxDotArgs *dot) {
+                     cudaStream_t stream, const nompk::AxDotArgs *dot, const nompk::AxXpayArgs *xpay) {
   using namespace nompk;
   if (!nompk_ax_supported(n)) {
     set_error("nompk_ax_f64: n = %d has no hand-written kernel (supported: 6, 8, 10, 12)", n);
@@ -653,10 +759,10 @@ static int ax_common(int n, size_t E, const double *u, const double *g, const do
     return NOMPK_EINVAL;
   }
   switch (n) {
-  case 6: return nompk_ax_run_n6(g_variant, E, u, g, D, w, flags, stream, dot);
-  case 8: return nompk_ax_run_n8(g_variant, E, u, g, D, w, flags, stream, dot);
-  case 10: return nompk_ax_run_n10(g_variant, E, u, g, D, w, flags, stream, dot);
-  case 12: return nompk_ax_run_n12(g_variant, E, u, g, D, w, flags, stream, dot);
+  case 6: return nompk_ax_run_n6(g_variant, E, u, g, D, w, flags, stream, dot, xpay);
+  case 8: return nompk_ax_run_n8(g_variant, E, u, g, D, w, flags, stream, dot, xpay);
+  case 10: return nompk_ax_run_n10(g_variant, E, u, g, D, w, flags, stream, dot, xpay);
+  case 12: return nompk_ax_run_n12(g_variant, E, u, g, D, w, flags, stream, dot, xpay);
   }
   return NOMPK_EUNSUPPORTED;
 }

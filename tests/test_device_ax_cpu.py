@@ -41,7 +41,9 @@ def device_source():
         assert n == 1, pattern
     body, n = re.subn(r"extern __shared__ double2 smem\[\];", "static double2 smem[1 << 16];", body)
     assert n == 1
-    wrappers = ["#include <utility>\n#include <type_traits>\n#define __constant__ static\n", finish, body,
+    wrappers = ["#include <utility>\n#include <type_traits>\n#define __constant__ static\n"
+                "static inline double __dadd_rn(double a, double b) { return a + b; }   // no contraction: -ffp-contract=off\n"
+                "static inline double __dmul_rn(double a, double b) { return a * b; }\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
         for dot in (0, 1, 2, 3):       # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight
@@ -52,7 +54,17 @@ def device_source():
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
                 f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
-                f" {'true' if dot >= 2 else 'false'}>(u, g, w, E, d, stride);\n}}\n")
+                f" {'true' if dot >= 2 else 'false'}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+        # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
+        wrappers.append(
+            f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"
+            f" double *w, unsigned long long E, void *ws, double *res, unsigned long long stride) {{\n"
+            f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk::nompk_ax_cD[i] = D[i];\n"
+            f"  __syncthreads();\n"
+            f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
+            f"  nompk::AxXpayArgs xp; xp.r = r; xp.p = p; xp.beta_dev = beta_dev; xp.beta = beta;\n"
+            f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {2 if n_ in (8, 12) else 3}, {4 if n_ in (8, 12) else 6}, false, 1, true, true, false, true>"
+            f"(p, g, w, E, d, stride, xp);\n}}\n")
     return "".join(wrappers)
 
 
@@ -107,3 +119,33 @@ def test_ax_kernel_text_against_the_analytic_known_answer(n):
         assert np.abs(w[interior]).max() <= 1e-11 * scale
         if dot:
             assert abs(pap - float(u @ want)) <= 1e-10 * abs(float(u @ want))
+
+
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_with_the_direction_update_fused_in_front(n):
+    """kXpay: p <- r + beta p, w <- A p, p.w in one kernel -- bitwise the stand-alone sequence (oracle map XPAY, oracle
+    Ax, exact dot product) on exact-integer data, with beta as a kernel parameter and read from device memory; p is
+    updated in place, partial last group included."""
+    G, W, GPC = SHAPES[n]
+    per_cta = G * GPC
+    src = device_source()
+    ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    for E, blocks, beta, from_dev in ((2 * per_cta + 1, 2, 2.0, False), (per_cta + 1, 1, -3.0, True)):
+        p0 = ffi.fill_int_f64(E * n ** 3, 15 + n, -2, 2)
+        r = ffi.fill_int_f64(E * n ** 3, 16 + n, -2, 2)
+        g = ffi.fill_int_f64(E * 6 * n ** 3, 17 + n, 0, 3)
+        D = ffi.fill_int_f64(n * n, 18 + n, -2, 2)
+        want_p = r + beta * p0
+        want_w = ffi.ax(n, want_p, g, D)
+        p, w = p0.copy(), np.full(E * n ** 3, np.nan)
+        ws = np.zeros(548928 // 8 + 8, dtype=np.uint64)
+        res = np.zeros(1)
+        beta_dev = np.array([beta])
+        emu.emulate_cooperative(src, f"axx{n}", (blocks, 1, 1), (GPC * W * 32, 1, 1),
+                                ["double *", "const double *", "double", "const double *", "const double *", "const double *", "double *",
+                                 "unsigned long long", "void *", "double *", "unsigned long long"],
+                                [ptr(p), ptr(r), C.c_double(0.0 if from_dev else beta), ptr(beta_dev) if from_dev else C.c_void_p(0), ptr(g), ptr(D),
+                                 ptr(w), C.c_ulonglong(E), ptr(ws), ptr(res), C.c_ulonglong(blocks * per_cta)], instance=41)
+        assert np.array_equal(p, want_p), (n, E)
+        assert np.array_equal(w, want_w), (n, E, int((w != want_w).sum()))
+        assert res[0] == float(want_p @ want_w)
