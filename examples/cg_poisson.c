@@ -8,9 +8,11 @@
  * With NOMP_COMM_SIZE > 1 every rank owns E elements of a larger mesh; the two dot products are all-reduced by the
  * runtime, nothing else changes (the local operator needs no halo exchange).
  *
- *   usage: cg_poisson [E [n [max_iter [tol [host|device|device3 [check_every]]]]]]  + the usual --nomp-* flags
+ *   usage: cg_poisson [E [n [max_iter [tol [host|fused|device|device3 [check_every]]]]]]  + the usual --nomp-* flags
  *          (prints one JSON object per line)
  *
+ * "fused" folds the direction update into the operator (the canonical xpay + Ax + dot kernel string ->
+ * nompk_ax_xpay_dot_peers_f64): two launches per iteration and 128 instead of 136 B/DOF, scalars on the host.
  * "device" keeps every scalar of the iteration in device memory (include/nomp-b200.h: nomp_b200_device_reductions):
  * the two dot products leave their results in mapped variables, alpha and beta are computed by one-iteration kernels,
  * the updates read them as alpha[0] / beta[0] -- five launches per iteration and no host round trip; the host fetches
@@ -63,7 +65,7 @@ static const char *XPAY_DEV3_SRC =
     "  for (int i = 0; i < N; i++) p[i] = r[i] + (rr_new[0] / rr[0]) * p[i];\n}\n";
 
 int main(int argc, const char **argv) {
-  int E = 1024, n = 8, max_iter = 200, device_scalars = 0, check_every = 10;
+  int E = 1024, n = 8, max_iter = 200, device_scalars = 0, check_every = 10, fused = 0;
   double tol = 1e-10;
   int pos = 0;
   for (int i = 1; i < argc; i++) {
@@ -72,7 +74,7 @@ int main(int argc, const char **argv) {
     else if (pos == 1) n = atoi(argv[i]);
     else if (pos == 2) max_iter = atoi(argv[i]);
     else if (pos == 3) tol = atof(argv[i]);
-    else if (pos == 4) device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : 0;
+    else if (pos == 4) device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : 0, fused = !strcmp(argv[i], "fused");
     else if (pos == 5) check_every = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
     pos++;
   }
@@ -183,7 +185,32 @@ int main(int argc, const char **argv) {
     for (int i = 0; device_scalars == 1 && i < 5 && i < it; i++)
       printf("{\"iter\": %d, \"pAp\": %.17g, \"alpha\": %.17g, \"rr\": %.17g}\n", i, trace[3 * i], trace[3 * i + 1], trace[3 * i + 2]);
   }
-  for (; !device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
+  if (fused) { /* p <- r + beta p is the first thing the operator kernel does: start from p = 0, beta = 0 */
+    int id_fused = -1;
+    CHECK(nomp_jit(&id_fused, AX_XPAY_DOT_SRC, red_pap, 9, "w", sizeof(double), NOMP_PTR, "u", sizeof(double), NOMP_PTR, "res",
+                   sizeof(double), NOMP_PTR, "g", sizeof(double), NOMP_PTR, "D", sizeof(double), NOMP_PTR, "beta", sizeof(double),
+                   NOMP_FLOAT, "E", sizeof(int), NOMP_INT, "n", sizeof(int), NOMP_INT | NOMP_JIT, &n, "pap", sizeof(double),
+                   NOMP_FLOAT));
+    memset(p, 0, N * sizeof(double));
+    CHECK(nomp_update(p, 0, N, 8, NOMP_TO));
+    double beta = 0.0;
+    CHECK(nomp_sync());
+    t0 = now_s();
+    for (; it < max_iter && rr > tol * tol * rr0; it++) {
+      if (it == 1) {
+        CHECK(nomp_sync());
+        t0 = now_s();
+      }
+      CHECK(nomp_run(id_fused, w, p, r, g, D, &beta, &E, &pap));
+      const double alpha = rr / pap;
+      double rr_new = 0;
+      CHECK(nomp_run(id_upd, x, r, p, w, &alpha, &Ni, &rr_new));
+      beta = rr_new / rr;
+      if (it < 5) printf("{\"iter\": %d, \"pAp\": %.17g, \"alpha\": %.17g, \"rr\": %.17g}\n", it, pap, alpha, rr_new);
+      rr = rr_new;
+    }
+  }
+  for (; !fused && !device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
     if (it == 1) { /* the first iteration loads every kernel (lazy module loading): time from the second one */
       CHECK(nomp_sync());
       t0 = now_s();
@@ -211,9 +238,9 @@ int main(int argc, const char **argv) {
   CHECK(nomp_run(id_axpy, p, w, &minus_one, &Ni)); /* p = b - A x */
   CHECK(nomp_run(id_dot, p, p, &Ni, &res2));
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
-         "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": 136, \"scalars\": \"%s\"}\n",
-         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0,
-         device_scalars == 3 ? "device3" : device_scalars ? "device" : "host");
+         "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": %d, \"scalars\": \"%s\"}\n",
+         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0, fused ? 128 : 136,
+         device_scalars == 3 ? "device3" : device_scalars ? "device" : fused ? "fused" : "host");
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

@@ -74,8 +74,9 @@ static void gll(int n, double *nodes, double *wt, double *D) {
 static void gll_derivative(int n, double *D) { gll(n, NULL, NULL, D); }
 
 /* The canonical kernel strings (identical to nomp_bridge.families.AX_KERNEL_SOURCE / AX_DOT_KERNEL_SOURCE). */
-#define AX_BODY(EXTRA)                                                                                            \
-  "  for (int e = 0; e < E; e++) {\n"                                                                             \
+#define AX_BODY(EXTRA) AX_BODY2("", EXTRA)
+#define AX_BODY2(PRE, EXTRA)                                                                                      \
+  "  for (int e = 0; e < E; e++) {\n" PRE                                                                         \
   "    double ur[n][n][n];\n    double us[n][n][n];\n    double ut[n][n][n];\n"                                   \
   "    for (int k = 0; k < n; k++)\n      for (int j = 0; j < n; j++)\n        for (int i = 0; i < n; i++) {\n"   \
   "          double r = 0;\n          double s = 0;\n          double t = 0;\n"                                   \
@@ -98,6 +99,15 @@ static const char *AX_SRC =
     "void nomp_ax(double *w, const double *u, const double *g, const double *D, int E, int n) {\n" AX_BODY("");
 static const char *AX_DOT_SRC =
     "void nomp_ax_dot(double *w, const double *u, const double *g, const double *D, int E, int n, double *pap) {\n" AX_BODY(
+        "          pap[0] += u[e * n * n * n + k * n * n + j * n + i] * acc;\n");
+
+/* ... and nomp_bridge.families.AX_XPAY_DOT_KERNEL_SOURCE up to the names of its identifiers: u <- res + beta u first */
+#define AX_POINT "e * n * n * n + k * n * n + j * n + i"
+static const char *AX_XPAY_DOT_SRC =
+    "void nomp_ax_xpay_dot(double *w, double *u, const double *res, const double *g, const double *D, double beta, int E, int n,"
+    " double *pap) {\n" AX_BODY2(
+        "    for (int k = 0; k < n; k++)\n      for (int j = 0; j < n; j++)\n        for (int i = 0; i < n; i++)\n"
+        "          u[" AX_POINT "] = res[" AX_POINT "] + beta * u[" AX_POINT "];\n",
         "          pap[0] += u[e * n * n * n + k * n * n + j * n + i] * acc;\n");
 
 #endif

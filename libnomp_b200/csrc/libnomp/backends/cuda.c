@@ -122,7 +122,7 @@ typedef struct {
 
 static cuda_state_t *g_state = NULL; /* for the nomp_b200_* accessors */
 
-typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT } family_t;
+typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT, FAM_AXXPAYDOT } family_t;
 
 #define SLOT_NONE (-1)
 #define SLOT_WS (-2)
@@ -147,6 +147,7 @@ typedef struct {
   int op, dtype, ax_n;
   int a_y, a_x, a_z, a_alpha, a_beta, a_n, a_out; /* argument indices (SLOT_NONE if unused) */
   int a_u, a_g, a_D, a_w, a_E;
+  int a_r, beta_dev; /* FAM_AXXPAYDOT: the residual vector; beta is a pointer into device memory (else a host scalar) */
   long n_literal; /* trip count when it is a literal in the source (a_n == SLOT_NONE) */
 } cuda_prog_t;
 
@@ -388,7 +389,7 @@ static int cuda_knl_build(nomp_backend_t *bnd, nomp_prog_t *prg, const char *sou
 
   cuda_prog_t *cp = nomp_calloc(cuda_prog_t, 1);
   cp->a_y = cp->a_x = cp->a_z = cp->a_alpha = cp->a_beta = cp->a_n = cp->a_out = SLOT_NONE;
-  cp->a_u = cp->a_g = cp->a_D = cp->a_w = cp->a_E = SLOT_NONE;
+  cp->a_u = cp->a_g = cp->a_D = cp->a_w = cp->a_E = cp->a_r = SLOT_NONE;
   int err = 0;
   if (!strcmp(kind, "nvrtc")) {
     cp->family = FAM_NVRTC;
@@ -408,9 +409,10 @@ static int cuda_knl_build(nomp_backend_t *bnd, nomp_prog_t *prg, const char *sou
       (void)((err = desc_arg(prg, source, "x", 1, &cp->a_x)) || (err = desc_arg(prg, source, "y", 0, &cp->a_y)) ||
              (err = desc_arg(prg, source, "out", 1, &cp->a_out)) ||
              (err = desc_count(prg, source, "n", &cp->a_n, &cp->n_literal)));
-    } else if (!strcmp(family, "ax") || !strcmp(family, "axdot")) {
-      cp->family = !strcmp(family, "ax") ? FAM_AX : FAM_AXDOT;
-      cp->is_reduce = cp->family == FAM_AXDOT;
+    } else if (!strcmp(family, "ax") || !strcmp(family, "axdot") || !strcmp(family, "axxpaydot")) {
+      cp->family = !strcmp(family, "ax") ? FAM_AX : !strcmp(family, "axdot") ? FAM_AXDOT : FAM_AXXPAYDOT;
+      cp->is_reduce = cp->family != FAM_AX;
+      cp->beta_dev = desc_get(source, "beta_dev", num, sizeof(num)) && num[0] == '1';
       cp->ax_n = desc_get(source, "n", num, sizeof(num)) ? atoi(num) : 0;
       if (!nompk_ax_supported(cp->ax_n))
         err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "No native Ax kernel for n = %d.", cp->ax_n);
@@ -418,7 +420,9 @@ static int cuda_knl_build(nomp_backend_t *bnd, nomp_prog_t *prg, const char *sou
         (void)((err = desc_arg(prg, source, "u", 1, &cp->a_u)) || (err = desc_arg(prg, source, "g", 1, &cp->a_g)) ||
                (err = desc_arg(prg, source, "D", 1, &cp->a_D)) || (err = desc_arg(prg, source, "w", 1, &cp->a_w)) ||
                (err = desc_arg(prg, source, "E", 1, &cp->a_E)) ||
-               (cp->family == FAM_AXDOT && (err = desc_arg(prg, source, "out", 1, &cp->a_out))));
+               (cp->family != FAM_AX && (err = desc_arg(prg, source, "out", 1, &cp->a_out))) ||
+               (cp->family == FAM_AXXPAYDOT && ((err = desc_arg(prg, source, "r", 1, &cp->a_r)) ||
+                                                (err = desc_arg(prg, source, "beta", 1, &cp->a_beta)))));
     } else {
       err = nomp_log(NOMP_LOOPY_CODEGEN_FAILURE, NOMP_ERROR, "Unknown native kernel family \"%s\".", family);
     }
@@ -482,7 +486,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     return 0;
   }
   case FAM_AX:
-  case FAM_AXDOT: {
+  case FAM_AXDOT:
+  case FAM_AXXPAYDOT: {
     long E = int_arg(prg, cp->a_E, 0);
     if (E < 0) E = 0;
     const void *D = ptr_arg(prg, cp->a_D);
@@ -495,9 +500,18 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     if (dm && !st->capturing && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
     /* a rank without elements launches nothing: it joins through the stand-alone all-reduce kernel of the finish,
      * which speaks the same protocol on the same buffers */
-    if (cp->family == FAM_AXDOT && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers))
+    if (cp->family != FAM_AX && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers))
       px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
-    if (cp->family == FAM_AXDOT)
+    if (cp->family == FAM_AXXPAYDOT) {
+      /* p <- r + beta p in front of the operator; beta is the caller's host scalar or a scalar in device memory */
+      const double beta = cp->beta_dev ? 0.0 : *(const double *)prg->args[cp->a_beta].ptr;
+      check_nompk(nompk_ax_xpay_dot_peers_f64(cp->ax_n, (size_t)E, (double *)ptr_arg(prg, cp->a_u),
+                                              (const double *)ptr_arg(prg, cp->a_r), beta,
+                                              cp->beta_dev ? (const double *)ptr_arg(prg, cp->a_beta) : NULL,
+                                              (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
+                                              (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result_arg,
+                                              (double *)result_host, ++st->host_seq, st->red_ws, px, flags, st->stream));
+    } else if (cp->family == FAM_AXDOT)
       check_nompk(nompk_ax_dot_peers_f64(cp->ax_n, (size_t)E, (const double *)ptr_arg(prg, cp->a_u),
                                          (const double *)ptr_arg(prg, cp->a_g), (const double *)D,
                                          (double *)ptr_arg(prg, cp->a_w), (double *)st->red_result_arg,

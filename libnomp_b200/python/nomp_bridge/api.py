@@ -100,8 +100,9 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         n_val = knl.fixed.get(roles["n"])
         if n_val is None or int(n_val) not in _SUPPORTED_AX_N:
             raise KernelError(f"the fused Ax + dot kernel needs n as a NOMP_JIT argument, one of {_SUPPORTED_AX_N}")
-        plan = (_header(original, kind="native", family="axdot", n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
-                        D=roles["D"], w=roles["w"], out=roles["pap"]), one, one)
+        extra = {"r": roles["res"], "beta": roles["beta"], "beta_dev": roles["beta_dev"]} if roles["family"] == "axxpaydot" else {}
+        plan = (_header(original, kind="native", family=roles["family"], n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
+                        D=roles["D"], w=roles["w"], out=roles["pap"], **extra), one, one)
         knl._plan = plan
         return plan
 

@@ -81,6 +81,24 @@ AX_DOT_KERNEL_SOURCE = AX_KERNEL_SOURCE.replace(
 assert "pap[0]" in AX_DOT_KERNEL_SOURCE and "nomp_ax_dot" in AX_DOT_KERNEL_SOURCE
 
 
+# The first kernel of a CG iteration: the direction update p = r + beta p in front of the operator, then w = A p and p.Ap
+# (nompk_ax_xpay_dot_peers_f64).  beta is a scalar argument, or -- second form -- a scalar in device memory read as beta[0].
+_POINT = "e * n * n * n + k * n * n + j * n + i"
+AX_XPAY_DOT_KERNEL_SOURCE = AX_DOT_KERNEL_SOURCE.replace(
+    "void nomp_ax_dot(double *w, const double *u, const double *g, const double *D, int E, int n, double *pap) {",
+    "void nomp_ax_xpay_dot(double *w, double *p, const double *res, const double *g, const double *D, double beta, int E, int n,"
+    " double *pap) {").replace(
+    "  for (int e = 0; e < E; e++) {\n",
+    "  for (int e = 0; e < E; e++) {\n"
+    "    for (int k = 0; k < n; k++)\n"
+    "      for (int j = 0; j < n; j++)\n"
+    "        for (int i = 0; i < n; i++)\n"
+    f"          p[{_POINT}] = res[{_POINT}] + beta * p[{_POINT}];\n", 1).replace(" u[", " p[")
+AX_XPAY_DOT_DEV_KERNEL_SOURCE = AX_XPAY_DOT_KERNEL_SOURCE.replace("double beta, int E", "const double *beta, int E").replace(
+    "+ beta * p[", "+ beta[0] * p[")
+assert AX_XPAY_DOT_KERNEL_SOURCE.count(" p[") == 6 and " u[" not in AX_XPAY_DOT_KERNEL_SOURCE and "beta[0]" in AX_XPAY_DOT_DEV_KERNEL_SOURCE
+
+
 def _canonical_tokens(src: str) -> Tuple[List[str], List[str]]:
     """Token list with identifiers renamed v0, v1, ... in order of first appearance (keywords/types kept)."""
     keep = set(c._TYPE_WORDS) | {"for", "if", "else", "break", "continue"}
@@ -99,21 +117,30 @@ def _canonical_tokens(src: str) -> Tuple[List[str], List[str]]:
 _AX_TOKENS, _AX_NAMES = _canonical_tokens(AX_KERNEL_SOURCE)
 
 
-_AX_DOT_TOKENS, _AX_DOT_NAMES = None, None
+_AX_FUSED = None   # [(family, beta in device memory, tokens, names)] of the canonical strings that end in a p.Ap
 
 
 def match_ax_dot(knl: Kernel) -> Optional[Dict[str, str]]:
-    """Same for the Ax + dot string."""
-    global _AX_DOT_TOKENS, _AX_DOT_NAMES
-    if _AX_DOT_TOKENS is None:
-        _AX_DOT_TOKENS, _AX_DOT_NAMES = _canonical_tokens(AX_DOT_KERNEL_SOURCE)
+    """Same for the strings fused with the dot product: Ax + dot, and (x)pay + Ax + dot in its two forms.  The roles carry
+    "family" ("axdot" / "axxpaydot") and, for the latter, "beta_dev" ("0" / "1")."""
+    global _AX_FUSED
+    if _AX_FUSED is None:
+        _AX_FUSED = [("axdot", None, *_canonical_tokens(AX_DOT_KERNEL_SOURCE)),
+                     ("axxpaydot", "0", *_canonical_tokens(AX_XPAY_DOT_KERNEL_SOURCE)),
+                     ("axxpaydot", "1", *_canonical_tokens(AX_XPAY_DOT_DEV_KERNEL_SOURCE))]
     try:
         toks, names = _canonical_tokens(knl.source)
     except Exception:
         return None
-    if toks != _AX_DOT_TOKENS or len(names) != len(_AX_DOT_NAMES):
-        return None
-    return dict(zip(_AX_DOT_NAMES, names))
+    for family, beta_dev, ref_toks, ref_names in _AX_FUSED:
+        if toks == ref_toks and len(names) == len(ref_names):
+            roles = dict(zip(ref_names, names))
+            roles["family"] = family
+            if beta_dev is not None:
+                roles["beta_dev"] = beta_dev
+                roles["u"] = roles["p"]
+            return roles
+    return None
 
 
 def match_ax(knl: Kernel) -> Optional[Dict[str, str]]:

@@ -120,11 +120,18 @@ typedef struct {
   void *w, *result, *result_host;
   unsigned long long host_seq;
   nompk_peers_t peers;
+  const double *r, *beta_dev; /* r != NULL: x <- r + beta x first */
+  double beta;
 } reduce_call_t;
 
 static int run_reduce(void *blob) {
   reduce_call_t *c = (reduce_call_t *)blob;
   unsigned long long value = 0;
+  if (c->r) { /* the direction update through the oracle's map (NOMPK_MAP_XPAY: y <- x + alpha y) */
+    int (*map)(int, int, size_t, void *, const void *, const void *, const void *, const void *) = oracle_sym("oracle_map");
+    const double beta = c->beta_dev ? c->beta_dev[0] : c->beta;
+    if (map(NOMPK_MAP_XPAY, NOMPK_F64, c->n * (size_t)c->n_ax * c->n_ax * c->n_ax, (void *)c->x, c->r, NULL, &beta, NULL)) return NOMPK_EINVAL;
+  }
   if (c->n_ax) {
     int (*ax)(int, size_t, const double *, const double *, const double *, double *) = oracle_sym("oracle_ax_f64");
     if (ax(c->n_ax, c->n, c->x, c->g, c->D, c->w)) return NOMPK_EINVAL;
@@ -147,7 +154,7 @@ EXPORT int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, con
                               void *result_host_mapped, unsigned long long host_seq, void *workspace,
                               const nompk_peers_t *peers, void *stream) {
   (void)workspace, (void)stream;
-  reduce_call_t c = {(int)op, (int)dt, 0, n, x, y, NULL, NULL, NULL, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}};
+  reduce_call_t c = {(int)op, (int)dt, 0, n, x, y, NULL, NULL, NULL, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, NULL, NULL, 0.0};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
   if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
@@ -180,7 +187,19 @@ EXPORT int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double
                                   double *result, double *result_host_mapped, unsigned long long host_seq,
                                   void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream) {
   (void)workspace, (void)flags, (void)stream;
-  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}};
+  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, NULL, NULL, 0.0};
+  if (peers && peers->world > 1) c.peers = *peers;
+  calls++;
+  if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
+  return run_reduce(&c);
+}
+
+EXPORT int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double *r, double beta, const double *beta_dev,
+                                       const double *g, const double *D, double *w, double *result, double *result_host_mapped,
+                                       unsigned long long host_seq, void *workspace, const nompk_peers_t *peers, unsigned flags,
+                                       void *stream) {
+  (void)workspace, (void)flags, (void)stream;
+  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, p, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, r, beta_dev, beta};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
   if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;

@@ -177,7 +177,7 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
         pytest.skip("examples/cg_poisson was not built")
     env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
     runs = {}
-    for mode in ("host", "device", "device3"):
+    for mode in ("host", "device", "device3", "fused"):
         r = subprocess.run([str(exe), "6", "8", "400", "1e-9", mode, "1", "--nomp-backend", "cuda", "--nomp-device", "0",
                             "--nomp-verbose", "1"], env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -188,6 +188,9 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
     assert dev[-1]["iterations"] == host[-1]["iterations"] and dev[-1]["rr_final"] == host[-1]["rr_final"]
     assert dev[-1]["true_residual_rel"] < 1e-7
     # three launches per iteration (alpha and beta folded into their consumers, the residual scalars swapped by name)
+    fused = runs["fused"]          # the direction update inside the operator kernel: two launches per iteration
+    assert fused[:6] == host[:6] and fused[-1]["scalars"] == "fused" and fused[-1]["bytes_per_dof"] == 128
+    assert fused[-1]["iterations"] == host[-1]["iterations"] and fused[-1]["rr_final"] == host[-1]["rr_final"]
     dev3 = runs["device3"]
     assert dev3[-1]["scalars"] == "device3" and dev3[0] == host[0]
     assert dev3[-1]["iterations"] == host[-1]["iterations"] and dev3[-1]["rr_final"] == host[-1]["rr_final"]
@@ -267,3 +270,55 @@ def test_cg_iterations_replayed_from_a_cuda_graph():
     free(g, D)
     assert rr_graph == rr_plain and np.array_equal(x_graph, x_plain)
     assert rr_plain < 1e-2 * float(b @ b)            # and the iteration does reduce the residual
+
+
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_direction_update_fused_into_the_operator(n):
+    """The canonical xpay + Ax + dot kernel strings (beta as a scalar argument, and as beta[0] in device memory) -> one
+    launch of nompk_ax_xpay_dot_peers_f64, against the two-kernel sequence p = r + beta p; w = A p, p.w through the same
+    API: bitwise on exact data, p updated in place."""
+    from nomp_bridge.families import AX_XPAY_DOT_DEV_KERNEL_SOURCE, AX_XPAY_DOT_KERNEL_SOURCE
+    lib = capi.nomp()
+    E = 13
+    p0 = ffi.fill_int_f64(E * n ** 3, 31, -2, 2)
+    r = ffi.fill_int_f64(E * n ** 3, 32, -2, 2)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 33, 0, 3)
+    D = ffi.fill_int_f64(n * n, 34, -2, 2)
+    beta = 3.0
+    # the two-kernel sequence
+    k_dir = jit("void dir(double *p, const double *r, double beta, int N) { for (int i = 0; i < N; i++) p[i] = r[i] + beta * p[i]; }",
+                capi.clauses(), [("p", 8, P), ("r", 8, P), ("beta", 8, F), ("N", 4, I)])
+    k_ax = jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")),
+               [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | capi.NOMP_JIT, C.c_int(n)), ("pap", 8, F)])
+    p, w = p0.copy(), np.zeros_like(p0)
+    to_device(p, r, g, D, w)
+    pap = C.c_double(0.0)
+    capi.check(capi.run(k_dir, p.ctypes.data, r.ctypes.data, C.c_double(beta), C.c_int(p.size)))
+    capi.check(capi.run(k_ax, w.ctypes.data, p.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E), pap))
+    from_device(p, w)
+    want_p, want_w, want_pap = p.copy(), w.copy(), pap.value
+    assert np.array_equal(want_p, r + beta * p0) and want_pap == float(want_p @ want_w)
+    # one launch, beta by value
+    args = [("w", 8, P), ("p", 8, P), ("res", 8, P), ("g", 8, P), ("D", 8, P), ("beta", 8, F), ("E", 4, I),
+            ("n", 4, I | capi.NOMP_JIT, C.c_int(n)), ("pap", 8, F)]
+    k_fused = jit(AX_XPAY_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")), args)
+    assert "family=axxpaydot" in lib.nomp_b200_prog_info(k_fused).decode()
+    p[:], w[:] = p0, np.nan
+    to_device(p, w)
+    launches = lib.nomp_b200_launch_count()
+    pap = C.c_double(0.0)
+    capi.check(capi.run(k_fused, w.ctypes.data, p.ctypes.data, r.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_double(beta), C.c_int(E), pap))
+    assert lib.nomp_b200_launch_count() - launches == 1
+    from_device(p, w)
+    assert np.array_equal(p, want_p) and np.array_equal(w, want_w) and pap.value == want_pap
+    # one launch, beta in device memory
+    args[5] = ("beta", 8, P)
+    k_fused_dev = jit(AX_XPAY_DOT_DEV_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")), args)
+    beta_d = np.array([beta])
+    p[:], w[:] = p0, np.nan
+    to_device(p, w, beta_d)
+    pap = C.c_double(0.0)
+    capi.check(capi.run(k_fused_dev, w.ctypes.data, p.ctypes.data, r.ctypes.data, g.ctypes.data, D.ctypes.data, beta_d.ctypes.data, C.c_int(E), pap))
+    from_device(p, w)
+    assert np.array_equal(p, want_p) and np.array_equal(w, want_w) and pap.value == want_pap
+    free(p, r, g, D, w, beta_d)

@@ -190,7 +190,7 @@ def test_api_level_gpu_tests_run_on_the_cuda_test_double(double):
     assert r.returncode == 0, tail + r.stderr[-2000:]
     import re
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 80 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+    assert m and int(m.group(1)) >= 84 and "failed" not in r.stdout and "skipped" not in r.stdout, tail
 
 
 # ---- several ranks: one process per rank, shared memory standing in for NVLink peer memory -------------------------------
@@ -217,7 +217,7 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
 
 
 @pytest.mark.parametrize("path,scalars", [("fused", "host"), ("fused", "device"), ("fused", "device3"), ("standalone", "host"),
-                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3")])
+                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3"), ("fused", "fused")])
 def test_two_ranks_of_the_cg_example(double, path, scalars):
     """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
     agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
