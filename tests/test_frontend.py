@@ -850,3 +850,31 @@ def test_loop_invariant_reads_keep_the_vector_schedules():
     assert got == want[0] and np.array_equal(x, xw) and np.array_equal(r, rw)
     ok, log = nvrtc_compile(cuda)
     assert ok, log
+
+
+def test_xpay_ax_dot_recognition_and_semantics():
+    """The canonical xpay + Ax + dot strings (beta by value / beta[0] in device memory), also with renamed identifiers,
+    bind to the native family axxpaydot for the n that have a kernel; a different update does not.  The string itself,
+    compiled by gcc, is the stand-alone sequence: p = r + beta p (oracle map), w = A p (oracle Ax), pap = p . w."""
+    from oracle import ffi
+    for src, dev in ((families.AX_XPAY_DOT_KERNEL_SOURCE, "0"), (families.AX_XPAY_DOT_DEV_KERNEL_SOURCE, "1")):
+        desc, _, _, _ = plan(src, reduce=("pap", "+"), fixed={"n": 10})
+        assert (desc["kind"], desc["family"], desc["beta_dev"]) == ("native", "axxpaydot", dev), desc
+        assert (desc["u"], desc["r"], desc["beta"], desc["out"], desc["n"]) == ("p", "res", "beta", "pap", "10")
+        renamed = src.replace("res", "resid").replace("beta", "b").replace(" p[", " dir[").replace("*p,", "*dir,").replace("pap", "energy")
+        desc, _, _, _ = plan(renamed, reduce=("energy", "+"), fixed={"n": 8})
+        assert (desc["family"], desc["u"], desc["r"], desc["beta"], desc["out"]) == ("axxpaydot", "dir", "resid", "b", "energy"), desc
+    other = families.AX_XPAY_DOT_KERNEL_SOURCE.replace("+ beta * p[", "- beta * p[")
+    with pytest.raises(Exception):
+        plan(other, reduce=("pap", "+"), fixed={"n": 8})          # a reduction over a loop nest without a native kernel
+    n, E, beta = 6, 3, 2.0
+    p0 = ffi.fill_int_f64(E * n ** 3, 1, -2, 2)
+    r = ffi.fill_int_f64(E * n ** 3, 2, -2, 2)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 3, 0, 3)
+    D = ffi.fill_int_f64(n * n, 4, -2, 2)
+    want_p = r + beta * p0
+    want_w = ffi.ax(n, want_p, g, D)
+    for src, b in ((families.AX_XPAY_DOT_KERNEL_SOURCE, beta), (families.AX_XPAY_DOT_DEV_KERNEL_SOURCE, np.array([beta]))):
+        p, w, pap = p0.copy(), np.zeros_like(p0), np.zeros(1)
+        run_kernel(src, w, p, r, g, D, b, E, n, pap)
+        assert np.array_equal(p, want_p) and np.array_equal(w, want_w) and pap[0] == float(want_p @ want_w)
