@@ -256,3 +256,22 @@ def test_four_ranks_mixing_host_and_device_results(double):
             for key in ("pAp", "alpha", "rr"):
                 assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
     assert len({json_line["rr_final"] for json_line in (lines[-1] for lines in per_rank)}) == 1
+
+
+def test_graph_extension_from_c_under_the_sanitizers(double):
+    """tests/hostdev/graph_smoke.c: capture / replay / refusals / free of nomp_b200_graph_* from C, with the runtime built
+    under the address and undefined-behaviour sanitizers where gcc has them."""
+    so, env = double
+    exe = HOSTDEV / "_build" / "graph_smoke"
+    src = HOSTDEV / "graph_smoke.c"
+    from libnomp_b200 import build as b
+    if not exe.exists() or src.stat().st_mtime > exe.stat().st_mtime:
+        subprocess.run(["gcc", "-O1", "-g", "-Wall", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L", str(b.LIB), "-lnomp",
+                        "-lm", f"-Wl,-rpath,{b.LIB}"], check=True)
+    sanitized = sanitized_runtime(so, env)
+    run_env, preload = sanitized if sanitized else (env, str(so))
+    r = subprocess.run([str(exe), "--nomp-backend", "cuda", "--nomp-verbose", "1"], env=dict(run_env, LD_PRELOAD=str(preload)),
+                       capture_output=True, text=True, timeout=600)
+    text = r.stdout + r.stderr
+    assert r.returncode == 0 and "graph smoke: ok" in r.stdout, text[-3000:]
+    assert "AddressSanitizer" not in text and "runtime error" not in text, text[-3000:]
