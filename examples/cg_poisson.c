@@ -8,9 +8,11 @@
  * With NOMP_COMM_SIZE > 1 every rank owns E elements of a larger mesh; the two dot products are all-reduced by the
  * runtime, nothing else changes (the local operator needs no halo exchange).
  *
- *   usage: cg_poisson [E [n [max_iter [tol [host|fused|device|device3 [check_every]]]]]]  + the usual --nomp-* flags
+ *   usage: cg_poisson [E [n [max_iter [tol [host|fused|device|device3|device_fused [check_every]]]]]]  + the usual --nomp-* flags
  *          (prints one JSON object per line)
  *
+ * "device_fused" is "fused" with the scalars in device memory: xpay + Ax + dot reading beta[0], the update with alpha
+ * folded in, and a one-thread kernel for beta -- three launches, 128 B/DOF, no round trip.
  * "fused" folds the direction update into the operator (the canonical xpay + Ax + dot kernel string ->
  * nompk_ax_xpay_dot_peers_f64): two launches per iteration and 128 instead of 136 B/DOF, scalars on the host.
  * "device" keeps every scalar of the iteration in device memory (include/nomp-b200.h: nomp_b200_device_reductions):
@@ -64,6 +66,10 @@ static const char *XPAY_DEV3_SRC =
     "void cg_direction_3(double *p, const double *r, const double *rr_new, const double *rr, int N) {\n"
     "  for (int i = 0; i < N; i++) p[i] = r[i] + (rr_new[0] / rr[0]) * p[i];\n}\n";
 
+static const char *BETA2_SRC =
+    "void cg_beta2(double *beta, double *rr, const double *rr_new) {\n"
+    "  for (int i = 0; i < 1; i++) { beta[i] = rr_new[i] / rr[i]; rr[i] = rr_new[i]; }\n}\n";
+
 int main(int argc, const char **argv) {
   int E = 1024, n = 8, max_iter = 200, device_scalars = 0, check_every = 10, fused = 0;
   double tol = 1e-10;
@@ -74,7 +80,9 @@ int main(int argc, const char **argv) {
     else if (pos == 1) n = atoi(argv[i]);
     else if (pos == 2) max_iter = atoi(argv[i]);
     else if (pos == 3) tol = atof(argv[i]);
-    else if (pos == 4) device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : 0, fused = !strcmp(argv[i], "fused");
+    else if (pos == 4)
+      device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : !strcmp(argv[i], "device_fused") ? 4 : 0,
+      fused = !strcmp(argv[i], "fused");
     else if (pos == 5) check_every = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
     pos++;
   }
@@ -130,7 +138,7 @@ int main(int argc, const char **argv) {
   double *pap_d = calloc(1, 8), *alpha_d = calloc(1, 8), *beta_d = calloc(1, 8), *rr_d = calloc(1, 8), *rrn_d = calloc(1, 8);
   double *trace = calloc(18, 8);
   double *scalars[] = {pap_d, alpha_d, beta_d, rr_d, rrn_d};
-  int id_alpha = -1, id_updd = -1, id_beta = -1, id_dird = -1, id_upd3 = -1, id_dir3 = -1;
+  int id_alpha = -1, id_updd = -1, id_beta = -1, id_dird = -1, id_upd3 = -1, id_dir3 = -1, id_fused_dev = -1, id_beta2 = -1;
   if (device_scalars) {
     const char *red_rrn[4] = {"reduce", "rr_new", "+", NULL};
     rr_d[0] = rr;
@@ -150,6 +158,16 @@ int main(int argc, const char **argv) {
                    NOMP_PTR, "N", sizeof(int), NOMP_INT, "rr_new", sizeof(double), NOMP_FLOAT));
     CHECK(nomp_jit(&id_dir3, XPAY_DEV3_SRC, none, 5, "p", sizeof(double), NOMP_PTR, "r", sizeof(double), NOMP_PTR, "rr_new",
                    sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "N", sizeof(int), NOMP_INT));
+    if (device_scalars == 4) { /* the direction update inside the operator kernel, beta read from device memory */
+      CHECK(nomp_jit(&id_fused_dev, AX_XPAY_DOT_DEV_SRC, red_pap, 9, "w", sizeof(double), NOMP_PTR, "u", sizeof(double), NOMP_PTR,
+                     "res", sizeof(double), NOMP_PTR, "g", sizeof(double), NOMP_PTR, "D", sizeof(double), NOMP_PTR, "beta",
+                     sizeof(double), NOMP_PTR, "E", sizeof(int), NOMP_INT, "n", sizeof(int), NOMP_INT | NOMP_JIT, &n, "pap",
+                     sizeof(double), NOMP_FLOAT));
+      CHECK(nomp_jit(&id_beta2, BETA2_SRC, none, 3, "beta", sizeof(double), NOMP_PTR, "rr", sizeof(double), NOMP_PTR, "rr_new",
+                     sizeof(double), NOMP_PTR));
+      memset(p, 0, N * sizeof(double)); /* p <- r + 0 p in the first iteration */
+      CHECK(nomp_update(p, 0, N, 8, NOMP_TO));
+    }
     nomp_b200_device_reductions(1);
   }
 
@@ -162,13 +180,18 @@ int main(int argc, const char **argv) {
       t0 = now_s();
     }
     const int slot = it < 5 ? it : 5; /* iterations beyond the fifth share a scratch slot of the trace */
-    CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
-    if (device_scalars == 3) {
+    if (device_scalars == 4) {
+      CHECK(nomp_run(id_fused_dev, w, p, r, g, D, beta_d, &E, pap_d));
+      CHECK(nomp_run(id_upd3, x, r, p, w, rr_d, pap_d, &Ni, rrn_d));
+      CHECK(nomp_run(id_beta2, beta_d, rr_d, rrn_d));
+    } else if (device_scalars == 3) {
+      CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
       CHECK(nomp_run(id_upd3, x, r, p, w, rr_d, pap_d, &Ni, rrn_d));
       CHECK(nomp_run(id_dir3, p, r, rrn_d, rr_d, &Ni));
       double *swap = rr_d; /* the new residual becomes the current one: a host-side change of names, no copy */
       rr_d = rrn_d, rrn_d = swap;
     } else {
+      CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
       CHECK(nomp_run(id_alpha, alpha_d, rr_d, pap_d, trace, &slot));
       CHECK(nomp_run(id_updd, x, r, p, w, alpha_d, &Ni, rrn_d));
       CHECK(nomp_run(id_beta, beta_d, rr_d, rrn_d, trace, &slot));
@@ -239,8 +262,8 @@ int main(int argc, const char **argv) {
   CHECK(nomp_run(id_dot, p, p, &Ni, &res2));
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
          "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": %d, \"scalars\": \"%s\"}\n",
-         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0, fused ? 128 : 136,
-         device_scalars == 3 ? "device3" : device_scalars ? "device" : fused ? "fused" : "host");
+         it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0, fused || device_scalars == 4 ? 128 : 136,
+         device_scalars == 4 ? "device_fused" : device_scalars == 3 ? "device3" : device_scalars ? "device" : fused ? "fused" : "host");
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

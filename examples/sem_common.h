@@ -110,4 +110,12 @@ static const char *AX_XPAY_DOT_SRC =
         "          u[" AX_POINT "] = res[" AX_POINT "] + beta * u[" AX_POINT "];\n",
         "          pap[0] += u[e * n * n * n + k * n * n + j * n + i] * acc;\n");
 
+/* ... and AX_XPAY_DOT_DEV_KERNEL_SOURCE: beta is a scalar in device memory, read as beta[0] */
+static const char *AX_XPAY_DOT_DEV_SRC =
+    "void nomp_ax_xpay_dot(double *w, double *u, const double *res, const double *g, const double *D, const double *beta, int E,"
+    " int n, double *pap) {\n" AX_BODY2(
+        "    for (int k = 0; k < n; k++)\n      for (int j = 0; j < n; j++)\n        for (int i = 0; i < n; i++)\n"
+        "          u[" AX_POINT "] = res[" AX_POINT "] + beta[0] * u[" AX_POINT "];\n",
+        "          pap[0] += u[e * n * n * n + k * n * n + j * n + i] * acc;\n");
+
 #endif

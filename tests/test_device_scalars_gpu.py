@@ -177,7 +177,7 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
         pytest.skip("examples/cg_poisson was not built")
     env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
     runs = {}
-    for mode in ("host", "device", "device3", "fused"):
+    for mode in ("host", "device", "device3", "fused", "device_fused"):
         r = subprocess.run([str(exe), "6", "8", "400", "1e-9", mode, "1", "--nomp-backend", "cuda", "--nomp-device", "0",
                             "--nomp-verbose", "1"], env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -191,6 +191,9 @@ def test_cg_example_gives_the_same_iterates_with_device_scalars():
     fused = runs["fused"]          # the direction update inside the operator kernel: two launches per iteration
     assert fused[:6] == host[:6] and fused[-1]["scalars"] == "fused" and fused[-1]["bytes_per_dof"] == 128
     assert fused[-1]["iterations"] == host[-1]["iterations"] and fused[-1]["rr_final"] == host[-1]["rr_final"]
+    both = runs["device_fused"]    # ... and with the scalars in device memory: three launches, 128 B/DOF, no round trip
+    assert both[0] == host[0] and both[-1]["scalars"] == "device_fused" and both[-1]["bytes_per_dof"] == 128
+    assert both[-1]["iterations"] == host[-1]["iterations"] and both[-1]["rr_final"] == host[-1]["rr_final"]
     dev3 = runs["device3"]
     assert dev3[-1]["scalars"] == "device3" and dev3[0] == host[0]
     assert dev3[-1]["iterations"] == host[-1]["iterations"] and dev3[-1]["rr_final"] == host[-1]["rr_final"]

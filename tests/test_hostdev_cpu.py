@@ -217,7 +217,7 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
 
 
 @pytest.mark.parametrize("path,scalars", [("fused", "host"), ("fused", "device"), ("fused", "device3"), ("standalone", "host"),
-                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3"), ("fused", "fused")])
+                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3"), ("fused", "fused"), ("fused", "device_fused")])
 def test_two_ranks_of_the_cg_example(double, path, scalars):
     """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
     agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
@@ -234,7 +234,7 @@ def test_two_ranks_of_the_cg_example(double, path, scalars):
     ref_final = _cg_reference(2 * E, n, 12)[-1]["rr"]
     for lines in per_rank:
         assert abs(lines[0]["rr0"] - ref[0]["rr0"]) <= 1e-12 * ref[0]["rr0"]
-        for it in range(5 if scalars != "device3" else 0):        # "device3" prints no per-iteration trace
+        for it in range(5 if scalars not in ("device3", "device_fused") else 0):        # those print no per-iteration trace
             for key in ("pAp", "alpha", "rr"):
                 assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
         assert lines[-1]["iterations"] == 12 and lines[-1]["scalars"] == scalars

@@ -17,14 +17,14 @@ python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest -
 NOMP_RUN_PENDING=1 python -m pytest tests/test_device_scalars_gpu.py -m gpu -q > "$OUT/pytest_pending.log" 2>&1
 echo "pending tests rc=$?" | tee -a "$OUT/summary.txt"
 
-for mode in host fused device device3; do
+for mode in host fused device device3 device_fused; do
   for rep in 1 2 3; do   # interleaved: the boards are power-capped and drift by a few per cent between runs
     libnomp_b200/build/cg_poisson 131072 8 60 1e-30 $mode 20 --nomp-backend cuda --nomp-device 0 --nomp-verbose 1 \
       | tail -1 | sed "s/^/{\"ranks\": 1, \"rep\": $rep, \"run\": /; s/$/}/" >> "$OUT/cg_scalars.jsonl"
   done
 done
 if [ "$RANKS" -gt 1 ]; then
-  for mode in host fused device device3; do
+  for mode in host fused device device3 device_fused; do
     for rep in 1 2 3; do
       tools/run_ranks.sh "$RANKS" libnomp_b200/build/cg_poisson $((131072 / RANKS)) 8 60 1e-30 $mode 20 --nomp-verbose 1 \
         | tail -1 | sed "s/^/{\"ranks\": $RANKS, \"rep\": $rep, \"run\": /; s/$/}/" >> "$OUT/cg_scalars.jsonl"
