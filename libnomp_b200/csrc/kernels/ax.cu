@@ -437,7 +437,13 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       if constexpr (kDot) {
         double ex = fma(ur.x, wr.x, fma(us.x, ws.x, ut.x * wt.x));
         double ey = fma(ur.y, wr.y, fma(us.y, ws.y, ut.y * wt.y));
-        energy = fma(dot_weight, ex + ey, energy);
+        if constexpr (kXpay) {
+          // an element that mirrors the last one may have read a half-updated p: its numbers are finite but meaningless,
+          // and a weight of zero would still let an overflow through (0 * inf) -- select instead of multiply
+          energy += dot_weight != 0.0 ? ex + ey : 0.0;
+        } else {
+          energy = fma(dot_weight, ex + ey, energy);
+        }
       }
       mirror_fence<G * T < GL>();
       B1[a] = wr;
