@@ -15,7 +15,9 @@
  *     (domain, size == 4) src/reduction.c:44-85).
  *   - Ax: NOT in the reference (tests/sem.py:10-36 only tags loops).  Restated from the definition in
  *     SURVEY.md 8(a-17) / include/nompk.h (Nekbone ax_e: local_grad3 -> geometric factors -> local_grad3_t).
- *     PARITY UNPINNED by the reference for this function; tests pin it with analytic properties instead.
+ *     PARITY UNPINNED by the reference for this function; tests pin it with analytic properties instead, among them
+ *     a known answer that owes nothing to any implementation (tests/ax_closed_form.py: the boundary fluxes of a
+ *     harmonic polynomial on a sheared element with a full constant metric, zero at interior nodes).
  *   - gather-scatter: NOT in the reference either.  Restated from the definition of gslib's gs_op as Nekbone uses
  *     it (every copy of a global id receives the combination of all copies; ids <= 0 do not take part), with the
  *     association order include/nompk.h documents.  PARITY UNPINNED by the reference; pinned by closed forms
