@@ -8,7 +8,7 @@
  * With NOMP_COMM_SIZE > 1 every rank owns E elements of a larger mesh; the two dot products are all-reduced by the
  * runtime, nothing else changes (the local operator needs no halo exchange).
  *
- *   usage: cg_poisson [E [n [max_iter [tol [host|fused|device|device3|device_fused [check_every]]]]]]  + the usual --nomp-* flags
+ *   usage: cg_poisson [E [n [max_iter [tol [host|fused|device|device3|device_fused|graph [check_every]]]]]]  + the usual --nomp-* flags
  *          (prints one JSON object per line)
  *
  * "device_fused" is "fused" with the scalars in device memory: xpay + Ax + dot reading beta[0], the update with alpha
@@ -22,6 +22,9 @@
  * "device3" folds alpha and beta into their consumers (x[i] += (rr[0] / pap[0]) * p[i], ...) and swaps the roles of the
  * two residual scalars on the host instead of copying one to the other: three launches per iteration, the same number as
  * "host", and still no round trip (it prints no per-iteration trace).
+ * "graph" is "device3" captured once as a CUDA graph of two iterations (the residual scalars swap names every iteration) and
+ * replayed (include/nomp-b200.h: nomp_b200_graph_*): six launches per cudaGraphLaunch, on any number of ranks -- the fused
+ * all-reduce counts its calls in device memory, so nothing in the graph is specific to one iteration.
  */
 #define _POSIX_C_SOURCE 200809L
 #define _DEFAULT_SOURCE
@@ -81,7 +84,8 @@ int main(int argc, const char **argv) {
     else if (pos == 2) max_iter = atoi(argv[i]);
     else if (pos == 3) tol = atof(argv[i]);
     else if (pos == 4)
-      device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : !strcmp(argv[i], "device_fused") ? 4 : 0,
+      device_scalars = !strcmp(argv[i], "device") ? 1 : !strcmp(argv[i], "device3") ? 3 : !strcmp(argv[i], "device_fused") ? 4 :
+                       !strcmp(argv[i], "graph") ? 5 : 0,
       fused = !strcmp(argv[i], "fused");
     else if (pos == 5) check_every = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
     pos++;
@@ -174,7 +178,34 @@ int main(int argc, const char **argv) {
   CHECK(nomp_sync());
   double t0 = now_s();
   int it = 0;
-  for (; device_scalars && it < max_iter && rr > tol * tol * rr0; it++) {
+  if (device_scalars == 5) { /* two iterations recorded once, then replayed */
+    int graph = -1;
+    CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d)); /* loads every kernel before the capture (lazy module loading) ... */
+    CHECK(nomp_run(id_upd3, x, r, p, w, rr_d, pap_d, &Ni, rrn_d));
+    CHECK(nomp_run(id_dir3, p, r, rrn_d, rr_d, &Ni));
+    it = 1;                                           /* ... and is the first iteration */
+    CHECK(nomp_b200_graph_begin());
+    CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
+    CHECK(nomp_run(id_upd3, x, r, p, w, rrn_d, pap_d, &Ni, rr_d));
+    CHECK(nomp_run(id_dir3, p, r, rr_d, rrn_d, &Ni));
+    CHECK(nomp_run(id_axdot, w, p, g, D, &E, pap_d));
+    CHECK(nomp_run(id_upd3, x, r, p, w, rr_d, pap_d, &Ni, rrn_d));
+    CHECK(nomp_run(id_dir3, p, r, rrn_d, rr_d, &Ni));
+    CHECK(nomp_b200_graph_end(&graph));
+    CHECK(nomp_sync());
+    t0 = now_s();
+    const int every = check_every > 1 ? check_every / 2 : 1;
+    for (int replays = 0; it + 2 <= max_iter && rr > tol * tol * rr0; it += 2) {
+      CHECK(nomp_b200_graph_launch(graph));
+      if (++replays % every == 0 || it + 4 > max_iter) { /* after an odd number of iterations the current residual is rr_new */
+        CHECK(nomp_update(rrn_d, 0, 1, 8, NOMP_FROM));
+        rr = rrn_d[0];
+      }
+    }
+    CHECK(nomp_sync());
+    CHECK(nomp_b200_graph_free(graph));
+  }
+  for (; device_scalars && device_scalars != 5 && it < max_iter && rr > tol * tol * rr0; it++) {
     if (it == 1) {
       CHECK(nomp_sync());
       t0 = now_s();
@@ -263,7 +294,7 @@ int main(int argc, const char **argv) {
   printf("{\"iterations\": %d, \"rr_final\": %.17g, \"true_residual_rel\": %.3e, \"seconds\": %.6f, \"ms_per_iter\": %.4f, "
          "\"GDOF_per_s_per_rank\": %.2f, \"bytes_per_dof\": %d, \"scalars\": \"%s\"}\n",
          it, rr, sqrt(res2 / rr0), dt, dt / (it > 1 ? it - 1 : 1) * 1e3, it > 1 ? (double)N * (it - 1) / dt / 1e9 : 0.0, fused || device_scalars == 4 ? 128 : 136,
-         device_scalars == 4 ? "device_fused" : device_scalars == 3 ? "device3" : device_scalars ? "device" : fused ? "fused" : "host");
+         device_scalars == 5 ? "graph" : device_scalars == 4 ? "device_fused" : device_scalars == 3 ? "device3" : device_scalars ? "device" : fused ? "fused" : "host");
   CHECK(nomp_finalize());
   return sqrt(res2 / rr0) < 1e-6 ? 0 : 2;
 }

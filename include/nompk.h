@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NOMPK_VERSION 100
+#define NOMPK_VERSION 200
 
 /* error codes */
 #define NOMPK_OK 0
@@ -111,6 +111,15 @@ typedef struct {
   void *const *peer_xchg; /* DEVICE array of `world` pointers to the ranks' exchange buffers as mapped here */
   int rank, world;
   unsigned long long seq; /* number of this collective call: 1, 2, 3, ... in the same order on all ranks */
+  /* Call number kept in DEVICE memory instead (non-NULL: `seq` is ignored): the kernel that finishes the reduction
+   * takes *seq_dev + 1 as the number of the call and stores it back.  Nothing about the collective is then a launch
+   * parameter, so a launch recorded in a CUDA graph can be replayed on every rank (include/nomp-b200.h:
+   * nomp_b200_graph_*), and the host keeps no count.  One counter per rank, zero-initialised, touched only by
+   * kernels on one stream. */
+  unsigned long long *seq_dev;
+  /* Device address of 8 bytes of mapped pinned host memory (may be NULL): receives the call number if a peer did not
+   * arrive within 20 s, also when no result_host_mapped block was given (results that stay on the device). */
+  unsigned long long *error_host_mapped;
 } nompk_peers_t;
 int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, const void *x, const void *y, void *result,
                        void *result_host_mapped, unsigned long long host_seq, void *workspace,
@@ -129,6 +138,9 @@ size_t nompk_allreduce_xchg_bytes(int world);
 int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
                            unsigned long long host_seq, void *const *peer_xchg, int rank, int world,
                            unsigned long long seq, void *stream);
+/* The same with the whole peer description (call number in device memory, error word): see nompk_peers_t. */
+int nompk_allreduce_scalar_peers(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
+                                 unsigned long long host_seq, const nompk_peers_t *peers, void *stream);
 
 /* Local Poisson operator on E hexahedral spectral elements with n = N+1 points per direction, fp64:
  *   w_e = D^T_r (g1 Dr u + g2 Ds u + g3 Dt u) + D^T_s (g2 Dr u + g4 Ds u + g5 Dt u)
@@ -161,8 +173,7 @@ int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, co
  * 80 algorithmic B/DOF instead of 24 (map) + 64 (Ax) and one launch less.  beta is the host value, or beta_dev[0] from
  * device memory when beta_dev != NULL (a scalar that a previous kernel left there).  p and r: double[E][n][n][n], 16-byte
  * aligned.  The lane that loads a pair of p for the operator is the one that updates it; nothing else reads p.
- * Not in the reference (it has no Ax); written after the last GPU run of round 1: verified on the host emulator
- * (bitwise against the stand-alone sequence), to be run and timed on the B200. */
+ * Not in the reference (it has no Ax). */
 int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double *r, double beta, const double *beta_dev,
                                 const double *g, const double *D, double *w, double *result, double *result_host_mapped,
                                 unsigned long long host_seq, void *workspace, const nompk_peers_t *peers, unsigned flags,

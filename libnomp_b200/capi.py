@@ -37,7 +37,7 @@ NOMP_CUDA_FAILURE = -512
 
 NOMPK_SYMBOLS = [
     "nompk_version", "nompk_last_error", "nompk_dtype_size", "nompk_map", "nompk_reduce_workspace_bytes", "nompk_reduce_workspace_layout",
-    "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_ax_f64", "nompk_ax_dot_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
+    "nompk_reduce", "nompk_allreduce_xchg_bytes", "nompk_allreduce_scalar", "nompk_allreduce_scalar_peers", "nompk_ax_f64", "nompk_ax_dot_f64", "nompk_ax_supported", "nompk_ax_set_variant", "nompk_launch_count",
     "nompk_reduce_peers", "nompk_ax_dot_peers_f64", "nompk_ax_xpay_dot_peers_f64",
     "nompk_gs_create", "nompk_gs_unique", "nompk_gs_match_peer", "nompk_gs_finalize_setup", "nompk_gs_recv_offsets",
     "nompk_gs_connect", "nompk_gs_apply", "nompk_gs_stats", "nompk_gs_destroy",
@@ -56,7 +56,8 @@ NOMP_SYMBOLS = [
 
 class NompkPeers(C.Structure):
     """nompk_peers_t of include/nompk.h."""
-    _fields_ = [("peer_xchg", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("seq", C.c_ulonglong)]
+    _fields_ = [("peer_xchg", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("seq", C.c_ulonglong),
+                ("seq_dev", C.c_void_p), ("error_host_mapped", C.c_void_p)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -98,6 +99,9 @@ def nompk() -> C.CDLL:
         lib.nompk_allreduce_scalar.restype = C.c_int
         lib.nompk_allreduce_scalar.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_int,
                                                C.c_int, C.c_ulonglong, C.c_void_p]
+        lib.nompk_allreduce_scalar_peers.restype = C.c_int
+        lib.nompk_allreduce_scalar_peers.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ulonglong, C.POINTER(NompkPeers),
+                                                     C.c_void_p]
         lib.nompk_ax_f64.restype = C.c_int
         lib.nompk_ax_f64.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
                                      C.c_void_p]

@@ -695,7 +695,7 @@ extern "C" int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const do
   dot.workspace = workspace;
   dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
   if (peers && peers->world > 1) {
-    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0) {
+    if (!dot.px.set(peers, kMaxFusedRanks)) {
       set_error("nompk_ax_dot_peers_f64: bad peer description (rank %d of %d; at most %d ranks)", peers->rank, peers->world,
                 kMaxFusedRanks);
       return NOMPK_EINVAL;
@@ -704,7 +704,6 @@ extern "C" int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const do
       set_error("nompk_ax_dot_peers_f64: every rank needs at least one element");
       return NOMPK_EINVAL;
     }
-    dot.px.peer_xchg = peers->peer_xchg, dot.px.rank = peers->rank, dot.px.world = peers->world, dot.px.seq = peers->seq;
   }
   if (E == 0) {  // identity, through the same publication protocol
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -733,13 +732,11 @@ extern "C" int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const dou
   dot.workspace = workspace;
   dot.result = result, dot.result_host = result_host_mapped, dot.host_seq = host_seq;
   if (peers && peers->world > 1) {
-    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0 ||
-        E == 0) {
+    if (E == 0 || !dot.px.set(peers, kMaxFusedRanks)) {
       set_error("nompk_ax_xpay_dot_peers_f64: bad peer description (rank %d of %d), or a rank without elements", peers->rank,
                 peers->world);
       return NOMPK_EINVAL;
     }
-    dot.px.peer_xchg = peers->peer_xchg, dot.px.rank = peers->rank, dot.px.world = peers->world, dot.px.seq = peers->seq;
   }
   if (E == 0)  // nothing to update; the dot product is the identity, through the same publication protocol
     return nompk_ax_dot_peers_f64(n, 0, p, g, D, w, result, result_host_mapped, host_seq, workspace, nullptr, flags, stream_);

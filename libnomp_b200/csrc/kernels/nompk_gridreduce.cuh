@@ -42,6 +42,15 @@ struct PeerExchange {
   void *const *peer_xchg = nullptr;
   int rank = 0, world = 1;
   unsigned long long seq = 0;
+  unsigned long long *seq_dev = nullptr;     // call number in device memory (then `seq` is unused): nompk.h, nompk_peers_t
+  unsigned long long *error_host = nullptr;  // mapped host word that receives the call number on a timeout
+
+  // host side: fill from the C-ABI description; false if it is malformed
+  template <typename P> bool set(const P *p, int max_ranks) {
+    if (p->world > max_ranks || p->rank < 0 || p->rank >= p->world || !p->peer_xchg || (p->seq == 0 && !p->seq_dev)) return false;
+    peer_xchg = p->peer_xchg, rank = p->rank, world = p->world, seq = p->seq, seq_dev = p->seq_dev, error_host = p->error_host_mapped;
+    return true;
+  }
 };
 
 constexpr int kMaxFusedRanks = 32;  // one lane of the finishing warp per rank
@@ -63,19 +72,27 @@ __device__ __forceinline__ void finish_result(T v, T *result, T *result_host, un
                                               const PeerExchange &px) {
   const int lane = threadIdx.x & 31;
   bool timed_out = false;
+  unsigned long long cseq = px.seq;
   if (px.world > 1) {
+    if (px.seq_dev) {  // the call number lives in device memory: this warp is its only user on the stream
+      if (lane == 0) {
+        cseq = *reinterpret_cast<volatile unsigned long long *>(px.seq_dev) + 1;
+        *reinterpret_cast<volatile unsigned long long *>(px.seq_dev) = cseq;
+      }
+      cseq = __shfl_sync(0xffffffffu, cseq, 0);
+    }
     v = __shfl_sync(0xffffffffu, v, 0);
-    const size_t slot = (size_t)(px.seq & 1ull) * (size_t)px.world;
+    const size_t slot = (size_t)(cseq & 1ull) * (size_t)px.world;
     T got = Op::identity();
     bool ok = true;
     if (lane < px.world) {
       char *dst = static_cast<char *>(px.peer_xchg[lane]) + (slot + (size_t)px.rank) * 16;
       *reinterpret_cast<volatile T *>(dst) = v;
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long *>(dst + 8) = px.seq;
+      *reinterpret_cast<volatile unsigned long long *>(dst + 8) = cseq;
       const char *src = static_cast<const char *>(px.peer_xchg[px.rank]) + (slot + (size_t)lane) * 16;
       const unsigned long long t0 = global_timer_ns();
-      while (*reinterpret_cast<const volatile unsigned long long *>(src + 8) != px.seq) {
+      while (*reinterpret_cast<const volatile unsigned long long *>(src + 8) != cseq) {
         if (global_timer_ns() - t0 > kPeerTimeoutNs) {  // a peer that never arrives must not hang the GPU
           ok = false;
           break;
@@ -91,11 +108,11 @@ __device__ __forceinline__ void finish_result(T v, T *result, T *result_host, un
   }
   if (lane == 0) {
     *result = v;
-    if (result_host) {
-      if (timed_out)
-        *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = px.seq;
-      publish_to_host(result_host, v, host_seq);
+    if (timed_out) {
+      if (px.error_host) *reinterpret_cast<volatile unsigned long long *>(px.error_host) = cseq;
+      else if (result_host) *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = cseq;
     }
+    if (result_host) publish_to_host(result_host, v, host_seq);
   }
 }
 

@@ -223,12 +223,22 @@ constexpr unsigned long long kAllreduceTimeoutNs = 20ull * 1000 * 1000 * 1000;  
 template <int OP, typename T>
 __global__ void __launch_bounds__(kMaxRanks)
 allreduce_scalar_kernel(T *__restrict__ value, T *__restrict__ result_host, unsigned long long host_seq,
-                        void *const *__restrict__ peer_xchg, int rank, int world, unsigned long long seq) {
+                        void *const *__restrict__ peer_xchg, int rank, int world, unsigned long long seq,
+                        unsigned long long *seq_dev, unsigned long long *error_host) {
   __shared__ T vals[kMaxRanks];
   __shared__ int timed_out;
+  __shared__ unsigned long long seq_shared;
   const int r = threadIdx.x;
-  if (r == 0) timed_out = 0;
+  if (r == 0) {
+    timed_out = 0;
+    if (seq_dev) {  // call number in device memory (nompk_peers_t): take the next one
+      seq = *reinterpret_cast<volatile unsigned long long *>(seq_dev) + 1;
+      *reinterpret_cast<volatile unsigned long long *>(seq_dev) = seq;
+    }
+    seq_shared = seq;
+  }
   __syncthreads();
+  seq = seq_shared;
   const size_t slot = (size_t)(seq & 1ull) * (size_t)world;
   if (r < world) {
     const T mine = *value;
@@ -256,24 +266,26 @@ allreduce_scalar_kernel(T *__restrict__ value, T *__restrict__ result_host, unsi
     T acc = vals[0];
     for (int i = 1; i < world; i++) acc = red_combine<OP, T>(acc, vals[i]);
     *value = acc;
-    if (result_host) {
-      if (timed_out)
-        *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = seq;
-      publish_to_host(result_host, acc, host_seq);
+    if (timed_out) {
+      if (error_host) *reinterpret_cast<volatile unsigned long long *>(error_host) = seq;
+      else if (result_host) *reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<char *>(result_host) + 16) = seq;
     }
+    if (result_host) publish_to_host(result_host, acc, host_seq);
   }
 }
 
 template <int OP, typename T>
 int launch_allreduce(void *value, void *result_host, unsigned long long host_seq, void *const *peer_xchg, int rank,
-                     int world, unsigned long long seq, cudaStream_t stream) {
+                     int world, unsigned long long seq, unsigned long long *seq_dev, unsigned long long *error_host,
+                     cudaStream_t stream) {
   allreduce_scalar_kernel<OP, T><<<1, kMaxRanks, 0, stream>>>(static_cast<T *>(value), static_cast<T *>(result_host),
-                                                             host_seq, peer_xchg, rank, world, seq);
+                                                             host_seq, peer_xchg, rank, world, seq, seq_dev, error_host);
   NOMPK_LAUNCH_CHECK("allreduce_scalar_kernel");
   return NOMPK_OK;
 }
 
-typedef int (*allreduce_fn)(void *, void *, unsigned long long, void *const *, int, int, unsigned long long, cudaStream_t);
+typedef int (*allreduce_fn)(void *, void *, unsigned long long, void *const *, int, int, unsigned long long,
+                            unsigned long long *, unsigned long long *, cudaStream_t);
 
 template <int OP> allreduce_fn pick_allreduce(nompk_dtype_t dt) {
   constexpr bool ring = (OP == NOMPK_RED_SUM || OP == NOMPK_RED_PROD);
@@ -300,9 +312,16 @@ extern "C" size_t nompk_allreduce_xchg_bytes(int world) { return (size_t)2 * (si
 extern "C" int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
                                       unsigned long long host_seq, void *const *peer_xchg, int rank, int world,
                                       unsigned long long seq, void *stream) {
+  const nompk_peers_t peers = {peer_xchg, rank, world, seq, nullptr, nullptr};
+  return nompk_allreduce_scalar_peers(op, dt, value, result_host_mapped, host_seq, &peers, stream);
+}
+
+extern "C" int nompk_allreduce_scalar_peers(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
+                                            unsigned long long host_seq, const nompk_peers_t *peers, void *stream) {
   using namespace nompk;
-  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !value || !peer_xchg || seq == 0) {
-    set_error("nompk_allreduce_scalar: bad arguments (world %d, rank %d)", world, rank);
+  PeerExchange px;
+  if (!value || !peers || peers->world < 1 || !px.set(peers, kMaxRanks)) {
+    set_error("nompk_allreduce_scalar: bad arguments (world %d, rank %d)", peers ? peers->world : 0, peers ? peers->rank : 0);
     return NOMPK_EINVAL;
   }
   allreduce_fn fn = nullptr;
@@ -317,7 +336,8 @@ extern "C" int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void 
     set_error("nompk_allreduce_scalar: unsupported op %d / dtype %d", (int)op, (int)dt);
     return NOMPK_EINVAL;
   }
-  return fn(value, result_host_mapped, host_seq, peer_xchg, rank, world, seq, static_cast<cudaStream_t>(stream));
+  return fn(value, result_host_mapped, host_seq, px.peer_xchg, px.rank, px.world, px.seq, px.seq_dev, px.error_host,
+            static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t nompk_reduce_workspace_bytes(void) { return nompk::kWsBytes; }
@@ -338,12 +358,11 @@ extern "C" int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n,
   using namespace nompk;
   PeerExchange px;
   if (peers && peers->world > 1) {
-    if (peers->world > kMaxFusedRanks || peers->rank < 0 || peers->rank >= peers->world || !peers->peer_xchg || peers->seq == 0) {
+    if (!px.set(peers, kMaxFusedRanks)) {
       set_error("nompk_reduce_peers: bad peer description (rank %d of %d; at most %d ranks)", peers->rank, peers->world,
                 kMaxFusedRanks);
       return NOMPK_EINVAL;
     }
-    px.peer_xchg = peers->peer_xchg, px.rank = peers->rank, px.world = peers->world, px.seq = peers->seq;
   }
   reduce_fn fn = nullptr;
   switch (op) {

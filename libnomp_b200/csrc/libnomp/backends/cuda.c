@@ -97,12 +97,13 @@ typedef struct {
   struct cudaDeviceProp prop;
   cudaStream_t stream;
   cudaStream_t stream_h2d, stream_d2h; /* copy streams of nomp_b200_update_async (created on first use) */
-  cudaEvent_t ev_compute, ev_h2d;
+  cudaEvent_t ev_compute, ev_h2d, ev_d2h;
+  unsigned long long d2h_issued, d2h_waited; /* asynchronous D2H copies issued / already ordered before the compute stream */
   int async_used;
   int fused_allreduce; /* the reduction kernel just launched all-reduces its result itself */
   void *nv_peers;      /* peer description handed to a generated reduction kernel (by address, cuLaunchKernel) */
   int nv_rank, nv_world;
-  unsigned long long nv_cseq;
+  void *nv_cseq_dev, *nv_err_host;
   void *pinned_host;   /* 64 bytes of mapped pinned memory: [0,8) reduction result, [8,16) its sequence number */
   unsigned long long host_seq; /* sequence number of the last reduction issued */
   void *pinned_dev;    /* its device alias */
@@ -132,7 +133,8 @@ typedef enum { FAM_NVRTC = 0, FAM_MAP, FAM_REDUCE, FAM_AX, FAM_AXDOT, FAM_AXXPAY
 #define SLOT_PEERS (-7)  /* fused all-reduce of a generated reduction: exchange-buffer table, rank, world, call number */
 #define SLOT_RANK (-8)
 #define SLOT_WORLD (-9)
-#define SLOT_CSEQ (-10)
+#define SLOT_CSEQ (-10) /* the collective call counter in device memory */
+#define SLOT_ERR (-11)  /* error word in mapped host memory */
 
 typedef struct {
   family_t family;
@@ -140,7 +142,7 @@ typedef struct {
   CUmodule module;
   CUfunction function;
   int nparams;
-  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 9]; /* index into prg->args, or SLOT_* */
+  int param_slot[NOMP_MAX_KERNEL_ARGS_SIZE + 10]; /* index into prg->args, or SLOT_* */
   int has_peers;                                  /* the kernel takes the peer description (SLOT_PEERS ...) */
   int is_reduce;
   /* native */
@@ -186,6 +188,16 @@ static int capture_forbids(const char *what) {
   return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "%s is not allowed while a graph is being captured.", what);
 }
 
+int nomp_cuda_before_write(nomp_mem_t *m) {
+  cuda_state_t *st = g_state;
+  if (st == NULL || m == NULL || m->d2h_ticket <= st->d2h_waited) return 0;
+  /* ev_d2h was recorded behind the LAST asynchronous D2H copy; the copy stream is in order, so waiting for it covers
+   * every earlier copy as well */
+  check_runtime(cudaStreamWaitEvent(st->stream, st->ev_d2h, 0));
+  st->d2h_waited = st->d2h_issued;
+  return 0;
+}
+
 static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direction_t op, size_t start, size_t end,
                        size_t usize) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
@@ -204,12 +216,13 @@ static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direct
     }
   }
   if (op & NOMP_TO) {
+    nomp_check(nomp_cuda_before_write(m));
     /* blocking on purpose: the caller may overwrite the host range as soon as nomp_update returns */
     check_runtime(cudaMemcpyAsync((char *)m->bptr + NOMP_MEM_OFFSET(start - m->idx0, usize),
                                   (const char *)m->hptr + NOMP_MEM_OFFSET(start, usize),
                                   NOMP_MEM_BYTES(start, end, usize), cudaMemcpyHostToDevice, st->stream));
     check_runtime(cudaStreamSynchronize(st->stream));
-    m->version++;
+    m->version = nomp_next_version();
   }
   if (op == NOMP_FROM) {
     check_runtime(cudaMemcpyAsync((char *)m->hptr + NOMP_MEM_OFFSET(start, usize),
@@ -218,6 +231,12 @@ static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direct
     check_runtime(cudaStreamSynchronize(st->stream));
   } else if (op == NOMP_FREE) {
     check_runtime(cudaStreamSynchronize(st->stream));
+    if (st->async_used) { /* asynchronous copies may still be using the device image and the page-locked host range */
+      check_runtime(cudaStreamSynchronize(st->stream_h2d));
+      check_runtime(cudaStreamSynchronize(st->stream_d2h));
+    }
+    if (st->ax_D && (const char *)st->ax_D >= (const char *)m->bptr && (const char *)st->ax_D < (const char *)m->bptr + (m->bsize ? m->bsize : 1))
+      st->ax_D = NULL; /* the staged derivative matrix came from this mapping */
     unpin_host_range(m);
     check_runtime(cudaFree(m->bptr));
     m->bptr = NULL; /* tells the core to drop the entry (reference src/nomp.c:360) */
@@ -307,14 +326,15 @@ static int build_nvrtc(cuda_state_t *st, cuda_prog_t *cp, nomp_prog_t *prg, cons
     else if (!strcmp(tok, "nomp_peers")) slot = SLOT_PEERS, cp->has_peers = 1;
     else if (!strcmp(tok, "nomp_rank")) slot = SLOT_RANK;
     else if (!strcmp(tok, "nomp_world")) slot = SLOT_WORLD;
-    else if (!strcmp(tok, "nomp_cseq")) slot = SLOT_CSEQ;
+    else if (!strcmp(tok, "nomp_cseq_dev")) slot = SLOT_CSEQ;
+    else if (!strcmp(tok, "nomp_err_host")) slot = SLOT_ERR;
     else {
       slot = arg_index(prg, tok);
       if (slot == SLOT_NONE)
         return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
                         "Kernel argument \"%s\" was not declared in nomp_jit().", tok);
     }
-    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 9)
+    if (cp->nparams >= NOMP_MAX_KERNEL_ARGS_SIZE + 10)
       return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Too many kernel arguments.");
     cp->param_slot[cp->nparams++] = slot;
   }
@@ -459,13 +479,15 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   /* nomp_b200_device_reductions: the result goes to the device copy of the (mapped) reduction variable instead of the
    * backend's slot; the kernels are the same, only the address differs */
   st->red_result_arg = prg->reduction_dev ? prg->reduction_dev : st->red_result;
-  if (st->capturing && cp->is_reduce) {
-    /* a captured reduction cannot hand its result to the host (nomp_run would have to wait for a stream that is only
-     * recording), and the collective call number of the fused all-reduce would be frozen into the graph */
-    if (!prg->reduction_dev)
-      return capture_forbids("A reduce clause whose variable is not device-resident (nomp_b200_device_reductions)");
-    if (nomp_comm_size() > 1) return capture_forbids("A reduce clause on more than one rank");
-  }
+  /* a captured reduction cannot hand its result to the host: nomp_run would have to wait for a stream that is only
+   * recording.  (Several ranks are fine: the number of the collective call is a counter in device memory.) */
+  if (st->capturing && cp->is_reduce && !prg->reduction_dev)
+    return capture_forbids("A reduce clause whose variable is not device-resident (nomp_b200_device_reductions)");
+  if (prg->reduction_dev) result_host = NULL; /* nobody waits for this result: no store across PCIe in the kernel's tail */
+  void *const err_host = (char *)st->pinned_dev + 16;
+  /* a kernel that writes a mapping must not overtake an asynchronous copy that is still reading it */
+  for (unsigned i = 0; i < prg->nargs; i++)
+    if (prg->args[i].mem && !prg->args[i].is_const) nomp_check(nomp_cuda_before_write((nomp_mem_t *)prg->args[i].mem));
 
   switch (cp->family) {
   case FAM_MAP: {
@@ -479,7 +501,10 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   case FAM_REDUCE: {
     long n = int_arg(prg, cp->a_n, cp->n_literal);
     if (n < 0) n = 0;
-    if (nomp_comm_size() > 1 && nomp_comm_peers(&peers)) px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
+    if (nomp_comm_size() > 1 && nomp_comm_peers(&peers, err_host)) {
+      px = &peers, st->fused_allreduce = 1;
+      if (!prg->reduction_dev) result_host = st->pinned_dev;
+    }
     check_nompk(nompk_reduce_peers((nompk_red_op_t)cp->op, (nompk_dtype_t)cp->dtype, (size_t)n, ptr_arg(prg, cp->a_x),
                                    ptr_arg(prg, cp->a_y), st->red_result_arg, result_host, ++st->host_seq, st->red_ws, px,
                                    st->stream));
@@ -500,8 +525,10 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     if (dm && !st->capturing && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
     /* a rank without elements launches nothing: it joins through the stand-alone all-reduce kernel of the finish,
      * which speaks the same protocol on the same buffers */
-    if (cp->family != FAM_AX && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers))
-      px = &peers, st->fused_allreduce = 1, result_host = st->pinned_dev;
+    if (cp->family != FAM_AX && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers, err_host)) {
+      px = &peers, st->fused_allreduce = 1;
+      if (!prg->reduction_dev) result_host = st->pinned_dev;
+    }
     if (cp->family == FAM_AXXPAYDOT) {
       /* p <- r + beta p in front of the operator; beta is the caller's host scalar or a scalar in device memory */
       const double beta = cp->beta_dev ? 0.0 : *(const double *)prg->args[cp->a_beta].ptr;
@@ -526,14 +553,16 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     return 0;
   }
   case FAM_NVRTC: {
-    st->nv_peers = NULL, st->nv_rank = 0, st->nv_world = 1, st->nv_cseq = 0;
-    if (cp->is_reduce && cp->has_peers && nomp_comm_size() > 1 && nomp_comm_peers(&peers)) {
-      st->nv_peers = (void *)peers.peer_xchg, st->nv_rank = peers.rank, st->nv_world = peers.world, st->nv_cseq = peers.seq;
-      st->fused_allreduce = 1, result_host = st->pinned_dev;
+    st->nv_peers = NULL, st->nv_rank = 0, st->nv_world = 1, st->nv_cseq_dev = NULL, st->nv_err_host = err_host;
+    if (cp->is_reduce && cp->has_peers && nomp_comm_size() > 1 && nomp_comm_peers(&peers, err_host)) {
+      st->nv_peers = (void *)peers.peer_xchg, st->nv_rank = peers.rank, st->nv_world = peers.world;
+      st->nv_cseq_dev = peers.seq_dev;
+      st->fused_allreduce = 1;
+      if (!prg->reduction_dev) result_host = st->pinned_dev;
     }
     st->red_result_host = result_host;
     if (cp->is_reduce) ++st->host_seq;
-    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 9];
+    void *vargs[NOMP_MAX_KERNEL_ARGS_SIZE + 10];
     for (int i = 0; i < cp->nparams; i++) {
       int s = cp->param_slot[i];
       if (s == SLOT_WS) vargs[i] = &st->red_ws;
@@ -543,7 +572,8 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
       else if (s == SLOT_PEERS) vargs[i] = &st->nv_peers;
       else if (s == SLOT_RANK) vargs[i] = &st->nv_rank;
       else if (s == SLOT_WORLD) vargs[i] = &st->nv_world;
-      else if (s == SLOT_CSEQ) vargs[i] = &st->nv_cseq;
+      else if (s == SLOT_CSEQ) vargs[i] = &st->nv_cseq_dev;
+      else if (s == SLOT_ERR) vargs[i] = &st->nv_err_host;
       else if (prg->args[s].type == NOMP_PTR) vargs[i] = &prg->args[s].ptr; /* device pointer by value */
       else vargs[i] = prg->args[s].ptr;                                       /* the caller's scalar */
     }
@@ -567,7 +597,7 @@ int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg, int dtype,
      * so itself, and return without waiting -- the next kernel on the stream reads it from device memory */
     int published = 0;
     if (nomp_comm_size() > 1 && !st->fused_allreduce)
-      nomp_check(nomp_comm_allreduce(prg->reduction_dev, dtype, (int)prg->reduction_op, st->pinned_dev, st->host_seq,
+      nomp_check(nomp_comm_allreduce(prg->reduction_dev, dtype, (int)prg->reduction_op, NULL, 0, (char *)st->pinned_dev + 16,
                                      st->stream, &published));
     return 0;
   }
@@ -576,7 +606,7 @@ int nomp_cuda_reduction_finish(nomp_backend_t *bnd, nomp_prog_t *prg, int dtype,
      * the NCCL fallback needs an explicit 8-byte copy */
     int published = 0;
     nomp_check(nomp_comm_allreduce(st->red_result, dtype, (int)prg->reduction_op, st->pinned_dev, st->host_seq,
-                                   st->stream, &published));
+                                   (char *)st->pinned_dev + 16, st->stream, &published));
     if (!published) {
       check_runtime(cudaMemcpyAsync(st->pinned_host, st->red_result, 8, cudaMemcpyDeviceToHost, st->stream));
       check_runtime(cudaStreamSynchronize(st->stream));
@@ -628,6 +658,14 @@ static int cuda_sync(nomp_backend_t *bnd) {
     check_runtime(cudaStreamSynchronize(st->stream_h2d));
     check_runtime(cudaStreamSynchronize(st->stream_d2h));
   }
+  /* a fused all-reduce whose result stays on the device has nobody waiting for it: a rank that never joined is
+   * reported here */
+  volatile unsigned long long *late = (volatile unsigned long long *)((char *)st->pinned_host + 16);
+  if (*late != 0) {
+    *late = 0;
+    return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, ERR_STR_CUDA_FAILURE, "all-reduce",
+                    "a rank did not join the reduction within 20 s");
+  }
   return 0;
 }
 
@@ -645,6 +683,7 @@ int nomp_cuda_update_async(nomp_backend_t *bnd, nomp_mem_t *m, nomp_map_directio
     check_runtime(cudaStreamCreateWithFlags(&st->stream_d2h, cudaStreamNonBlocking));
     check_runtime(cudaEventCreateWithFlags(&st->ev_compute, cudaEventDisableTiming));
     check_runtime(cudaEventCreateWithFlags(&st->ev_h2d, cudaEventDisableTiming));
+    check_runtime(cudaEventCreateWithFlags(&st->ev_d2h, cudaEventDisableTiming));
   }
   st->async_used = 1;
   if (m->transfers++ == 1) pin_host_range(m);
@@ -658,9 +697,13 @@ int nomp_cuda_update_async(nomp_backend_t *bnd, nomp_mem_t *m, nomp_map_directio
     check_runtime(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, cs));
     check_runtime(cudaEventRecord(st->ev_h2d, cs));
     check_runtime(cudaStreamWaitEvent(st->stream, st->ev_h2d, 0));
-    m->version++;
+    m->version = nomp_next_version();
   } else {
+    /* later work on the compute stream that WRITES this mapping waits for the copy (nomp_cuda_before_write); work that
+     * only reads it, or touches other mappings, overlaps with it */
     check_runtime(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, cs));
+    check_runtime(cudaEventRecord(st->ev_d2h, cs));
+    m->d2h_ticket = ++st->d2h_issued;
   }
   return 0;
 }
@@ -678,7 +721,7 @@ static int cuda_finalize(nomp_backend_t *bnd) {
   if (st->stream_h2d) {
     cudaStreamSynchronize(st->stream_h2d), cudaStreamSynchronize(st->stream_d2h);
     cudaStreamDestroy(st->stream_h2d), cudaStreamDestroy(st->stream_d2h);
-    cudaEventDestroy(st->ev_compute), cudaEventDestroy(st->ev_h2d);
+    cudaEventDestroy(st->ev_compute), cudaEventDestroy(st->ev_h2d), cudaEventDestroy(st->ev_d2h);
   }
   if (st->pinned_host) cudaFreeHost(st->pinned_host);
   if (g_state == st) g_state = NULL;
@@ -761,6 +804,11 @@ NOMP_EXPORT int nomp_b200_graph_begin(void) {
   if (!st) return nomp_log(NOMP_INITIALIZE_FAILURE, NOMP_ERROR, "libnomp is not initialized.");
   if (st->capturing) return capture_forbids("nomp_b200_graph_begin");
   check_runtime(cudaStreamSynchronize(st->stream));
+  if (st->async_used) { /* nothing recorded in the graph may depend on work outside it */
+    check_runtime(cudaStreamSynchronize(st->stream_h2d));
+    check_runtime(cudaStreamSynchronize(st->stream_d2h));
+    st->d2h_waited = st->d2h_issued;
+  }
   check_runtime(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeRelaxed));
   st->capturing = 1;
   return 0;
@@ -791,6 +839,7 @@ NOMP_EXPORT int nomp_b200_graph_launch(int graph) {
   if (!st || graph < 0 || graph >= NOMP_MAX_GRAPHS || !st->graphs[graph] || st->capturing)
     return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR, "Graph id %d passed to nomp_b200_graph_launch is not valid.", graph);
   check_runtime(cudaGraphLaunch(st->graphs[graph], st->stream));
+  st->ax_D = NULL; /* a captured Ax launch re-stages ITS derivative matrix: the cached one is no longer what is staged */
   return 0;
 }
 

@@ -75,7 +75,9 @@ typedef struct {
   void *hptr;
   void *bptr;
   size_t bsize;
-  unsigned long version; /* bumped whenever the device image may have changed */
+  unsigned long version; /* changes whenever the device image may have changed; values come from one process-wide
+                            counter, so a new mapping at a recycled device address never repeats an old one */
+  unsigned long long d2h_ticket; /* number of the last asynchronous device-to-host copy out of this mapping */
   unsigned transfers;    /* host <-> device copies of this mapping so far */
   int host_registered;   /* the backend page-locked the host range (cudaHostRegister) and must release it */
 } nomp_mem_t;
@@ -113,6 +115,10 @@ int nomp_cuda_reduction_finish(nomp_backend_t *backend, nomp_prog_t *prg, int dt
 int nomp_cuda_update_async(nomp_backend_t *backend, nomp_mem_t *m, nomp_map_direction_t op, size_t start, size_t end,
                            size_t usize);
 
+/* Orders the compute stream behind an asynchronous device-to-host copy that may still be reading `m`; called before
+ * anything that writes the mapping (kernels with a non-const pointer to it, nomp_update(TO), the gather-scatter). */
+int nomp_cuda_before_write(nomp_mem_t *m);
+
 /* core helpers used by the backend */
 nomp_mem_t *nomp_lookup_mem(const void *hptr);
 
@@ -127,8 +133,9 @@ int nomp_comm_size(void);
 /* in-place allreduce of one scalar on `stream`; dtype codes of include/nompk.h, op = nomp_reduction_op_t.
  * *published = 1 if {value, host_seq} was also written to result_host_mapped (NVLink one-shot path). */
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
-                        void *stream, int *published);
-int nomp_comm_peers(void *peers /* nompk_peers_t * */);
+                        void *error_host_mapped, void *stream, int *published);
+int nomp_comm_peers(void *peers /* nompk_peers_t * */, void *error_host_mapped);
+unsigned long nomp_next_version(void);
 int nomp_b200_exchange_blob(const char *path, int rank, void *blob, size_t bytes);
 /* all[r] <- rank r's `bytes`-byte record, through files "<id file>.<tag>.<r>" (small setup-time records only) */
 int nomp_comm_allgather(const char *tag, const void *mine, void *all, size_t bytes);

@@ -44,7 +44,8 @@ static struct {
   void *mine;          /* this rank's exchange buffer (cudaMalloc) */
   void *peers[64];     /* every rank's buffer as mapped into this process */
   void **table_dev;    /* device copy of peers[] */
-  unsigned long long seq;
+  unsigned long long *seq_dev; /* number of the last collective call, in DEVICE memory: the kernels count (nompk.h,
+                                  nompk_peers_t), so a captured launch can be replayed and ranks need no host agreement */
 } p2p;
 
 #define check_nccl(call)                                                                                         \
@@ -145,6 +146,12 @@ int nomp_comm_init(int device) {
     flag = 0;
   }
   p2p.enabled = flag;
+  /* every rank has read what it needed (the all-reduce above is also a barrier): remove the rendezvous files so that a
+   * later job, or a re-init in this process, that reuses the path cannot pick up a stale id or stale IPC handles */
+  char name[PATH_MAX + 64];
+  snprintf(name, sizeof(name), "%s.ipc.%d", path, rank);
+  unlink(name);
+  if (rank == 0) unlink(path);
   nomp_info("multi-GPU reductions use %s", p2p.enabled ? "the NVLink one-shot all-reduce kernel" : "ncclAllReduce");
   return 0;
 }
@@ -178,12 +185,15 @@ static void p2p_setup(const char *path, int rank, int size) {
     else if (cudaIpcOpenMemHandle(&p2p.peers[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
   }
   if (ok && cudaMalloc((void **)&p2p.table_dev, sizeof(void *) * (size_t)size) == cudaSuccess &&
-      cudaMemcpy(p2p.table_dev, p2p.peers, sizeof(void *) * (size_t)size, cudaMemcpyHostToDevice) == cudaSuccess)
+      cudaMemcpy(p2p.table_dev, p2p.peers, sizeof(void *) * (size_t)size, cudaMemcpyHostToDevice) == cudaSuccess &&
+      cudaMalloc((void **)&p2p.seq_dev, sizeof(unsigned long long)) == cudaSuccess &&
+      cudaMemset(p2p.seq_dev, 0, sizeof(unsigned long long)) == cudaSuccess)
     p2p.enabled = 1;
+  cudaDeviceSynchronize();
   cudaGetLastError(); /* clear sticky-free errors of the probing above */
-  snprintf(name, sizeof(name), "%s.ipc.%d", path, rank);
-  /* every rank must agree: all-reduce the flag through NCCL-free means is overkill -- a rank that failed simply keeps
-   * enabled = 0 and the others would wait for it forever, so agreement is checked with one NCCL allreduce below */
+  /* every rank must agree: a rank that failed keeps enabled = 0 and the others would wait for it forever, so
+   * nomp_comm_init() takes the minimum over the ranks with one NCCL all-reduce (which is also the barrier after which
+   * the rendezvous files are removed) */
 }
 
 /* Every rank publishes its record as "<id file>.<tag>.<rank>" and reads everybody else's.  The files are removed by
@@ -233,6 +243,7 @@ int nomp_comm_finalize(void) {
       if (r != comm_rank && p2p.peers[r]) cudaIpcCloseMemHandle(p2p.peers[r]);
     cudaFree(p2p.mine);
     if (p2p.table_dev) cudaFree(p2p.table_dev);
+    if (p2p.seq_dev) cudaFree(p2p.seq_dev);
     memset(&p2p, 0, sizeof(p2p));
   }
   if (comm) {
@@ -245,10 +256,11 @@ int nomp_comm_finalize(void) {
 
 NOMP_EXPORT int nomp_b200_comm_uses_nvlink_kernel(void) { return p2p.enabled; }
 
-/* Peer description for a reduction kernel that all-reduces its own result (nompk_reduce_peers, nompk_ax_dot_peers_f64):
- * takes the next collective sequence number.  Returns 0 when the kernels cannot do it (one rank, no peer access, more
- * ranks than a warp has lanes, or NOMP_COMM_FUSED=0) and the caller must use nomp_comm_allreduce after the kernel. */
-int nomp_comm_peers(void *peers_) {
+/* Peer description for a reduction kernel that all-reduces its own result (nompk_reduce_peers, nompk_ax_dot_peers_f64).
+ * The number of the collective call is a counter in device memory that the kernels advance themselves.  Returns 0 when
+ * the kernels cannot do it (one rank, no peer access, more ranks than a warp has lanes, or NOMP_COMM_FUSED=0) and the
+ * caller must use nomp_comm_allreduce after the kernel. */
+int nomp_comm_peers(void *peers_, void *error_host_mapped) {
   nompk_peers_t *peers = (nompk_peers_t *)peers_;
   static int fused = -1;
   if (fused < 0) {
@@ -258,17 +270,20 @@ int nomp_comm_peers(void *peers_) {
   if (comm_size == 1 || !p2p.enabled || !fused || comm_size > 32) return 0;
   peers->peer_xchg = (void *const *)p2p.table_dev;
   peers->rank = comm_rank, peers->world = comm_size;
-  peers->seq = ++p2p.seq;
+  peers->seq = 0, peers->seq_dev = p2p.seq_dev;
+  peers->error_host_mapped = (unsigned long long *)error_host_mapped;
   return 1;
 }
 
 int nomp_comm_allreduce(void *dev_scalar, int dtype, int op, void *result_host_mapped, unsigned long long host_seq,
-                        void *stream, int *published) {
+                        void *error_host_mapped, void *stream, int *published) {
   *published = 0;
   if (comm_size == 1) return 0;
   if (p2p.enabled) {
-    int rc = nompk_allreduce_scalar((nompk_red_op_t)op, (nompk_dtype_t)dtype, dev_scalar, result_host_mapped, host_seq,
-                                    (void *const *)p2p.table_dev, comm_rank, comm_size, ++p2p.seq, stream);
+    const nompk_peers_t peers = {(void *const *)p2p.table_dev, comm_rank, comm_size, 0, p2p.seq_dev,
+                                 (unsigned long long *)error_host_mapped};
+    int rc = nompk_allreduce_scalar_peers((nompk_red_op_t)op, (nompk_dtype_t)dtype, dev_scalar, result_host_mapped, host_seq,
+                                          &peers, stream);
     if (rc != NOMPK_OK)
       return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "CUDA kernel library failure: %s.", nompk_last_error());
     *published = 1;

@@ -206,9 +206,10 @@ NOMP_EXPORT int nomp_b200_gs(int handle, void *ptr, size_t unit_size, int type, 
   if (dtype < 0 || rop < 0)
     return nomp_log(NOMP_USER_INPUT_IS_INVALID, NOMP_ERROR,
                     "Gather-scatter needs a 4- or 8-byte NOMP_INT / NOMP_UINT / NOMP_FLOAT and one of \"+\", \"*\", \"min\", \"max\".");
+  nomp_check(nomp_cuda_before_write(m)); /* an asynchronous copy out of v may still be reading it */
   if (nompk_gs_apply(h->gs, (nompk_red_op_t)rop, (nompk_dtype_t)dtype, m->bptr, h->err_dev, nomp_b200_stream()) != NOMPK_OK)
     return nomp_log(NOMP_CUDA_FAILURE, NOMP_ERROR, "CUDA kernel library failure: %s.", nompk_last_error());
-  m->version++;
+  m->version = nomp_next_version();
   return 0;
 }
 

@@ -193,6 +193,13 @@ static void table_remove(mem_node_t *node) {
   n_mems--;
 }
 
+/* Versions of device images come from one counter that never restarts: a mapping created after NOMP_FREE at the same
+ * host and device addresses cannot repeat a (pointer, version) pair that a cache (the staged D of the Ax family) holds. */
+unsigned long nomp_next_version(void) {
+  static unsigned long counter = 0;
+  return ++counter;
+}
+
 NOMP_EXPORT int nomp_update(void *ptr, size_t idx0, size_t idx1, size_t unit_size, nomp_map_direction_t op) {
   if (!initialized) return nomp_log(NOMP_INITIALIZE_FAILURE, NOMP_ERROR, "libnomp is not initialized.");
   mem_node_t *node = lookup_range(ptr, idx0, idx1, unit_size);
@@ -205,7 +212,7 @@ NOMP_EXPORT int nomp_update(void *ptr, size_t idx0, size_t idx1, size_t unit_siz
     op |= NOMP_ALLOC; /* NOMP_TO on a new range implies allocation */
     node = nomp_calloc(mem_node_t, 1);
     node->m.idx0 = idx0, node->m.idx1 = idx1, node->m.usize = unit_size, node->m.hptr = ptr;
-    node->m.version = 1;
+    node->m.version = nomp_next_version();
     created = 1;
   }
 
@@ -586,7 +593,7 @@ NOMP_EXPORT int nomp_run(int id, ...) {
   }
   nomp_check(nomp.knl_run(&nomp, prg));
   for (unsigned i = 0; i < prg->nargs; i++) {
-    if (args[i].mem && !args[i].is_const) ((nomp_mem_t *)args[i].mem)->version++;
+    if (args[i].mem && !args[i].is_const) ((nomp_mem_t *)args[i].mem)->version = nomp_next_version();
   }
   if (prg->reduction_index >= 0) nomp_check(nomp_device_side_reduction(&nomp, prg));
   return 0;

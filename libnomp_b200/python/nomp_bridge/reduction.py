@@ -42,9 +42,13 @@ def _dtype_code(t):
 
 
 class ReductionInfo:
+    """`pre` / `post`: the top-level statements of the loop body in front of / behind the accumulation, in source order
+    (the reference keeps program order: seq_dependencies=True, reference python/loopy_api.py:817)."""
+
     def __init__(self, loop: c.For, var: str, vtype: c.CType, op: str, rhs: c.Node, preds: List[c.Node],
-                 pre: List[c.Node]):
+                 pre: List[c.Node], post: Optional[List[c.Node]] = None):
         self.loop, self.var, self.vtype, self.op, self.rhs, self.preds, self.pre = loop, var, vtype, op, rhs, preds, pre
+        self.post = post or []
 
 
 def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
@@ -67,6 +71,7 @@ def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
 
     found: List[Tuple[c.Assign, List[c.Node]]] = []
     pre: List[c.Node] = []
+    post: List[c.Node] = []
 
     def scan(nodes, preds, top):
         for n in nodes:
@@ -76,7 +81,7 @@ def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
                 scan(n.then, preds + [n.cond], False)
                 scan(n.other, preds + [c.UnOp("!", n.cond)], False)
             elif top:
-                pre.append(n)
+                (post if found else pre).append(n)     # a statement behind the accumulation stays behind it
             else:
                 raise KernelError("reduce: only the accumulation may appear under a condition")
 
@@ -106,18 +111,30 @@ def analyse_reduction(func: c.Function, var: str, op: str) -> ReductionInfo:
     # iteration i is then owned by exactly one thread and fusing the update with the reduction is safe
     # (e.g. the CG update  x[i] += a*p[i]; r[i] -= a*w[i]; rr[0] += r[i]*r[i];).
     arrays = {k for k, p in params.items() if p.is_array}
-    for n in walk(pre):
+    for n in walk(pre + post):
         if isinstance(n, c.Assign):
             if isinstance(n.target, c.Name) and n.target.id in params:
                 raise KernelError("reduce: a reduction kernel may not assign to its scalar arguments")
             if isinstance(n.target, c.Subscript) and isinstance(n.target.base, c.Name) and n.target.base.id in arrays:
                 if _is_elem(n.target, {k: params[k] for k in arrays}, loop.var) is None:
                     raise KernelError("reduce: other arguments may only be written elementwise (a[i]) in a reduction kernel")
-    return ReductionInfo(loop, var, vtype, op, rhs, preds, pre)
+    if any(var in expr_names(e) for n in walk(pre + post) for e in _stmt_exprs(n)):
+        raise KernelError(f"reduce: {var} may only appear in its own update")
+    return ReductionInfo(loop, var, vtype, op, rhs, preds, pre, post)
+
+
+def _stmt_exprs(n: c.Node) -> List[c.Node]:
+    if isinstance(n, c.Assign):
+        return [n.target, n.value]
+    if isinstance(n, c.Decl):
+        return [n.init] if n.init is not None else []
+    if isinstance(n, c.If):
+        return [n.cond]
+    return []
 
 
 def match_native_reduce(func: c.Function, info: ReductionInfo) -> Optional[Dict[str, str]]:
-    if info.preds or info.pre:
+    if info.preds or info.pre or info.post:
         return None
     params = _params(func)
     count = _loop_count(info.loop, params)
@@ -173,7 +190,7 @@ def _elementwise_arrays(func: c.Function, info: "ReductionInfo"):
     from .ir import map_expr
     params = _params(func)
     arrays = {k: p for k, p in params.items() if p.is_array and k != info.var}
-    invariant = _fam().invariant_arrays(info.pre, list(info.preds) + [info.rhs], arrays)
+    invariant = _fam().invariant_arrays(info.pre + info.post, list(info.preds) + [info.rhs], arrays)
     arrays = {k: p for k, p in arrays.items() if k not in invariant}    # `alpha[0]`: a scalar in device memory
     used, written, ok = [], [], [True]
 
@@ -185,7 +202,7 @@ def _elementwise_arrays(func: c.Function, info: "ReductionInfo"):
                 used.append(e.base.id)
         return e
 
-    for n in walk(info.pre):
+    for n in walk(info.pre + info.post):
         if isinstance(n, c.Assign):
             map_expr(n.target, visit)
             map_expr(n.value, visit)
@@ -214,16 +231,16 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
     optional conditions and elementwise updates in front of the accumulation.  One tile of 256 threads per CTA (up to
     65536 CTAs, then the CTAs stride), 128-bit loads/stores when every array is elementwise and 16-byte aligned, and
     the two-level deterministic ticket finish of nompk_gridreduce.cuh.
-    Returns (source, grid exprs, block exprs, kernel parameter names); the trailing eight parameters (workspace,
+    Returns (source, grid exprs, block exprs, kernel parameter names); the trailing nine parameters (workspace,
     result, result_host, seq, and the peer description of the fused all-reduce: exchange-buffer table, rank, world,
-    collective call number) are supplied by the backend."""
+    the collective call counter in device memory, the error word in mapped host memory) are supplied by the backend."""
     from .emit_cuda import GenericEmitter
     from .ir import map_expr, map_stmts
     T = cuda_type(info.vtype)
     func = knl.func
     params = [p for p in func.params if p.name != info.var]
     written_any = set()
-    for node in walk(info.pre):
+    for node in walk(info.pre + info.post):
         if isinstance(node, c.Assign) and isinstance(node.target, c.Subscript) and isinstance(node.target.base, c.Name):
             written_any.add(node.target.base.id)
     sig_parts = []
@@ -235,7 +252,7 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
             sig_parts.append(f"{cuda_type(t)} {prm.name}")
     sig_parts += ["void *__restrict__ nomp_ws", f"{T} *__restrict__ nomp_result", f"{T} *__restrict__ nomp_result_host",
                   "unsigned long long nomp_seq", "void *const *__restrict__ nomp_peers", "int nomp_rank", "int nomp_world",
-                  "unsigned long long nomp_cseq"]
+                  "unsigned long long *nomp_cseq_dev", "unsigned long long *nomp_err_host"]
     int_params = {p.name for p in params if not p.is_array and not p.ctype.is_float}
     it = cuda_type(info.loop.vtype)
     lo, hi = expr_str(info.loop.lo), expr_str(info.loop.hi)
@@ -271,7 +288,10 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         acc = [f"{pad}{{ const {T} nomp_v = ({T})({expr_str(map_expr(info.rhs, scalarise))}); nomp_acc = {comb('nomp_acc', 'nomp_v')}; }}"]
         if cond:
             acc = [f"{pad}if ({cond})", "  " + acc[0]]
-        return "\n".join(ge.lines + acc)
+        front = ge.lines
+        ge.lines = []
+        ge.stmts(map_stmts(info.post, scalarise), depth, True, False)   # behind the accumulation, as written
+        return "\n".join(front + acc + ge.lines)
 
     shfl = f"nomp_o = __shfl_xor_sync(0xffffffffu, nomp_acc, nomp_s); nomp_acc = {comb('nomp_acc', 'nomp_o')};"
     tree = f"for (int nomp_s = 16; nomp_s > 0; nomp_s >>= 1) {{ {shfl} }}"
@@ -345,10 +365,16 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
 // for rank r's value in this rank's buffer, and the values are folded in rank order.
 __device__ __forceinline__ void nomp_finish({T} nomp_v, {T} *nomp_result, {T} *nomp_result_host, unsigned long long nomp_seq,
                                             void *const *nomp_peers, int nomp_rank, int nomp_world,
-                                            unsigned long long nomp_cseq) {{
+                                            unsigned long long *nomp_cseq_dev, unsigned long long *nomp_err_host) {{
   const int nomp_lane = threadIdx.x & 31;
   bool nomp_late = false;
+  unsigned long long nomp_cseq = 0;
   if (nomp_world > 1) {{
+    if (nomp_lane == 0) {{   // number of this collective call: a counter in device memory (nothing for a graph to freeze)
+      nomp_cseq = *(volatile unsigned long long *)nomp_cseq_dev + 1;
+      *(volatile unsigned long long *)nomp_cseq_dev = nomp_cseq;
+    }}
+    nomp_cseq = __shfl_sync(0xffffffffu, nomp_cseq, 0);
     nomp_v = __shfl_sync(0xffffffffu, nomp_v, 0);
     const size_t nomp_slot = (size_t)(nomp_cseq & 1ull) * (size_t)nomp_world;
     {T} nomp_got = {ident};
@@ -378,8 +404,8 @@ __device__ __forceinline__ void nomp_finish({T} nomp_v, {T} *nomp_result, {T} *n
   }}
   if (nomp_lane == 0) {{
     *nomp_result = nomp_v;
+    if (nomp_late && nomp_err_host) *(volatile unsigned long long *)nomp_err_host = nomp_cseq;
     if (nomp_result_host) {{
-      if (nomp_late) *(volatile unsigned long long *)((char *)nomp_result_host + 16) = nomp_cseq;
       *(volatile {T} *)nomp_result_host = nomp_v;
       __threadfence_system();
       *(volatile unsigned long long *)((char *)nomp_result_host + 8) = nomp_seq;
@@ -434,7 +460,7 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
       }}
     }}
     if (threadIdx.x == 0 && nomp_nb > 1) *nomp_ticket = 0u;
-    if (threadIdx.x < 32) nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq);
+    if (threadIdx.x < 32) nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq_dev, nomp_err_host);
     return;
   }}
   const unsigned int nomp_g = nomp_b / {RED_GROUP}, nomp_ng = (nomp_nb + {RED_GROUP - 1}) / {RED_GROUP};
@@ -472,7 +498,7 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     nomp_acc = threadIdx.x < 8 ? nomp_warp[threadIdx.x] : {ident};
     {tree}
     if (threadIdx.x == 0) *nomp_ticket = 0u;
-    nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq);
+    nomp_finish(nomp_acc, nomp_result, nomp_result_host, nomp_seq, nomp_peers, nomp_rank, nomp_world, nomp_cseq_dev, nomp_err_host);
   }}
 }}
 """
@@ -486,5 +512,5 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
     except KernelError:
         grid = str(max(1, sm_count) * 8)  # data-dependent bounds: a full grid, the loop guards itself
     names = [p.name for p in params] + ["nomp_ws", "nomp_result", "nomp_result_host", "nomp_seq", "nomp_peers", "nomp_rank",
-                                        "nomp_world", "nomp_cseq"]
+                                        "nomp_world", "nomp_cseq_dev", "nomp_err_host"]
     return src, [grid, "1", "1"], ["256", "1", "1"], names

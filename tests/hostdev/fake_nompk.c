@@ -104,6 +104,30 @@ EXPORT int nompk_allreduce_scalar(nompk_red_op_t op, nompk_dtype_t dt, void *val
   return finish_with_peers((int)op, (int)dt, &mine, value, result_host_mapped, host_seq, peer_xchg, rank, world, seq);
 }
 
+typedef struct {
+  int op, dt;
+  void *value, *result_host;
+  unsigned long long host_seq;
+  nompk_peers_t peers;
+} allreduce_call_t;
+
+static int run_allreduce(void *blob) {
+  allreduce_call_t *c = (allreduce_call_t *)blob;
+  unsigned long long mine = 0;
+  memcpy(&mine, c->value, 8);
+  return finish_with_peers(c->op, c->dt, &mine, c->value, c->result_host, c->host_seq, c->peers.peer_xchg, c->peers.rank,
+                           c->peers.world, c->peers.seq_dev ? ++*c->peers.seq_dev : c->peers.seq);
+}
+
+EXPORT int nompk_allreduce_scalar_peers(nompk_red_op_t op, nompk_dtype_t dt, void *value, void *result_host_mapped,
+                                        unsigned long long host_seq, const nompk_peers_t *peers, void *stream) {
+  (void)stream;
+  allreduce_call_t c = {(int)op, (int)dt, value, result_host_mapped, host_seq, *peers};
+  calls++;
+  if (nomp_hostdev_record(run_allreduce, &c, sizeof(c))) return NOMPK_OK; /* captured: runs at every replay */
+  return run_allreduce(&c);
+}
+
 static void publish(const void *value, void *result, void *result_host_mapped, unsigned long long host_seq) {
   memcpy(result, value, 8);
   if (result_host_mapped) {
@@ -143,9 +167,9 @@ static int run_reduce(void *blob) {
     int (*f)(int, int, size_t, const void *, const void *, void *) = oracle_sym("oracle_reduce");
     if (f(c->op, c->dt, c->n, c->x, c->y, &value)) return NOMPK_EINVAL;
   }
-  if (c->peers.world > 1)
+  if (c->peers.world > 1) /* the call number is taken when the launch EXECUTES (a replayed graph takes a new one) */
     return finish_with_peers(c->op, c->dt, &value, c->result, c->result_host, c->host_seq, c->peers.peer_xchg, c->peers.rank,
-                             c->peers.world, c->peers.seq);
+                             c->peers.world, c->peers.seq_dev ? ++*c->peers.seq_dev : c->peers.seq);
   publish(&value, c->result, c->result_host, c->host_seq);
   return NOMPK_OK;
 }
@@ -154,7 +178,7 @@ EXPORT int nompk_reduce_peers(nompk_red_op_t op, nompk_dtype_t dt, size_t n, con
                               void *result_host_mapped, unsigned long long host_seq, void *workspace,
                               const nompk_peers_t *peers, void *stream) {
   (void)workspace, (void)stream;
-  reduce_call_t c = {(int)op, (int)dt, 0, n, x, y, NULL, NULL, NULL, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, NULL, NULL, 0.0};
+  reduce_call_t c = {(int)op, (int)dt, 0, n, x, y, NULL, NULL, NULL, result, result_host_mapped, host_seq, {NULL, 0, 1, 0, NULL, NULL}, NULL, NULL, 0.0};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
   if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
@@ -187,7 +211,7 @@ EXPORT int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double
                                   double *result, double *result_host_mapped, unsigned long long host_seq,
                                   void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream) {
   (void)workspace, (void)flags, (void)stream;
-  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, NULL, NULL, 0.0};
+  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0, NULL, NULL}, NULL, NULL, 0.0};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
   if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;
@@ -199,7 +223,7 @@ EXPORT int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double 
                                        unsigned long long host_seq, void *workspace, const nompk_peers_t *peers, unsigned flags,
                                        void *stream) {
   (void)workspace, (void)flags, (void)stream;
-  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, p, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0}, r, beta_dev, beta};
+  reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, p, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0, NULL, NULL}, r, beta_dev, beta};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
   if (nomp_hostdev_record(run_reduce, &c, sizeof(c))) return NOMPK_OK;

@@ -35,7 +35,7 @@ def test_headers_and_libraries_agree():
     for sym in want_n:
         assert hasattr(n, sym), f"libnomp.so does not export {sym}"
     assert sorted(capi.NOMPK_SYMBOLS) == want_k
-    assert k.nompk_version() == 100 and k.nompk_reduce_workspace_bytes() >= 65536 * 8
+    assert k.nompk_version() == 200 and k.nompk_reduce_workspace_bytes() >= 65536 * 8
     assert [k.nompk_dtype_size(d) for d in range(6)] == [4, 4, 8, 8, 4, 8]
     assert [k.nompk_ax_supported(x) for x in (6, 7, 8, 9, 10, 12)] == [1, 0, 1, 0, 1, 1]
 

@@ -31,7 +31,7 @@ struct MaxL {
 // every thread sums a strided share, thread 0 folds the block through shared memory, then the grid-wide finish
 template <typename Op, typename T> static void finish_kernel(const T *x, unsigned long long n, void *ws, T *result, T *result_host,
                                                               unsigned long long seq, void *const *peers, int rank, int world,
-                                                              unsigned long long cseq) {
+                                                              unsigned long long cseq, unsigned long long *cseq_dev) {
   __shared__ T part[256];
   T v = Op::identity();
   for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
@@ -41,13 +41,13 @@ template <typename Op, typename T> static void finish_kernel(const T *x, unsigne
   if (threadIdx.x == 0)
     for (int i = 1; i < 256; i++) v = Op::combine(v, part[i]);
   nompk::PeerExchange px;
-  px.peer_xchg = peers, px.rank = rank, px.world = world, px.seq = cseq;
+  px.peer_xchg = peers, px.rank = rank, px.world = world, px.seq = cseq, px.seq_dev = cseq_dev;
   nompk::grid_finish<Op, T, 256>(v, ws, result, result_host, seq, px);
 }
 static void sum_f64(const double *x, unsigned long long n, void *ws, double *r, double *rh, unsigned long long seq, void **p, int rank,
-                    int world, unsigned long long cseq) { finish_kernel<Sum, double>(x, n, ws, r, rh, seq, p, rank, world, cseq); }
+                    int world, unsigned long long cseq, unsigned long long *cd) { finish_kernel<Sum, double>(x, n, ws, r, rh, seq, p, rank, world, cseq, cd); }
 static void max_i64(const long long *x, unsigned long long n, void *ws, long long *r, long long *rh, unsigned long long seq, void **p,
-                    int rank, int world, unsigned long long cseq) { finish_kernel<MaxL, long long>(x, n, ws, r, rh, seq, p, rank, world, cseq); }
+                    int rank, int world, unsigned long long cseq, unsigned long long *cd) { finish_kernel<MaxL, long long>(x, n, ws, r, rh, seq, p, rank, world, cseq, cd); }
 """
 
 
@@ -60,15 +60,16 @@ def device_source():
     return text + KERNEL
 
 
-def run(kernel, T, x, blocks, seq, peers=None, rank=0, world=1, cseq=0, state=None, instance=0):
+def run(kernel, T, x, blocks, seq, peers=None, rank=0, world=1, cseq=0, state=None, instance=0, counter=None):
     dt = {"double": np.float64, "long long": np.int64}[T]
     state = state or dict(ws=np.zeros(548928 // 8 + 8, dtype=np.uint64), res=np.zeros(1, dtype=dt), pub=np.zeros(3, dtype=np.uint64))
     ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
     emu.emulate_cooperative(device_source(), kernel, (blocks, 1, 1), (256, 1, 1),
                             [f"const {T} *", "unsigned long long", "void *", f"{T} *", f"{T} *", "unsigned long long", "void **", "int",
-                             "int", "unsigned long long"],
+                             "int", "unsigned long long", "unsigned long long *"],
                             [ptr(x), C.c_ulonglong(x.size), ptr(state["ws"]), ptr(state["res"]), ptr(state["pub"]), C.c_ulonglong(seq),
-                             ptr(peers) if peers is not None else C.c_void_p(0), C.c_int(rank), C.c_int(world), C.c_ulonglong(cseq)],
+                             ptr(peers) if peers is not None else C.c_void_p(0), C.c_int(rank), C.c_int(world), C.c_ulonglong(cseq),
+                             ptr(counter) if counter is not None else C.c_void_p(0)],
                             instance=instance)
     return state
 
@@ -95,18 +96,21 @@ def test_grid_finish_in_every_regime(blocks):
 def test_finish_fused_with_the_all_reduce_between_host_ranks(world, blocks):
     """finish_result with peers: `world` copies of the kernel run at the same time in `world` threads (each its own
     library instance, workspace and exchange buffer; "peer memory" is plain host memory).  Every rank ends with the
-    fold of all partial sums in rank order and publishes it; three calls in a row alternate the two slots."""
+    fold of all partial sums in rank order and publishes it; three calls in a row alternate the two slots.  Odd ranks
+    take the number of the call from a counter in their own "device" memory (nompk_peers_t.seq_dev: what the runtime
+    uses, so that a captured launch can be replayed), even ranks get it as a launch parameter: one protocol."""
     xchg = [np.zeros(2 * world * 2, dtype=np.uint64) for _ in range(world)]
     table = np.array([b.ctypes.data for b in xchg], dtype=np.uint64)
     data = [(np.arange(3000 + 17 * r) * (3 + r) % 11).astype(np.float64) for r in range(world)]
     states = [None] * world
+    counters = [np.zeros(1, dtype=np.uint64) for _ in range(world)]
     for call in (1, 2, 3):
         errors = []
 
         def rank_main(r):
             try:
-                states[r] = run("sum_f64", "double", data[r], blocks, 100 + call, peers=table, rank=r, world=world, cseq=call,
-                                state=states[r], instance=10 + r)
+                states[r] = run("sum_f64", "double", data[r], blocks, 100 + call, peers=table, rank=r, world=world,
+                                cseq=0 if r % 2 else call, counter=counters[r] if r % 2 else None, state=states[r], instance=10 + r)
             except BaseException as exc:   # pragma: no cover
                 errors.append(exc)
 
@@ -122,6 +126,7 @@ def test_finish_fused_with_the_all_reduce_between_host_ranks(world, blocks):
         for r in range(world):
             assert states[r]["res"][0] == want == states[r]["pub"].view(np.float64)[0]
             assert states[r]["pub"][1] == 100 + call and states[r]["pub"][2] == 0
+            assert counters[r][0] == (call if r % 2 else 0)
 
 
 def allreduce_source():
@@ -136,7 +141,8 @@ def allreduce_source():
             "template <> struct Limits<double> { static double lo() { return -INFINITY; } static double hi() { return INFINITY; } };\n"
             + text[a:b] + text[c:d] + "}\n")
     body += ("static void allreduce_sum_f64(double *value, double *host, unsigned long long host_seq, void **peers, int rank, int world,"
-             " unsigned long long seq) { nompk::allreduce_scalar_kernel<NOMPK_RED_SUM, double>(value, host, host_seq, peers, rank, world, seq); }\n")
+             " unsigned long long seq, unsigned long long *seq_dev, unsigned long long *err) {"
+             " nompk::allreduce_scalar_kernel<NOMPK_RED_SUM, double>(value, host, host_seq, peers, rank, world, seq, seq_dev, err); }\n")
     return body
 
 
@@ -146,6 +152,7 @@ def test_stand_alone_all_reduce_kernel_between_host_ranks(world):
     table = np.array([b.ctypes.data for b in xchg], dtype=np.uint64)
     values = [np.array([1000.5 + 3 * r]) for r in range(world)]
     pubs = [np.zeros(3, dtype=np.uint64) for _ in range(world)]
+    counters = [np.zeros(1, dtype=np.uint64) for _ in range(world)]
     src = allreduce_source()
     for call in (1, 2):
         contributions = [float(v[0]) for v in values]
@@ -155,9 +162,11 @@ def test_stand_alone_all_reduce_kernel_between_host_ranks(world):
             try:
                 ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
                 emu.emulate_cooperative(src, "allreduce_sum_f64", (1, 1, 1), (64, 1, 1),
-                                        ["double *", "double *", "unsigned long long", "void **", "int", "int", "unsigned long long"],
+                                        ["double *", "double *", "unsigned long long", "void **", "int", "int", "unsigned long long",
+                                         "unsigned long long *", "unsigned long long *"],
                                         [ptr(values[r]), ptr(pubs[r]), C.c_ulonglong(50 + call), ptr(table), C.c_int(r), C.c_int(world),
-                                         C.c_ulonglong(call)], instance=30 + r)
+                                         C.c_ulonglong(0 if r % 2 else call), ptr(counters[r]) if r % 2 else C.c_void_p(0),
+                                         ptr(pubs[r][2:])], instance=30 + r)
             except BaseException as exc:   # pragma: no cover
                 errors.append(exc)
 

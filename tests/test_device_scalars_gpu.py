@@ -1,9 +1,7 @@
 """Device-resident reduction results (include/nomp-b200.h: nomp_b200_device_reductions) and kernels that read their
 scalars from device memory: a conjugate-gradient iteration enqueued without a single host round trip.
 
-State: verified on the CUDA test double of the CPU tier (tests/test_hostdev_cpu.py runs this file there); the first run
-on the B200 is pending (the feature was written after the round's GPU budget was spent), so on a real device the tests
-skip instead of gating the tier on code that has never seen one.  Remove `first_gpu_run_pending` once it has passed.
+The CPU tier runs this file on the CUDA test double as well (tests/test_hostdev_cpu.py).
 """
 import ctypes as C
 import os
@@ -20,9 +18,7 @@ from libnomp_b200 import capi  # noqa: E402
 from nomp_bridge.families import AX_DOT_KERNEL_SOURCE  # noqa: E402
 from oracle import ffi  # noqa: E402
 
-first_gpu_run_pending = pytest.mark.skipif(os.environ.get("NOMP_HOSTDEV_ACTIVE") != "1" and os.environ.get("NOMP_RUN_PENDING") != "1",
-                                           reason="verified on the CUDA test double; first B200 run pending (set NOMP_RUN_PENDING=1)")
-pytestmark = [pytest.mark.gpu, first_gpu_run_pending]
+pytestmark = [pytest.mark.gpu]
 
 P, I, F = capi.NOMP_PTR, capi.NOMP_INT, capi.NOMP_FLOAT
 

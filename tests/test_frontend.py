@@ -207,7 +207,7 @@ def test_reduce_recognition_and_errors():
     for body in ("s[0] += 1;", "s[0] += i;", "if (a[i] > 0) s[0] += 1;", "s[0] += a[i] * a[i] + 1;"):
         desc, cuda, grid, _ = plan(f"void f(double *a, int N, double *s) {{ for (int i = 0; i < N; i++) {{ {body} }} }}", None, ("s", "+"))
         assert desc["kind"] == "nvrtc" and desc["family"] == "reduce" and desc["out"] == "s"
-        assert desc["params"].endswith("nomp_ws,nomp_result,nomp_result_host,nomp_seq,nomp_peers,nomp_rank,nomp_world,nomp_cseq")
+        assert desc["params"].endswith("nomp_ws,nomp_result,nomp_result_host,nomp_seq,nomp_peers,nomp_rank,nomp_world,nomp_cseq_dev,nomp_err_host")
         ok, log = nvrtc_compile(cuda)
         assert ok, log
     with pytest.raises(nb.KernelError):   # two loops
@@ -607,7 +607,7 @@ def test_mutated_kernel_strings_fail_cleanly():
 
 # ---- kernels whose threads cooperate, executed on the host (tests/cuda_emulation.py: emulate_cooperative) -------------------
 
-REDUCE_TAIL = ["void *", "{T} *", "{T} *", "unsigned long long", "void **", "int", "int", "unsigned long long"]
+REDUCE_TAIL = ["void *", "{T} *", "{T} *", "unsigned long long", "void **", "int", "int", "unsigned long long *", "unsigned long long *"]
 
 
 def _run_reduce_skeleton(src, var, op, T, arrays, scalars, n, grid_override=None):
@@ -621,7 +621,7 @@ def _run_reduce_skeleton(src, var, op, T, arrays, scalars, n, grid_override=None
     dt = NP[T]
     ws = np.zeros(548928 // 8 + 8, dtype=np.uint64)      # nompk_reduce_workspace_bytes()
     res, pub = np.zeros(1, dtype=dt), np.zeros(24, dtype=np.uint8)
-    params = desc["params"].split(",")[:-8]
+    params = desc["params"].split(",")[:-9]
     types, args = [], []
     for prm in params:
         if prm in arrays:
@@ -634,7 +634,7 @@ def _run_reduce_skeleton(src, var, op, T, arrays, scalars, n, grid_override=None
             args.append(val)
     types += [t.format(T=cuda_t) for t in REDUCE_TAIL]
     args += [C.c_void_p(ws.ctypes.data), C.c_void_p(res.ctypes.data), C.c_void_p(pub.ctypes.data), C.c_ulonglong(41),
-             C.c_void_p(0), C.c_int(0), C.c_int(1), C.c_ulonglong(0)]
+             C.c_void_p(0), C.c_int(0), C.c_int(1), C.c_void_p(0), C.c_void_p(0)]
     g = grid_override or grid_eval(grid[0], {"N": n})
     emulate_cooperative(cuda, name, (g, 1, 1), (256, 1, 1), types, args)
     return res[0], pub[:dt().nbytes].view(dt)[0], int(pub[8:16].view(np.uint64)[0]), ws[:2].copy()
@@ -679,6 +679,32 @@ def test_min_max_and_fused_update_skeletons_run_on_the_host():
                                         {"x": (x, "double *"), "r": (r, "double *"), "p": (p, "const double *"), "w": (w, "const double *")},
                                         {"alpha": ("double", C.c_double(0.5)), "N": ("int", C.c_int(n))}, n)
     assert got == want[0] and np.array_equal(x, xw) and np.array_equal(r, rw)
+
+
+def test_statements_behind_the_accumulation_stay_behind_it():
+    """`s[0] += a[i]; a[i] = 0;` -- the write follows the accumulation in program order (the reference keeps it:
+    seq_dependencies=True, ref python/loopy_api.py:817).  Vectorised (aligned) and scalar (misaligned) schedules, and a
+    statement on either side of a conditional accumulation."""
+    n = 5003
+    rng = np.random.default_rng(5)
+    for off in (0, 1):
+        base = rng.integers(-9, 10, n + 1).astype(np.float64)
+        a = base[off:off + n]
+        src = "void clr(double *a, int N, double *s) { for (int i = 0; i < N; i++) { s[0] += a[i]; a[i] = 0; } }"
+        aw, want = a.copy(), np.zeros(1)
+        run_kernel(src, aw, n, want)
+        got, _, _, _ = _run_reduce_skeleton(src, "s", "+", "double", {"a": (a, "double *")}, {"N": ("int", C.c_int(n))}, n)
+        assert got == want[0] != 0 and np.array_equal(a, aw) and not a.any()
+    src = ("void both(double *a, double *b, int N, double *s) { for (int i = 0; i < N; i++) {"
+           " b[i] = a[i] * 2; if (b[i] > 3) s[0] += a[i] + b[i]; a[i] = b[i] + 1; b[i] = a[i] * a[i]; } }")
+    a, b = rng.integers(-9, 10, n).astype(np.float64), np.zeros(n)
+    aw, bw, want = a.copy(), b.copy(), np.zeros(1)
+    run_kernel(src, aw, bw, n, want)
+    got, _, _, _ = _run_reduce_skeleton(src, "s", "+", "double", {"a": (a, "double *"), "b": (b, "double *")},
+                                        {"N": ("int", C.c_int(n))}, n)
+    assert got == want[0] and np.array_equal(a, aw) and np.array_equal(b, bw)
+    with pytest.raises(nb.KernelError):      # the accumulator may only appear in its own update
+        plan("void bad(double *a, int N, double *s) { for (int i = 0; i < N; i++) { s[0] += a[i]; a[i] = s[0]; } }", reduce=("s", "+"))
 
 
 def test_annotated_element_kernel_runs_on_the_host():
@@ -738,7 +764,8 @@ def test_generated_reduction_all_reduces_between_two_host_ranks():
         run_kernel(src, a, b, a.size, w)
         parts.append(w[0])
     types = ["const double *", "const double *", "int", "void *", "double *", "double *", "unsigned long long", "void **", "int",
-             "int", "unsigned long long"]
+             "int", "unsigned long long *", "unsigned long long *"]
+    counters = [np.zeros(1, dtype=np.uint64) for _ in range(world)]   # the call number: a counter in each rank's "device" memory
     ws = [np.zeros(548928 // 8 + 8, dtype=np.uint64) for _ in range(world)]
     res, pub = [np.zeros(1) for _ in range(world)], [np.zeros(3, dtype=np.uint64) for _ in range(world)]
     for call in (1, 2, 3):
@@ -750,7 +777,7 @@ def test_generated_reduction_all_reduces_between_two_host_ranks():
                 ptr = lambda v: C.c_void_p(v.ctypes.data)  # noqa: E731
                 emulate_cooperative(cuda, "red", (grid_eval(grid[0], {"N": a.size}), 1, 1), (256, 1, 1), types,
                                     [ptr(a), ptr(b), C.c_int(a.size), ptr(ws[r]), ptr(res[r]), ptr(pub[r]), C.c_ulonglong(100 + call),
-                                     ptr(table), C.c_int(r), C.c_int(world), C.c_ulonglong(call)], instance=r)
+                                     ptr(table), C.c_int(r), C.c_int(world), ptr(counters[r]), ptr(pub[r][2:])], instance=r)
             except Exception as exc:   # pragma: no cover
                 errors.append(exc)
 
@@ -763,6 +790,7 @@ def test_generated_reduction_all_reduces_between_two_host_ranks():
         for r in range(world):
             assert res[r][0] == parts[0] + parts[1] == pub[r].view(np.float64)[0]
             assert pub[r][1] == 100 + call and pub[r][2] == 0                              # published, nobody was late
+            assert counters[r][0] == call                                                  # the kernel counted the call itself
         slot = (call & 1) * world
         assert all(int(xchg[r][2 * (slot + q) + 1]) == call for r in range(world) for q in range(world))
 

@@ -136,6 +136,41 @@ def test_reduce_f64_random_data(n):
     assert abs(_reduce(capi.RED_SUM, capi.F64, x, y) - d) <= 1e-12 * abs(d)
 
 
+LARGE_N = [(1 << 26) + 5, 1 << 28]   # both take one tile per CTA and the TWO-level ticket finish (reduce.cu: launch_reduce)
+
+
+@pytest.mark.parametrize("n", LARGE_N)
+def test_reduce_two_level_finish_f64(n):
+    """BASELINE configs[1] (sum / dot, n = 2^28 fp64) and the smallest ragged size on the same code path.
+    Set X (integer-valued doubles): bitwise equal to the oracle's serial loop; Set R: 1e-12 relative against the
+    compensated oracle (reduction-order tolerance).  Replaces ref src/reduction.c:33-88 (whose scratch overflows beyond
+    n = 2^24); closed forms of ref tests/nomp-api-500-impl.h:172-196 are covered at these sizes in test_nomp_api_gpu.py."""
+    x = ffi.fill_int_f64(n, 1, 0, 7)
+    y = ffi.fill_int_f64(n, 2, 0, 7)
+    assert _reduce(capi.RED_SUM, capi.F64, x) == ffi.reduce_(capi.RED_SUM, capi.F64, x)
+    assert _reduce(capi.RED_SUM, capi.F64, x, y) == ffi.reduce_(capi.RED_SUM, capi.F64, x, y)
+    x[n - 3], x[n // 2 + 1] = -5.0, 11.0       # extrema in the last (partial) tile and in the middle
+    assert _reduce(capi.RED_MIN, capi.F64, x) == -5.0 == ffi.reduce_(capi.RED_MIN, capi.F64, x)
+    assert _reduce(capi.RED_MAX, capi.F64, x) == 11.0 == ffi.reduce_(capi.RED_MAX, capi.F64, x)
+    del x, y
+    x = ffi.fill_uniform_f64(n, 1234, 0.5, 1.5)
+    y = ffi.fill_uniform_f64(n, 4321, 0.5, 1.5)
+    s, d = ffi.sum_compensated(x), ffi.sum_compensated(x, y)
+    assert abs(_reduce(capi.RED_SUM, capi.F64, x) - s) <= 1e-12 * abs(s)
+    assert abs(_reduce(capi.RED_SUM, capi.F64, x, y) - d) <= 1e-12 * abs(d)
+
+
+@pytest.mark.parametrize("n", LARGE_N)
+def test_reduce_two_level_finish_i64_bit_exact(n):
+    """Full-range int64 (splitmix64): wrap-around sums and dots are associative -> bit-exact in any order."""
+    x = ffi.fill_i64(n, 1)
+    y = ffi.fill_i64(n, 2)
+    assert _reduce(capi.RED_SUM, capi.I64, x) == ffi.reduce_(capi.RED_SUM, capi.I64, x)
+    assert _reduce(capi.RED_SUM, capi.I64, x, y) == ffi.reduce_(capi.RED_SUM, capi.I64, x, y)
+    assert _reduce(capi.RED_MIN, capi.I64, x) == ffi.reduce_(capi.RED_MIN, capi.I64, x) == x.min()
+    assert _reduce(capi.RED_MAX, capi.U64, x.view(np.uint64)) == ffi.reduce_(capi.RED_MAX, capi.U64, x.view(np.uint64))
+
+
 def test_reduce_f32_small_ints():
     for n in (10, 50):
         x = np.arange(n, dtype=np.float32)
@@ -305,7 +340,13 @@ def test_reduction_fused_with_the_all_reduce_on_emulated_ranks(world):
     wss = [torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda") for _ in range(world)]
     ress = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
     pins = [torch.zeros(3, dtype=torch.int64).pin_memory() for _ in range(world)]
+    counters = torch.zeros(world, dtype=torch.int64, device="cuda")   # odd ranks: call number in device memory (seq_dev)
     seq = 0
+
+    def peers_of(r):
+        if r % 2:
+            return capi.NompkPeers(table.data_ptr(), r, world, 0, counters.data_ptr() + 8 * r, pins[r].data_ptr() + 16)
+        return capi.NompkPeers(table.data_ptr(), r, world, seq, None, None)
 
     def fold(op, parts):
         acc = parts[0]
@@ -342,10 +383,11 @@ def test_reduction_fused_with_the_all_reduce_on_emulated_ranks(world):
             if r == world - 1 and seq % 2 == 0:      # this rank takes the two-kernel path
                 capi.nompk_check(lib.nompk_reduce(op, dtype, xs[r].size, txs[r].data_ptr(), ty, ress[r].data_ptr(), None, 0,
                                                   wss[r].data_ptr(), st))
-                capi.nompk_check(lib.nompk_allreduce_scalar(op, dtype, ress[r].data_ptr(), pins[r].data_ptr(), 1000 + seq,
-                                                            table.data_ptr(), r, world, seq, st))
+                peers = peers_of(r)
+                capi.nompk_check(lib.nompk_allreduce_scalar_peers(op, dtype, ress[r].data_ptr(), pins[r].data_ptr(), 1000 + seq,
+                                                                  C.byref(peers), st))
             else:
-                peers = capi.NompkPeers(table.data_ptr(), r, world, seq)
+                peers = peers_of(r)
                 capi.nompk_check(lib.nompk_reduce_peers(op, dtype, xs[r].size, txs[r].data_ptr(), ty, ress[r].data_ptr(),
                                                         pins[r].data_ptr(), 1000 + seq, wss[r].data_ptr(), C.byref(peers), st))
         torch.cuda.synchronize()
@@ -366,7 +408,7 @@ def test_reduction_fused_with_the_all_reduce_on_emulated_ranks(world):
     seq += 1
     torch.cuda.synchronize()
     for r in range(world):
-        peers = capi.NompkPeers(table.data_ptr(), r, world, seq)
+        peers = peers_of(r)
         capi.nompk_check(lib.nompk_ax_dot_peers_f64(n, 3 + r, tus[r].data_ptr(), tgs[r].data_ptr(), tD.data_ptr(), tws[r].data_ptr(),
                                                     fres[r].data_ptr(), None, 0, wss[r].data_ptr(), C.byref(peers), 0,
                                                     C.c_void_p(streams[r].cuda_stream)))
@@ -375,3 +417,53 @@ def test_reduction_fused_with_the_all_reduce_on_emulated_ranks(world):
     for r in range(world):
         assert np.array_equal(host(tws[r], np.float64), ffi.ax(n, us[r], gs_[r], D))
         assert fres[r].item() == fold(capi.RED_SUM, parts)
+    assert counters.cpu().tolist() == [seq if r % 2 else 0 for r in range(world)]   # the kernels counted the calls themselves
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_all_reduce_replayed_from_cuda_graphs(world):
+    """The number of a collective call is a counter in device memory that the finishing warp advances
+    (nompk_peers_t.seq_dev), so nothing in a launch is specific to one call: each emulated rank captures
+    `dot -> all-reduce` ONCE into a CUDA graph and replays it; every replay gives the fold of the ranks' current data in
+    rank order, bit for bit, and the two exchange slots keep alternating."""
+    lib = capi.nompk()
+    n = 70001
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    bufs = [torch.zeros(lib.nompk_allreduce_xchg_bytes(world), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    wss = [torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ress = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+    counters = torch.zeros(world, dtype=torch.int64, device="cuda")
+    errs = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(world)]
+    xs = [dev(ffi.fill_int_f64(n + r, 50 + r, 0, 7)) for r in range(world)]
+    ys = [dev(ffi.fill_int_f64(n + r, 70 + r, 0, 7)) for r in range(world)]
+    peers = [capi.NompkPeers(table.data_ptr(), r, world, 0, counters.data_ptr() + 8 * r, errs[r].data_ptr()) for r in range(world)]
+
+    def launch(r):
+        capi.nompk_check(lib.nompk_reduce_peers(capi.RED_SUM, capi.F64, n + r, xs[r].data_ptr(), ys[r].data_ptr(), ress[r].data_ptr(),
+                                                None, 0, wss[r].data_ptr(), C.byref(peers[r]), C.c_void_p(streams[r].cuda_stream)))
+
+    for r in range(world):          # call 1, launched normally (also loads the kernel before anything is captured)
+        launch(r)
+    torch.cuda.synchronize()
+    graphs = []
+    for r in range(world):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=streams[r]):
+            launch(r)
+        graphs.append(g)
+    torch.cuda.synchronize()
+    assert counters.cpu().tolist() == [1] * world                    # capturing executed nothing
+    for replay in range(1, 6):
+        for r in range(world):
+            xs[r].mul_(2.0)                                            # new data for every replay
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                graphs[r].replay()
+        torch.cuda.synchronize()
+        want = sum(float(torch.dot(xs[r], ys[r]).item()) for r in range(world))   # small integers times 2^k: exact
+        for r in range(world):
+            assert ress[r].item() == want, (replay, r)
+            assert errs[r].item() == 0
+        assert counters.cpu().tolist() == [1 + replay] * world

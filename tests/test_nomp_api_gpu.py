@@ -429,6 +429,71 @@ def test_reduce_large_sizes():
         assert abs(s.value - ref) <= 1e-12 * abs(ref)
 
 
+@pytest.mark.parametrize("n", [(1 << 26) + 5, 1 << 28])
+def test_reduce_clause_at_baseline_size_two_level_finish(n):
+    """BASELINE configs[1]: reduce-clause sum / dot at n = 2^28, fp64 and int64, through nomp_jit / nomp_run (and the
+    ragged 2^26 + 5, the smallest size on the same path: one tile per CTA, two ticket levels).  The reference cannot
+    run these sizes (one partial per 512 elements into a 256 KiB scratch, ref src/reduction.c:41); what it pins are the
+    closed forms of ref tests/nomp-api-500-impl.h:17-59 (sum of 1, sum of i), :87-108 (a[i] = i) and :172-196 (dot),
+    evaluated here mod 2^64 for `long`.  Native kernels and the generated skeleton both take the two-level finish."""
+    red = capi.clauses(("reduce", "s", "+"))
+    k_sum = jit("void f(const double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", red,
+                [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    k_dot = jit("void f(const double *a, const double *b, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i] * b[i]; }",
+                red, [("a", 8, P), ("b", 8, P), ("N", 4, I), ("s", 8, F)])
+    k_isum = jit("void f(const long *a, int N, long *s) { for (int i = 0; i < N; i++) s[0] += a[i]; }", red,
+                 [("a", 8, P), ("N", 4, I), ("s", 8, I)])
+    k_idot = jit("void f(const long *a, const long *b, int N, long *s) { for (int i = 0; i < N; i++) s[0] += a[i] * b[i]; }", red,
+                 [("a", 8, P), ("b", 8, P), ("N", 4, I), ("s", 8, I)])
+    k_one = jit("void f(long *s, int N) { for (int i = 0; i < N; i++) { s[0] += 1; } }", red, [("s", 8, I), ("N", 4, I)])
+    k_idx = jit("void f(long *s, int N) { for (int i = 0; i < N; i++) { s[0] += i; } }", red, [("s", 8, I), ("N", 4, I)])
+    k_sq = jit("void f(const double *a, int N, double *s) { for (int i = 0; i < N; i++) s[0] += a[i] * a[i] + 1; }", red,
+               [("a", 8, P), ("N", 4, I), ("s", 8, F)])
+    assert family(k_sum) == family(k_dot) == family(k_isum) == family(k_idot) == ("native", "reduce")
+    assert family(k_one) == family(k_idx) == family(k_sq) == ("nvrtc", "reduce")
+    s, si = C.c_double(), C.c_long()
+    wrap = lambda v: (v + (1 << 63)) % (1 << 64) - (1 << 63)  # noqa: E731
+
+    capi.check(capi.run(k_one, C.byref(si), C.c_int(n)))
+    assert si.value == n
+    capi.check(capi.run(k_idx, C.byref(si), C.c_int(n)))
+    assert si.value == n * (n - 1) // 2
+
+    x = ffi.fill_int_f64(n, 1, 0, 7)         # Set X: every order exact -> bitwise
+    y = ffi.fill_int_f64(n, 2, 0, 7)
+    with Mapped(x, y):
+        capi.check(capi.run(k_sum, x.ctypes.data, C.c_int(n), s))
+        assert s.value == ffi.reduce_(0, ffi.F64, x)
+        capi.check(capi.run(k_dot, x.ctypes.data, y.ctypes.data, C.c_int(n), s))
+        assert s.value == ffi.reduce_(0, ffi.F64, x, y)
+        capi.check(capi.run(k_sq, x.ctypes.data, C.c_int(n), s))
+        assert s.value == ffi.reduce_(0, ffi.F64, x, x) + n
+    x = ffi.fill_uniform_f64(n, 1234, 0.5, 1.5)      # Set R: 1e-12 relative against the compensated oracle
+    y = ffi.fill_uniform_f64(n, 4321, 0.5, 1.5)
+    with Mapped(x, y):
+        capi.check(capi.run(k_sum, x.ctypes.data, C.c_int(n), s))
+        ref = ffi.sum_compensated(x)
+        assert abs(s.value - ref) <= 1e-12 * abs(ref)
+        capi.check(capi.run(k_dot, x.ctypes.data, y.ctypes.data, C.c_int(n), s))
+        ref = ffi.sum_compensated(x, y)
+        assert abs(s.value - ref) <= 1e-12 * abs(ref)
+    del x, y
+    xi = ffi.fill_i64(n, 1)                          # full-range int64: bit-exact
+    yi = ffi.fill_i64(n, 2)
+    with Mapped(xi, yi):
+        capi.check(capi.run(k_isum, xi.ctypes.data, C.c_int(n), si))
+        assert si.value == ffi.reduce_(0, ffi.I64, xi)
+        capi.check(capi.run(k_idot, xi.ctypes.data, yi.ctypes.data, C.c_int(n), si))
+        assert si.value == ffi.reduce_(0, ffi.I64, xi, yi)
+    del yi
+    xi[:] = np.arange(n, dtype=np.int64)             # the reference's own fixture a[i] = i and its closed forms
+    with Mapped(xi):
+        capi.check(capi.run(k_isum, xi.ctypes.data, C.c_int(n), si))
+        assert si.value == n * (n - 1) // 2
+        capi.check(capi.run(k_idot, xi.ctypes.data, xi.ctypes.data, C.c_int(n), si))
+        assert si.value == wrap(n * (2 * n - 1) * (n - 1) // 6)
+
+
 @pytest.mark.parametrize("T", ["int", "unsigned long", "double", "float"])
 def test_min_max_and_product_clauses(T):
     dt, kind = TYPES[T]

@@ -44,6 +44,18 @@ def test_bench_contract():
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert "family=ax" in line["config"]["kernel"]
+    assert line["ms_per_step_min"] <= line["ms_per_step_median"] and line["roofline"]["protocol_50_launches"]["reps"] == 50
+    # the run checks itself: p.Ap against the oracle on a sampled slab, BASELINE configs[1] values against closed forms
+    sc, ex = line["selfcheck"], line["extras"]
+    assert sc["ok"] and sc["pAp_rel_diff_vs_oracle_sample"] <= 1e-12 and sc["pAp_rel_diff_fused_vs_unfused"] <= 1e-12, sc
+    for key in ("sum_f64", "dot_f64", "sum_i64", "dot_i64"):
+        assert ex[key]["checked"] and ex[key]["n_total"] == 1 << 28 and ex[key]["value"] == ex[key]["expected"], ex[key]
+    assert ex["dot_f64_device_resident"]["checked"]
+    for key in ("cg_step", "cg_step_fused", "cg_step_fused_graph"):     # device-resident scalars / graph replay: same p.Ap
+        assert ex[key]["pAp_equals_host_semantics"], ex[key]
+    n10 = ex["n10"]                                                    # BASELINE configs[3] at N = 9
+    assert "family=ax n=10" in n10["ax"]["kernel"] and n10["ax"]["roofline"]["frac"] > 0.5 and n10["selfcheck"]["ok"], n10
+    assert n10["cg_step_fused_graph"]["pAp_equals_host_semantics"]
 
 
 def _cg_reference(E_total, n, iters):
@@ -76,7 +88,7 @@ def _cg_reference(E_total, n, iters):
     return out
 
 
-def _run_cg(world, E, n, tmp_path):
+def _run_cg(world, E, n, tmp_path, mode=None, iters="400", tol="1e-9"):
     exe = ROOT / "libnomp_b200" / "build" / "cg_poisson"
     if not exe.exists():
         pytest.skip("examples/cg_poisson was not built")
@@ -86,8 +98,9 @@ def _run_cg(world, E, n, tmp_path):
         env = dict(os.environ, NOMP_INSTALL_DIR=str(ROOT / "libnomp_b200"))
         if world > 1:
             env.update(NOMP_COMM_SIZE=str(world), NOMP_COMM_RANK=str(r), NOMP_COMM_ID_FILE=idfile)
-        procs.append(subprocess.Popen([str(exe), str(E), str(n), "400", "1e-9", "--nomp-backend", "cuda", "--nomp-device", str(r),
-                                       "--nomp-verbose", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        procs.append(subprocess.Popen([str(exe), str(E), str(n), iters, tol, *([mode, "10"] if mode else []), "--nomp-backend", "cuda",
+                                       "--nomp-device", str(r), "--nomp-verbose", "1"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
     outs = [p.communicate(timeout=900)[0] for p in procs]
     for f in [idfile] + [f"{idfile}.ipc.{r}" for r in range(world)]:
         try:
@@ -95,7 +108,7 @@ def _run_cg(world, E, n, tmp_path):
         except OSError:
             pass
     for p, o in zip(procs, outs):
-        assert p.returncode == 0, o[-3000:]
+        assert p.returncode in ((0, 2) if mode else (0,)), o[-3000:]     # 2: not converged within a fixed iteration count
     return [[json.loads(l) for l in o.splitlines() if l.startswith("{")] for o in outs]
 
 
@@ -126,6 +139,26 @@ def test_cg_example_on_two_gpus(tmp_path):
             for key in ("pAp", "alpha", "rr"):
                 assert abs(lines[1 + it][key] - ref[1 + it][key]) <= 1e-10 * abs(ref[1 + it][key]), (it, key)
     assert per_rank[0][1:6] == per_rank[1][1:6], "ranks must see bit-identical reduction results"
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_cg_with_device_scalars_and_graph_replay(tmp_path, world):
+    """examples/cg_poisson.c with its scalars in device memory ("device3": three launches per iteration, no host round
+    trip) and the same iterations replayed from a CUDA graph ("graph"), on one rank and -- the collective call number
+    being a device counter -- on two: 41 iterations give the same residual bit for bit either way, equal to the
+    host-scalar run up to rounding, and all ranks see the same bits."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    E, n = 24, 8
+    runs = {mode: _run_cg(world, E, n, tmp_path, mode, iters="41", tol="1e-30") for mode in ("host", "device3", "graph")}
+    finals = {mode: [lines[-1] for lines in per_rank] for mode, per_rank in runs.items()}
+    for mode, per_rank in finals.items():
+        assert all(f["iterations"] == 41 and f["scalars"] == mode for f in per_rank), (mode, per_rank)
+        assert all(f["rr_final"] == per_rank[0]["rr_final"] for f in per_rank), "ranks must see bit-identical scalars"
+    assert finals["graph"][0]["rr_final"] == finals["device3"][0]["rr_final"]
+    host = finals["host"][0]["rr_final"]
+    assert abs(finals["graph"][0]["rr_final"] - host) <= 1e-6 * abs(host)      # 41 iterations of rounding differences
+    assert finals["graph"][0]["true_residual_rel"] == finals["device3"][0]["true_residual_rel"]
 
 
 def _poisson_reference(ex, ey, ez, n, iters):
