@@ -53,6 +53,11 @@ def realize_reduction(knl: Kernel, var: str, op: str, context: Dict) -> Kernel:
         new.reduction = (var, op)
         new.ax_dot = roles          # the one reduction over a loop NEST that has a native kernel
         return new
+    if op == "+" and fam.may_be_ax_dot(new.original, var):
+        # another spelling of Ax + p.Ap?  Decided by what it computes (axprobe.py) once n is known: get_knl_src()
+        new.reduction = (var, op)
+        new.ax_probe = True
+        return new
     fam.analyse_reduction(new.original, var, op)
     new.reduction = (var, op)
     return new
@@ -64,6 +69,8 @@ def fix_parameters(knl: Kernel, params: Dict) -> Kernel:
     new.original = _fix_parameters(orig, **params).func
     if hasattr(knl, "ax_dot"):
         new.ax_dot = knl.ax_dot
+    if hasattr(knl, "ax_probe"):
+        new.ax_probe = knl.ax_probe
     return new
 
 
@@ -106,6 +113,16 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         knl._plan = plan
         return plan
 
+    if knl.reduction is not None and getattr(knl, "ax_probe", False):
+        found = fam.match_ax_structural(original, knl.fixed, _SUPPORTED_AX_N, knl.reduction[0])
+        if found is not None:
+            n_val, roles = found
+            plan = (_header(original, kind="native", family="axdot", n=n_val, E=roles["E"], u=roles["u"], g=roles["g"],
+                            D=roles["D"], w=roles["w"], out=roles["pap"]), one, one)
+            knl._plan = plan
+            return plan
+        # not the operator: the ordinary reduce clause decides (and reports what it cannot do)
+
     if knl.reduction is not None:
         var, op = knl.reduction
         info = fam.analyse_reduction(original, var, op)
@@ -146,6 +163,15 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
                 outer = roles["e"]
                 k2 = split_iname(knl, outer, 32)
                 knl = tag_inames(k2, {f"{outer}_outer": "g.0", f"{outer}_inner": "l.0"})
+
+    if knl.reduction is None and roles is None:
+        found = fam.match_ax_structural(original, knl.fixed, _SUPPORTED_AX_N, None)
+        if found is not None:    # any other spelling of the operator (axprobe.py)
+            n_val, sroles = found
+            plan = (_header(original, kind="native", family="ax", n=n_val, E=sroles["E"], u=sroles["u"], g=sroles["g"],
+                            D=sroles["D"], w=sroles["w"]), one, one)
+            knl._plan = plan
+            return plan
 
     if knl.reduction is None:
         native = fam.match_native_map(original)

@@ -266,6 +266,16 @@ def emit_reduce_skeleton(knl: Kernel, info: ReductionInfo, sm_count: int) -> Tup
         ident = _limits(info.vtype, False)
         comb = lambda a, b: f"(({b}) > ({a}) ? ({b}) : ({a}))"  # noqa: E731
 
+    # loop-invariant subexpressions (scalars in device memory, divisions of them) are evaluated once per CTA
+    all_arrays = {p.name: p for p in params if p.is_array}
+    inv_arrays = _fam().invariant_arrays(info.pre + info.post, list(info.preds) + [info.rhs], all_arrays)
+    assigned = {n.target.id for n in walk(info.pre + info.post) if isinstance(n, c.Assign) and isinstance(n.target, c.Name)}
+    declared = {n.name for n in walk(info.pre + info.post) if isinstance(n, c.Decl)}
+    inv_scalars = {p.name for p in params if not p.is_array} - assigned - declared - {info.loop.var}
+    npre = len(info.pre)
+    stmts, exprs, prologue = _fam().hoist_invariants(info.pre + info.post, list(info.preds) + [info.rhs], inv_arrays, inv_scalars)
+    info = ReductionInfo(info.loop, info.var, info.vtype, info.op, exprs[-1], exprs[:-1], stmts[:npre], stmts[npre:])
+
     ew = _elementwise_arrays(func, info)
     arrays = {p.name: p for p in params if p.is_array}
     if ew is not None:    # loop-invariant reads keep their subscript
@@ -419,7 +429,7 @@ extern "C" __global__ void __launch_bounds__(256) {knl.name}({', '.join(sig_part
   {T} nomp_o;
   const long long nomp_lo = (long long)({lo}), nomp_hi = (long long)({hi});
   const long long nomp_n = nomp_hi - nomp_lo;
-{loop}
+{prologue}{loop}
   // ---- block tree, then the two-level deterministic ticket finish of nompk_gridreduce.cuh -----------------------------
   __shared__ {T} nomp_warp[8];
   __shared__ int nomp_role;

@@ -247,6 +247,58 @@ def test_ax_recognition():
     assert "family=ax" not in nb.get_knl_src(other, CTX)
 
 
+def _signature_order(src):
+    import re
+    params = re.search(r"\(([^)]*)\)", src).group(1).split(",")
+    return [re.sub(r"\[.*", "", prm.strip()).split()[-1].lstrip("*") for prm in params]
+
+
+def _run_variant_with_gcc(src, roles, n, E, seed):
+    """The variant's own C text on exact data -> (w, pap or None) and the arrays it was given."""
+    rng = np.random.default_rng(seed)
+    n3 = n ** 3
+    data = {"w": rng.integers(-9, 10, E * n3).astype(np.float64), "u": rng.integers(-4, 5, E * n3).astype(np.float64),
+            "g": rng.integers(0, 4, 6 * E * n3).astype(np.float64), "D": rng.integers(-2, 3, n * n).astype(np.float64),
+            "E": E, "n": n, "pap": np.zeros(1)}
+    by_name = dict(zip(roles, ("w", "u", "g", "D", "E", "n", "pap")))
+    run_kernel(src, *[data[by_name[name]] for name in _signature_order(src)])
+    return data
+
+
+@pytest.mark.parametrize("n", [8, 6])
+def test_every_spelling_of_ax_reaches_the_native_kernel(n):
+    """The structural recogniser (nomp_bridge/axprobe.py): six spellings of the operator that share no token sequence
+    with the canonical string -- other names and argument order, g[e][f][k][j][i] and D[a][l], flat / merged / extra
+    temporaries, loops and statements in another order, `+=` into a zeroed w -- are all routed to nompk_ax_f64 with the
+    right argument roles, and so are two spellings of Ax + p.Ap under a reduce clause.  The texts themselves are the
+    operator: gcc runs each against the oracle first.  Near misses keep the generic schedule."""
+    from oracle import ffi
+    from tests import ax_variants as V
+    E = 3
+    for name, src, roles in V.variants() + V.fused_variants():
+        d = _run_variant_with_gcc(src, roles, 4, E, 7)
+        want = ffi.ax(4, d["u"], d["g"], d["D"])
+        assert np.array_equal(d["w"], want), f"the test's own variant {name} is not the operator"
+        fused = len(roles) == 7
+        if fused:
+            assert d["pap"][0] == float(d["u"] @ want)
+        k = nb.c_to_loopy(src)
+        if fused:
+            k = nb.realize_reduction(k, roles[6], "+", CTX)
+        header = nb.get_knl_src(nb.fix_parameters(k, {roles[5]: n}), CTX).splitlines()[0]
+        want_header = (f"//!nomp kind=native family={'axdot' if fused else 'ax'} n={n} E={roles[4]} u={roles[1]} g={roles[2]} "
+                       f"D={roles[3]} w={roles[0]}" + (f" out={roles[6]}" if fused else ""))
+        assert header.startswith(want_header), (name, header)
+    for name, src in V.not_ax():
+        header = nb.get_knl_src(nb.fix_parameters(nb.c_to_loopy(src), {"n": n}), CTX).splitlines()[0]
+        assert "kind=nvrtc" in header and "family=ax" not in header, (name, header)
+    # a reduce clause over a nest that is not the operator is still reported, at code generation
+    bad = V.fused_variants()[0][1].replace("pap[0] += acc * u[", "pap[0] += 2 * acc * u[")
+    k = nb.fix_parameters(nb.realize_reduction(nb.c_to_loopy(bad), "pap", "+", CTX), {"n": n})
+    with pytest.raises(nb.KernelError):
+        nb.get_knl_src(k, CTX)
+
+
 def test_fused_cg_families():
     k = nb.c_to_loopy(families.AX_DOT_KERNEL_SOURCE)
     k = nb.fix_parameters(nb.realize_reduction(k, "pap", "+", CTX), {"n": 10})
@@ -858,6 +910,24 @@ def test_loop_invariant_reads_keep_the_vector_schedules():
             ["double *", "double *", "const double *", "const double *", "const double *", "int"],
             [_ptr(p), _ptr(x), _ptr(r), _ptr(q), _ptr(coef), C.c_int(n)])
     assert np.array_equal(p, pw) and np.array_equal(x, xw)
+    # ... and evaluated once per CTA, not once per element (families.hoist_invariants): the coefficient of a CG update whose
+    # scalars stay on the device is a division of two of them
+    assert "__shared__ decltype(+(coef[1])) nomp_inv_s0;" in cuda and "nomp_inv_1" in cuda
+    src3 = ("void upd3(double *x, const double *p, const double *rr, const double *pap, double c, int N) {"
+            " for (int i = 0; i < N; i++) x[i] += (c * rr[0] / pap[0]) * p[i] + pap[0]; }")
+    desc, cuda3, (grid3, _), _ = plan(src3)
+    assert desc["family"] == "map" and "nomp_inv_s0 = (((c * rr[0]) / pap[0]));" in cuda3 and "nomp_inv_s1 = (pap[0]);" in cuda3
+    assert all("/ pap[0]" not in line for line in cuda3.splitlines() if "nomp_x_i" in line), "no division per element"
+    xs, ps = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    rr_, pap_ = np.array([3.7]), np.array([1.3])
+    xs_w = xs.copy()
+    run_kernel(src3, xs_w, ps, rr_, pap_, 0.7, n)
+    emulate(cuda3, "upd3", (grid_eval(grid3[0], {"N": n}), 1, 1), (256, 1, 1),
+            ["double *", "const double *", "const double *", "const double *", "double", "int"],
+            [_ptr(xs), _ptr(ps), _ptr(rr_), _ptr(pap_), C.c_double(0.7), C.c_int(n)])
+    assert np.array_equal(xs, xs_w)
+    ok, log = nvrtc_compile(cuda3)
+    assert ok, log
     # an array that is also written, or read at i as well, is not a scalar: no vector schedule through this rule
     for bad in ("void k(double *a, double *s, int N) { for (int i = 0; i < N; i++) { a[i] += s[0]; s[0] = a[i]; } }",
                 "void k(double *a, const double *s, int N) { for (int i = 0; i < N; i++) a[i] += s[0] + s[i + 1]; }"):

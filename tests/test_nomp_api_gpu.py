@@ -454,9 +454,9 @@ def test_reduce_clause_at_baseline_size_two_level_finish(n):
     s, si = C.c_double(), C.c_long()
     wrap = lambda v: (v + (1 << 63)) % (1 << 64) - (1 << 63)  # noqa: E731
 
-    capi.check(capi.run(k_one, C.byref(si), C.c_int(n)))
+    capi.check(capi.run(k_one, si, C.c_int(n)))
     assert si.value == n
-    capi.check(capi.run(k_idx, C.byref(si), C.c_int(n)))
+    capi.check(capi.run(k_idx, si, C.c_int(n)))
     assert si.value == n * (n - 1) // 2
 
     x = ffi.fill_int_f64(n, 1, 0, 7)         # Set X: every order exact -> bitwise
@@ -548,6 +548,61 @@ def test_ax_kernel_string(n, expect_family):
         capi.check(capi.update(first.ctypes.data, 0, 1, 8, capi.NOMP_FREE))
     assert np.array_equal(w, ffi.ax(n, u, g, D))
     assert np.array_equal(w, 4 * ffi.ax(n, u, g, D / 2))
+
+
+def test_every_spelling_of_ax_runs_the_native_kernel():
+    """Six spellings of the operator that share no token sequence with the canonical string (tests/ax_variants.py: other
+    names and argument order, g[e][f][k][j][i], merged / flat / extra temporaries, loops and statements reordered, `+=`
+    into a zeroed w) and two of Ax + p.Ap under a reduce clause: nomp_jit routes every one to the hand-written kernel
+    (structural recogniser, nomp_bridge/axprobe.py) and nomp_run gives the oracle's bits; near misses run through the
+    generic path and give what their own C text gives."""
+    from tests import ax_variants as V
+    from tests.test_frontend import _signature_order
+    n, E = 8, 41
+    u = ffi.fill_int_f64(E * n ** 3, 5, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 6, 0, 3)
+    D = ffi.fill_int_f64(n * n, 7, -2, 2)
+    want = ffi.ax(n, u, g, D)
+    for name, src, roles in V.variants() + V.fused_variants():
+        fused = len(roles) == 7
+        by_name = dict(zip(roles, ("w", "u", "g", "D", "E", "n", "pap")))
+        order = _signature_order(src)
+        spec = {"w": 8, "u": 8, "g": 8, "D": 8}
+        args = []
+        for prm in order:
+            role = by_name[prm]
+            if role in spec:
+                args.append((prm, 8, P))
+            elif role == "E":
+                args.append((prm, 4, I))
+            elif role == "n":
+                args.append((prm, 4, I | JIT, C.c_int(n)))
+            else:
+                args.append((prm, 8, F))
+        kid = jit(src, capi.clauses(("reduce", roles[6], "+")) if fused else capi.clauses(), args)
+        assert family(kid) == ("native", "axdot" if fused else "ax"), name
+        w = np.full_like(u, 7.0)                      # garbage in: the operator overwrites
+        pap = C.c_double(-1.0)
+        values = {"w": w.ctypes.data, "u": u.ctypes.data, "g": g.ctypes.data, "D": D.ctypes.data, "E": C.c_int(E), "pap": pap}
+        with Mapped(u, g, D, w, out=(w,)):
+            capi.check(capi.run(kid, *[values[by_name[prm]] for prm in order if by_name[prm] != "n"]))
+        assert np.array_equal(w, want), name
+        if fused:
+            assert pap.value == float(u @ want), name
+    for name, src in V.not_ax()[:4]:
+        order = _signature_order(src)
+        kid = jit(src, capi.clauses(), [(prm, 8, P) if prm in ("w", "u", "g", "D", "out", "in", "dm") else
+                                        (prm, 4, I | JIT, C.c_int(n)) if prm == "n" else (prm, 4, I) for prm in order])
+        assert family(kid)[0] == "nvrtc", name
+        w0 = ffi.fill_int_f64(u.size, 9, -3, 3)
+        w = w0.copy()
+        from tests.test_frontend import _run_variant_with_gcc  # noqa: F401  (same helper module)
+        values = {"w": w.ctypes.data, "u": u.ctypes.data, "g": g.ctypes.data, "D": D.ctypes.data, "E": C.c_int(E)}
+        with Mapped(u, g, D, w, out=(w,)):
+            capi.check(capi.run(kid, *[values[prm] for prm in order if prm != "n"]))
+        ref = w0.copy()
+        run_kernel(src, *[{"w": ref, "u": u, "g": g, "D": D, "E": E, "n": n}[prm] for prm in order])
+        assert np.array_equal(w, ref) and not np.array_equal(w, want), name
 
 
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
