@@ -92,11 +92,56 @@ template <int N> struct Layout {
   static constexpr int T = N * N / 2;              // work items per element and direction
   static constexpr int WPE = (T + 31) / 32;        // warps per element
   static constexpr int LPE = 32 * WPE;             // lanes per element
-  __device__ static __forceinline__ int at(int k, int j, int p) {
-    if constexpr (N == 8) return k * SK + j * NP + (p ^ ((j >> 1) & 3));
-    else return k * SK + j * NP + p;
+  // A 128-bit shared-memory access is served 8 lanes per wavefront; the 8 lanes are conflict-free when their chunk
+  // addresses differ mod 8 (8 x 16 B = all 32 banks).  SK = NP (mod 8) makes the k-column pattern (address = tt + const)
+  // and the j-line pattern (address = SK q + p = tt (mod 8)) walk through consecutive residues.  Groups of several
+  // elements (N != 8) put element el at lanes [el T, (el + 1) T): the progression continues across the element boundary
+  // when the elements' buffers are T (mod 8) chunks apart -- kElemStride pads for that.
+  template <int BUFS>
+  static constexpr int kElemStride = N == 8 ? BUFS * kChunks : BUFS * kChunks + (((T - BUFS * kChunks) % 8) + 8) % 8;
+  // N = 12: the rows are 6 chunks long, every row starts at an even chunk and an i-line access (all lanes at the same
+  // chunk c of their own row) could only ever reach 4 of the 8 residues.  Bit 2 of k + j flips the chunks of a row in
+  // pairs (p ^ 1 stays inside the row), which gives the row a parity; pairs are never split by a wavefront boundary in
+  // the other two patterns (8 lanes cut a row of 6 at an even chunk), so those stay conflict-free.
+  __device__ static __forceinline__ int swz(int k, int j) {
+    if constexpr (N == 8) return (j >> 1) & 3;
+    else if constexpr (N == 12) return ((k + j) >> 2) & 1;
+    else return 0;
+  }
+  __device__ static __forceinline__ int at(int k, int j, int p) { return k * SK + j * NP + (p ^ swz(k, j)); }
+};
+
+// The i-line stages (S2, S6) give every lane two whole rows (k, j) of an element; which two is free.  With the layouts
+// above a row's residue class is (k + j) mod 8 for N = 6, 10, 12 (row base = SK k + NP j = NP (k + j) (mod 8), NP odd; for
+// N = 12 the parity swizzle supplies the missing bit), so lane tt takes a row of class tt (mod 8) as its first row and one
+// of class tt + 1 as its second: any 8 consecutive lanes then hit 8 different residues, also across the element boundaries
+// of a group (see kElemStride).  Adjacent rows (2 tt, 2 tt + 1), the obvious choice, cost 7 (N = 10) and 10 (N = 12)
+// wavefronts per access instead of 4 (ncu, profiles/r02_*).  Where the classes do not divide evenly (N = 12: 16 to 20 rows
+// per class, 18 needed) the few surplus rows go where they collide least.  Built at compile time; entry 2 tt, 2 tt + 1 = the
+// rows (k * N + j) of work item tt.
+template <int N> struct RowTable {
+  static constexpr int T = N * N / 2;
+  unsigned short rows[2 * T];
+  constexpr RowTable() : rows() {
+    bool used[N * N] = {};
+    for (int which = 0; which < 2; which++) {
+      for (int tt = 0; tt < T; tt++) {
+        const int want = (tt + which) % 8;
+        int pick = -1;
+        for (int pass = 0; pass < 8 && pick < 0; pass++) {   // the wanted class first, then the nearest ones
+          const int cls = (want + pass) % 8;
+          for (int r = 0; r < N * N && pick < 0; r++)
+            if (!used[r] && (r / N + r % N) % 8 == cls) pick = r;
+        }
+        used[pick] = true;
+        rows[2 * tt + which] = (unsigned short)pick;
+      }
+    }
   }
 };
+
+// (N = 8 keeps the adjacent rows 2 tt, 2 tt + 1: its XOR swizzle already makes them conflict-free.)
+template <int N> __constant__ RowTable<N> nompk_ax_rows = RowTable<N>();
 
 __device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
 
@@ -112,6 +157,22 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) 
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// the same, asking L2 to keep the line until somebody uses it (the streams of w and of the other CTAs' factors push a
+// line that was prefetched with normal priority out again before its demand load arrives: 14 - 30 % of the factors are
+// read from DRAM twice with three CTAs per SM, profiles/r02_ax_dram.md)
+__device__ __forceinline__ void prefetch_l2_keep(const void *p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
+
+// ... and the demand load that uses such a line tells L2 it is the first to go
+__device__ __forceinline__ double2 ldg2_last_use(const double2 *p) {
+  double2 r;
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+  return r;
 }
 
 // Groups whose lanes outnumber their work items (n = 10: 160 lanes, 150 items) let the surplus lanes mirror the last
@@ -227,8 +288,11 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 // kernels without it keep their parameter layout -- and their SASS.)
 struct AxNoXpay {};
 
+//
+// kPfMode: eviction priority of the rolling L2 prefetch.  0: normal; 1: the prefetched lines are kept (evict_last);
+// 2: kept, and the demand load of a factor marks its line as the first to go (evict_first).
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent, bool kTwoBuf = false, bool kXpay = false>
+          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
           size_t pf_stride, std::conditional_t<kXpay, AxXpayArgs, AxNoXpay> xp) {
@@ -251,11 +315,14 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
   const int t = tt;
   // k-column item: (p, j);  j-line item: (p, k) -- the same split of t.
   const int p = tt % NP, q = tt / NP;
-  // i-line items: rows r0 = 2t and r0 + 1 (same k, adjacent j).
-  const int rk = (2 * tt) / N, rj = (2 * tt) % N;
+  // i-line items: two rows (k, j) of the element per lane -- rows 2t and 2t + 1 for N = 8, the conflict-free assignment
+  // of RowTable otherwise.  oa / ob: chunk offset of the row, sa / sb: its swizzle (chunk c sits at o + (c ^ s)).
+  const int row_a = N == 8 ? 2 * tt : nompk_ax_rows<N>.rows[2 * tt], row_b = N == 8 ? 2 * tt + 1 : nompk_ax_rows<N>.rows[2 * tt + 1];
+  const int oa = (row_a / N) * L::SK + (row_a % N) * NP, sa = L::swz(row_a / N, row_a % N);
+  const int ob = (row_b / N) * L::SK + (row_b % N) * NP, sb = L::swz(row_b / N, row_b % N);
 
   constexpr int kBufs = kTwoBuf ? 2 : 3;
-  double2 *B0 = smem + (size_t)(grp * G + el) * kBufs * L::kChunks;
+  double2 *B0 = smem + (size_t)(grp * G + el) * L::template kElemStride<kBufs>;
   double2 *B1 = kTwoBuf ? B0 : B0 + L::kChunks;   // ur, then wr
   double2 *B2 = B0 + (kBufs - 1) * L::kChunks;    // us, then ws
 
@@ -288,11 +355,21 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     constexpr int kLinesPerFactor = (N * N * 8 + 127) / 128;
     const int pf_f = t / kLinesPerFactor, pf_l = t % kLinesPerFactor;
     const size_t e_next = (e + estride < E) ? e + estride : e;
+    auto prefetch_slab = [&](size_t ee, int ks) {
+      const double *line = g + (ee * 6 + pf_f) * N3 + ks * N * N + pf_l * 16;
+      if (pf_f < 6) {
+        if constexpr (kPfMode == 0) prefetch_l2(line);
+        else prefetch_l2_keep(line);
+      }
+    };
+    auto load_g = [&](const double2 *src) {
+      if constexpr (kPfMode == 2) return ldg2_last_use(src);
+      else return kStreamLoads ? ldg2_stream(src) : ldg2(src);
+    };
     if constexpr (kPf >= 2) {
       if (eb == (size_t)blockIdx.x * EPB) {  // first element of this CTA: warm the window
 #pragma unroll
-        for (int k = kGeoAhead; k < kPf && k < N; k++)
-          if (pf_f < 6) prefetch_l2(g + (e * 6 + pf_f) * N3 + k * N * N + pf_l * 16);
+        for (int k = kGeoAhead; k < kPf && k < N; k++) prefetch_slab(e, k);
       }
     }
 
@@ -328,7 +405,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     for (int a = 0; a < kGeoAhead; a++)
 #pragma unroll
       for (int f = 0; f < 6; f++)
-        gq[a][f] = kStreamLoads ? ldg2_stream(ge + f * (N3 / 2) + a * SLAB2) : ldg2(ge + f * (N3 / 2) + a * SLAB2);
+        gq[a][f] = load_g(ge + f * (N3 / 2) + a * SLAB2);
 #pragma unroll
     for (int k = 0; k < N; k++) B0[L::at(k, q, p)] = col[k];
     // ---- S1: ut = D_t u along the k-column, in registers ---------------------------------------------
@@ -359,14 +436,14 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       {
         double2 v0[NP], v1[NP];
 #pragma unroll
-        for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
+        for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
         mirror_fence<G * T < GL>();  // the mirrors of a lane have read the same two lines
         static_for(SeqNP{}, [&](auto C) {
           constexpr int c = decltype(C)::value;
           double2 o0, o1;
           dot_rows<N, false, c>(v0, v1, o0, o1, z2);
-          B0[L::at(rk, rj, c)] = o0;
-          B0[L::at(rk, rj + 1, c)] = o1;
+          B0[oa + (c ^ sa)] = o0;
+          B0[ob + (c ^ sb)] = o1;
         });
       }
       element_sync<GL>(grp);
@@ -375,13 +452,13 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       {
         double2 v0[NP], v1[NP];
   #pragma unroll
-        for (int c = 0; c < NP; c++) v0[c] = B0[L::at(rk, rj, c)], v1[c] = B0[L::at(rk, rj + 1, c)];
+        for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
         static_for(SeqNP{}, [&](auto C) {
           constexpr int c = decltype(C)::value;
           double2 o0, o1;
           dot_rows<N, false, c>(v0, v1, o0, o1, z2);
-          B1[L::at(rk, rj, c)] = o0;
-          B1[L::at(rk, rj + 1, c)] = o1;
+          B1[oa + (c ^ sa)] = o0;
+          B1[ob + (c ^ sb)] = o1;
         });
       }
       // ---- S3: us = D_s u on a j-line pair (p, k = q) -> B2 ---------------------------------------------
@@ -407,17 +484,13 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       if (k + kGeoAhead < N) {
 #pragma unroll
         for (int f = 0; f < 6; f++)
-          gq[slot][f] = kStreamLoads ? ldg2_stream(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2)
-                                     : ldg2(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2);
+          gq[slot][f] = load_g(ge + f * (N3 / 2) + (k + kGeoAhead) * SLAB2);
       }
       if constexpr (kPf >= 2) {
         // slab k + kPf of this element, or slab (k + kPf - N) of the next one; next element's u with slab 0
         const int ks = k + kPf;
-        if (ks < N) {
-          if (pf_f < 6) prefetch_l2(g + (e * 6 + pf_f) * N3 + ks * N * N + pf_l * 16);
-        } else if (ks - N < N) {
-          if (pf_f < 6) prefetch_l2(g + (e_next * 6 + pf_f) * N3 + (ks - N) * N * N + pf_l * 16);
-        }
+        if (ks < N) prefetch_slab(e, ks);
+        else if (ks - N < N) prefetch_slab(e_next, ks - N);
         if (k == 0) {
           constexpr int kULines = (N3 * 8 + 127) / 128;
 #pragma unroll
@@ -462,14 +535,14 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     {
       double2 v0[NP], v1[NP];
 #pragma unroll
-      for (int c = 0; c < NP; c++) v0[c] = B1[L::at(rk, rj, c)], v1[c] = B1[L::at(rk, rj + 1, c)];
+      for (int c = 0; c < NP; c++) v0[c] = B1[oa + (c ^ sa)], v1[c] = B1[ob + (c ^ sb)];
       if constexpr (kTwoBuf) mirror_fence<G * T < GL>();  // B1 is B0: in place, mirrors must have read first
       static_for(SeqNP{}, [&](auto C) {
         constexpr int c = decltype(C)::value;
         double2 o0, o1;
         dot_rows<N, true, c>(v0, v1, o0, o1, z6);
-        B0[L::at(rk, rj, c)] = o0;
-        B0[L::at(rk, rj + 1, c)] = o1;
+        B0[oa + (c ^ sa)] = o0;
+        B0[ob + (c ^ sb)] = o1;
       });
     }
     element_sync<GL>(grp);
@@ -528,12 +601,12 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 }
 
 template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
-          bool TWOBUF = false>
+          bool TWOBUF = false, int PFMODE = 0>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
-  const size_t smem = (size_t)kElems * (TWOBUF ? 2 : 3) * L::kChunks * sizeof(double2);
+  const size_t smem = (size_t)kElems * L::template kElemStride<(TWOBUF ? 2 : 3)> * sizeof(double2);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
@@ -555,7 +628,7 @@ int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream
   using L = Layout<N>;
   auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
-  const size_t smem = (size_t)kElems * 3 * L::kChunks * sizeof(double2);
+  const size_t smem = (size_t)kElems * L::template kElemStride<3> * sizeof(double2);
   static bool configured = false;
   static int blocks_per_sm = 1;
   if (!configured) {
@@ -632,6 +705,19 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 21: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true>(E, u, g, w, s);
   case 22: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
   case 23: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);  // one slab in flight
+  // round 2: eviction priority of the prefetch (kPfMode) and shorter windows on the three-CTA shapes
+  case 30: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
+  case 31: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
+  case 32: return launch_ax<N, G, W, GPC, 2, 0, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
+  case 33: return launch_ax<N, G, W, GPC, 2, 3, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
+  case 34: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
+  case 35: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
+  case 36: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
+  case 37: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
+  case 38: return launch_ax<N, G, W, GPC, 1, 3, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
+  case 39: return launch_ax<N, G, W, GPC, 1, 6, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
+  case 40: return launch_ax<N, G, W, GPC, 1, 2, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
+  case 41: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 1>(E, u, g, w, s);   // three buffers, two CTAs
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }

@@ -253,11 +253,13 @@ def invariant_arrays(stmts, exprs, arrays: Dict[str, c.Param]) -> set:
 
 def hoist_invariants(stmts: List[c.Node], exprs: List[c.Node], invariant: set, scalars: set):
     """Loop-invariant subexpressions of an elementwise loop body -- built from literals, scalar arguments and reads of
-    device-resident scalars (`rr[0]`, arrays in `invariant`) -- that cost something (a load, a division, a call) are
-    evaluated ONCE PER CTA instead of once per element: thread 0 computes them into shared memory, one barrier, every
+    device-resident scalars (`rr[0]`, arrays in `invariant`) -- that are EXPENSIVE (a division, a remainder, a call) are
+    evaluated once per CTA instead of once per element: thread 0 computes them into shared memory, one barrier, every
     thread keeps them in registers.  `x[i] += (rr[0] / pap[0]) * p[i]` (the update of a CG iteration whose scalars stay on
-    the device) otherwise pays an fp64 division per element and stops being bandwidth-bound (+23 % measured on B200).
-    The subtree is moved as a whole, so every rounding stays where the C text has it.
+    the device) otherwise pays an fp64 division per element and is no longer bandwidth-bound.  The barrier has a price
+    of its own -- a CTA issues its streaming loads only after thread 0's dependent loads and division, about a
+    microsecond -- so the callers give such kernels four tiles per CTA, and plain reads like `alpha[0]` (one cached load
+    per thread) are left where they are.  The subtree is moved as a whole: every rounding stays where the C text has it.
     Returns (statements, expressions, CUDA prologue text) with the hoisted subtrees replaced by `nomp_inv_<k>`."""
     table: Dict[str, int] = {}
 
@@ -282,7 +284,7 @@ def hoist_invariants(stmts: List[c.Node], exprs: List[c.Node], invariant: set, s
         hit = [False]
 
         def visit(x):
-            if isinstance(x, (c.Subscript, c.Call)) or (isinstance(x, c.BinOp) and x.op in ("/", "%")):
+            if isinstance(x, c.Call) or (isinstance(x, c.BinOp) and x.op in ("/", "%")):
                 hit[0] = True
             return x
         map_expr(e, visit)
@@ -635,6 +637,7 @@ def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, Lis
     ext = grid_expr_str(extent, int_params)
     # one vector per thread, one tile per CTA: on B200 the hardware CTA scheduler streams faster than a persistent
     # grid-stride loop (tools/exp/exp_map.cu); the loops in the kernel still stride, so any grid size is correct
-    per_block = 256 * lanes
+    # (four tiles per CTA when the CTA starts with the barrier of hoisted invariants: hoist_invariants)
+    per_block = 256 * lanes * (4 if prologue else 1)
     grid = f"max(1, ({ext} + {per_block - 1}) / {per_block})"
     return src, [grid, "1", "1"], ["256", "1", "1"]

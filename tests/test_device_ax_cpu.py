@@ -32,13 +32,15 @@ def device_source():
     body = text[s0:s1] + text[a:b] + "}  // namespace\n}  // namespace nompk\n"
     body, n = re.subn(r'__constant__ double nompk_ax_cD\[12 \* 12\];', "double nompk_ax_cD[12 * 12];", body)
     assert n == 1
-    swaps = [(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.v2\.f64[^;]*;"[^;]*;', "r = *p;"),
-             (r'asm volatile\("cp\.async\.bulk\.prefetch\.L2\.global[^;]*;"[^;]*;', ";"),
-             (r'asm volatile\("prefetch\.global\.L2[^;]*;"[^;]*;', ";"),
-             (r'asm volatile\("bar\.sync %0, %1;"[^;]*;', "nomp_emu_named_barrier(grp + 1, GL);")]
-    for pattern, repl in swaps:
+    swaps = [(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.v2\.f64[^;]*;"[^;]*;', "r = *p;", 1),
+             (r'asm volatile\("cp\.async\.bulk\.prefetch\.L2\.global[^;]*;"[^;]*;', ";", 1),
+             (r'asm volatile\("prefetch\.global\.L2[^;]*;"[^;]*;', ";", 2),               # normal and evict_last priority
+             (r'asm volatile\("createpolicy\.fractional\.L2::evict_first\.b64[^;]*;"[^;]*;', "policy = 0;", 1),
+             (r'asm volatile\("ld\.global\.nc\.L2::cache_hint\.v2\.f64[^;]*;"[^;]*;', "r = *p; (void)policy;", 1),
+             (r'asm volatile\("bar\.sync %0, %1;"[^;]*;', "nomp_emu_named_barrier(grp + 1, GL);", 1)]
+    for pattern, repl, count in swaps:
         body, n = re.subn(pattern, repl, body)
-        assert n == 1, pattern
+        assert n == count, pattern
     body, n = re.subn(r"extern __shared__ double2 smem\[\];", "static double2 smem[1 << 16];", body)
     assert n == 1
     wrappers = ["#include <utility>\n#include <type_traits>\n#define __constant__ static\n"
@@ -46,7 +48,8 @@ def device_source():
                 "static inline double __dmul_rn(double a, double b) { return a * b; }\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
-        for dot in (0, 1, 2, 3):       # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight
+        for dot in (0, 1, 2, 3, 4):    # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight;
+            #                            4 = two buffers, prefetch with evict_last and last-use demand loads (kPfMode 2)
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
@@ -54,7 +57,7 @@ def device_source():
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
                 f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
-                f" {'true' if dot >= 2 else 'false'}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+                f" {'true' if dot >= 2 else 'false'}, false, {2 if dot == 4 else 0}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
         # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
         wrappers.append(
             f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"
@@ -83,7 +86,7 @@ def run_ax(n, E, u, g, D, dot, blocks):
 
 
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
-@pytest.mark.parametrize("dot", [0, 1, 2, 3])
+@pytest.mark.parametrize("dot", [0, 1, 2, 3, 4])
 def test_ax_kernel_on_the_host(n, dot):
     """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
     size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""

@@ -77,7 +77,8 @@ class Rank:
         active = (counts >= 2) | (npeers > 0)
         act = np.flatnonzero(active)
         first_idx = order[starts[act]]
-        act = act[np.argsort(first_idx, kind="stable")]   # groups ordered by their first local copy
+        # groups shared with a peer first (their partial results leave early), then by their first local copy
+        act = act[np.lexsort((first_idx, npeers[act] == 0))]
         offsets, indices, remote_slot, rgroup, roffsets, rpeer, rpos = [0], [], [], [], [0], [], []
         for g, u in enumerate(act):
             idx = order[starts[u]:starts[u] + counts[u]]
@@ -215,7 +216,7 @@ SETUP_KERNELS = {
     "match_kernel": ["const long long *", "size_t", "const long long *", "size_t", "unsigned *"],
     "position_kernel": ["const unsigned *", "unsigned *", "size_t"],
     "classify_kernel": ["const long long *", "const unsigned *", "unsigned **", "int", "size_t", "unsigned char *", "unsigned *"],
-    "first_index_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "unsigned *", "size_t"],
+    "first_index_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *", "unsigned long long *", "size_t"],
     "group_sizes_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "unsigned *", "unsigned *", "unsigned *", "size_t"],
     "fill_kernel": ["const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *", "const unsigned *",
                     "const unsigned *", "const unsigned *", "unsigned **", "int", "unsigned *", "int *", "unsigned *", "unsigned *", "int *",
@@ -276,8 +277,8 @@ def device_setup(rank, id_parts):
     launch("classify_kernel", U, uniq, counts, table, world, U, active, rcount)
     sel = np.flatnonzero(active).astype(np.uint32)                        # cub::DeviceSelect::Flagged
     G = sel.size
-    first = np.zeros(max(G, 1), dtype=np.uint32)
-    launch("first_index_kernel", G, sel, run_start, sorted_idx, first, G)
+    first = np.zeros(max(G, 1), dtype=np.uint64)
+    launch("first_index_kernel", G, sel, run_start, sorted_idx, rcount, first, G)
     order_g = sel[np.argsort(first[:G], kind="stable")]                  # SortPairs(first, sel)
     cnt, rcnt, rflag = (np.zeros(max(G, 1), dtype=np.uint32) for _ in range(3))
     launch("group_sizes_kernel", G, order_g, counts, rcount, cnt, rcnt, rflag, G)

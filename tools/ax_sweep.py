@@ -83,7 +83,9 @@ def main():
         # the next, so every variant is timed once per round, round after round, and the median over rounds is kept.
         variants = [int(v) for v in os.environ.get("AX_VARIANTS", "0,1,7,8,11,21,22,23").split(",")]
         rounds = int(os.environ.get("AX_ROUNDS", "7"))
-        for n, E in ((10, 131072), (12, 65536), (8, 262144), (6, 524288)):
+        shapes = [tuple(int(x) for x in sh.split(":")) for sh in
+                  os.environ.get("AX_SHAPES", "10:131072,12:65536,8:262144,6:524288").split(",")]
+        for n, E in shapes:
             n3 = n ** 3
             u = torch.rand(E * n3, dtype=torch.float64, device="cuda")
             g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
