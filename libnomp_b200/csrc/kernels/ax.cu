@@ -11,18 +11,23 @@
 // Design
 //   * n even.  A "work item" is a PAIR of adjacent-i lines of n points; an element has T = n^2/2 items per
 //     direction, one item per lane.  n = 8: T = 32, one WARP per element, no block-level barrier at all
-//     (__syncwarp only).  n = 10: T = 50, two warps per element and a 64-thread named barrier.
+//     (__syncwarp only), four independent warps per CTA.  The other sizes pack G elements onto a group of W warps
+//     (Shape<N>: n = 10: 3 elements on 5 warps, 150 of 160 lanes; n = 12: 2 on 5; n = 6: 7 on 4) with one named
+//     barrier per stage; surplus lanes mirror the last item so that control flow stays uniform.
 //   * Every global access is a 128-bit coalesced LDG/STG (a pair of adjacent i); a warp instruction moves 512
 //     contiguous bytes.  The six geometric factors (75 % of the traffic) go straight from HBM to registers and
-//     never touch shared memory; loads for slab k+kGeoAhead are in flight while slab k is consumed, and the next
-//     element's 28 KB are pulled into L2 with one bulk prefetch so those loads find their lines there.
+//     never touch shared memory; loads for slab k+kGeoAhead are in flight while slab k is consumed, and a rolling
+//     window of `prefetch.global.L2` (kPf slabs ahead, one line per lane, running on into the group's next element)
+//     lets those loads find their lines in L2.  (A bulk prefetch of the whole next element was measured and dropped:
+//     it is a whole element-time ahead, ~15 us, and the lines do not survive that long in L2.)
 //   * D lives in __constant__ memory.  All contractions are fully unrolled, so every DFMA takes its D entry
-//     as a constant-bank operand: no register, no shared-memory read and no load instruction for D.
+//     as a uniform-register operand (LDCU): no vector register, no shared-memory read for D.
 //   * The three 1-D contractions (and their transposes) are done by the lane that owns the whole line in
 //     registers: 2 x n inputs -> 2 x n outputs, n^2 DFMAs each, 2n independent accumulation chains.  Between
-//     directions the data is transposed through three n^3 shared-memory buffers using only LDS.128/STS.128;
-//     the buffer layout (slab stride + XOR swizzle, tools/check_banks.py) makes all three access patterns
-//     bank-conflict-free for n = 8.
+//     directions the data is transposed through two or three n^3 shared-memory buffers using only LDS.128/STS.128;
+//     the buffer layout (slab stride, padded element stride, XOR swizzles) and the choice of the two rows a lane takes
+//     in the i-line stages (RowTable) make all three access patterns bank-conflict-free: tools/check_banks.py models
+//     them and reproduces the wavefront counts of the ncu source page.
 //   * FP64 FMA on the CUDA cores; tensor cores are not used (the kernel is HBM-bound).
 //
 // Build: this file is compiled once per supported n with -DNOMPK_AX_N=<n> (the kernels of that n, its own copy of D
@@ -289,8 +294,16 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 struct AxNoXpay {};
 
 //
-// kPfMode: eviction priority of the rolling L2 prefetch.  0: normal; 1: the prefetched lines are kept (evict_last);
-// 2: kept, and the demand load of a factor marks its line as the first to go (evict_first).
+// kPfMode: shape and eviction priority of the rolling L2 prefetch.
+//   0: the window runs on into the group's NEXT element (its first kPf slabs and its u are requested during the last
+//      slabs of this one), normal priority;  1: the same, prefetched lines are kept (evict_last);  2: kept, and the demand
+//      load of a factor marks its line as the first to go (evict_first).
+//   3: LOCAL window -- every element warms its own window in S0 (slabs kGeoAhead .. kPf - 1, consumed after S1 - S3) and
+//      S4 only prefetches inside the element; the next element's u is requested after S6.  Every prefetch then leads its
+//      demand load by 2 - 4 us.  With modes 0 - 2 the lines of the next element wait for a whole S5 .. S8, S0 .. S3 --
+//      about 9 us with three CTAs per SM -- and L2 (126 MB under 8.5 TB/s of traffic: ~12 us of residence) has dropped
+//      part of them by then: 14 % (n = 10) to 30 % (n = 12) of the factors came from DRAM twice (profiles/r02_ax_dram.md).
+//   4: local window, and demand loads mark their lines evict_first.
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
           bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
@@ -355,19 +368,26 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     constexpr int kLinesPerFactor = (N * N * 8 + 127) / 128;
     const int pf_f = t / kLinesPerFactor, pf_l = t % kLinesPerFactor;
     const size_t e_next = (e + estride < E) ? e + estride : e;
+    constexpr bool kLocalWindow = kPfMode >= 3;
     auto prefetch_slab = [&](size_t ee, int ks) {
       const double *line = g + (ee * 6 + pf_f) * N3 + ks * N * N + pf_l * 16;
       if (pf_f < 6) {
-        if constexpr (kPfMode == 0) prefetch_l2(line);
-        else prefetch_l2_keep(line);
+        if constexpr (kPfMode == 1 || kPfMode == 2) prefetch_l2_keep(line);
+        else prefetch_l2(line);
       }
     };
     auto load_g = [&](const double2 *src) {
-      if constexpr (kPfMode == 2) return ldg2_last_use(src);
+      if constexpr (kPfMode == 2 || kPfMode == 4) return ldg2_last_use(src);
       else return kStreamLoads ? ldg2_stream(src) : ldg2(src);
     };
+    auto prefetch_next_u = [&]() {
+      constexpr int kULines = (N3 * 8 + 127) / 128;
+#pragma unroll
+      for (int l0 = 0; l0 < kULines; l0 += T)
+        if (l0 + t < kULines) prefetch_l2(u + e_next * N3 + (l0 + t) * 16);
+    };
     if constexpr (kPf >= 2) {
-      if (eb == (size_t)blockIdx.x * EPB) {  // first element of this CTA: warm the window
+      if (kLocalWindow || eb == (size_t)blockIdx.x * EPB) {  // warm the window (wrapping window: first element of the CTA only)
 #pragma unroll
         for (int k = kGeoAhead; k < kPf && k < N; k++) prefetch_slab(e, k);
       }
@@ -490,13 +510,8 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         // slab k + kPf of this element, or slab (k + kPf - N) of the next one; next element's u with slab 0
         const int ks = k + kPf;
         if (ks < N) prefetch_slab(e, ks);
-        else if (ks - N < N) prefetch_slab(e_next, ks - N);
-        if (k == 0) {
-          constexpr int kULines = (N3 * 8 + 127) / 128;
-#pragma unroll
-          for (int l0 = 0; l0 < kULines; l0 += T)
-            if (l0 + t < kULines) prefetch_l2(u + e_next * N3 + (l0 + t) * 16);
-        }
+        else if (!kLocalWindow && ks - N < N) prefetch_slab(e_next, ks - N);
+        if (!kLocalWindow && k == 0) prefetch_next_u();
       }
       const int a = L::at(k, q, p);
       const double2 ur = B1[a], us = B2[a], ut = col[k];
@@ -546,6 +561,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       });
     }
     element_sync<GL>(grp);
+    if constexpr (kPf >= 2 && kLocalWindow) prefetch_next_u();
 
     // ---- S7: + D_s^T ws on the j-line pair (p, k = q): B2, B0 -> B0 -------------------------------------
     {
@@ -626,7 +642,7 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
 template <int N, int G, int W, int GPC, int GA, int PF, int MB>
 int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream, AxDotArgs dot, AxXpayArgs xp) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true, (N == 8 ? 0 : 3)>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * L::template kElemStride<3> * sizeof(double2);
   static bool configured = false;
@@ -657,8 +673,10 @@ template <int N> int dispatch_ax_dot(size_t E, const double *u, const double *g,
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  // the shapes of dispatch_ax (variant 0), with the dot product
   if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
-  else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true>(E, u, g, w, s, dot);
+  else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), true, true, true, 4>(E, u, g, w, s, dot);
+  else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3>(E, u, g, w, s, dot);
 }
 
 // p <- r + beta p fused in front (the shapes of dispatch_ax_dot).
@@ -675,16 +693,20 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB128 = 65536 / (128 * kThreads), MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  // one element per group of ceil(T / 32) warps, about 128 threads per CTA
+  constexpr int W1 = Layout<N>::WPE, GPC1 = (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), kThreads1 = GPC1 * W1 * 32;
+  constexpr int MB128_1 = 65536 / (128 * kThreads1), MB168_1 = 65536 / (168 * kThreads1);
   // Variants are kept for profiling (tools/ax_sweep.py sweeps them); 0 is the production choice.
   switch (variant) {
   default:
-  case 0:  // production choice (gpurun sweeps of round 1, profiles/r01_kernel_sweeps.jsonl)
+  case 0:  // production choice (interleaved sweeps of round 2, profiles/r02_kernel_sweeps.jsonl)
+    // n = 8: one warp per element, three buffers, 168 registers, window running on into the next element (no over-read
+    // at this element time).  The others: two shared buffers per element, one CTA more per SM (128 registers) and the
+    // LOCAL prefetch window, which removed the 14 - 30 % of DRAM reads that the wrapping window fetched twice on these
+    // shapes: n = 10 +6 %, n = 12 +9 %, n = 6 +13 % over the round-1 choices in the same interleaved sweeps.
     if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
-    else if constexpr (N == 6) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, false>(E, u, g, w, s);
-    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
-    // n = 10: two shared buffers per element and three CTAs per SM (128 registers, 16 bytes of spill): 80.2-80.3 GDOF/s
-    // against 75.8-76.4 for the three-buffer kernel in two interleaved sweeps (profiles/r01_kernel_sweeps.jsonl)
-    else return launch_ax<N, G, W, GPC, 2, 4, false, MB168 + 1, false, true, true>(E, u, g, w, s);
+    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
+    else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
   case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
   case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
   case 3: return launch_ax<N, G, W, GPC, 2, 2, false, MB128>(E, u, g, w, s);
@@ -705,19 +727,28 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 21: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true>(E, u, g, w, s);
   case 22: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
   case 23: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);  // one slab in flight
-  // round 2: eviction priority of the prefetch (kPfMode) and shorter windows on the three-CTA shapes
-  case 30: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
-  case 31: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
-  case 32: return launch_ax<N, G, W, GPC, 2, 0, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
-  case 33: return launch_ax<N, G, W, GPC, 2, 3, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
-  case 34: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
-  case 35: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
-  case 36: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
-  case 37: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
-  case 38: return launch_ax<N, G, W, GPC, 1, 3, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
-  case 39: return launch_ax<N, G, W, GPC, 1, 6, false, (MB168 + 1), false, true, true, 1>(E, u, g, w, s);
-  case 40: return launch_ax<N, G, W, GPC, 1, 2, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
-  case 41: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 1>(E, u, g, w, s);   // three buffers, two CTAs
+  // round 2: shape and eviction priority of the prefetch window (kPfMode) on the three-CTA / two-buffer shapes ...
+  case 30: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+  case 31: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
+  case 32: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+  case 33: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
+  case 34: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+  case 35: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
+  case 36: return launch_ax<N, G, W, GPC, 1, 6, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+  case 37: return launch_ax<N, G, W, GPC, 2, 8, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+  case 38: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 2>(E, u, g, w, s);
+  // ... and on the three-buffer / two-CTA shapes
+  case 39: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 3>(E, u, g, w, s);
+  case 40: return launch_ax<N, G, W, GPC, 2, 6, false, MB168, false, true, false, 3>(E, u, g, w, s);
+  case 41: return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, true, false, 3>(E, u, g, w, s);
+  // ... and one element per ceil(T / 32) warps (n = 10: 2 warps, 50 of 64 lanes; n = 12: 3 warps, 72 of 96): fewer lanes do
+  // useful work, but the groups are small and many -- barriers of 2 - 3 warps, 6 - 8 independent groups per SM
+  case 42: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB168_1, false, true, false, 3>(E, u, g, w, s);
+  case 43: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB128_1, false, true, true, 3>(E, u, g, w, s);
+  case 44: return launch_ax<N, 1, W1, GPC1, 1, 4, false, MB128_1, false, true, true, 3>(E, u, g, w, s);
+  case 45: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB128_1, false, true, true, 4>(E, u, g, w, s);
+  case 46: return launch_ax<N, 1, W1, GPC1, 3, 6, false, MB168_1, false, true, false, 3>(E, u, g, w, s);
+  case 47: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB168_1, false, true, true, 3>(E, u, g, w, s);
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
   }

@@ -108,10 +108,18 @@ static int mkdir_p(const char *path) {
   for (char *p = tmp + 1; *p; p++) {
     if (*p != '/') continue;
     *p = '\0';
-    if (mkdir(tmp, 0777) && errno != EEXIST) return 1;
+    if (mkdir(tmp, 0777) && errno != EEXIST) return 1; /* parents: the user's umask decides, as for ~/.cache itself */
     *p = '/';
   }
-  return mkdir(tmp, 0777) && errno != EEXIST;
+  return mkdir(tmp, 0700) && errno != EEXIST; /* the cache directory itself: private */
+}
+
+/* Entries are loaded through cuModuleLoadData and run: their checksum protects against damage, not against somebody
+ * else writing a valid entry.  So the directory must belong to this user and be writable by nobody else. */
+static int private_dir(const char *path) {
+  struct stat st;
+  if (stat(path, &st) || !S_ISDIR(st.st_mode)) return 0;
+  return st.st_uid == geteuid() && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0;
 }
 
 const char *nomp_jit_cache_dir(void) {
@@ -125,6 +133,10 @@ const char *nomp_jit_cache_dir(void) {
     else if (home && home[0]) snprintf(cache_dir, sizeof(cache_dir), "%s/.cache/libnomp_b200", home);
     else return NULL;
     if (mkdir_p(cache_dir) || access(cache_dir, W_OK)) return NULL;
+    if (!private_dir(cache_dir)) {
+      nomp_log(0, NOMP_WARNING, "JIT cache directory \"%s\" is not owned by this user or is writable by others: cache off.", cache_dir);
+      return NULL;
+    }
     cache_state = 1;
   }
   return cache_state == 1 ? cache_dir : NULL;

@@ -48,16 +48,17 @@ def device_source():
                 "static inline double __dmul_rn(double a, double b) { return a * b; }\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
-        for dot in (0, 1, 2, 3, 4):    # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight;
-            #                            4 = two buffers, prefetch with evict_last and last-use demand loads (kPfMode 2)
+        for dot in (0, 1, 2, 3, 4, 5):  # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight;
+            #                            4 = two buffers, local prefetch window and last-use demand loads (kPfMode 4);
+            #                            5 = two buffers with the fused p.Ap and the local window (the production shape of n = 6, 10, 12)
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
                 f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk::nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
-                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot == 1 else 'false'}, true,"
-                f" {'true' if dot >= 2 else 'false'}, false, {2 if dot == 4 else 0}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot in (1, 5) else 'false'}, true,"
+                f" {'true' if dot >= 2 else 'false'}, false, {4 if dot == 4 else 3 if dot == 5 else 0}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
         # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
         wrappers.append(
             f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"
@@ -86,7 +87,7 @@ def run_ax(n, E, u, g, D, dot, blocks):
 
 
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
-@pytest.mark.parametrize("dot", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("dot", [0, 1, 2, 3, 4, 5])
 def test_ax_kernel_on_the_host(n, dot):
     """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
     size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""
@@ -99,7 +100,7 @@ def test_ax_kernel_on_the_host(n, dot):
         w, pap, ws = run_ax(n, E, u, g, D, dot, blocks)
         want = ffi.ax(n, u, g, D)
         assert np.array_equal(w, want), (n, E, blocks, int((w != want).sum()))
-        if dot == 1:
+        if dot in (1, 5):
             assert pap == float(u @ want) and not ws[: (64 + 4 * 2048) // 8].any()
 
 

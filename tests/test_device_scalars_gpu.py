@@ -271,6 +271,45 @@ def test_cg_iterations_replayed_from_a_cuda_graph():
     assert rr_plain < 1e-2 * float(b @ b)            # and the iteration does reduce the residual
 
 
+def test_staged_derivative_matrix_survives_graph_replays_and_remapping():
+    """The Ax family stages D into __constant__ memory and skips the copy while the same device image is reused.  A
+    replayed graph re-stages ITS matrix behind the runtime's back, and a mapping freed and created again can come back
+    at the same device address: in both cases the next launch must stage its own D again."""
+    lib = capi.nomp()
+    n, E = 8, 9
+    u = ffi.fill_int_f64(E * n ** 3, 5, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 6, 0, 3)
+    D1, D2 = ffi.fill_int_f64(n * n, 7, -2, 2), ffi.fill_int_f64(n * n, 8, -2, 2)
+    w, pap = np.zeros_like(u), np.zeros(1)
+    from nomp_bridge.families import AX_KERNEL_SOURCE
+    k_ax = jit(AX_KERNEL_SOURCE, capi.clauses(), [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I),
+                                                  ("n", 4, I | capi.NOMP_JIT, C.c_int(n))])
+    to_device(u, g, D1, D2, w, pap)
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    ax = lambda D: capi.check(capi.run(k_ax, ptr(w), ptr(u), ptr(g), ptr(D), C.c_int(E)))  # noqa: E731
+    ax(D1)                                             # loads the kernel
+    graph = C.c_int(-1)
+    capi.check(lib.nomp_b200_graph_begin())
+    ax(D1)
+    capi.check(lib.nomp_b200_graph_end(C.byref(graph)))
+    ax(D2)                                             # caches D2 ...
+    capi.check(lib.nomp_b200_graph_launch(graph.value))  # ... the replay stages D1 ...
+    from_device(w)
+    assert np.array_equal(w, ffi.ax(n, u, g, D1))
+    ax(D2)                                             # ... so this launch must not trust its cache
+    from_device(w)
+    assert np.array_equal(w, ffi.ax(n, u, g, D2))
+    capi.check(lib.nomp_b200_graph_free(graph.value))
+    # free D2 and map a matrix with other values at the same host address (and, usually, the same device address)
+    free(D2)
+    D2[:] = ffi.fill_int_f64(n * n, 9, -2, 2)
+    to_device(D2)
+    ax(D2)
+    from_device(w)
+    assert np.array_equal(w, ffi.ax(n, u, g, D2))
+    free(u, g, D1, D2, w, pap)
+
+
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
 def test_direction_update_fused_into_the_operator(n):
     """The canonical xpay + Ax + dot kernel strings (beta as a scalar argument, and as beta[0] in device memory) -> one

@@ -2,6 +2,7 @@
 serves nomp_jit() from disk -- the bridge's output (.knl) and NVRTC's CUBIN (.cubin) -- with identical results, and
 anything that can change a kernel (script text, clauses, NOMP_JIT values) changes the key."""
 import ctypes as C
+import os
 import shutil
 import sys
 import time
@@ -199,3 +200,16 @@ def test_cache_can_be_turned_off(cache, monkeypatch):
     _, d = session(cache, workload)
     assert d == {"knl_hits": 0, "knl_misses": 0, "cubin_hits": 0, "cubin_misses": 0}
     assert not (cache / "jit").exists()
+
+
+def test_cache_directory_must_be_private(cache):
+    """Entries are loaded as device code: a directory that others can write to (or that belongs to somebody else) is not
+    used at all, and a directory the runtime creates itself is created for this user only."""
+    _, d = session(cache, workload)
+    assert d["knl_misses"] == 4 and (os.stat(cache / "jit").st_mode & 0o077) == 0
+    os.chmod(cache / "jit", 0o777)
+    _, d = session(cache, workload)
+    assert d == {"knl_hits": 0, "knl_misses": 0, "cubin_hits": 0, "cubin_misses": 0}, d     # cache off, kernels still built
+    os.chmod(cache / "jit", 0o700)
+    _, d = session(cache, workload)
+    assert d == {"knl_hits": 4, "knl_misses": 0, "cubin_hits": 2, "cubin_misses": 0}

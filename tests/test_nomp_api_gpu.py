@@ -707,6 +707,30 @@ def test_async_update_pipeline():
         capi.check(capi.update(yb, 0, n, 8, capi.NOMP_FREE))
 
 
+def test_async_copy_out_is_ordered_before_later_writers():
+    """nomp_b200_update_async(FROM) returns at once; whatever writes the mapping afterwards -- a kernel with a non-const
+    pointer to it, a blocking nomp_update(TO) -- must wait for the copy, which would otherwise deliver new or torn data."""
+    n = 1 << 23                                            # 64 MiB: the copy takes milliseconds, a kernel microseconds
+    pin = (lambda t: t) if os.environ.get("NOMP_HOSTDEV_ACTIVE") == "1" else (lambda t: t.pin_memory())
+    y = pin(torch.zeros(n, dtype=torch.float64))
+    fresh = np.full(n, 7.0)
+    inc = jit("void inc(double *y, int N) { for (int i = 0; i < N; i++) y[i] += 1; }", capi.clauses(), [("y", 8, P), ("N", 4, I)])
+    capi.check(capi.update(y.data_ptr(), 0, n, 8, capi.NOMP_TO))
+    for rep in range(3):
+        capi.check(capi.run(inc, y.data_ptr(), C.c_int(n)))                     # device: rep + 1
+        capi.check(capi.update_async(y.data_ptr(), 0, n, 8, capi.NOMP_FROM))   # host gets rep + 1 ...
+        capi.check(capi.run(inc, y.data_ptr(), C.c_int(n)))                     # ... although the device moves on at once
+        capi.check(capi.run(inc, y.data_ptr(), C.c_int(n)))
+        capi.check(capi.nomp().nomp_sync())
+        assert torch.all(y == 3.0 * rep + 1.0), (rep, y[:4], y[-4:])
+    capi.check(capi.update_async(y.data_ptr(), 0, n, 8, capi.NOMP_FROM))       # host gets 9 ...
+    capi.check(capi.nomp().nomp_sync())
+    assert torch.all(y == 9.0)
+    capi.check(capi.update(y.data_ptr(), 0, n, 8, capi.NOMP_FREE))              # FREE with copies possibly in flight
+    capi.check(capi.update(fresh.ctypes.data, 0, n, 8, capi.NOMP_TO))
+    capi.check(capi.update(fresh.ctypes.data, 0, n, 8, capi.NOMP_FREE))
+
+
 def test_extensions_and_launch_counter():
     lib = capi.nomp()
     assert lib.nomp_b200_stream() is not None
