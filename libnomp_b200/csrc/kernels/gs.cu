@@ -13,6 +13,11 @@
 //   exchange   one buffer per rank, mapped into every peer (CUDA IPC over NVLink): arrival flags, then two slots
 //              (alternating by call parity) of 8-byte values, one segment per peer.
 //
+//   warp layout  (built when no group has more than 32 local copies, i.e. for every mesh numbering): the copies of the
+//              groups once more as `pidx`, padded so that no group straddles a multiple of 32, with one bit mask per
+//              32 slots that marks the first copy of each group.  gs_local_warp_kernel works on it with one COPY per
+//              lane -- see there.
+//
 // apply = two launches.  gs_local_kernel folds the local copies of each group in ascending index order; local-only
 // groups are written back at once; for shared groups the partial is kept and stored straight into the peers'
 // exchange buffers (P2P stores over NVLink, no staging copy, no NCCL), and the last of the CTAs that hold shared groups
@@ -21,6 +26,8 @@
 // With one rank the second launch does not happen.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "nompk_common.cuh"
@@ -39,6 +46,13 @@ struct nompk_gs {
   size_t G = 0, nnz = 0, Q = 0, R = 0, total_shared = 0;
   unsigned remote_ctas = 0;  // CTAs of gs_local_kernel (kGsThreads consecutive groups each) that hold a shared group
   unsigned *offsets = nullptr, *indices = nullptr;
+  // warp layout (nwarps == 0: not built, gs_local_kernel is used)
+  size_t nwarps = 0;
+  unsigned *pidx = nullptr, *heads = nullptr, *wgroup = nullptr;
+  unsigned short *rowinfo = nullptr;   // per row of 32 slots: longest group | occupied slots << 8
+  unsigned remote_ctas_warp = 0;
+  int rows = 4;                      // rows of 32 slots per warp of gs_local_warp_kernel
+  bool force_group_kernel = false;   // NOMPK_GS_KERNEL=group: profiling / tests of the one-group-per-thread kernel
   int *remote_slot = nullptr;
   unsigned *rgroup = nullptr, *roffsets = nullptr, *rpos = nullptr;
   int *rpeer = nullptr;
@@ -171,9 +185,65 @@ __global__ void mark_remote_ctas_kernel(const int *__restrict__ remote_slot, siz
   if (g < G && remote_slot[g] >= 0) blk[g / threads] = 1u;
 }
 
+// ---- warp layout ------------------------------------------------------------------------------------------------
+// The copies of the groups, in group order, placed so that no group straddles a multiple of 32 slots (a group that
+// would is moved to the next multiple; the slots in between stay empty = 0xffffffff).  One thread lays out a tile of
+// kLayoutTile consecutive groups (a sequential recurrence, 256 short steps); tiles start at multiples of 32.
+constexpr int kLayoutTile = 256;
+constexpr int kGsWarps = 256 / 32;   // warps per CTA of gs_local_warp_kernel (kGsThreads / 32)
+constexpr int kGsRowsDefault = 4;    // rows of 32 slots per warp (NOMPK_GS_ROWS=8 at setup time selects eight)
+
+__global__ void layout_size_kernel(const unsigned *__restrict__ offsets, size_t G, unsigned *__restrict__ tile_warps) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g0 = t * kLayoutTile;
+  if (g0 >= G) return;
+  const size_t g1 = g0 + kLayoutTile < G ? g0 + kLayoutTile : G;
+  unsigned pos = 0;
+  for (size_t g = g0; g < g1; g++) {
+    const unsigned m = offsets[g + 1] - offsets[g];
+    if ((pos & 31u) + m > 32u) pos = (pos + 31u) & ~31u;
+    pos += m;
+  }
+  tile_warps[t] = (pos + 31u) / 32u;
+}
+
+// tile_start holds the exclusive scan of tile_warps on entry; pidx is 0xff-filled, heads zero-filled
+__global__ void layout_fill_kernel(const unsigned *__restrict__ offsets, const unsigned *__restrict__ indices, size_t G,
+                                   const unsigned *__restrict__ tile_start, unsigned *__restrict__ pidx,
+                                   unsigned *__restrict__ heads, unsigned *__restrict__ wgroup,
+                                   unsigned short *__restrict__ rowinfo) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g0 = t * kLayoutTile;
+  if (g0 >= G) return;
+  const size_t g1 = g0 + kLayoutTile < G ? g0 + kLayoutTile : G;
+  const size_t base = (size_t)tile_start[t] * 32;
+  unsigned pos = 0;
+  for (size_t g = g0; g < g1; g++) {
+    const unsigned b = offsets[g], m = offsets[g + 1] - b;
+    if ((pos & 31u) + m > 32u) pos = (pos + 31u) & ~31u;
+    const size_t at = base + pos;
+    for (unsigned c = 0; c < m; c++) pidx[at + c] = indices[b + c];
+    if ((at & 31) == 0) wgroup[at / 32] = (unsigned)g;   // every 32 slots start with the first copy of a group
+    heads[at / 32] |= 1u << (at & 31);                    // (the tile's slots belong to this thread alone)
+    const unsigned longest = rowinfo[at / 32] & 0xffu;    // row summary: longest group, occupied slots
+    rowinfo[at / 32] = (unsigned short)((longest > m ? longest : m) | (((unsigned)(at & 31) + m) << 8));
+    pos += m;
+  }
+}
+
+// blk[c] = 1 if CTA c of gs_local_warp_kernel holds a group shared with a peer (the shared groups are the first Q)
+__global__ void mark_remote_warp_ctas_kernel(const unsigned *__restrict__ wgroup, size_t nwarps, size_t Q, int rows_per_cta,
+                                             unsigned *__restrict__ blk) {
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nwarps && wgroup[w] < Q) blk[w / rows_per_cta] = 1u;
+}
+
 // ---- apply ----------------------------------------------------------------------------------------------------
 struct GsView {
   const unsigned *offsets, *indices;
+  const unsigned *pidx, *heads, *wgroup;   // warp layout
+  const unsigned short *rowinfo;
+  size_t nwarps;
   const int *remote_slot;
   const unsigned *rgroup, *roffsets, *rpos;
   const int *rpeer;
@@ -224,6 +294,82 @@ template <int OP, typename T> __global__ void __launch_bounds__(kGsThreads) gs_l
   // This rank's values are complete on every neighbour once all CTAs that hold shared groups have passed here; the
   // last of THEM raises the flags.  (One ticket per CTA of the whole grid would serialise 10^4 - 10^5 atomics on one
   // address: tens of microseconds for a kernel of a few hundred.)
+  if (!__syncthreads_or(remote_here)) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(s.ticket, 1u);
+    if (t == s.remote_ctas - 1) {
+      *s.ticket = 0;
+      __threadfence_system();
+      for (int i = 0; i < s.n_neighbours; i++) {
+        unsigned long long *flags = static_cast<unsigned long long *>(s.peer_xchg[s.neighbours[i]]);
+        *reinterpret_cast<volatile unsigned long long *>(flags + (size_t)s.slot * s.world + s.rank) = s.seq;
+      }
+    }
+  }
+}
+
+// One COPY per lane instead of one group per thread.  gs_local_kernel walks offsets -> indices -> values: three loads that
+// each wait for the one before, 40 warp-cycles of long-scoreboard stall per issued instruction, DRAM half idle (ncu,
+// profiles/r02_ncu_summary.md).  Here a warp reads kGsRows rows of 32 consecutive slots of `pidx` (coalesced loads that
+// depend on nothing), gathers the values, and folds every group inside its row with shuffles: two dependent loads, no
+// offsets, and the index traffic is one 128-byte line per row.  0.504 ms against 0.580 ms on 1.3e8 points.  The fold is SERIAL in ascending copy order, led by the
+// lane of a group's first copy (head), so the bits are those of gs_local_kernel and of the oracle: step s combines
+// what the lane s places further on holds, for the heads whose group is longer than s.  Groups shared with a peer are
+// the first Q groups (first_index_kernel), so "shared" is a comparison and the slot of the partial is the group number.
+template <int OP, typename T, int kGsRows> __global__ void __launch_bounds__(kGsThreads) gs_local_warp_kernel(T *__restrict__ v, GsView s) {
+  const unsigned lane = threadIdx.x & 31u;
+  // a warp takes kGsRows consecutive rows of 32 slots: all index loads, then all value loads are in flight together
+  const size_t w0 = ((size_t)blockIdx.x * kGsWarps + (threadIdx.x >> 5)) * kGsRows;
+  bool remote_here = false;
+  unsigned idx[kGsRows], hm[kGsRows], info[kGsRows];
+  T val[kGsRows];
+#pragma unroll
+  for (int r = 0; r < kGsRows; r++) {
+    const bool on = w0 + r < s.nwarps;   // warp-uniform
+    idx[r] = on ? s.pidx[(w0 + r) * 32 + lane] : 0xffffffffu;
+    hm[r] = on ? s.heads[w0 + r] : 1u;
+    info[r] = on ? s.rowinfo[w0 + r] : 0x0101u;
+  }
+#pragma unroll
+  for (int r = 0; r < kGsRows; r++) {
+    val[r] = T(0);
+    if (idx[r] != 0xffffffffu) val[r] = v[idx[r]];   // empty slots are the last slots of a row
+  }
+  const unsigned le = 0xffffffffu >> (31u - lane);                        // lanes up to and including this one
+#pragma unroll
+  for (int r = 0; r < kGsRows; r++) {
+    if (w0 + r >= s.nwarps) break;                                        // warp-uniform
+    const bool valid = idx[r] != 0xffffffffu;
+    const int maxlen = (int)(info[r] & 0xffu), occupied = (int)(info[r] >> 8);   // the same for the whole row
+    const unsigned vm = occupied >= 32 ? 0xffffffffu : (1u << occupied) - 1u;
+    const int head = 31 - __clz((int)(hm[r] & le));                       // first copy of this lane's group (slot 0 is a head)
+    const bool is_head = valid && ((hm[r] >> lane) & 1u);
+    const unsigned after = (hm[r] & ~le) | ~vm;                           // the next head, or the first empty slot
+    const int len = (after ? __ffs((int)after) - 1 : 32) - (int)lane;     // copies of the group, for its head
+    T acc = val[r];
+    for (int step = 1; step < maxlen; step++) {
+      const T x = __shfl_sync(0xffffffffu, val[r], (int)((lane + step) & 31u));
+      if (is_head && step < len) acc = combine<OP, T>(acc, x);
+    }
+    const T res = __shfl_sync(0xffffffffu, acc, head);
+    const size_t g = (size_t)s.wgroup[w0 + r] + (unsigned)__popc(hm[r] & ((1u << head) - 1u));
+    const bool shared = g < s.Q;
+    if (valid && !shared) v[idx[r]] = res;
+    if (is_head && shared) {
+      unsigned long long word = 0;
+      memcpy(&word, &acc, sizeof(T));
+      s.partial[g] = word;
+      for (unsigned k = s.roffsets[g]; k < s.roffsets[g + 1]; k++) {
+        const int rk = s.rpeer[k];
+        char *dst = static_cast<char *>(s.peer_xchg[rk]) + s.flags_bytes + (s.send_off[s.slot * s.world + rk] + s.rpos[k]) * 8;
+        *reinterpret_cast<volatile unsigned long long *>(dst) = word;
+      }
+      __threadfence_system();
+      remote_here = true;
+    }
+  }
+  if (s.Q == 0) return;
   if (!__syncthreads_or(remote_here)) return;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -290,14 +436,19 @@ template <int OP, typename T> int launch_gs(nompk_gs *gs, void *v, unsigned long
   s.rgroup = gs->rgroup, s.roffsets = gs->roffsets, s.rpos = gs->rpos, s.rpeer = gs->rpeer;
   s.partial = gs->partial, s.ticket = gs->ticket, s.recv_off = gs->d_recv_off, s.send_off = gs->d_send_off;
   s.peer_xchg = gs->d_peer_xchg, s.neighbours = gs->d_neighbours;
-  s.G = gs->G, s.Q = gs->Q, s.remote_ctas = gs->remote_ctas;
-  const unsigned blocks = (unsigned)((gs->G + kGsThreads - 1) / kGsThreads);
+  const bool warp_layout = gs->nwarps > 0 && !gs->force_group_kernel;
+  s.pidx = gs->pidx, s.heads = gs->heads, s.wgroup = gs->wgroup, s.rowinfo = gs->rowinfo, s.nwarps = gs->nwarps;
+  s.G = gs->G, s.Q = gs->Q, s.remote_ctas = warp_layout ? gs->remote_ctas_warp : gs->remote_ctas;
+  const unsigned blocks = warp_layout ? (unsigned)((gs->nwarps + kGsWarps * gs->rows - 1) / (kGsWarps * gs->rows))
+                                      : (unsigned)((gs->G + kGsThreads - 1) / kGsThreads);
   s.slot = (int)(gs->seq & 1ull);
   s.flags_bytes = flags_bytes(gs->world);
   s.values_base = s.flags_bytes + (size_t)s.slot * gs->total_shared * 8;
   s.n_neighbours = gs->n_neighbours, s.rank = gs->rank, s.world = gs->world;
   s.seq = gs->seq, s.error_host = error_host;
-  gs_local_kernel<OP, T><<<blocks, kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
+  if (warp_layout && gs->rows == 8) gs_local_warp_kernel<OP, T, 8><<<blocks, kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
+  else if (warp_layout) gs_local_warp_kernel<OP, T, kGsRowsDefault><<<blocks, kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
+  else gs_local_kernel<OP, T><<<blocks, kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
   NOMPK_LAUNCH_CHECK("gs_local_kernel");
   if (gs->Q > 0) {
     gs_remote_kernel<OP, T><<<(unsigned)((gs->Q + kGsThreads - 1) / kGsThreads), kGsThreads, 0, stream>>>(static_cast<T *>(v), s);
@@ -360,7 +511,7 @@ using namespace nompk;
 extern "C" void nompk_gs_destroy(nompk_gs_t *gs) {
   if (!gs) return;
   for (unsigned *p : gs->peer_pos) cudaFree(p);
-  void *ptrs[] = {gs->unique_ids, gs->run_count, gs->run_start, gs->sorted_idx, gs->offsets, gs->indices,
+  void *ptrs[] = {gs->unique_ids, gs->run_count, gs->run_start, gs->sorted_idx, gs->offsets, gs->indices, gs->pidx, gs->heads, gs->wgroup, gs->rowinfo,
                   gs->remote_slot, gs->rgroup, gs->roffsets, gs->rpos, gs->rpeer, gs->partial, gs->ticket,
                   gs->d_recv_off, gs->d_send_off, gs->d_peer_xchg, gs->d_neighbours};
   for (void *p : ptrs) cudaFree(p);
@@ -571,6 +722,68 @@ extern "C" int nompk_gs_finalize_setup(nompk_gs_t *gs, int rank, int world, size
       cudaFree(blk), cudaFree(blk_scan);
       if (e) return e;
       gs->remote_ctas = (unsigned)count;
+    }
+    // warp layout for gs_local_warp_kernel: only if every group fits into one warp (true for any mesh numbering: a point is
+    // shared by at most 8 hexahedra; an artificial numbering with longer groups keeps the one-group-per-thread kernel)
+    if (G > 0) {
+      unsigned *maxcnt = nullptr, *tile_warps = nullptr, *tile_start = nullptr;
+      void *tmp2 = nullptr;
+      auto layout = [&]() -> int {
+        if (int e = dev_alloc(&maxcnt, 1)) return e;
+        size_t bytes = 0;
+        NOMPK_CUDA_TRY(cub::DeviceReduce::Max(nullptr, bytes, cnt, maxcnt, (int)G, stream));
+        NOMPK_CUDA_TRY(cudaMalloc(&tmp2, bytes ? bytes : 1));
+        NOMPK_CUDA_TRY(cub::DeviceReduce::Max(tmp2, bytes, cnt, maxcnt, (int)G, stream));
+        unsigned h = 0;
+        NOMPK_CUDA_TRY(cudaMemcpyAsync(&h, maxcnt, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        NOMPK_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h > 32 || G > 0x7fffffffull) return NOMPK_OK;   // no layout: gs->nwarps stays 0
+        const char *rows_env = getenv("NOMPK_GS_ROWS");
+        gs->rows = rows_env && atoi(rows_env) == 8 ? 8 : kGsRowsDefault;
+        const size_t ntiles = (G + kLayoutTile - 1) / kLayoutTile;
+        if (int e = dev_alloc(&tile_warps, ntiles)) return e;
+        if (int e = dev_alloc(&tile_start, ntiles + 1)) return e;
+        layout_size_kernel<<<blocks_for(ntiles), 256, 0, stream>>>(gs->offsets, G, tile_warps);
+        NOMPK_LAUNCH_CHECK("layout_size_kernel");
+        size_t nwarps = 0;
+        if (int e = exclusive_sum(tile_warps, tile_start, ntiles, &nwarps, stream)) return e;
+        if (nwarps * 32 >= 0xffffffffull) return NOMPK_OK;
+        if (int e = dev_alloc(&gs->pidx, nwarps * 32)) return e;
+        if (int e = dev_alloc(&gs->heads, nwarps)) return e;
+        if (int e = dev_alloc(&gs->wgroup, nwarps)) return e;
+        if (int e = dev_alloc(&gs->rowinfo, nwarps)) return e;
+        NOMPK_CUDA_TRY(cudaMemsetAsync(gs->rowinfo, 0, nwarps * sizeof(unsigned short), stream));
+        NOMPK_CUDA_TRY(cudaMemsetAsync(gs->pidx, 0xff, nwarps * 32 * sizeof(unsigned), stream));
+        NOMPK_CUDA_TRY(cudaMemsetAsync(gs->heads, 0, nwarps * sizeof(unsigned), stream));
+        NOMPK_CUDA_TRY(cudaMemsetAsync(gs->wgroup, 0xff, nwarps * sizeof(unsigned), stream));
+        layout_fill_kernel<<<blocks_for(ntiles), 256, 0, stream>>>(gs->offsets, gs->indices, G, tile_start, gs->pidx, gs->heads, gs->wgroup, gs->rowinfo);
+        NOMPK_LAUNCH_CHECK("layout_fill_kernel");
+        if (Q > 0) {
+          const size_t nblk = (nwarps + kGsWarps * gs->rows - 1) / (kGsWarps * gs->rows);
+          unsigned *blk = nullptr, *blk_scan = nullptr;
+          if (int e = dev_alloc(&blk, nblk)) return e;
+          if (int e = dev_alloc(&blk_scan, nblk + 1)) {
+            cudaFree(blk);
+            return e;
+          }
+          size_t count = 0;
+          cudaMemsetAsync(blk, 0, nblk * sizeof(unsigned), stream);
+          mark_remote_warp_ctas_kernel<<<blocks_for(nwarps), 256, 0, stream>>>(gs->wgroup, nwarps, Q, kGsWarps * gs->rows, blk);
+          const int e = exclusive_sum(blk, blk_scan, nblk, &count, stream);
+          cudaFree(blk), cudaFree(blk_scan);
+          if (e) return e;
+          gs->remote_ctas_warp = (unsigned)count;
+        }
+        NOMPK_CUDA_TRY(cudaStreamSynchronize(stream));
+        gs->nwarps = nwarps;
+        return NOMPK_OK;
+      };
+      const int e = layout();
+      cudaStreamSynchronize(stream);
+      cudaFree(maxcnt), cudaFree(tile_warps), cudaFree(tile_start), cudaFree(tmp2);
+      if (e) return e;
+      const char *force = getenv("NOMPK_GS_KERNEL");
+      gs->force_group_kernel = force && !strcmp(force, "group");
     }
     const unsigned r32 = (unsigned)R;
     NOMPK_CUDA_TRY(cudaMemcpyAsync(gs->roffsets + Q, &r32, sizeof(unsigned), cudaMemcpyHostToDevice, stream));

@@ -186,6 +186,14 @@ static inline int __any_sync(unsigned, int pred) {
   for (int l = 0; l < 32; l++) any |= nomp_emu_exchange<int>(pred != 0, l);
   return any;
 }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) m |= (unsigned)nomp_emu_exchange<int>(pred != 0, l) << l;
+  return m;
+}
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 """
 
 _COOP_DRIVER = r"""

@@ -1,4 +1,5 @@
-"""The two device kernels of the gather-scatter (libnomp_b200/csrc/kernels/gs.cu: gs_local_kernel, gs_remote_kernel)
+"""The device kernels of the gather-scatter (libnomp_b200/csrc/kernels/gs.cu: gs_local_kernel -- one group per thread --,
+gs_local_warp_kernel -- one copy per lane, groups folded with shuffles -- and gs_remote_kernel)
 compiled for the HOST -- their text is cut out of gs.cu unchanged -- and executed with the cooperative emulator, one
 thread per rank and host memory as "peer memory".  The index structures the CUDA setup builds with CUB are rebuilt here
 with numpy from their documented meaning, so this checks the protocol between the ranks (segments and slot strides in
@@ -23,11 +24,14 @@ enum { NOMPK_RED_SUM = 0, NOMPK_RED_PROD = 1, NOMPK_RED_MIN = 2, NOMPK_RED_MAX =
 template <typename T> static inline T op_add(T a, T b) { return a + b; }
 template <typename T> static inline T op_mul(T a, T b) { return a * b; }
 constexpr int kGsThreads = 256;
+constexpr int kGsWarps = 256 / 32;
 constexpr unsigned long long kGsTimeoutNs = 20ull * 1000 * 1000 * 1000;
 static inline unsigned long long timer_ns() { return nomp_emu_now_ns(); }
 """
 WRAPPERS = r"""
 static void local_sum_f64(double *v, GsView s) { gs_local_kernel<NOMPK_RED_SUM, double>(v, s); }
+static void warp_sum_f64(double *v, GsView s) { gs_local_warp_kernel<NOMPK_RED_SUM, double, 4>(v, s); }
+static void warp_max_i64(long long *v, GsView s) { gs_local_warp_kernel<NOMPK_RED_MAX, long long, 4>(v, s); }
 static void remote_sum_f64(double *v, GsView s) { gs_remote_kernel<NOMPK_RED_SUM, double>(v, s); }
 static void local_max_i64(long long *v, GsView s) { gs_local_kernel<NOMPK_RED_MAX, long long>(v, s); }
 static void remote_max_i64(long long *v, GsView s) { gs_remote_kernel<NOMPK_RED_MAX, long long>(v, s); }
@@ -44,7 +48,8 @@ def device_source():
 
 
 class GsView(C.Structure):
-    _fields_ = [("offsets", C.c_void_p), ("indices", C.c_void_p), ("remote_slot", C.c_void_p), ("rgroup", C.c_void_p),
+    _fields_ = [("offsets", C.c_void_p), ("indices", C.c_void_p), ("pidx", C.c_void_p), ("heads", C.c_void_p), ("wgroup", C.c_void_p),
+                ("rowinfo", C.c_void_p), ("nwarps", C.c_size_t), ("remote_slot", C.c_void_p), ("rgroup", C.c_void_p),
                 ("roffsets", C.c_void_p), ("rpos", C.c_void_p), ("rpeer", C.c_void_p), ("partial", C.c_void_p),
                 ("ticket", C.c_void_p), ("recv_off", C.c_void_p), ("send_off", C.c_void_p), ("peer_xchg", C.c_void_p),
                 ("neighbours", C.c_void_p), ("G", C.c_size_t), ("Q", C.c_size_t), ("values_base", C.c_size_t),
@@ -107,6 +112,34 @@ class Rank:
         self.n_neighbours = sum(1 for c in self.counts if c > 0)
         blocks = {g // 256 for g, q in enumerate(remote_slot) if q >= 0}
         self.remote_ctas = len(blocks)
+        # warp layout: tiles of 256 groups start at multiples of 32 slots; inside a tile a group that would straddle a
+        # multiple of 32 moves to the next one; heads = first copy of each group; wgroup = group of a warp's first slot
+        pidx, heads, wgroup, rowinfo = [], [], [], []
+        sizes = np.diff(self.offsets)
+        self.warp_layout = sizes.size > 0 and int(sizes.max()) <= 32
+        if self.warp_layout:
+            for t0 in range(0, self.G, 256):
+                pos = len(pidx)
+                assert pos % 32 == 0
+                for g in range(t0, min(self.G, t0 + 256)):
+                    m = int(sizes[g])
+                    if len(pidx) % 32 + m > 32:
+                        pidx += [0xffffffff] * (-len(pidx) % 32)
+                    at = len(pidx)
+                    while len(heads) <= at // 32:
+                        heads.append(0)
+                        wgroup.append(0xffffffff)
+                        rowinfo.append(0)
+                    rowinfo[at // 32] = max(rowinfo[at // 32] & 0xff, m) | ((at % 32 + m) << 8)   # longest group | occupied slots << 8
+                    if at % 32 == 0:
+                        wgroup[at // 32] = g
+                    heads[at // 32] |= 1 << (at % 32)
+                    pidx += indices[offsets[g]:offsets[g + 1]]
+                pidx += [0xffffffff] * (-len(pidx) % 32)
+        self.pidx, self.heads, self.wgroup = u32(pidx + [0]), u32(heads + [0]), u32(wgroup + [0])
+        self.rowinfo = np.array(rowinfo + [0], dtype=np.uint16)
+        self.nwarps = len(heads)
+        self.remote_ctas_warp = len({w // 32 for w in range(self.nwarps) if wgroup[w] < len(rgroup)})
         self.partial = np.zeros(max(self.Q, 1), dtype=np.uint64)
         self.ticket = np.zeros(2, dtype=np.uint32)
         self.xchg = np.zeros((flags_bytes(world) + 2 * self.total * 8) // 8 + 1, dtype=np.uint64)
@@ -122,17 +155,21 @@ class Rank:
             send[world + r] = ranks[r].total + int(ranks[r].recv_off[self.rank])
         self.send_off = send
 
-    def view(self):
+    def view(self, warp=False):
         self.seq += 1
         slot = self.seq & 1
         p = lambda a: a.ctypes.data  # noqa: E731
-        return GsView(p(self.offsets), p(self.indices), p(self.remote_slot), p(self.rgroup), p(self.roffsets), p(self.rpos),
+        return GsView(p(self.offsets), p(self.indices), p(self.pidx), p(self.heads), p(self.wgroup), p(self.rowinfo), self.nwarps, p(self.remote_slot),
+                      p(self.rgroup), p(self.roffsets), p(self.rpos),
                       p(self.rpeer), p(self.partial), p(self.ticket), p(self.recv_off), p(self.send_off), p(self.table),
-                      p(self.neighbours), self.G, self.Q, flags_bytes(self.world) + slot * self.total * 8, self.remote_ctas,
+                      p(self.neighbours), self.G, self.Q, flags_bytes(self.world) + slot * self.total * 8,
+                      self.remote_ctas_warp if warp else self.remote_ctas,
                       flags_bytes(self.world), self.n_neighbours, self.rank, self.world, slot, self.seq, p(self.error))
 
 
-def apply(ranks, parts, kind):
+def apply(ranks, parts, kind, warp=None):
+    """`warp`: per rank, use gs_local_warp_kernel (default: wherever the layout exists, as the library does; a list mixes
+    the two local kernels between the ranks -- they speak one protocol)."""
     T = {"sum_f64": "double", "max_i64": "long long"}[kind]
     src = device_source()
     errors = []
@@ -142,10 +179,15 @@ def apply(ranks, parts, kind):
             rk = ranks[r]
             if rk.G == 0:
                 return
-            view = rk.view()
+            use_warp = rk.warp_layout if warp is None else (warp[r] and rk.warp_layout)
+            view = rk.view(use_warp)
             v = C.c_void_p(parts[r].ctypes.data)
-            emu.emulate_cooperative(src, f"local_{kind}", ((rk.G + 255) // 256, 1, 1), (256, 1, 1), [f"{T} *", "GsView"], [v, view],
-                                    instance=20 + r)
+            if use_warp:
+                emu.emulate_cooperative(src, f"warp_{kind}", ((rk.nwarps + 31) // 32, 1, 1), (256, 1, 1), [f"{T} *", "GsView"], [v, view],
+                                        instance=20 + r)
+            else:
+                emu.emulate_cooperative(src, f"local_{kind}", ((rk.G + 255) // 256, 1, 1), (256, 1, 1), [f"{T} *", "GsView"], [v, view],
+                                        instance=20 + r)
             if rk.Q:
                 emu.emulate_cooperative(src, f"remote_{kind}", ((rk.Q + 255) // 256, 1, 1), (256, 1, 1), [f"{T} *", "GsView"],
                                         [v, view], instance=20 + r)
@@ -178,9 +220,11 @@ def test_gs_kernels_between_host_ranks(world):
         full = rng.uniform(0.5, 1.5, ids_all.size)
         want = ffi.gs(0, ffi.F64, ids_all, full.copy(), seg)
         parts = [full[seg[r]:seg[r + 1]].copy() for r in range(world)]
-        apply(ranks, parts, "sum_f64")
+        # call 0: every rank with the warp kernel, call 1: every rank with the group kernel, call 2: mixed
+        apply(ranks, parts, "sum_f64", warp=[None, [False] * world, [r % 2 == 0 for r in range(world)]][call])
         for r in range(world):
             assert np.array_equal(parts[r], want[seg[r]:seg[r + 1]]), (world, call, r)
+    assert all(rk.warp_layout for rk in ranks)
     full = rng.integers(-1000, 1000, ids_all.size).astype(np.int64)
     want = ffi.gs(3, ffi.I64, ids_all, full.copy(), seg)
     parts = [full[seg[r]:seg[r + 1]].copy() for r in range(world)]
@@ -223,11 +267,18 @@ SETUP_KERNELS = {
                     "unsigned *", "size_t"],
     "mark_remote_ctas_kernel": ["const int *", "size_t", "int", "unsigned *"],
 }
+LAYOUT_KERNELS = {
+    "layout_size_kernel": ["const unsigned *", "size_t", "unsigned *"],
+    "layout_fill_kernel": ["const unsigned *", "const unsigned *", "size_t", "const unsigned *", "unsigned *", "unsigned *", "unsigned *",
+                           "unsigned short *"],
+    "mark_remote_warp_ctas_kernel": ["const unsigned *", "size_t", "size_t", "int", "unsigned *"],
+}
+SETUP_KERNELS.update(LAYOUT_KERNELS)
 
 
 def setup_source():
     text = GS_CU.read_text()
-    a, b = text.index("// ---- setup kernels"), text.index("// ---- apply")
+    a, b = text.index("// ---- setup kernels"), text.index("// ---- apply")      # includes the warp-layout kernels
     return "#include <cstddef>\n" + text[a:b]
 
 
@@ -292,8 +343,23 @@ def device_setup(rank, id_parts):
     roffsets[Q] = R
     blk = np.zeros((G + 255) // 256 + 1, dtype=np.uint32)
     launch("mark_remote_ctas_kernel", G, remote_slot, G, 256, blk)
-    return dict(G=G, Q=Q, offsets=offsets, indices=indices[:nnz], remote_slot=remote_slot[:G], rgroup=rgroup[:Q], roffsets=roffsets,
-                rpeer=rpeer[:R], rpos=rpos[:R], shared=shared, remote_ctas=int(blk.sum()))
+    out = dict(G=G, Q=Q, offsets=offsets, indices=indices[:nnz], remote_slot=remote_slot[:G], rgroup=rgroup[:Q], roffsets=roffsets,
+               rpeer=rpeer[:R], rpos=rpos[:R], shared=shared, remote_ctas=int(blk.sum()), nwarps=0)
+    if G and int(cnt[:G].max()) <= 32:                                    # cub::DeviceReduce::Max
+        ntiles = (G + 255) // 256
+        tile_warps = np.zeros(ntiles, dtype=np.uint32)
+        launch("layout_size_kernel", ntiles, offsets, G, tile_warps)
+        tile_start = excl(tile_warps)
+        nwarps = int(tile_start[ntiles])
+        pidx = np.full(nwarps * 32 + 1, 0xffffffff, dtype=np.uint32)
+        heads, wgroup = np.zeros(nwarps + 1, dtype=np.uint32), np.full(nwarps + 1, 0xffffffff, dtype=np.uint32)
+        rowinfo = np.zeros(nwarps + 1, dtype=np.uint16)
+        launch("layout_fill_kernel", ntiles, offsets, indices, G, tile_start, pidx, heads, wgroup, rowinfo)
+        wblk = np.zeros((nwarps + 31) // 32 + 1, dtype=np.uint32)
+        launch("mark_remote_warp_ctas_kernel", nwarps, wgroup, nwarps, Q, 32, wblk)
+        out.update(nwarps=nwarps, pidx=pidx[:nwarps * 32], heads=heads[:nwarps], wgroup=wgroup[:nwarps], rowinfo=rowinfo[:nwarps],
+                   remote_ctas_warp=int(wblk.sum()))
+    return out
 
 
 @pytest.mark.parametrize("kind", ["slabs", "random"])
@@ -309,6 +375,7 @@ def test_setup_kernels_build_the_documented_structures(kind):
     else:
         rng = np.random.default_rng(4)
         id_parts = [rng.integers(-1, 700, 3000).astype(np.int64) for _ in range(world)]
+        id_parts[1][100:140] = 77            # a group of more than 32 copies: rank 1 keeps the one-group-per-thread kernel
     for rank in range(world):
         got, want = device_setup(rank, id_parts), Rank(rank, id_parts)
         assert got["G"] == want.G and got["Q"] == want.Q and got["shared"] == want.counts
@@ -317,3 +384,11 @@ def test_setup_kernels_build_the_documented_structures(kind):
             assert np.array_equal(got[name], getattr(want, name)), (rank, name)
         for name in ("indices", "remote_slot", "rgroup", "rpeer", "rpos"):
             assert np.array_equal(got[name], getattr(want, name)[:got[name].size]), (rank, name)
+        assert (got["nwarps"] > 0) == want.warp_layout
+        if want.warp_layout:
+            assert got["nwarps"] == want.nwarps and got["remote_ctas_warp"] == want.remote_ctas_warp
+            for name in ("pidx", "heads", "wgroup", "rowinfo"):
+                assert np.array_equal(got[name], getattr(want, name)[:got[name].size]), (rank, name)
+            assert np.array_equal(got["rgroup"], np.arange(got["Q"])), "the groups shared with a peer must be the first groups"
+    if kind == "random":
+        assert [Rank(r, id_parts).warp_layout for r in range(world)] == [True, False, True]

@@ -26,14 +26,24 @@ TORCH = {capi.F64: torch.float64, capi.F32: torch.float32, capi.I32: torch.int32
 class Gs:
     """nompk_gs_* on one GPU (world = 1)."""
 
-    def __init__(self, ids):
+    def __init__(self, ids, kernel=None):
+        """kernel: None = what the library picks (one copy per lane wherever no group has more than 32 copies),
+        "group" = the one-group-per-thread kernel (NOMPK_GS_KERNEL=group at setup time)."""
         self.lib = capi.nompk()
         self.st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         ids_dev = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).cuda()
         self.h = C.c_void_p()
         capi.nompk_check(self.lib.nompk_gs_create(ids_dev.data_ptr(), ids_dev.numel(), C.byref(self.h), self.st))
         xb = C.c_size_t(99)
-        capi.nompk_check(self.lib.nompk_gs_finalize_setup(self.h, 0, 1, C.byref(xb), self.st))
+        old = os.environ.pop("NOMPK_GS_KERNEL", None)
+        if kernel:
+            os.environ["NOMPK_GS_KERNEL"] = kernel
+        try:
+            capi.nompk_check(self.lib.nompk_gs_finalize_setup(self.h, 0, 1, C.byref(xb), self.st))
+        finally:
+            os.environ.pop("NOMPK_GS_KERNEL", None)
+            if old is not None:
+                os.environ["NOMPK_GS_KERNEL"] = old
         assert xb.value == 0
 
     def stats(self):
@@ -55,13 +65,14 @@ def values(dtype, n, seed):
     return rng.integers(-1000, 1000, n).astype(NP[dtype])
 
 
-@pytest.mark.parametrize("shape", [(4, 3, 2, 2), (8, 4, 3, 2), (2, 5, 5, 5), (6, 1, 1, 7)])
-def test_box_mesh_multiplicities_and_sum(shape):
+@pytest.mark.parametrize("kernel", [None, "group"])
+@pytest.mark.parametrize("shape", [(4, 3, 2, 2), (8, 4, 3, 2), (2, 5, 5, 5), (6, 1, 1, 7), (8, 9, 7, 5)])
+def test_box_mesh_multiplicities_and_sum(shape, kernel):
     """Summing ones gives the multiplicity of each point of a box of elements: 1 inside, 2 on faces, 4 on edges, 8 at
     corners shared by eight elements; random data agree with the oracle bit for bit."""
     n, ex, ey, ez = shape
     ids = ffi.box_ids(n, ex, ey, ez)
-    gs = Gs(ids)
+    gs = Gs(ids, kernel)
     st = gs.stats()
     N = n - 1
     points = (N * ex + 1) * (N * ey + 1) * (N * ez + 1)
@@ -79,13 +90,17 @@ def test_box_mesh_multiplicities_and_sum(shape):
     gs.close()
 
 
+@pytest.mark.parametrize("big_group", [False, True])
 @pytest.mark.parametrize("dtype", [capi.F64, capi.F32, capi.I32, capi.I64])
 @pytest.mark.parametrize("op", [capi.RED_SUM, capi.RED_PROD, capi.RED_MIN, capi.RED_MAX])
-def test_all_types_and_operators_on_random_numbering(dtype, op):
-    """Ids drawn at random (groups of 1 .. ~20 copies, some ids <= 0 that must be left alone)."""
+def test_all_types_and_operators_on_random_numbering(dtype, op, big_group):
+    """Ids drawn at random (groups of 1 .. ~20 copies, some ids <= 0 that must be left alone): folded by the warp kernel
+    in serial order; with one group of 50 copies the handle falls back to the one-group-per-thread kernel."""
     rng = np.random.default_rng(17)
     n = 200003
     ids = rng.integers(-3, n // 8, n).astype(np.int64)
+    if big_group:
+        ids[rng.choice(n, 50, replace=False)] = 5
     v = values(dtype, n, 5)
     if op == capi.RED_PROD:
         v = (np.sign(v) * (1 + (np.abs(v) % 3) / 4)).astype(NP[dtype]) if dtype in (capi.F64, capi.F32) else (v % 3 + 1).astype(NP[dtype])

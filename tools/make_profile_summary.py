@@ -20,7 +20,7 @@ prof = ROOT / "profiles"
 
 CAPTURES = [
     ("ax8", "ax 8 262144 0 5", "Ax N=7, E=262144 (the headline workload)", 262144 * 512 * 64),
-    ("ax10", "ax 10 131072 0 5", "Ax N=9", 131072 * 1000 * 64),
+    ("ax10", "ax 10 262144 0 5", "Ax N=9, E=262144 (BASELINE configs[3])", 262144 * 1000 * 64),
     ("ax12", "ax 12 65536 0 5", "Ax N=11", 65536 * 1728 * 64),
     ("ax6", "ax 6 524288 0 5", "Ax N=5", 524288 * 216 * 64),
     ("axdot8", "axdot 8 262144 0 5", "Ax N=7 fused with p.Ap", 262144 * 512 * 64),
@@ -40,6 +40,62 @@ def counter(text, name):
     if not m:
         return None
     return float(m.group(1).replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1.0, "us": 1e-3}[m.group(2)]
+
+
+def variant_study(src, rnd):
+    """Section 4: DRAM bytes and interleaved timings of every Ax variant (tools/ax_dram_probe.py, tools/ax_sweep.py)."""
+    import collections
+    import csv
+    names = ("n", "elements per group", "warps per group", "groups per CTA", "slabs in registers (kGeoAhead)", "prefetch distance (kPf)",
+             "streaming loads", "min CTAs / SM", "fused dot", "persistent", "two buffers", "xpay", "kPfMode")
+    text = ["\n## 4. The prefetch window of the Ax kernel: DRAM bytes and time per variant\n\n"
+            "`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:ax_kernel python "
+            "tools/ax_dram_probe.py <n> <E> <variants>` (second launch of each variant), and the medians of five interleaved rounds of "
+            "`tools/ax_sweep.py axrobust` (CUDA events, not under ncu; `" + rnd + "_kernel_sweeps.jsonl`).  Template arguments: "
+            + ", ".join(names) + ".  kPfMode: 0 = the window runs on into the group's next element, 1 / 2 = the same with evict_last "
+            "prefetches / and evict_first demand loads, 3 = local window (each element warms its own), 4 = local window and "
+            "evict_first demand loads (DESIGN.md 5.3).\n"]
+    sweeps = collections.defaultdict(dict)
+    f = src / "ax_interleaved.jsonl"
+    if f.exists():
+        for line in open(f):
+            try:
+                r = json.loads(line)
+                sweeps[r["n"]][r["variant"]] = r
+            except Exception:
+                pass
+    variants = [0, 7, 22, 23] + list(range(30, 48))
+    for n, E in ((10, 32768), (12, 16384), (6, 131072), (8, 65536)):
+        f = src / f"dram_n{n}.csv"
+        if not f.exists():
+            continue
+        rows = list(csv.reader(open(f)))
+        hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"]
+        if not hi:
+            continue
+        hdr = rows[hi[0]]
+        ix = {h: i for i, h in enumerate(hdr)}
+        per = collections.OrderedDict()
+        for r in rows[hi[0] + 1:]:
+            if len(r) < len(hdr):
+                continue
+            name = re.sub(r"\(int\)|\(bool\)", "", r[ix["Kernel Name"]].split("ax_kernel<")[1].split(">")[0])
+            per.setdefault((r[ix["ID"]], name), {})[r[ix["Metric Name"]]] = (float(r[ix["Metric Value"]].replace(",", "")), r[ix["Metric Unit"]])
+        alg_r, alg_w = E * n ** 3 * 56 / 1e9, E * n ** 3 * 8 / 1e9
+        unit = {"Gbyte": 1, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
+        text.append(f"\n### n = {n} (ncu at E = {E})\n\n| template arguments | DRAM read / algorithmic | DRAM write / algorithmic | ms under ncu |\n|---|---:|---:|---:|\n")
+        seen = collections.Counter()
+        for (_, name), m in per.items():
+            seen[name] += 1
+            if seen[name] != 2 or "dram__bytes_read.sum" not in m:
+                continue
+            rd, wr, t = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"], m["gpu__time_duration.sum"]
+            ms = t[0] * {"ms": 1, "us": 1e-3, "ns": 1e-6}.get(t[1], 1)
+            text.append(f"| `{name}` | {rd[0] * unit[rd[1]] / alg_r:.3f} | {wr[0] * unit[wr[1]] / alg_w:.3f} | {ms:.3f} |\n")
+        if sweeps.get(n):
+            text.append(f"\nInterleaved timings (variant number of `dispatch_ax`, E = {next(iter(sweeps[n].values()))['E']}): "
+                        + ", ".join(f"v{v}: {sweeps[n][v]['gdofs']:.1f} GDOF/s ({sweeps[n][v]['frac']:.3f})" for v in variants if v in sweeps[n]) + "\n")
+    return "".join(text)
 
 
 out = [f"""# Round {rnd[1:].lstrip('0') or '0'} -- ncu evidence (B200, sm_100a)
@@ -88,16 +144,23 @@ for name, t in traffic.items():
     out.append(f"| {name} | {t['ms']:.3f} | {t['read_bytes'] / 1e9:.3f} | {t['write_bytes'] / 1e9:.3f} | "
                f"{(alg or 0) / 1e9:.3f} | {ratio} |\n")
 out.append("""
-Reading: the Ax kernels move 1.00-1.03x their algorithmic bytes (nothing is read twice); issue slots are about a third
-busy and the fp64 pipe about 35 %, the n = 8 kernel waits on HBM (long scoreboard), n = 10 / 12 have 9-10 resident warps
-per SM (two CTAs of 5 warps at 168 registers) to cover the same latency and lose 15-25 %; dot / add move exactly their
-operands; the gather-scatter reads and writes the whole vector once (both 32-byte sectors of every 64-byte line hold a
-point of a face normal to the fastest index) plus its index arrays.
+Reading: the Ax kernels move 1.00-1.03x their algorithmic bytes (nothing is read twice -- since round 2 also on the
+three-CTA shapes of n = 6 / 10 / 12, section 4); issue slots are about a third busy and the fp64 pipe 35-40 %; what is left
+is memory latency that 12-15 warps per SM do not hide (long scoreboard in the geometric stage, DESIGN.md 5.3); dot / add
+move exactly their operands; the gather-scatter reads and writes the whole vector once (both 32-byte sectors of every
+64-byte line hold a point of a face normal to the fastest index) plus its index arrays, and is bound by three dependent
+loads per group (DESIGN.md 5.4).
 """)
+out.append(variant_study(src, rnd))
 (prof / f"{rnd}_ncu_summary.md").write_text("".join(out))
 
+for name in ("racecheck.txt", "cg_scalars.jsonl", "launch_overhead.jsonl", "ax_interleaved.jsonl"):
+    if (src / name).exists() and (src / name).stat().st_size > 0:
+        target = {"ax_interleaved.jsonl": f"{rnd}_kernel_sweeps.jsonl"}.get(name, f"{rnd}_{name}")
+        shutil.copy(src / name, prof / target)
+
 ax = {}
-for name, key in (("ax8", "n8_E262144"), ("ax10", "n10_E131072"), ("ax12", "n12_E65536"), ("ax6", "n6_E524288"), ("axdot8", "dot_n8_E262144")):
+for name, key in (("ax8", "n8_E262144"), ("ax10", "n10_E262144"), ("ax12", "n12_E65536"), ("ax6", "n6_E524288"), ("axdot8", "dot_n8_E262144")):
     if name in traffic:
         t = traffic[name]
         ax[key] = dict(read_bytes=t["read_bytes"], write_bytes=t["write_bytes"], algorithmic_bytes=t["algorithmic_bytes"], capture=name)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, multi-GPU call (gpurun --gpus 8): the tests that need several GPUs, bench.py at N = 8 (and N = 2) launched the way
+# Multi-GPU evidence of a round (gpurun --gpus 8 -- bash tools/multi_gpu_round.sh): the tests that need several GPUs, bench.py at N = 8 (and N = 2) launched the way
 # the driver launches it, the CG example with host / device scalars / graph replay on 8 ranks.
 set -u
 OUT=gpurun_out/r2m
