@@ -575,24 +575,28 @@ def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, Lis
     from .emit_cuda import GenericEmitter
     ge = GenericEmitter(knl)
     ge.lines = []
-    ge.stmts(body_nodes, 4, True, False)
-    body = "\n".join(ge.lines)
-    ge.lines = []
     ge.stmts(body_nodes, 3, True, False)
     body_scalar = "\n".join(ge.lines)
     it = cuda_type(loop.vtype)
     lo, hi = expr_str(loop.lo), expr_str(loop.hi)
     ety = {a: cuda_type(arrays[a].ctype) for a in used}
     align = " | ".join(f"(nomp_u64_t)({a} + nomp_lo)" for a in used) or "0"
-    vec_decl = "\n".join(f"      struct __align__(16) {{ {ety[a]} v[{lanes}]; }} nomp_{a}_v;" for a in used)
+    # U vectors per thread and trip: with hoisted invariants a CTA takes four tiles (below), and the loads of all four
+    # are issued before the first store -- the pointers are not __restrict__, so the compiler would not move them there
+    U = 4 if prologue else 1
+    vec_decl = "\n".join(f"      struct __align__(16) {{ {ety[a]} v[{lanes}]; }} nomp_{a}_v[{U}];" for a in used)
     vec_load = "\n".join(
-        f"      *reinterpret_cast<int4 *>(&nomp_{a}_v) = *reinterpret_cast<const int4 *>({a} + nomp_e);" for a in used)
+        f"        *reinterpret_cast<int4 *>(&nomp_{a}_v[nomp_q]) = *reinterpret_cast<const int4 *>({a} + nomp_lo + nomp_v * {lanes});"
+        for a in used)
     vec_store = "\n".join(
-        f"      *reinterpret_cast<int4 *>({a} + nomp_e) = *reinterpret_cast<int4 *>(&nomp_{a}_v);" for a in written)
-    lane_in = "\n".join(f"        {ety[a]} nomp_{a}_i = nomp_{a}_v.v[nomp_l];" for a in used)
-    lane_out = "\n".join(f"        nomp_{a}_v.v[nomp_l] = nomp_{a}_i;" for a in written)
+        f"        *reinterpret_cast<int4 *>({a} + nomp_e) = *reinterpret_cast<int4 *>(&nomp_{a}_v[nomp_q]);" for a in written)
+    lane_in = "\n".join(f"          {ety[a]} nomp_{a}_i = nomp_{a}_v[nomp_q].v[nomp_l];" for a in used)
+    lane_out = "\n".join(f"          nomp_{a}_v[nomp_q].v[nomp_l] = nomp_{a}_i;" for a in written)
     sc_in = "\n".join(f"      {ety[a]} nomp_{a}_i = {a}[nomp_e];" for a in used)
     sc_out = "\n".join(f"      {a}[nomp_e] = nomp_{a}_i;" for a in written)
+    ge.lines = []
+    ge.stmts(body_nodes, 5, True, False)
+    body = "\n".join(ge.lines)
     src = f"""{PRELUDE}
 // elementwise loop over `{loop.var}`: vectorised grid-stride schedule of libnompk map.cu with a generated body
 {signature(knl)} {{
@@ -603,18 +607,28 @@ def emit_map_skeleton(knl: Kernel, loop: c.For, sm_count: int) -> Tuple[str, Lis
   const long long nomp_nthreads = (long long)gridDim.x * blockDim.x;
   if ((({align}) & 15u) == 0) {{
     const long long nomp_nvec = nomp_n / {lanes};
-    for (long long nomp_v = nomp_tid; nomp_v < nomp_nvec; nomp_v += nomp_nthreads) {{
-      const long long nomp_e = nomp_lo + nomp_v * {lanes};
+    for (long long nomp_v0 = (long long)blockIdx.x * (blockDim.x * {U}) + threadIdx.x; nomp_v0 < nomp_nvec; nomp_v0 += nomp_nthreads * {U}) {{
 {vec_decl}
-{vec_load}
 #pragma unroll
-      for (int nomp_l = 0; nomp_l < {lanes}; nomp_l++) {{
-        const {it} {loop.var} = ({it})(nomp_e + nomp_l);
+      for (int nomp_q = 0; nomp_q < {U}; nomp_q++) {{
+        const long long nomp_v = nomp_v0 + (long long)nomp_q * blockDim.x;
+        if (nomp_v >= nomp_nvec) break;
+{vec_load}
+      }}
+#pragma unroll
+      for (int nomp_q = 0; nomp_q < {U}; nomp_q++) {{
+        const long long nomp_v = nomp_v0 + (long long)nomp_q * blockDim.x;
+        if (nomp_v >= nomp_nvec) break;
+        const long long nomp_e = nomp_lo + nomp_v * {lanes};
+#pragma unroll
+        for (int nomp_l = 0; nomp_l < {lanes}; nomp_l++) {{
+          const {it} {loop.var} = ({it})(nomp_e + nomp_l);
 {lane_in}
 {body}
 {lane_out}
-      }}
+        }}
 {vec_store}
+      }}
     }}
     for (long long nomp_e = nomp_lo + nomp_nvec * {lanes} + nomp_tid; nomp_e < nomp_hi; nomp_e += nomp_nthreads) {{
       const {it} {loop.var} = ({it})nomp_e;

@@ -3,6 +3,7 @@
 usage: gs_bench.py [n] [ex] [ey] [ez] [reps]   ->  one JSON line"""
 import ctypes as C
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -54,7 +55,8 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 alg = copies * (8 + 8 + 4) + (groups + 1) * 4
-print(json.dumps({"kernel": "gs_local_kernel", "n": n, "elements": ex * ey * ez, "dofs": ndof, "distinct": distinct,
+kernel = "gs_local_kernel" if os.environ.get("NOMPK_GS_KERNEL") == "group" else "gs_local_warp_kernel"
+print(json.dumps({"kernel": kernel, "n": n, "elements": ex * ey * ez, "dofs": ndof, "distinct": distinct,
                   "groups": groups, "copies": copies, "setup_s": round(setup_s, 4), "ms": ms,
                   "algorithmic_bytes": alg, "GB/s": alg / ms / 1e6, "bytes_per_dof": alg / ndof,
                   "ns_per_dof_vs_ax64": {"gs": ms * 1e6 / ndof, "ax_at_6548GB/s": 64 / 6548.5}}))

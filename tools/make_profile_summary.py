@@ -148,8 +148,8 @@ Reading: the Ax kernels move 1.00-1.03x their algorithmic bytes (nothing is read
 three-CTA shapes of n = 6 / 10 / 12, section 4); issue slots are about a third busy and the fp64 pipe 35-40 %; what is left
 is memory latency that 12-15 warps per SM do not hide (long scoreboard in the geometric stage, DESIGN.md 5.3); dot / add
 move exactly their operands; the gather-scatter reads and writes the whole vector once (both 32-byte sectors of every
-64-byte line hold a point of a face normal to the fastest index) plus its index arrays, and is bound by three dependent
-loads per group (DESIGN.md 5.4).
+64-byte line hold a point of a face normal to the fastest index) plus its index arrays (DESIGN.md 5.4: 1.5 x is the
+floor of an in-place schedule on this numbering); the capture is `gs_local_warp_kernel`, one copy per lane.
 """)
 out.append(variant_study(src, rnd))
 (prof / f"{rnd}_ncu_summary.md").write_text("".join(out))

@@ -23,7 +23,7 @@ $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/ax6" python tools/run_kernel_once.py 
 $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/axdot8" python tools/run_kernel_once.py axdot 8 262144 0 5 > /dev/null 2>&1
 $NCU -k regex:reduce_kernel -s 3 -c 1 -o "$OUT/dot" python tools/run_kernel_once.py reduce 1 268435456 0 5 > /dev/null 2>&1
 $NCU -k regex:map_vec -s 3 -c 1 -o "$OUT/add" python tools/run_kernel_once.py map 0 268435456 0 5 > /dev/null 2>&1
-$NCU -k regex:gs_local_kernel -s 2 -c 1 -o "$OUT/gs" python tools/gs_bench.py 8 64 64 64 3 --no-warmup > /dev/null 2>&1
+$NCU -k regex:gs_local -s 2 -c 1 -o "$OUT/gs" python tools/gs_bench.py 8 64 64 64 3 --no-warmup > /dev/null 2>&1
 # racecheck of the four Ax shapes, launch-overhead sweep (BASELINE configs[4]), CG with host / device scalars / graph
 for n in 6 8 10 12; do
   timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/run_kernel_once.py ax $n 301 0 2 > "$OUT/racecheck.ax$n.log" 2>&1
