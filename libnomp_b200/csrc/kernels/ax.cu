@@ -150,6 +150,13 @@ template <int N> __constant__ RowTable<N> nompk_ax_rows = RowTable<N>();
 
 __device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
 
+// A weak (coherent) load: unlike an .nc load, ptxas may not sink it below a barrier (see kPinGeo in ax_kernel).
+__device__ __forceinline__ double2 ldg2_ordered(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ double2 ldg2_stream(const double2 *p) {
   double2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -166,7 +173,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 
 // the same, asking L2 to keep the line until somebody uses it (the streams of w and of the other CTAs' factors push a
 // line that was prefetched with normal priority out again before its demand load arrives: 14 - 30 % of the factors are
-// read from DRAM twice with three CTAs per SM, profiles/r02_ax_dram.md)
+// read from DRAM twice with three CTAs per SM, profiles/r02_ncu_summary.md, section 4)
 __device__ __forceinline__ void prefetch_l2_keep(const void *p) {
   asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
 }
@@ -302,10 +309,21 @@ struct AxNoXpay {};
 //      S4 only prefetches inside the element; the next element's u is requested after S6.  Every prefetch then leads its
 //      demand load by 2 - 4 us.  With modes 0 - 2 the lines of the next element wait for a whole S5 .. S8, S0 .. S3 --
 //      about 9 us with three CTAs per SM -- and L2 (126 MB under 8.5 TB/s of traffic: ~12 us of residence) has dropped
-//      part of them by then: 14 % (n = 10) to 30 % (n = 12) of the factors came from DRAM twice (profiles/r02_ax_dram.md).
+//      part of them by then: 14 % (n = 10) to 30 % (n = 12) of the factors came from DRAM twice (profiles/r02_ncu_summary.md, section 4).
 //   4: local window, and demand loads mark their lines evict_first.
+//   5: local window, and the first kGeoAhead slabs are prefetched too, at the start of the element, instead of being
+//      fetched by the loads that fill the register ring (a mode 6 did it at the end of the previous element).  Measured:
+//      no gain (profiles/r02_dot_pin_experiment.jsonl) -- the stall in front of S4 is L2 latency, not DRAM latency.
+// kPin: the loads that fill the register ring stand in the source at S0 ("in flight during S1 .. S3"), but at 128
+//   registers ptxas sinks them to the end of the stage before S4 -- and in the kernels with the fused dot product, whose
+//   two more live values sit on the register cliff of S4, BELOW the barrier in front of S4, next to their use: the fused
+//   kernel was 21 % slower than the plain one at n = 10 (long-scoreboard stalls per issue 5.5 instead of 3.2).  kPin = 1
+//   issues them at the end of the stage before S4 as weak loads (ld.global, not .nc), which ptxas may not move across the
+//   barrier: 0.71 -> 0.79 of the peak at n = 10 (the plain kernel: 0.87 on the same box).  No gain at n = 6, 12 or for
+//   the plain kernels.  Also tried for the fused kernel and dropped: u . w formed in S8 from a copy of u in shared
+//   memory instead of the energy form in S4 (slower: 0.71 - 0.74), 32-bit element numbers (more spills).
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0>
+          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0, int kPin = 0>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
           size_t pf_stride, std::conditional_t<kXpay, AxXpayArgs, AxNoXpay> xp) {
@@ -350,7 +368,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     it++;
     size_t e = eb + grp * G + el;
     // lanes that only mirror another work item / element must not contribute to the dot product
-    const double dot_weight = (gid < G * T && e < E) ? 1.0 : 0.0;
+    const bool dot_counts = gid < G * T && e < E;
     const bool e_valid = e < E;  // kXpay: an element that only mirrors the last one must not store (see S0)
     e = e < E ? e : E - 1;
     const double2 *ue = reinterpret_cast<const double2 *>(u + e * N3) + q * NP + p;
@@ -388,8 +406,11 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     };
     if constexpr (kPf >= 2) {
       if (kLocalWindow || eb == (size_t)blockIdx.x * EPB) {  // warm the window (wrapping window: first element of the CTA only)
+        // the first kGeoAhead slabs are fetched by the loads that fill the register ring -- which ptxas issues only in
+        // the stage before S4 (register pressure).  Mode 5 prefetches them here as well (measured: no gain).
+        constexpr int kFirst = kPfMode == 5 ? 0 : kGeoAhead;
 #pragma unroll
-        for (int k = kGeoAhead; k < kPf && k < N; k++) prefetch_slab(e, k);
+        for (int k = kFirst; k < kPf && k < N; k++) prefetch_slab(e, k);
       }
     }
 
@@ -420,12 +441,18 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
       for (int k = 0; k < N; k++) col[k] = kStreamLoads ? ldg2_stream(ue + k * SLAB2) : ldg2(ue + k * SLAB2);
     }
-    // first slabs of geometric factors: in flight during S1..S3
+    // first slabs of geometric factors: in flight during S1..S3 (as far as the registers allow: at 128 registers ptxas
+    // issues them in the last stage before S4).  kPinGeo: the dot product costs the registers that made ptxas sink most
+    // of these loads BELOW the barrier in front of S4, next to their use (n = 10: 0.71 instead of 0.87 of the peak);
+    // there they are issued in the stage before S4 as weak loads, which may not cross the barrier.
+    constexpr bool kPinGeo = kPin != 0 && kTwoBuf;
+    if constexpr (!kPinGeo) {
 #pragma unroll
-    for (int a = 0; a < kGeoAhead; a++)
+      for (int a = 0; a < kGeoAhead; a++)
 #pragma unroll
-      for (int f = 0; f < 6; f++)
-        gq[a][f] = load_g(ge + f * (N3 / 2) + a * SLAB2);
+        for (int f = 0; f < 6; f++)
+          gq[a][f] = load_g(ge + f * (N3 / 2) + a * SLAB2);
+    }
 #pragma unroll
     for (int k = 0; k < N; k++) B0[L::at(k, q, p)] = col[k];
     // ---- S1: ut = D_t u along the k-column, in registers ---------------------------------------------
@@ -465,6 +492,13 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
           B0[oa + (c ^ sa)] = o0;
           B0[ob + (c ^ sb)] = o1;
         });
+      }
+      if constexpr (kPinGeo) {
+#pragma unroll
+        for (int a = 0; a < kGeoAhead; a++)
+#pragma unroll
+          for (int f = 0; f < 6; f++)
+            gq[a][f] = ldg2_ordered(ge + f * (N3 / 2) + a * SLAB2);
       }
       element_sync<GL>(grp);
     } else {
@@ -525,13 +559,11 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       if constexpr (kDot) {
         double ex = fma(ur.x, wr.x, fma(us.x, ws.x, ut.x * wt.x));
         double ey = fma(ur.y, wr.y, fma(us.y, ws.y, ut.y * wt.y));
-        if constexpr (kXpay) {
-          // an element that mirrors the last one may have read a half-updated p: its numbers are finite but meaningless,
-          // and a weight of zero would still let an overflow through (0 * inf) -- select instead of multiply
-          energy += dot_weight != 0.0 ? ex + ey : 0.0;
-        } else {
-          energy = fma(dot_weight, ex + ey, energy);
-        }
+        // select, not multiply by a weight: with kXpay an element that mirrors the last one may have read a half-updated
+        // p -- its numbers are finite but meaningless, and 0 * inf would let an overflow through; and a predicate costs
+        // no register pair (at 128 registers the weight pushed the first loads of the geometric factors behind the
+        // barrier of S4: 0.71 instead of 0.87 of the peak at n = 10)
+        energy += dot_counts ? ex + ey : 0.0;
       }
       mirror_fence<G * T < GL>();
       B1[a] = wr;
@@ -617,10 +649,10 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 }
 
 template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
-          bool TWOBUF = false, int PFMODE = 0>
+          bool TWOBUF = false, int PFMODE = 0, int PIN = 0>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE, PIN>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * L::template kElemStride<(TWOBUF ? 2 : 3)> * sizeof(double2);
   static bool configured = false;
@@ -669,13 +701,24 @@ template <> struct Shape<10> { static constexpr int G = 3, W = 5, GPC = 1; };   
 template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   // 144 / 160
 
 // Ax fused with u . A u (production shapes only).
-template <int N> int dispatch_ax_dot(size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
+template <int N> int dispatch_ax_dot(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  // kept for profiling (tools/ax_sweep.py axdot): round 1's three-buffer shape, two CTAs with the local window, three
+  // CTAs with the wrapping window
+  if (variant == 63) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1>(E, u, g, w, s, dot);
+  if (variant == 64) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 0>(E, u, g, w, s, dot);
+  if (variant == 67) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 5, 1>(E, u, g, w, s, dot);
+#ifndef NOMPK_AX_PRODUCTION_ONLY
+  if (variant == 60) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
+  if (variant == 61) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, true, 3>(E, u, g, w, s, dot);
+  if (variant == 62) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 0>(E, u, g, w, s, dot);
+#endif
   // the shapes of dispatch_ax (variant 0), with the dot product
   if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
   else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), true, true, true, 4>(E, u, g, w, s, dot);
+  else if constexpr (N == 10) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1>(E, u, g, w, s, dot);   // kPin
   else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3>(E, u, g, w, s, dot);
 }
 
@@ -707,6 +750,7 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
     if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
     else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
     else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+#ifndef NOMPK_AX_PRODUCTION_ONLY   // -DNOMPK_AX_PRODUCTION_ONLY: a quick build without the profiling variants
   case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
   case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
   case 3: return launch_ax<N, G, W, GPC, 2, 2, false, MB128>(E, u, g, w, s);
@@ -749,8 +793,14 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 45: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB128_1, false, true, true, 4>(E, u, g, w, s);
   case 46: return launch_ax<N, 1, W1, GPC1, 3, 6, false, MB168_1, false, true, false, 3>(E, u, g, w, s);
   case 47: return launch_ax<N, 1, W1, GPC1, 2, 4, false, MB168_1, false, true, true, 3>(E, u, g, w, s);
+  // ... the first slabs of an element prefetched too (kPfMode 5), and the loads that fill the register ring pinned in
+  // front of the barrier of S4 (kPin)
+  case 48: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
+  case 50: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
+  case 52: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 1>(E, u, g, w, s);
   case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
     return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
+#endif
   }
 }
 
@@ -767,7 +817,7 @@ NOMPK_AX_RUN_DEFINE(NOMPK_AX_N) {
   }
   if (dot && xpay)
     return dispatch_ax_xpay_dot<n>(E, g, w, stream, *static_cast<const AxDotArgs *>(dot), *static_cast<const AxXpayArgs *>(xpay));
-  if (dot) return dispatch_ax_dot<n>(E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
+  if (dot) return dispatch_ax_dot<n>(variant, E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
   return dispatch_ax<n>(variant, E, u, g, w, stream);
 }
 

@@ -22,6 +22,18 @@ KERNELS = ROOT / "libnomp_b200" / "csrc" / "kernels"
 SHAPES = {6: (7, 4, 1), 8: (1, 1, 4), 10: (3, 5, 1), 12: (2, 5, 1)}
 
 
+# what the emulated kernels instantiate: (geometric slabs in flight, fused p.Ap, two shared buffers, kPfMode, kPin)
+VARIANTS = {0: (2, False, False, 0, 0),      # three buffers, wrapping prefetch window (n = 8 in production)
+            1: (2, True, False, 0, 0),       # ... with the fused p.Ap
+            2: (2, False, True, 0, 0),       # two buffers
+            3: (1, False, True, 0, 0),       # two buffers, one slab in flight
+            4: (2, False, True, 4, 0),       # local prefetch window, last-use demand loads
+            5: (2, True, True, 3, 0),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
+            6: (2, True, True, 5, 1),        # ... first slabs prefetched too, ring fill pinned in front of S4
+            7: (2, False, True, 5, 1)}       # the same without the dot product
+DOT_VARIANTS = [v for v, spec in VARIANTS.items() if spec[1]]
+
+
 def device_source():
     finish = (KERNELS / "nompk_gridreduce.cuh").read_text().replace('#include "nompk_common.cuh"', "").replace("#pragma once", "")
     finish = re.sub(r'asm volatile\("mov\.u64 %0, %globaltimer;" : "=l"\((\w+)\)\);', r"\1 = nomp_emu_now_ns();", finish)
@@ -37,6 +49,7 @@ def device_source():
              (r'asm volatile\("prefetch\.global\.L2[^;]*;"[^;]*;', ";", 2),               # normal and evict_last priority
              (r'asm volatile\("createpolicy\.fractional\.L2::evict_first\.b64[^;]*;"[^;]*;', "policy = 0;", 1),
              (r'asm volatile\("ld\.global\.nc\.L2::cache_hint\.v2\.f64[^;]*;"[^;]*;', "r = *p; (void)policy;", 1),
+             (r'asm volatile\("ld\.global\.v2\.f64[^;]*;"[^;]*;', "r = *p;", 1),               # the pinned (weak) load
              (r'asm volatile\("bar\.sync %0, %1;"[^;]*;', "nomp_emu_named_barrier(grp + 1, GL);", 1)]
     for pattern, repl, count in swaps:
         body, n = re.subn(pattern, repl, body)
@@ -48,17 +61,15 @@ def device_source():
                 "static inline double __dmul_rn(double a, double b) { return a * b; }\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
-        for dot in (0, 1, 2, 3, 4, 5):  # 2 = the two-buffer variant (no dot); 3 = two buffers, one geometric slab in flight;
-            #                            4 = two buffers, local prefetch window and last-use demand loads (kPfMode 4);
-            #                            5 = two buffers with the fused p.Ap and the local window (the production shape of n = 6, 10, 12)
+        for dot, (ga, with_dot, twobuf, pfmode, pin) in VARIANTS.items():
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
                 f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk::nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
-                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {1 if dot == 3 else 2}, 4, false, 1, {'true' if dot in (1, 5) else 'false'}, true,"
-                f" {'true' if dot >= 2 else 'false'}, false, {4 if dot == 4 else 3 if dot == 5 else 0}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+                f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {ga}, 4, false, 1, {'true' if with_dot else 'false'}, true,"
+                f" {'true' if twobuf else 'false'}, false, {pfmode}, {pin}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
         # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
         wrappers.append(
             f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"
@@ -87,7 +98,7 @@ def run_ax(n, E, u, g, D, dot, blocks):
 
 
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
-@pytest.mark.parametrize("dot", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dot", sorted(VARIANTS))
 def test_ax_kernel_on_the_host(n, dot):
     """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
     size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""
@@ -100,7 +111,7 @@ def test_ax_kernel_on_the_host(n, dot):
         w, pap, ws = run_ax(n, E, u, g, D, dot, blocks)
         want = ffi.ax(n, u, g, D)
         assert np.array_equal(w, want), (n, E, blocks, int((w != want).sum()))
-        if dot in (1, 5):
+        if dot in DOT_VARIANTS:
             assert pap == float(u @ want) and not ws[: (64 + 4 * 2048) // 8].any()
 
 

@@ -218,7 +218,7 @@ def test_ax_exact_data_bitwise(n, E):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", list(range(18)) + [21, 22, 23] + list(range(30, 48)))
+@pytest.mark.parametrize("variant", list(range(18)) + [21, 22, 23] + list(range(30, 49)) + [50, 52])
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
 def test_ax_variants_agree(variant, n):
     """Every shape / prefetch / buffer variant kept for profiling (ax.cu: dispatch_ax) computes the same bits."""
@@ -327,6 +327,31 @@ def test_ax_fused_with_dot_product(n):
     ref = ffi.sum_compensated(u, ref_w)
     assert np.abs(host(tw, np.float64) - ref_w).max() <= 1e-12 * np.abs(ref_w).max()
     assert abs(res.item() - ref) <= 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("variant", [0, 60, 61, 62, 63, 64, 67])
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_dot_variants_agree(variant, n):
+    """The shapes of the fused Ax + p.Ap kept for profiling (ax.cu: dispatch_ax_dot): same w, same u . (A u), bit for bit."""
+    lib = capi.nompk()
+    E = 333 if n <= 10 else 167
+    u = ffi.fill_int_f64(E * n ** 3, 31, -4, 4)
+    g = ffi.fill_int_f64(E * 6 * n ** 3, 32, 0, 3)
+    D = ffi.fill_int_f64(n * n, 33, -2, 2)
+    tu, tg, tD = dev(u), dev(g), dev(D)
+    tw = torch.full_like(tu, float("nan"))
+    ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lib.nompk_ax_set_variant(variant)
+    try:
+        capi.nompk_check(lib.nompk_ax_dot_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), res.data_ptr(),
+                                              None, 0, ws.data_ptr(), 0, stream()))
+        torch.cuda.synchronize()
+    finally:
+        lib.nompk_ax_set_variant(0)
+    w = ffi.ax(n, u, g, D)
+    assert np.array_equal(host(tw, np.float64), w)
+    assert res.item() == float(u @ w)
 
 
 def test_ax_unsupported_n_is_reported():

@@ -107,6 +107,51 @@ def main():
                 emit(kernel="ax_interleaved", n=n, E=E, variant=v, rounds=rounds, ms=med, ms_min=ts[0], ms_max=ts[-1],
                      gdofs=E * n3 / med / 1e6, frac=gb / med * 1e3 / PEAK)
             del u, g, w
+    if "axdot" in which:
+        # the fused forms next to the plain operator, interleaved: Ax, Ax + p.Ap, (p <- r + beta p) + Ax + p.Ap
+        rounds = int(os.environ.get("AX_ROUNDS", "7"))
+        shapes = [tuple(int(x) for x in sh.split(":")) for sh in
+                  os.environ.get("AX_SHAPES", "10:262144,12:65536,8:262144,6:524288").split(",")]
+        ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+        res = torch.zeros(1, dtype=torch.float64, device="cuda")
+        for n, E in shapes:
+            n3 = n ** 3
+            u = torch.rand(E * n3, dtype=torch.float64, device="cuda")
+            r = torch.rand(E * n3, dtype=torch.float64, device="cuda")
+            g = torch.rand(E * 6 * n3, dtype=torch.float64, device="cuda")
+            D = torch.rand(n * n, dtype=torch.float64, device="cuda")
+            w = torch.empty_like(u)
+
+            def ax():
+                capi.nompk_check(lib.nompk_ax_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(), 0, st))
+
+            def axdot():
+                capi.nompk_check(lib.nompk_ax_dot_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(),
+                                                      res.data_ptr(), None, 0, ws.data_ptr(), 0, st))
+
+            def axxpay():
+                capi.nompk_check(lib.nompk_ax_xpay_dot_peers_f64(n, E, u.data_ptr(), r.data_ptr(), C.c_double(1e-9), None,
+                                                                 g.data_ptr(), D.data_ptr(), w.data_ptr(), res.data_ptr(),
+                                                                 None, 0, ws.data_ptr(), None, 0, st))
+            def variant_of(fn, v):
+                def go():
+                    lib.nompk_ax_set_variant(v)
+                    fn()
+                return go
+            dot_variants = [int(v) for v in os.environ.get("AX_DOT_VARIANTS", "60,61,63,64,67").split(",") if v]
+            kinds = [("ax", variant_of(ax, 0), 64), ("ax_dot", variant_of(axdot, 0), 64)] + \
+                    [(f"ax_dot_v{v}", variant_of(axdot, v), 64) for v in dot_variants] + [("ax_xpay_dot", variant_of(axxpay, 0), 80)]
+            samples = {k: [] for k, _, _ in kinds}
+            for _ in range(rounds):
+                for k, fn, _ in kinds:
+                    samples[k].append(timeit(fn, reps=10, warm=3)[0])
+            lib.nompk_ax_set_variant(0)
+            for k, _, bpd in kinds:
+                ts = sorted(samples[k])
+                med = ts[len(ts) // 2]
+                emit(kernel=k, n=n, E=E, rounds=rounds, ms=med, ms_min=ts[0], ms_max=ts[-1], gdofs=E * n3 / med / 1e6,
+                     bytes_per_dof=bpd, frac=E * n3 * bpd / med / 1e6 / PEAK)
+            del u, r, g, w
     if "map" in which:
         for lg in (20, 24, 26, 28):
             n = 1 << lg
