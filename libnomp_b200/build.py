@@ -34,11 +34,14 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"),
 ]
 
-# (source, object name, extra flags).  ax.cu is compiled once per supported n (-DNOMPK_AX_N=<n>: the kernels of that n, in
-# parallel -- a single unit with every n and variant takes 7 minutes) and once without the macro (its C ABI).
-KERNEL_UNITS = [("map.cu", "map.cu.o", []), ("reduce.cu", "reduce.cu.o", []), ("gs.cu", "gs.cu.o", []),
-                ("nompk.cu", "nompk.cu.o", []), ("ax.cu", "ax.cu.o", [])] + \
-               [("ax.cu", f"ax_n{n}.cu.o", [f"-DNOMPK_AX_N={n}"]) for n in (12, 10, 8, 6)]
+# (source, object name, extra flags).  ax.cu is compiled without a macro (its C ABI) and, per supported n, in three parts
+# (-DNOMPK_AX_N=<n> -DNOMPK_AX_PART=<0|1|2>: the production and fused kernels, and two halves of the shapes kept for
+# profiling) -- in parallel: a single unit with every n and shape takes most of an hour, one unit per n ten minutes.
+# Longest first.
+KERNEL_UNITS = [("ax.cu", f"ax_n{n}" + (f"_p{part}" if part else "") + ".cu.o", [f"-DNOMPK_AX_N={n}", f"-DNOMPK_AX_PART={part}"])
+                for n in (12, 10, 6, 8) for part in (2, 1, 0)] + \
+               [("gs.cu", "gs.cu.o", []), ("reduce.cu", "reduce.cu.o", []), ("map.cu", "map.cu.o", []),
+                ("nompk.cu", "nompk.cu.o", []), ("ax.cu", "ax.cu.o", [])]
 LIBNOMP_SRCS = ["src/nomp.c", "src/log.c", "src/aux.c", "src/loopy.c", "src/reduction.c", "src/gridexpr.c", "src/comm.c", "src/jitcache.c", "src/gs.c",
                 "backends/cuda.c"]
 
@@ -71,7 +74,7 @@ def build_kernels(force=False):
             jobs.append([NVCC, *NVCC_FLAGS, *extra, "-c", str(src_dir / s), "-o", str(o)])
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-            list(ex.map(_run, sorted(jobs, key=lambda j: "-DNOMPK_AX_N" not in " ".join(j))))   # the long ones first
+            list(ex.map(_run, jobs))   # KERNEL_UNITS is ordered longest first
     objs = [str(OBJ / oname) for _, oname, _ in KERNEL_UNITS]
     if force or jobs or _stale(out, objs):
         _run([NVCC, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a",

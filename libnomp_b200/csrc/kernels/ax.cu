@@ -77,6 +77,17 @@ NOMPK_AX_RUN_DECL(8);
 NOMPK_AX_RUN_DECL(10);
 NOMPK_AX_RUN_DECL(12);
 
+// The shapes kept for profiling are compiled in two more units per n (-DNOMPK_AX_PART=1, 2; the production kernels and the
+// fused forms are part 0): build time -- one unit with all the kernels of n = 12 takes ten minutes.  Every unit has its
+// own __constant__ copy of D, so these entry points stage D themselves.  NOMPK_AX_NO_SUCH_VARIANT: not one of mine.
+#ifndef NOMPK_AX_PART
+#define NOMPK_AX_PART 0
+#endif
+#define NOMPK_AX_NO_SUCH_VARIANT (-4711)
+#define NOMPK_AX_VARIANTS_DECL(part, n)                                                                                 \
+  extern "C" __attribute__((visibility("hidden"))) int nompk_ax_variants##part##_n##n(                                  \
+      int variant, size_t E, const double *u, const double *g, const double *D, double *w, cudaStream_t stream)
+
 #if NOMPK_AX_N != 0
 
 namespace nompk {
@@ -700,6 +711,7 @@ template <> struct Shape<8> { static constexpr int G = 1, W = 1, GPC = 4; };    
 template <> struct Shape<10> { static constexpr int G = 3, W = 5, GPC = 1; };   // 150 / 160
 template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   // 144 / 160
 
+#if NOMPK_AX_PART == 0
 // Ax fused with u . A u (production shapes only).
 template <int N> int dispatch_ax_dot(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
@@ -710,11 +722,9 @@ template <int N> int dispatch_ax_dot(int variant, size_t E, const double *u, con
   if (variant == 63) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1>(E, u, g, w, s, dot);
   if (variant == 64) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 0>(E, u, g, w, s, dot);
   if (variant == 67) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 5, 1>(E, u, g, w, s, dot);
-#ifndef NOMPK_AX_PRODUCTION_ONLY
   if (variant == 60) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
   if (variant == 61) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, true, 3>(E, u, g, w, s, dot);
   if (variant == 62) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 0>(E, u, g, w, s, dot);
-#endif
   // the shapes of dispatch_ax (variant 0), with the dot product
   if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true>(E, u, g, w, s, dot);
   else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), true, true, true, 4>(E, u, g, w, s, dot);
@@ -731,7 +741,25 @@ template <int N> int dispatch_ax_xpay_dot(size_t E, const double *g, double *w, 
   else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168>(E, g, w, s, dot, xp);
 }
 
-template <int N> int dispatch_ax(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
+#endif
+
+#if NOMPK_AX_PART == 0
+template <int N> int dispatch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
+  constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
+  constexpr int kThreads = GPC * W * 32;
+  constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  // production choice (interleaved sweeps of round 2, profiles/r02_kernel_sweeps.jsonl)
+  // n = 8: one warp per element, three buffers, 168 registers, window running on into the next element (no over-read
+  // at this element time).  The others: two shared buffers per element, one CTA more per SM (128 registers) and the
+  // LOCAL prefetch window, which removed the 14 - 30 % of DRAM reads that the wrapping window fetched twice on these
+  // shapes: n = 10 +6 %, n = 12 +9 %, n = 6 +13 % over the round-1 choices in the same interleaved sweeps.
+  if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
+  else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
+  else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
+}
+#else
+// Variants kept for profiling (tools/ax_sweep.py sweeps them).
+template <int N> int dispatch_ax_variants(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
   // MBr = resident CTAs per SM that cap the kernel at r registers per thread.
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
@@ -739,18 +767,8 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   // one element per group of ceil(T / 32) warps, about 128 threads per CTA
   constexpr int W1 = Layout<N>::WPE, GPC1 = (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), kThreads1 = GPC1 * W1 * 32;
   constexpr int MB128_1 = 65536 / (128 * kThreads1), MB168_1 = 65536 / (168 * kThreads1);
-  // Variants are kept for profiling (tools/ax_sweep.py sweeps them); 0 is the production choice.
   switch (variant) {
-  default:
-  case 0:  // production choice (interleaved sweeps of round 2, profiles/r02_kernel_sweeps.jsonl)
-    // n = 8: one warp per element, three buffers, 168 registers, window running on into the next element (no over-read
-    // at this element time).  The others: two shared buffers per element, one CTA more per SM (128 registers) and the
-    // LOCAL prefetch window, which removed the 14 - 30 % of DRAM reads that the wrapping window fetched twice on these
-    // shapes: n = 10 +6 %, n = 12 +9 %, n = 6 +13 % over the round-1 choices in the same interleaved sweeps.
-    if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168>(E, u, g, w, s);
-    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
-    else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
-#ifndef NOMPK_AX_PRODUCTION_ONLY   // -DNOMPK_AX_PRODUCTION_ONLY: a quick build without the profiling variants
+#if NOMPK_AX_PART == 1
   case 1: return launch_ax<N, G, W, GPC, 2, 4, false, MB128>(E, u, g, w, s);
   case 2: return launch_ax<N, G, W, GPC, 2, 3, false, MB128>(E, u, g, w, s);
   case 3: return launch_ax<N, G, W, GPC, 2, 2, false, MB128>(E, u, g, w, s);
@@ -771,6 +789,9 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 21: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true>(E, u, g, w, s);
   case 22: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);
   case 23: return launch_ax<N, G, W, GPC, 1, 4, false, (MB168 + 1), false, true, true>(E, u, g, w, s);  // one slab in flight
+  case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
+    return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
+#else
   // round 2: shape and eviction priority of the prefetch window (kPfMode) on the three-CTA / two-buffer shapes ...
   case 30: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3>(E, u, g, w, s);
   case 31: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 4>(E, u, g, w, s);
@@ -798,28 +819,50 @@ template <int N> int dispatch_ax(int variant, size_t E, const double *u, const d
   case 48: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
   case 50: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
   case 52: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 1>(E, u, g, w, s);
-  case 12:  // the one-element-on-ceil(T/32)-warps shape of the first version, for comparison
-    return launch_ax<N, 1, Layout<N>::WPE, (128 / Layout<N>::LPE > 0 ? 128 / Layout<N>::LPE : 1), 2, 4, false, 1>(E, u, g, w, s);
 #endif
+  default: return NOMPK_AX_NO_SUCH_VARIANT;
   }
 }
+#endif
 
 }  // namespace
 }  // namespace nompk
 
+#define NOMPK_AX_VARIANTS_DECL_(part, n) NOMPK_AX_VARIANTS_DECL(part, n)
+#if NOMPK_AX_PART == 0
+NOMPK_AX_VARIANTS_DECL_(1, NOMPK_AX_N);
+NOMPK_AX_VARIANTS_DECL_(2, NOMPK_AX_N);
+#define NOMPK_AX_CALL_VARIANTS__(part, n) nompk_ax_variants##part##_n##n
+#define NOMPK_AX_CALL_VARIANTS_(part, n) NOMPK_AX_CALL_VARIANTS__(part, n)
 #define NOMPK_AX_RUN_DEFINE_(n) NOMPK_AX_RUN_DECL(n)
 #define NOMPK_AX_RUN_DEFINE(n) NOMPK_AX_RUN_DEFINE_(n)
 NOMPK_AX_RUN_DEFINE(NOMPK_AX_N) {
   using namespace nompk;
   constexpr int n = NOMPK_AX_N;
+  if (!dot && variant != 0) {   // a profiling shape?  (unknown numbers run the production kernel)
+    int rc = NOMPK_AX_CALL_VARIANTS_(1, NOMPK_AX_N)(variant, E, u, g, D, w, stream);
+    if (rc == NOMPK_AX_NO_SUCH_VARIANT) rc = NOMPK_AX_CALL_VARIANTS_(2, NOMPK_AX_N)(variant, E, u, g, D, w, stream);
+    if (rc != NOMPK_AX_NO_SUCH_VARIANT) return rc;
+  }
   if (!(flags & NOMPK_AX_D_CACHED)) {
     NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
   }
   if (dot && xpay)
     return dispatch_ax_xpay_dot<n>(E, g, w, stream, *static_cast<const AxDotArgs *>(dot), *static_cast<const AxXpayArgs *>(xpay));
   if (dot) return dispatch_ax_dot<n>(variant, E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
-  return dispatch_ax<n>(variant, E, u, g, w, stream);
+  return dispatch_ax<n>(E, u, g, w, stream);
 }
+#else
+NOMPK_AX_VARIANTS_DECL_(NOMPK_AX_PART, NOMPK_AX_N) {
+  using namespace nompk;
+  constexpr int n = NOMPK_AX_N;
+  if (!((NOMPK_AX_PART == 1 && ((variant >= 1 && variant <= 17) || (variant >= 21 && variant <= 23))) ||
+        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 52)))
+    return NOMPK_AX_NO_SUCH_VARIANT;   // before D is staged for nothing
+  NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+  return dispatch_ax_variants<n>(variant, E, u, g, w, stream);
+}
+#endif
 
 #else  // NOMPK_AX_N == 0: the C ABI
 

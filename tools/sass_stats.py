@@ -59,10 +59,11 @@ def main():
     print("| n | G,W,GPC | GA | PF | minCTA | dot | persistent | two-buf | xpay | registers | stack B | instructions | DFMA | with UR operand | LDS | STS | LDG | STG | LDCU |")
     print("|---|---|---|---|---|---|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for n in (6, 8, 10, 12):
-        obj = OBJ / f"ax_n{n}.cu.o"
-        if not obj.exists():
-            continue
-        res, mix = resource_usage(obj), sass_mix(obj)
+        res, mix = {}, {}
+        for obj in (OBJ / f"ax_n{n}.cu.o", OBJ / f"ax_n{n}_p1.cu.o", OBJ / f"ax_n{n}_p2.cu.o"):   # production + profiling shapes
+            if obj.exists():
+                res.update(resource_usage(obj))
+                mix.update(sass_mix(obj))
         rows = []
         for name, r in res.items():
             a = template_args(name)
