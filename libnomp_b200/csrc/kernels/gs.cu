@@ -5,7 +5,9 @@
 //
 // Data layout in HBM (built once per numbering by the setup entry points, all on the device):
 //   groups     one per global id that needs work here: at least two local copies, or shared with another rank.
-//              Ordered by the position of their first local copy, so neighbouring threads touch neighbouring memory.
+//              The groups shared with another rank come first (their partial results travel while the rest is
+//              folded, and "shared" is a comparison with Q), each part ordered by the position of its first local
+//              copy, so neighbouring threads touch neighbouring memory.
 //   offsets    unsigned[G+1], indices unsigned[nnz]: CSR of the local copies of each group, ascending.
 //   remote     for the Q groups shared with other ranks: the group, and a CSR of (peer rank, position) pairs.  The
 //              position indexes the list S(me, peer) of ids the two ranks share, in ascending id order -- both
