@@ -96,6 +96,10 @@ namespace {
 // D[a][l] at nompk_ax_cD[a * n + l] (constant bank 3; read with LDCU into uniform registers, see ld_D); one copy per
 // compiled n.
 __constant__ double nompk_ax_cD[12 * 12];
+// Even-odd split of a centro-antisymmetric D (D[a][l] == -D[n-1-a][n-1-l], what a differentiation matrix on symmetric
+// nodes is): four (n/2)^2 tables, [2 * TRANS + odd][a * (n/2) + l] = (M(a,l) +- M(a,n-1-l)) / 2 with M = D or D^T.  See
+// eo_apply.  Written by ax_stage_eo when the caller vouches for the symmetry (NOMPK_AX_D_ANTISYMMETRIC).
+__constant__ double nompk_ax_cEO[4 * 36];
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -277,6 +281,69 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
   o1 = a1;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Even-odd contraction (kEO).  With e[l] = in[l] + in[n-1-l], o[l] = in[l] - in[n-1-l] (l < n/2) and the tables above,
+//   out[a]     = sum_l De(a,l) e[l] + Do(a,l) o[l] = P + Q         (any D)
+//   out[n-1-a] = Q - P                                             (centro-antisymmetric D)
+// n^2/2 + 2n operations per line instead of n^2: 30 % fewer FP64 instructions at n = 10, a third fewer at n = 12.  The
+// sums are taken in another order than in dot_pair / dot_rows (and D enters as its symmetrised halves), so the result
+// differs from the general path in the last bits -- the caller opts in, bit-exact data keeps the general path.
+// ---------------------------------------------------------------------------------------------------
+template <int IDX> __device__ __forceinline__ double ld_EO(int z) { return nompk_ax_cEO[IDX + z]; }
+
+template <int N, bool TRANS>
+__device__ __forceinline__ void eo_apply(const double2 (&in)[N], double2 (&out)[N], int z) {
+  constexpr int H = N / 2;
+  double2 e[H], o[H];
+#pragma unroll
+  for (int l = 0; l < H; l++) {
+    e[l].x = in[l].x + in[N - 1 - l].x, e[l].y = in[l].y + in[N - 1 - l].y;
+    o[l].x = in[l].x - in[N - 1 - l].x, o[l].y = in[l].y - in[N - 1 - l].y;
+  }
+  static_for(std::make_integer_sequence<int, H>{}, [&](auto Ac) {
+    constexpr int a = decltype(Ac)::value;
+    double2 P = make_double2(0.0, 0.0), Q = make_double2(0.0, 0.0);
+    static_for(std::make_integer_sequence<int, H>{}, [&](auto Lc) {
+      constexpr int l = decltype(Lc)::value;
+      const double de = ld_EO<(TRANS ? 72 : 0) + a * H + l>(z);
+      const double dq = ld_EO<(TRANS ? 108 : 36) + a * H + l>(z);
+      P.x = fma(de, e[l].x, P.x), P.y = fma(de, e[l].y, P.y);
+      Q.x = fma(dq, o[l].x, Q.x), Q.y = fma(dq, o[l].y, Q.y);
+    });
+    out[a].x = P.x + Q.x, out[a].y = P.y + Q.y;
+    out[N - 1 - a].x = Q.x - P.x, out[N - 1 - a].y = Q.y - P.y;
+  });
+}
+
+// The same for two i-lines held as chunks (v[c] = points 2c, 2c + 1): regrouped as pairs (row 0, row 1) per point.
+template <int N, bool TRANS>
+__device__ __forceinline__ void eo_apply_rows(const double2 (&v0)[N / 2], const double2 (&v1)[N / 2], double2 (&o0)[N / 2],
+                                              double2 (&o1)[N / 2], int z) {
+  double2 in[N], out[N];
+#pragma unroll
+  for (int c = 0; c < N / 2; c++) {
+    in[2 * c] = make_double2(v0[c].x, v1[c].x);
+    in[2 * c + 1] = make_double2(v0[c].y, v1[c].y);
+  }
+  eo_apply<N, TRANS>(in, out, z);
+#pragma unroll
+  for (int c = 0; c < N / 2; c++) {
+    o0[c] = make_double2(out[2 * c].x, out[2 * c + 1].x);
+    o1[c] = make_double2(out[2 * c].y, out[2 * c + 1].y);
+  }
+}
+
+// One thread per table entry; `eo` is the address of nompk_ax_cEO of the unit that launches it.
+__global__ void ax_stage_eo(const double *__restrict__ D, double *__restrict__ eo, int n) {
+  const int h = n / 2, idx = threadIdx.x;
+  if (idx >= 4 * h * h) return;
+  const int t = idx / (h * h), a = (idx / h) % h, l = idx % h;
+  const bool trans = t >= 2, odd = t & 1;
+  const double m1 = trans ? D[l * n + a] : D[a * n + l];
+  const double m2 = trans ? D[(n - 1 - l) * n + a] : D[a * n + (n - 1 - l)];
+  eo[t * 36 + a * h + l] = 0.5 * (odd ? m1 - m2 : m1 + m2);
+}
+
 // kGeoAhead: how many k-slabs of geometric factors are in flight in registers ahead of their use.
 // kPf: L2 prefetch policy.  0 = none; 1 = one bulk prefetch of the whole next element (measured: doubles DRAM reads,
 // the 66 MB that 2368 warps keep "reserved" do not survive in L2); >= 2 = rolling window: while slab k of the
@@ -334,7 +401,7 @@ struct AxNoXpay {};
 //   the plain kernels.  Also tried for the fused kernel and dropped: u . w formed in S8 from a copy of u in shared
 //   memory instead of the energy form in S4 (slower: 0.71 - 0.74), 32-bit element numbers (more spills).
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0, int kPin = 0>
+          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0, int kPin = 0, bool kEO = false>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
           size_t pf_stride, std::conditional_t<kXpay, AxXpayArgs, AxNoXpay> xp) {
@@ -469,10 +536,14 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     // ---- S1: ut = D_t u along the k-column, in registers ---------------------------------------------
     {
       double2 ut[N];
-      static_for(SeqN{}, [&](auto A) {
-        constexpr int a = decltype(A)::value;
-        ut[a] = dot_pair<N, false, a>(col, make_double2(0.0, 0.0), z1);
-      });
+      if constexpr (kEO) {
+        eo_apply<N, false>(col, ut, z1);
+      } else {
+        static_for(SeqN{}, [&](auto A) {
+          constexpr int a = decltype(A)::value;
+          ut[a] = dot_pair<N, false, a>(col, make_double2(0.0, 0.0), z1);
+        });
+      }
 #pragma unroll
       for (int k = 0; k < N; k++) col[k] = ut[k];
     }
@@ -484,10 +555,17 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double2 in[N];
 #pragma unroll
         for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
-        static_for(SeqN{}, [&](auto A) {
-          constexpr int j = decltype(A)::value;
-          B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
-        });
+        if constexpr (kEO) {
+          double2 us[N];
+          eo_apply<N, false>(in, us, z3);
+#pragma unroll
+          for (int j = 0; j < N; j++) B2[L::at(q, j, p)] = us[j];
+        } else {
+          static_for(SeqN{}, [&](auto A) {
+            constexpr int j = decltype(A)::value;
+            B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
+          });
+        }
       }
       element_sync<GL>(grp);  // nobody reads u from B0 any more
       // ---- S2: ur = D_r u on two i-lines, in place in B0 ---------------------------------------------------
@@ -496,13 +574,20 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
         for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
         mirror_fence<G * T < GL>();  // the mirrors of a lane have read the same two lines
-        static_for(SeqNP{}, [&](auto C) {
-          constexpr int c = decltype(C)::value;
-          double2 o0, o1;
-          dot_rows<N, false, c>(v0, v1, o0, o1, z2);
-          B0[oa + (c ^ sa)] = o0;
-          B0[ob + (c ^ sb)] = o1;
-        });
+        if constexpr (kEO) {
+          double2 r0[NP], r1[NP];
+          eo_apply_rows<N, false>(v0, v1, r0, r1, z2);
+#pragma unroll
+          for (int c = 0; c < NP; c++) B0[oa + (c ^ sa)] = r0[c], B0[ob + (c ^ sb)] = r1[c];
+        } else {
+          static_for(SeqNP{}, [&](auto C) {
+            constexpr int c = decltype(C)::value;
+            double2 o0, o1;
+            dot_rows<N, false, c>(v0, v1, o0, o1, z2);
+            B0[oa + (c ^ sa)] = o0;
+            B0[ob + (c ^ sb)] = o1;
+          });
+        }
       }
       if constexpr (kPinGeo) {
 #pragma unroll
@@ -518,23 +603,37 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double2 v0[NP], v1[NP];
   #pragma unroll
         for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
-        static_for(SeqNP{}, [&](auto C) {
-          constexpr int c = decltype(C)::value;
-          double2 o0, o1;
-          dot_rows<N, false, c>(v0, v1, o0, o1, z2);
-          B1[oa + (c ^ sa)] = o0;
-          B1[ob + (c ^ sb)] = o1;
-        });
+        if constexpr (kEO) {
+          double2 r0[NP], r1[NP];
+          eo_apply_rows<N, false>(v0, v1, r0, r1, z2);
+#pragma unroll
+          for (int c = 0; c < NP; c++) B1[oa + (c ^ sa)] = r0[c], B1[ob + (c ^ sb)] = r1[c];
+        } else {
+          static_for(SeqNP{}, [&](auto C) {
+            constexpr int c = decltype(C)::value;
+            double2 o0, o1;
+            dot_rows<N, false, c>(v0, v1, o0, o1, z2);
+            B1[oa + (c ^ sa)] = o0;
+            B1[ob + (c ^ sb)] = o1;
+          });
+        }
       }
       // ---- S3: us = D_s u on a j-line pair (p, k = q) -> B2 ---------------------------------------------
       {
         double2 in[N];
   #pragma unroll
         for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
-        static_for(SeqN{}, [&](auto A) {
-          constexpr int j = decltype(A)::value;
-          B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
-        });
+        if constexpr (kEO) {
+          double2 us[N];
+          eo_apply<N, false>(in, us, z3);
+#pragma unroll
+          for (int j = 0; j < N; j++) B2[L::at(q, j, p)] = us[j];
+        } else {
+          static_for(SeqN{}, [&](auto A) {
+            constexpr int j = decltype(A)::value;
+            B2[L::at(q, j, p)] = dot_pair<N, false, j>(in, make_double2(0.0, 0.0), z3);
+          });
+        }
       }
       element_sync<GL>(grp);
     }
@@ -583,10 +682,14 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     }
     // ---- S5: w = D_t^T wt along the k-column, in registers --------------------------------------------
     double2 wacc[N];
-    static_for(SeqN{}, [&](auto A) {
-      constexpr int a = decltype(A)::value;
-      wacc[a] = dot_pair<N, true, a>(col, make_double2(0.0, 0.0), z5);
-    });
+    if constexpr (kEO) {
+      eo_apply<N, true>(col, wacc, z5);
+    } else {
+      static_for(SeqN{}, [&](auto A) {
+        constexpr int a = decltype(A)::value;
+        wacc[a] = dot_pair<N, true, a>(col, make_double2(0.0, 0.0), z5);
+      });
+    }
     element_sync<GL>(grp);
 
     // ---- S6: D_r^T wr on two i-lines: B1 -> B0 ----------------------------------------------------------
@@ -595,13 +698,20 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
       for (int c = 0; c < NP; c++) v0[c] = B1[oa + (c ^ sa)], v1[c] = B1[ob + (c ^ sb)];
       if constexpr (kTwoBuf) mirror_fence<G * T < GL>();  // B1 is B0: in place, mirrors must have read first
-      static_for(SeqNP{}, [&](auto C) {
-        constexpr int c = decltype(C)::value;
-        double2 o0, o1;
-        dot_rows<N, true, c>(v0, v1, o0, o1, z6);
-        B0[oa + (c ^ sa)] = o0;
-        B0[ob + (c ^ sb)] = o1;
-      });
+      if constexpr (kEO) {
+        double2 r0[NP], r1[NP];
+        eo_apply_rows<N, true>(v0, v1, r0, r1, z6);
+#pragma unroll
+        for (int c = 0; c < NP; c++) B0[oa + (c ^ sa)] = r0[c], B0[ob + (c ^ sb)] = r1[c];
+      } else {
+        static_for(SeqNP{}, [&](auto C) {
+          constexpr int c = decltype(C)::value;
+          double2 o0, o1;
+          dot_rows<N, true, c>(v0, v1, o0, o1, z6);
+          B0[oa + (c ^ sa)] = o0;
+          B0[ob + (c ^ sb)] = o1;
+        });
+      }
     }
     element_sync<GL>(grp);
     if constexpr (kPf >= 2 && kLocalWindow) prefetch_next_u();
@@ -611,13 +721,26 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       double2 in[N];
 #pragma unroll
       for (int l = 0; l < N; l++) in[l] = B2[L::at(q, l, p)];
-      static_for(SeqN{}, [&](auto A) {
-        constexpr int j = decltype(A)::value;
-        const int a = L::at(q, j, p);
-        const double2 sum = dot_pair<N, true, j>(in, B0[a], z7);
+      if constexpr (kEO) {
+        double2 ws[N];
+        eo_apply<N, true>(in, ws, z7);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          const double2 r = B0[L::at(q, j, p)];
+          ws[j].x += r.x, ws[j].y += r.y;
+        }
         mirror_fence<G * T < GL>();
-        B0[a] = sum;
-      });
+#pragma unroll
+        for (int j = 0; j < N; j++) B0[L::at(q, j, p)] = ws[j];
+      } else {
+        static_for(SeqN{}, [&](auto A) {
+          constexpr int j = decltype(A)::value;
+          const int a = L::at(q, j, p);
+          const double2 sum = dot_pair<N, true, j>(in, B0[a], z7);
+          mirror_fence<G * T < GL>();
+          B0[a] = sum;
+        });
+      }
     }
     element_sync<GL>(grp);
 
@@ -660,10 +783,10 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 }
 
 template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
-          bool TWOBUF = false, int PFMODE = 0, int PIN = 0>
+          bool TWOBUF = false, int PFMODE = 0, int PIN = 0, bool EO = false>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE, PIN>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE, PIN, EO>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * L::template kElemStride<(TWOBUF ? 2 : 3)> * sizeof(double2);
   static bool configured = false;
@@ -682,10 +805,10 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
   return NOMPK_OK;
 }
 
-template <int N, int G, int W, int GPC, int GA, int PF, int MB>
+template <int N, int G, int W, int GPC, int GA, int PF, int MB, bool EO = false>
 int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream, AxDotArgs dot, AxXpayArgs xp) {
   using L = Layout<N>;
-  auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true, (N == 8 ? 0 : 3)>;
+  auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true, (N == 8 ? 0 : 3), 0, EO>;
   constexpr int kThreads = GPC * W * 32, kElems = GPC * G;
   const size_t smem = (size_t)kElems * L::template kElemStride<3> * sizeof(double2);
   static bool configured = false;
@@ -713,10 +836,19 @@ template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   
 
 #if NOMPK_AX_PART == 0
 // Ax fused with u . A u (production shapes only).
-template <int N> int dispatch_ax_dot(int variant, size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
+// Even-odd contractions where they pay (interleaved sweeps, profiles/r02_even_odd.jsonl): n = 8 and n = 10.
+template <int N> constexpr bool kUseEO = (N == 8 || N == 10);
+
+template <int N> int dispatch_ax_dot(int variant, bool eo, size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  if constexpr (kUseEO<N>) {
+    if (eo && variant == 0) {
+      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 0, 0, true>(E, u, g, w, s, dot);
+      else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1, true>(E, u, g, w, s, dot);
+    }
+  }
   // kept for profiling (tools/ax_sweep.py axdot): round 1's three-buffer shape, two CTAs with the local window, three
   // CTAs with the wrapping window
   if (variant == 63) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1>(E, u, g, w, s, dot);
@@ -733,21 +865,44 @@ template <int N> int dispatch_ax_dot(int variant, size_t E, const double *u, con
 }
 
 // p <- r + beta p fused in front (the shapes of dispatch_ax_dot).
-template <int N> int dispatch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t s, AxDotArgs dot, AxXpayArgs xp) {
+template <int N> int dispatch_ax_xpay_dot(bool eo, size_t E, const double *g, double *w, cudaStream_t s, AxDotArgs dot, AxXpayArgs xp) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  if constexpr (kUseEO<N>) {
+    if (eo) {
+      if constexpr (N == 8) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168, true>(E, g, w, s, dot, xp);
+      else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168, true>(E, g, w, s, dot, xp);
+    }
+  }
   if constexpr (N == 8 || N == 12) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168>(E, g, w, s, dot, xp);   // n = 12: no spills this way
   else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168>(E, g, w, s, dot, xp);
 }
 
 #endif
 
+// The even-odd tables of this unit from D (device memory), on `stream`.
+inline cudaError_t stage_eo(const double *D, int n, cudaStream_t stream) {
+  static double *eo = nullptr;
+  if (!eo) {
+    cudaError_t err = cudaGetSymbolAddress(reinterpret_cast<void **>(&eo), nompk_ax_cEO);
+    if (err != cudaSuccess) return err;
+  }
+  ax_stage_eo<<<1, 256, 0, stream>>>(D, eo, n);
+  return cudaGetLastError();
+}
+
 #if NOMPK_AX_PART == 0
-template <int N> int dispatch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
+template <int N> int dispatch_ax(bool eo, size_t E, const double *u, const double *g, double *w, cudaStream_t s) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
   constexpr int kThreads = GPC * W * 32;
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
+  if constexpr (kUseEO<N>) {
+    if (eo) {
+      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, true>(E, u, g, w, s);
+      else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, true>(E, u, g, w, s);
+    }
+  }
   // production choice (interleaved sweeps of round 2, profiles/r02_kernel_sweeps.jsonl)
   // n = 8: one warp per element, three buffers, 168 registers, window running on into the next element (no over-read
   // at this element time).  The others: two shared buffers per element, one CTA more per SM (128 registers) and the
@@ -819,6 +974,13 @@ template <int N> int dispatch_ax_variants(int variant, size_t E, const double *u
   case 48: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
   case 50: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 5>(E, u, g, w, s);
   case 52: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 1>(E, u, g, w, s);
+  // even-odd contractions (kEO) on the production shapes; D must be centro-antisymmetric
+  case 54:
+    if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, true>(E, u, g, w, s);
+    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, true>(E, u, g, w, s);
+    else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, true>(E, u, g, w, s);
+  case 55:   // ... with the 168-register budget (two CTAs per SM for n = 10, 12)
+    return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true, 3, 0, true>(E, u, g, w, s);
 #endif
   default: return NOMPK_AX_NO_SUCH_VARIANT;
   }
@@ -844,22 +1006,25 @@ NOMPK_AX_RUN_DEFINE(NOMPK_AX_N) {
     if (rc == NOMPK_AX_NO_SUCH_VARIANT) rc = NOMPK_AX_CALL_VARIANTS_(2, NOMPK_AX_N)(variant, E, u, g, D, w, stream);
     if (rc != NOMPK_AX_NO_SUCH_VARIANT) return rc;
   }
+  const bool eo = kUseEO<n> && (flags & NOMPK_AX_D_ANTISYMMETRIC);
   if (!(flags & NOMPK_AX_D_CACHED)) {
     NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+    if (eo) NOMPK_CUDA_TRY(stage_eo(D, n, stream));
   }
   if (dot && xpay)
-    return dispatch_ax_xpay_dot<n>(E, g, w, stream, *static_cast<const AxDotArgs *>(dot), *static_cast<const AxXpayArgs *>(xpay));
-  if (dot) return dispatch_ax_dot<n>(variant, E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
-  return dispatch_ax<n>(E, u, g, w, stream);
+    return dispatch_ax_xpay_dot<n>(eo, E, g, w, stream, *static_cast<const AxDotArgs *>(dot), *static_cast<const AxXpayArgs *>(xpay));
+  if (dot) return dispatch_ax_dot<n>(variant, eo, E, u, g, w, stream, *static_cast<const AxDotArgs *>(dot));
+  return dispatch_ax<n>(eo, E, u, g, w, stream);
 }
 #else
 NOMPK_AX_VARIANTS_DECL_(NOMPK_AX_PART, NOMPK_AX_N) {
   using namespace nompk;
   constexpr int n = NOMPK_AX_N;
   if (!((NOMPK_AX_PART == 1 && ((variant >= 1 && variant <= 17) || (variant >= 21 && variant <= 23))) ||
-        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 52)))
+        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 55)))
     return NOMPK_AX_NO_SUCH_VARIANT;   // before D is staged for nothing
   NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
+  if (variant >= 54) NOMPK_CUDA_TRY(stage_eo(D, n, stream));
   return dispatch_ax_variants<n>(variant, E, u, g, w, stream);
 }
 #endif

@@ -115,6 +115,12 @@ typedef struct {
   const void *ax_D;
   unsigned long ax_D_version;
   int ax_n;
+  /* ... and what was found out about a D: is it centro-antisymmetric (even-odd contractions, ax_D_antisymmetric) */
+  const void *ax_sym_D;
+  unsigned long ax_sym_version;
+  int ax_sym_n, ax_sym;
+  cudaStream_t stream_aux; /* created on first use */
+  unsigned long capture_version0; /* mappings with a younger version were written inside the capture in progress */
   unsigned long long nvrtc_launches;
   /* CUDA graphs of nomp_run sequences (nomp_b200_graph_*) */
   int capturing;
@@ -237,6 +243,9 @@ static int cuda_update(nomp_backend_t *bnd, nomp_mem_t *m, const nomp_map_direct
     }
     if (st->ax_D && (const char *)st->ax_D >= (const char *)m->bptr && (const char *)st->ax_D < (const char *)m->bptr + (m->bsize ? m->bsize : 1))
       st->ax_D = NULL; /* the staged derivative matrix came from this mapping */
+    if (st->ax_sym_D && (const char *)st->ax_sym_D >= (const char *)m->bptr &&
+        (const char *)st->ax_sym_D < (const char *)m->bptr + (m->bsize ? m->bsize : 1))
+      st->ax_sym_D = NULL;
     unpin_host_range(m);
     check_runtime(cudaFree(m->bptr));
     m->bptr = NULL; /* tells the core to drop the entry (reference src/nomp.c:360) */
@@ -467,6 +476,34 @@ static long int_arg(const nomp_prog_t *prg, int idx, long literal) {
 
 static void *ptr_arg(const nomp_prog_t *prg, int idx) { return idx < 0 ? NULL : prg->args[idx].ptr; }
 
+
+/* Is the n x n matrix at device address D centro-antisymmetric, D[a][l] == -D[n-1-a][n-1-l] bit for bit -- what every
+ * differentiation matrix on symmetric nodes is?  Then the Ax kernels may take their even-odd contractions
+ * (NOMPK_AX_D_ANTISYMMETRIC, include/nompk.h).  Decided from the device image itself (the host array may have changed
+ * since it was copied), once per (mapping, version): one 1 KB copy.  While a graph is captured the copy runs on a
+ * stream of its own (nomp_b200_graph_begin has drained the compute stream); a D that a captured kernel may have
+ * written -- its version is younger than the capture -- is not looked at, the general path is always right. */
+static int ax_D_antisymmetric(cuda_state_t *st, const void *D, int n, unsigned long version, int have_mem) {
+  if (getenv("NOMP_B200_NO_EVEN_ODD") || !have_mem || n > 16) return 0;
+  if (st->ax_sym_D == D && st->ax_sym_n == n && st->ax_sym_version == version) return st->ax_sym;
+  if (st->capturing && version > st->capture_version0) return 0;
+  double h[16 * 16];
+  if (!st->stream_aux && cudaStreamCreateWithFlags(&st->stream_aux, cudaStreamNonBlocking) != cudaSuccess) return 0;
+  if (!st->capturing && cudaStreamSynchronize(st->stream) != cudaSuccess) return 0;
+  if (cudaMemcpyAsync(h, D, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st->stream_aux) != cudaSuccess ||
+      cudaStreamSynchronize(st->stream_aux) != cudaSuccess)
+    return 0;
+  int sym = 1;
+  for (int a = 0; a < n && sym; a++)
+    for (int l = 0; l < n; l++)
+      if (h[a * n + l] != -h[(n - 1 - a) * n + (n - 1 - l)]) { /* (NaN fails, -0.0 == 0.0 passes: both fine) */
+        sym = 0;
+        break;
+      }
+  st->ax_sym_D = D, st->ax_sym_n = n, st->ax_sym_version = version, st->ax_sym = sym;
+  return sym;
+}
+
 static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
   cuda_state_t *st = (cuda_state_t *)bnd->bptr;
   cuda_prog_t *cp = (cuda_prog_t *)prg->bptr;
@@ -523,6 +560,7 @@ static int cuda_knl_run(nomp_backend_t *bnd, nomp_prog_t *prg) {
     unsigned flags = 0;
     /* (while a graph is being captured the copy is recorded with the launch and the cache state is left alone) */
     if (dm && !st->capturing && st->ax_D == D && st->ax_n == cp->ax_n && st->ax_D_version == version) flags = NOMPK_AX_D_CACHED;
+    if (ax_D_antisymmetric(st, D, cp->ax_n, version, dm != NULL)) flags |= NOMPK_AX_D_ANTISYMMETRIC;
     /* a rank without elements launches nothing: it joins through the stand-alone all-reduce kernel of the finish,
      * which speaks the same protocol on the same buffers */
     if (cp->family != FAM_AX && E > 0 && nomp_comm_size() > 1 && nomp_comm_peers(&peers, err_host)) {
@@ -723,6 +761,7 @@ static int cuda_finalize(nomp_backend_t *bnd) {
     cudaStreamDestroy(st->stream_h2d), cudaStreamDestroy(st->stream_d2h);
     cudaEventDestroy(st->ev_compute), cudaEventDestroy(st->ev_h2d), cudaEventDestroy(st->ev_d2h);
   }
+  if (st->stream_aux) cudaStreamDestroy(st->stream_aux);
   if (st->pinned_host) cudaFreeHost(st->pinned_host);
   if (g_state == st) g_state = NULL;
   free(st);
@@ -809,6 +848,7 @@ NOMP_EXPORT int nomp_b200_graph_begin(void) {
     check_runtime(cudaStreamSynchronize(st->stream_d2h));
     st->d2h_waited = st->d2h_issued;
   }
+  st->capture_version0 = nomp_next_version();
   check_runtime(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeRelaxed));
   st->capturing = 1;
   return 0;

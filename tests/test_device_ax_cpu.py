@@ -22,15 +22,17 @@ KERNELS = ROOT / "libnomp_b200" / "csrc" / "kernels"
 SHAPES = {6: (7, 4, 1), 8: (1, 1, 4), 10: (3, 5, 1), 12: (2, 5, 1)}
 
 
-# what the emulated kernels instantiate: (geometric slabs in flight, fused p.Ap, two shared buffers, kPfMode, kPin)
-VARIANTS = {0: (2, False, False, 0, 0),      # three buffers, wrapping prefetch window (n = 8 in production)
-            1: (2, True, False, 0, 0),       # ... with the fused p.Ap
-            2: (2, False, True, 0, 0),       # two buffers
-            3: (1, False, True, 0, 0),       # two buffers, one slab in flight
-            4: (2, False, True, 4, 0),       # local prefetch window, last-use demand loads
-            5: (2, True, True, 3, 0),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
-            6: (2, True, True, 5, 1),        # ... first slabs prefetched too, ring fill pinned in front of S4
-            7: (2, False, True, 5, 1)}       # the same without the dot product
+# what the emulated kernels instantiate: (geometric slabs in flight, fused p.Ap, two shared buffers, kPfMode, kPin, kEO)
+VARIANTS = {0: (2, False, False, 0, 0, False),      # three buffers, wrapping prefetch window (n = 8 in production)
+            1: (2, True, False, 0, 0, False),       # ... with the fused p.Ap
+            2: (2, False, True, 0, 0, False),       # two buffers
+            3: (1, False, True, 0, 0, False),       # two buffers, one slab in flight
+            4: (2, False, True, 4, 0, False),       # local prefetch window, last-use demand loads
+            5: (2, True, True, 3, 0, False),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
+            6: (2, True, True, 5, 1, False),        # ... first slabs prefetched too, ring fill pinned in front of S4
+            7: (2, False, True, 5, 1, False),       # the same without the dot product
+            8: (2, True, True, 3, 1, True),         # even-odd contractions (centro-antisymmetric D): n = 10 in production
+            9: (2, False, False, 0, 0, True)}       # ... on three buffers: n = 8 in production
 DOT_VARIANTS = [v for v, spec in VARIANTS.items() if spec[1]]
 
 
@@ -43,6 +45,8 @@ def device_source():
     a, b = text.index("#if NOMPK_AX_N != 0\n") + len("#if NOMPK_AX_N != 0\n"), text.index("template <int N, int G, int W, int GPC, int GA, int PF")
     body = text[s0:s1] + text[a:b] + "}  // namespace\n}  // namespace nompk\n"
     body, n = re.subn(r'__constant__ double nompk_ax_cD\[12 \* 12\];', "double nompk_ax_cD[12 * 12];", body)
+    assert n == 1
+    body, n = re.subn(r'__constant__ double nompk_ax_cEO\[4 \* 36\];', "double nompk_ax_cEO[4 * 36];", body)
     assert n == 1
     swaps = [(r'asm volatile\("ld\.global\.nc\.L1::no_allocate\.v2\.f64[^;]*;"[^;]*;', "r = *p;", 1),
              (r'asm volatile\("cp\.async\.bulk\.prefetch\.L2\.global[^;]*;"[^;]*;', ";", 1),
@@ -61,15 +65,19 @@ def device_source():
                 "static inline double __dmul_rn(double a, double b) { return a * b; }\n", finish, body,
                 ]
     for n_, (G, W, GPC) in SHAPES.items():
-        for dot, (ga, with_dot, twobuf, pfmode, pin) in VARIANTS.items():
+        for dot, (ga, with_dot, twobuf, pfmode, pin, eo) in VARIANTS.items():
             wrappers.append(
                 f"static void ax{n_}_{dot}(const double *u, const double *g, const double *D, double *w, unsigned long long E, void *ws,"
                 f" double *res, unsigned long long stride) {{\n"
                 f"  if (threadIdx.x == 0) for (int i = 0; i < {n_ * n_}; i++) nompk::nompk_ax_cD[i] = D[i];   // the __constant__ copy\n"
+                f"  if (threadIdx.x == 0) for (int idx = 0; idx < {n_ * n_}; idx++) {{   // what ax_stage_eo writes\n"
+                f"    const int n = {n_}, h = n / 2, t = idx / (h * h), a = (idx / h) % h, l = idx % h;\n"
+                f"    const double m1 = t >= 2 ? D[l * n + a] : D[a * n + l], m2 = t >= 2 ? D[(n - 1 - l) * n + a] : D[a * n + (n - 1 - l)];\n"
+                f"    nompk::nompk_ax_cEO[t * 36 + a * h + l] = 0.5 * ((t & 1) ? m1 - m2 : m1 + m2);\n  }}\n"
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
                 f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {ga}, 4, false, 1, {'true' if with_dot else 'false'}, true,"
-                f" {'true' if twobuf else 'false'}, false, {pfmode}, {pin}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+                f" {'true' if twobuf else 'false'}, false, {pfmode}, {pin}, {'true' if eo else 'false'}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
         # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
         wrappers.append(
             f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"
@@ -108,6 +116,8 @@ def test_ax_kernel_on_the_host(n, dot):
         u = ffi.fill_int_f64(E * n ** 3, 5 + n, -4, 4)
         g = ffi.fill_int_f64(E * 6 * n ** 3, 6 + n, 0, 3)
         D = ffi.fill_int_f64(n * n, 7 + n, -2, 2)
+        if VARIANTS[dot][5]:      # even-odd: D[a][l] == -D[n-1-a][n-1-l]; its halves are multiples of 1/2 -- still exact
+            D = np.ascontiguousarray((D.reshape(n, n) - D.reshape(n, n)[::-1, ::-1]).ravel())
         w, pap, ws = run_ax(n, E, u, g, D, dot, blocks)
         want = ffi.ax(n, u, g, D)
         assert np.array_equal(w, want), (n, E, blocks, int((w != want).sum()))

@@ -354,6 +354,65 @@ def test_ax_dot_variants_agree(variant, n):
     assert res.item() == float(u @ w)
 
 
+@pytest.mark.parametrize("n", [6, 8, 10, 12])
+def test_ax_even_odd_contractions(n):
+    """NOMPK_AX_D_ANTISYMMETRIC (include/nompk.h): with a centro-antisymmetric D the contractions take their even-odd form
+    (n = 8, 10; the flag is ignored for n = 6, 12).  Exact data (integer D - flip(D): its halves are multiples of 1/2) ->
+    w and u . (A u) bitwise the oracle's, from the plain, the fused-dot and the xpay-fused kernel; random data with the GLL
+    matrix -> 1e-12 against the extended-precision oracle, and the three kernels agree with each other bit for bit."""
+    lib = capi.nompk()
+    EO = 2
+    ws = torch.zeros(lib.nompk_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def three(u, g, D, E):
+        tu, tg, tD = dev(u), dev(g), dev(D)
+        out = []
+        tw = torch.full_like(tu, float("nan"))
+        capi.nompk_check(lib.nompk_ax_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), EO, stream()))
+        out.append((host(tw, np.float64), None))
+        tw = torch.full_like(tu, float("nan"))
+        capi.nompk_check(lib.nompk_ax_dot_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), res.data_ptr(),
+                                              None, 0, ws.data_ptr(), EO, stream()))
+        torch.cuda.synchronize()
+        out.append((host(tw, np.float64), res.item()))
+        # p <- r + 0 * p = u, then the operator
+        tp, tr = torch.zeros_like(tu), tu.clone()
+        tw = torch.full_like(tu, float("nan"))
+        capi.nompk_check(lib.nompk_ax_xpay_dot_peers_f64(n, E, tp.data_ptr(), tr.data_ptr(), C.c_double(0.0), None, tg.data_ptr(),
+                                                         tD.data_ptr(), tw.data_ptr(), res.data_ptr(), None, 0, ws.data_ptr(), None,
+                                                         EO, stream()))
+        torch.cuda.synchronize()
+        out.append((host(tw, np.float64), res.item()))
+        return out
+
+    for E in (1, 333, 1400):
+        u = ffi.fill_int_f64(E * n ** 3, 41, -4, 4)
+        g = ffi.fill_int_f64(E * 6 * n ** 3, 42, 0, 3)
+        R = ffi.fill_int_f64(n * n, 43, -2, 2).reshape(n, n)
+        D = np.ascontiguousarray((R - R[::-1, ::-1]).ravel())
+        want = ffi.ax(n, u, g, D)
+        for w, pap in three(u, g, D, E):
+            assert np.array_equal(w, want), (n, E)
+            assert pap is None or pap == float(u @ want)
+    E = 257
+    Dr = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    u = ffi.fill_uniform_f64(E * n ** 3, 1234, 0.5, 1.5)
+    g = ffi.fill_uniform_f64(E * 6 * n ** 3, 99, 0.5, 1.5)
+    ref = ffi.ax(n, u, g, Dr, "extended")
+    (w0, _), (w1, pap1), (w2, pap2) = three(u, g, Dr, E)
+    assert np.abs(w0 - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.array_equal(w0, w1) and np.array_equal(w0, w2) and pap1 == pap2
+    assert abs(pap1 - ffi.sum_compensated(u, ref)) <= 1e-12 * abs(pap1)
+    # the general path on the same data is as close to the oracle, and (n = 8, 10) not the same bits
+    tu, tg, tD = dev(u), dev(g), dev(Dr)
+    tw = torch.empty_like(tu)
+    capi.nompk_check(lib.nompk_ax_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), 0, stream()))
+    wg = host(tw, np.float64)
+    assert np.abs(wg - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.array_equal(wg, w0) == (n in (6, 12))
+
+
 def test_ax_unsupported_n_is_reported():
     lib = capi.nompk()
     t = torch.zeros(9 ** 3 * 6, dtype=torch.float64, device="cuda")

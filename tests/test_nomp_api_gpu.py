@@ -637,6 +637,46 @@ def test_ax_closed_form_on_a_sheared_element(n):
     assert abs(pap.value - float(u @ want)) <= 1e-10 * abs(float(u @ want))
 
 
+@pytest.mark.parametrize("n", [8, 10])
+def test_ax_takes_the_even_odd_path_for_an_antisymmetric_D(n):
+    """The backend reads D from the device once per version: a centro-antisymmetric D (every GLL matrix) runs the even-odd
+    kernels -- the bits of nompk_ax_f64(..., NOMPK_AX_D_ANTISYMMETRIC) --, any other D the general ones; the decision
+    follows nomp_update(D, TO)."""
+    import torch
+    from nomp_bridge.families import AX_KERNEL_SOURCE
+    lib = capi.nompk()
+    E = 61
+    u = ffi.fill_uniform_f64(E * n ** 3, 7, 0.5, 1.5)
+    g = ffi.fill_uniform_f64(E * 6 * n ** 3, 8, 0.5, 1.5)
+    Dgll = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+    Dany = Dgll.copy()
+    Dany[1] += 0.25
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def direct(D, flags):
+        tu, tg, tD = (torch.from_numpy(a).cuda() for a in (u, g, D))
+        tw = torch.empty_like(tu)
+        capi.nompk_check(lib.nompk_ax_f64(n, E, tu.data_ptr(), tg.data_ptr(), tD.data_ptr(), tw.data_ptr(), flags, st))
+        torch.cuda.synchronize()
+        return tw.cpu().numpy()
+
+    eo, general, other = direct(Dgll, 2), direct(Dgll, 0), direct(Dany, 0)
+    assert not np.array_equal(eo, general)
+    D = Dgll.copy()
+    w = np.zeros_like(u)
+    kid = jit(AX_KERNEL_SOURCE, capi.clauses(), [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I),
+                                                 ("n", 4, I | JIT, C.c_int(n))])
+    with Mapped(u, g, D, w, out=(w,)):
+        for want, Dnew in ((eo, None), (other, Dany), (eo, Dgll)):
+            if Dnew is not None:
+                D[:] = Dnew
+                capi.check(capi.update(D.ctypes.data, 0, D.size, 8, capi.NOMP_TO))
+            for _ in range(2):            # the second run uses the cached decision and the staged tables
+                capi.check(capi.run(kid, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E)))
+            capi.check(capi.update(w.ctypes.data, 0, w.size, 8, capi.NOMP_FROM))
+            assert np.array_equal(w, want)
+
+
 def test_fused_cg_kernels():
     """Row (f): Ax fused with p.Ap through the canonical Ax+dot kernel string, and the fused CG update
     x += a p; r -= a w; rr = r.r through the reduce skeleton (elementwise writes in front of the accumulation)."""

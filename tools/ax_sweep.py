@@ -122,17 +122,26 @@ def main():
             D = torch.rand(n * n, dtype=torch.float64, device="cuda")
             w = torch.empty_like(u)
 
+            FL = [0]     # 2 = NOMPK_AX_D_ANTISYMMETRIC (timing only: the random D is not antisymmetric)
+
             def ax():
-                capi.nompk_check(lib.nompk_ax_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(), 0, st))
+                capi.nompk_check(lib.nompk_ax_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(), FL[0], st))
 
             def axdot():
                 capi.nompk_check(lib.nompk_ax_dot_f64(n, E, u.data_ptr(), g.data_ptr(), D.data_ptr(), w.data_ptr(),
-                                                      res.data_ptr(), None, 0, ws.data_ptr(), 0, st))
+                                                      res.data_ptr(), None, 0, ws.data_ptr(), FL[0], st))
 
             def axxpay():
                 capi.nompk_check(lib.nompk_ax_xpay_dot_peers_f64(n, E, u.data_ptr(), r.data_ptr(), C.c_double(1e-9), None,
                                                                  g.data_ptr(), D.data_ptr(), w.data_ptr(), res.data_ptr(),
-                                                                 None, 0, ws.data_ptr(), None, 0, st))
+                                                                 None, 0, ws.data_ptr(), None, FL[0], st))
+
+            def with_flags(fn, fl):
+                def go():
+                    FL[0] = fl
+                    fn()
+                    FL[0] = 0
+                return go
             def variant_of(fn, v):
                 def go():
                     lib.nompk_ax_set_variant(v)
@@ -140,7 +149,9 @@ def main():
                 return go
             dot_variants = [int(v) for v in os.environ.get("AX_DOT_VARIANTS", "60,61,63,64,67").split(",") if v]
             kinds = [("ax", variant_of(ax, 0), 64), ("ax_dot", variant_of(axdot, 0), 64)] + \
-                    [(f"ax_dot_v{v}", variant_of(axdot, v), 64) for v in dot_variants] + [("ax_xpay_dot", variant_of(axxpay, 0), 80)]
+                    [(f"ax_dot_v{v}", variant_of(axdot, v), 64) for v in dot_variants] + [("ax_xpay_dot", variant_of(axxpay, 0), 80)] + \
+                    [("ax_eo", with_flags(variant_of(ax, 0), 2), 64), ("ax_dot_eo", with_flags(variant_of(axdot, 0), 2), 64),
+                     ("ax_xpay_dot_eo", with_flags(variant_of(axxpay, 0), 2), 80)]
             samples = {k: [] for k, _, _ in kinds}
             for _ in range(rounds):
                 for k, fn, _ in kinds:
