@@ -846,11 +846,24 @@ template <int N> int dispatch_ax_dot(int variant, bool eo, size_t E, const doubl
   if constexpr (kUseEO<N>) {
     if (eo && variant == 0) {
       if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 0, 0, true>(E, u, g, w, s, dot);
-      else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1, true>(E, u, g, w, s, dot);
+      // n = 10: with the even-odd stages the shape of the xpay-fused kernel (three buffers, three slabs in flight, 168
+      // registers, two CTAs) beats the three-CTA shape for the fused dot product: 0.87 against 0.78 of the peak
+      else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
     }
   }
   // kept for profiling (tools/ax_sweep.py axdot): round 1's three-buffer shape, two CTAs with the local window, three
   // CTAs with the wrapping window
+  // the shapes of the xpay-fused kernel (three buffers, 168 registers, local window) for the dot product alone
+  if (variant == 70 || variant == 71) {
+    if constexpr (kUseEO<N>) {
+      if (eo) {
+        if (variant == 70) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
+        return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
+      }
+    }
+    if (variant == 70) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3>(E, u, g, w, s, dot);
+    return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 3>(E, u, g, w, s, dot);
+  }
   if (variant == 63) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 1>(E, u, g, w, s, dot);
   if (variant == 64) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 3, 0>(E, u, g, w, s, dot);
   if (variant == 67) return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), true, true, true, 5, 1>(E, u, g, w, s, dot);
@@ -981,6 +994,8 @@ template <int N> int dispatch_ax_variants(int variant, size_t E, const double *u
     else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, true>(E, u, g, w, s);
   case 55:   // ... with the 168-register budget (two CTAs per SM for n = 10, 12)
     return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true, 3, 0, true>(E, u, g, w, s);
+  case 56: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 3, 0, true>(E, u, g, w, s);   // ... three buffers
+  case 57: return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, true, false, 3, 0, true>(E, u, g, w, s);   // ... three slabs in flight
 #endif
   default: return NOMPK_AX_NO_SUCH_VARIANT;
   }
@@ -1021,7 +1036,7 @@ NOMPK_AX_VARIANTS_DECL_(NOMPK_AX_PART, NOMPK_AX_N) {
   using namespace nompk;
   constexpr int n = NOMPK_AX_N;
   if (!((NOMPK_AX_PART == 1 && ((variant >= 1 && variant <= 17) || (variant >= 21 && variant <= 23))) ||
-        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 55)))
+        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 57)))
     return NOMPK_AX_NO_SUCH_VARIANT;   // before D is staged for nothing
   NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
   if (variant >= 54) NOMPK_CUDA_TRY(stage_eo(D, n, stream));

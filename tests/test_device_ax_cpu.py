@@ -31,8 +31,9 @@ VARIANTS = {0: (2, False, False, 0, 0, False),      # three buffers, wrapping pr
             5: (2, True, True, 3, 0, False),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
             6: (2, True, True, 5, 1, False),        # ... first slabs prefetched too, ring fill pinned in front of S4
             7: (2, False, True, 5, 1, False),       # the same without the dot product
-            8: (2, True, True, 3, 1, True),         # even-odd contractions (centro-antisymmetric D): n = 10 in production
-            9: (2, False, False, 0, 0, True)}       # ... on three buffers: n = 8 in production
+            8: (2, True, True, 3, 1, True),         # even-odd contractions (centro-antisymmetric D)
+            9: (2, False, False, 0, 0, True),       # ... on three buffers: n = 8 in production
+            10: (3, True, False, 3, 0, True)}       # fused p.Ap, three buffers, three slabs in flight, local window: n = 10
 DOT_VARIANTS = [v for v, spec in VARIANTS.items() if spec[1]]
 
 

@@ -329,7 +329,7 @@ def test_ax_fused_with_dot_product(n):
     assert abs(res.item() - ref) <= 1e-12 * abs(ref)
 
 
-@pytest.mark.parametrize("variant", [0, 60, 61, 62, 63, 64, 67])
+@pytest.mark.parametrize("variant", [0, 60, 61, 62, 63, 64, 67, 70, 71])
 @pytest.mark.parametrize("n", [6, 8, 10, 12])
 def test_ax_dot_variants_agree(variant, n):
     """The shapes of the fused Ax + p.Ap kept for profiling (ax.cu: dispatch_ax_dot): same w, same u . (A u), bit for bit."""

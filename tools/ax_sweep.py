@@ -151,7 +151,8 @@ def main():
             kinds = [("ax", variant_of(ax, 0), 64), ("ax_dot", variant_of(axdot, 0), 64)] + \
                     [(f"ax_dot_v{v}", variant_of(axdot, v), 64) for v in dot_variants] + [("ax_xpay_dot", variant_of(axxpay, 0), 80)] + \
                     [("ax_eo", with_flags(variant_of(ax, 0), 2), 64), ("ax_dot_eo", with_flags(variant_of(axdot, 0), 2), 64),
-                     ("ax_xpay_dot_eo", with_flags(variant_of(axxpay, 0), 2), 80)]
+                     ("ax_xpay_dot_eo", with_flags(variant_of(axxpay, 0), 2), 80)] + \
+                    [(f"ax_dot_v{v}_eo", with_flags(variant_of(axdot, v), 2), 64) for v in dot_variants]
             samples = {k: [] for k, _, _ in kinds}
             for _ in range(rounds):
                 for k, fn, _ in kinds:
