@@ -24,7 +24,10 @@ CAPTURES = [
     ("ax12", "ax 12 65536 0 5", "Ax N=11", 65536 * 1728 * 64),
     ("ax6", "ax 6 524288 0 5", "Ax N=5", 524288 * 216 * 64),
     ("axdot8", "axdot 8 262144 0 5", "Ax N=7 fused with p.Ap", 262144 * 512 * 64),
-    ("axdot10", "axdot 10 262144 0 5", "Ax N=9 fused with p.Ap (ring fill pinned in front of S4)", 262144 * 1000 * 64),
+    ("axdot10", "axdot 10 262144 0 5", "Ax N=9 fused with p.Ap (general contractions: ring fill pinned in front of S4)", 262144 * 1000 * 64),
+    ("ax8eo", "axeo 8 262144 0 5", "Ax N=7, even-odd contractions (what a GLL matrix runs: the headline kernel)", 262144 * 512 * 64),
+    ("ax10eo", "axeo 10 262144 0 5", "Ax N=9, even-odd contractions", 262144 * 1000 * 64),
+    ("axdot10eo", "axdoteo 10 262144 0 5", "Ax N=9 fused with p.Ap, even-odd contractions", 262144 * 1000 * 64),
     ("dot", "reduce 1 268435456 0 5", "fp64 dot product, n = 2^28", 2 ** 28 * 16),
     ("add", "map 0 268435456 0 5", "fp64 a += b, n = 2^28", 2 ** 28 * 24),
     ("gs", "(tools/gs_bench.py 8 64 64 64 3 --no-warmup)", "gather-scatter, 64^3 elements, N=7: 1.34e8 points", 76705272 * 20 + 33006394 * 4),
@@ -161,7 +164,8 @@ for name in ("racecheck.txt", "cg_scalars.jsonl", "launch_overhead.jsonl", "ax_i
         shutil.copy(src / name, prof / target)
 
 ax = {}
-for name, key in (("ax8", "n8_E262144"), ("ax10", "n10_E262144"), ("ax12", "n12_E65536"), ("ax6", "n6_E524288"), ("axdot8", "dot_n8_E262144"), ("axdot10", "dot_n10_E262144")):
+for name, key in (("ax8", "n8_E262144"), ("ax10", "n10_E262144"), ("ax12", "n12_E65536"), ("ax6", "n6_E524288"), ("axdot8", "dot_n8_E262144"), ("axdot10", "dot_n10_E262144"),
+                  ("ax8eo", "eo_n8_E262144"), ("ax10eo", "eo_n10_E262144"), ("axdot10eo", "eo_dot_n10_E262144")):
     if name in traffic:
         t = traffic[name]
         ax[key] = dict(read_bytes=t["read_bytes"], write_bytes=t["write_bytes"], algorithmic_bytes=t["algorithmic_bytes"], capture=name)

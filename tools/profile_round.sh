@@ -22,6 +22,9 @@ $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/ax12" python tools/run_kernel_once.py
 $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/ax6" python tools/run_kernel_once.py ax 6 524288 0 5 > /dev/null 2>&1
 $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/axdot8" python tools/run_kernel_once.py axdot 8 262144 0 5 > /dev/null 2>&1
 $NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/axdot10" python tools/run_kernel_once.py axdot 10 262144 0 5 > /dev/null 2>&1
+$NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/ax8eo" python tools/run_kernel_once.py axeo 8 262144 0 5 > /dev/null 2>&1
+$NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/ax10eo" python tools/run_kernel_once.py axeo 10 262144 0 5 > /dev/null 2>&1
+$NCU -k regex:ax_kernel -s 3 -c 1 -o "$OUT/axdot10eo" python tools/run_kernel_once.py axdoteo 10 262144 0 5 > /dev/null 2>&1
 $NCU -k regex:reduce_kernel -s 3 -c 1 -o "$OUT/dot" python tools/run_kernel_once.py reduce 1 268435456 0 5 > /dev/null 2>&1
 $NCU -k regex:map_vec -s 3 -c 1 -o "$OUT/add" python tools/run_kernel_once.py map 0 268435456 0 5 > /dev/null 2>&1
 $NCU -k regex:gs_local -s 2 -c 1 -o "$OUT/gs" python tools/gs_bench.py 8 64 64 64 3 --no-warmup > /dev/null 2>&1
@@ -42,7 +45,7 @@ done
 for r in "$OUT"/*.ncu-rep; do ncu -i "$r" --page raw --csv > "${r%.ncu-rep}.raw.csv" 2> /dev/null; done
 for r in ax10 ax12; do ncu -i "$OUT/$r.ncu-rep" --page source --csv 2> /dev/null | gzip > "$OUT/$r.source.csv.gz"; done
 # DRAM bytes of every Ax variant kept for profiling (the prefetch-window study of round 2)
-V=0,7,22,23,30,31,32,33,34,35,36,37,38,39,40,41,42,43,48,50,52
+V=0,7,22,23,30,31,32,33,34,35,36,37,38,39,40,41,42,43,48,50,52,54,56
 for shape in "10 32768" "12 16384" "6 131072" "8 65536"; do
   set -- $shape
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:ax_kernel \
