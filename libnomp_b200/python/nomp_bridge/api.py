@@ -86,11 +86,14 @@ def get_knl_name(knl: Kernel) -> str:
     return knl.name
 
 
-def _header(func=None, **kv) -> str:
+def _header(func=None, _ro=(), **kv) -> str:
+    """`ro`: the arrays the backend may treat as read-only (their mappings keep their version: cached staging of D, no
+    ordering against copies in flight) -- the ones declared const, and for the native operators also the ones the
+    operator only reads by definition (`_ro`), whatever the spelling declares."""
     if func is not None:
-        ro = ",".join(p.name for p in func.params if p.is_array and p.ctype.const)
-        if ro:
-            kv["ro"] = ro
+        names = [p.name for p in func.params if p.is_array and (p.ctype.const or p.name in _ro)]
+        if names:
+            kv["ro"] = ",".join(names)
     return "//!nomp " + " ".join(f"{k}={v}" for k, v in kv.items() if v is not None) + "\n"
 
 
@@ -108,7 +111,8 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         if n_val is None or int(n_val) not in _SUPPORTED_AX_N:
             raise KernelError(f"the fused Ax + dot kernel needs n as a NOMP_JIT argument, one of {_SUPPORTED_AX_N}")
         extra = {"r": roles["res"], "beta": roles["beta"], "beta_dev": roles["beta_dev"]} if roles["family"] == "axxpaydot" else {}
-        plan = (_header(original, kind="native", family=roles["family"], n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
+        ro = (roles["res"], roles["g"], roles["D"]) if roles["family"] == "axxpaydot" else (roles["u"], roles["g"], roles["D"])
+        plan = (_header(original, _ro=ro, kind="native", family=roles["family"], n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
                         D=roles["D"], w=roles["w"], out=roles["pap"], **extra), one, one)
         knl._plan = plan
         return plan
@@ -117,8 +121,8 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         found = fam.match_ax_structural(original, knl.fixed, _SUPPORTED_AX_N, knl.reduction[0])
         if found is not None:
             n_val, roles = found
-            plan = (_header(original, kind="native", family="axdot", n=n_val, E=roles["E"], u=roles["u"], g=roles["g"],
-                            D=roles["D"], w=roles["w"], out=roles["pap"]), one, one)
+            plan = (_header(original, _ro=(roles["u"], roles["g"], roles["D"]), kind="native", family="axdot", n=n_val, E=roles["E"],
+                            u=roles["u"], g=roles["g"], D=roles["D"], w=roles["w"], out=roles["pap"]), one, one)
             knl._plan = plan
             return plan
         # not the operator: the ordinary reduce clause decides (and reports what it cannot do)
@@ -147,8 +151,8 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         n_name = roles["n"]
         n_val = knl.fixed.get(n_name)
         if n_val is not None and int(n_val) in _SUPPORTED_AX_N:
-            plan = (_header(original, kind="native", family="ax", n=int(n_val), E=roles["E"], u=roles["u"], g=roles["g"],
-                            D=roles["D"], w=roles["w"]), one, one)
+            plan = (_header(original, _ro=(roles["u"], roles["g"], roles["D"]), kind="native", family="ax", n=int(n_val), E=roles["E"],
+                            u=roles["u"], g=roles["g"], D=roles["D"], w=roles["w"]), one, one)
             knl._plan = plan
             return plan
         if n_val is not None and all(t is None for t in knl.tags().values()):
@@ -168,8 +172,8 @@ def _plan(knl: Kernel, context: Dict) -> Tuple[str, List[str], List[str]]:
         found = fam.match_ax_structural(original, knl.fixed, _SUPPORTED_AX_N, None)
         if found is not None:    # any other spelling of the operator (axprobe.py)
             n_val, sroles = found
-            plan = (_header(original, kind="native", family="ax", n=n_val, E=sroles["E"], u=sroles["u"], g=sroles["g"],
-                            D=sroles["D"], w=sroles["w"]), one, one)
+            plan = (_header(original, _ro=(sroles["u"], sroles["g"], sroles["D"]), kind="native", family="ax", n=n_val, E=sroles["E"],
+                            u=sroles["u"], g=sroles["g"], D=sroles["D"], w=sroles["w"]), one, one)
             knl._plan = plan
             return plan
 

@@ -289,6 +289,10 @@ def test_every_spelling_of_ax_reaches_the_native_kernel(n):
         want_header = (f"//!nomp kind=native family={'axdot' if fused else 'ax'} n={n} E={roles[4]} u={roles[1]} g={roles[2]} "
                        f"D={roles[3]} w={roles[0]}" + (f" out={roles[6]}" if fused else ""))
         assert header.startswith(want_header), (name, header)
+        # what the operator only reads is read-only for the backend whether or not the spelling says const: the mapping
+        # of D keeps its version, so D is staged (and looked at for its symmetry) once, not at every launch
+        ro = header.split(" ro=")[1].split()[0].split(",")
+        assert {roles[1], roles[2], roles[3]} <= set(ro) and roles[0] not in ro, (name, header)
     for name, src in V.not_ax():
         header = nb.get_knl_src(nb.fix_parameters(nb.c_to_loopy(src), {"n": n}), CTX).splitlines()[0]
         assert "kind=nvrtc" in header and "family=ax" not in header, (name, header)
