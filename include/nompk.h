@@ -154,7 +154,8 @@ int nompk_allreduce_scalar_peers(nompk_red_op_t op, nompk_dtype_t dt, void *valu
  * that the previous call with the same n used identical D values (and the same flags).
  * NOMPK_AX_D_ANTISYMMETRIC: the caller vouches that D[a][l] == -D[n-1-a][n-1-l] bit for bit (a differentiation matrix on
  * symmetric nodes: every Gauss-Lobatto-Legendre D is).  The six contractions then take their even-odd form, n^2/2 + 2n
- * instead of n^2 operations per line (used for n = 8 and 10, where it is 5 % faster; ignored for n = 6 and 12).  Sums
+ * instead of n^2 operations per line (n = 8 and 10: all six stages, 5 - 10 % faster; n = 12: four of them, 6 %; ignored for
+ * n = 6).  Sums
  * are taken in another order: the result differs from the general path in the last bits (1e-16 relative), identically
  * in nompk_ax_f64, nompk_ax_dot*_f64 and nompk_ax_xpay_dot_peers_f64.  libnomp's backend decides it by reading D. */
 #define NOMPK_AX_D_CACHED 1

@@ -282,7 +282,7 @@ __device__ __forceinline__ void dot_rows(const double2 (&v0)[N / 2], const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Even-odd contraction (kEO).  With e[l] = in[l] + in[n-1-l], o[l] = in[l] - in[n-1-l] (l < n/2) and the tables above,
+// Even-odd contraction (kEO: a mask of the stages that use it, see kEOAll).  With e[l] = in[l] + in[n-1-l], o[l] = in[l] - in[n-1-l] (l < n/2) and the tables above,
 //   out[a]     = sum_l De(a,l) e[l] + Do(a,l) o[l] = P + Q         (any D)
 //   out[n-1-a] = Q - P                                             (centro-antisymmetric D)
 // n^2/2 + 2n operations per line instead of n^2: 30 % fewer FP64 instructions at n = 10, a third fewer at n = 12.  The
@@ -401,7 +401,7 @@ struct AxNoXpay {};
 //   the plain kernels.  Also tried for the fused kernel and dropped: u . w formed in S8 from a copy of u in shared
 //   memory instead of the energy form in S4 (slower: 0.71 - 0.74), 32-bit element numbers (more spills).
 template <int N, int G, int W, int GPC, int kGeoAhead, int kPf, bool kStreamLoads, int kMinBlocks, bool kDot,
-          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0, int kPin = 0, bool kEO = false>
+          bool kPersistent, bool kTwoBuf = false, bool kXpay = false, int kPfMode = 0, int kPin = 0, int kEO = 0>
 __global__ void __launch_bounds__(GPC * W * 32, kMinBlocks)
 ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, size_t E, AxDotArgs dot,
           size_t pf_stride, std::conditional_t<kXpay, AxXpayArgs, AxNoXpay> xp) {
@@ -536,7 +536,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     // ---- S1: ut = D_t u along the k-column, in registers ---------------------------------------------
     {
       double2 ut[N];
-      if constexpr (kEO) {
+      if constexpr ((kEO & 1) != 0) {
         eo_apply<N, false>(col, ut, z1);
       } else {
         static_for(SeqN{}, [&](auto A) {
@@ -555,7 +555,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double2 in[N];
 #pragma unroll
         for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
-        if constexpr (kEO) {
+        if constexpr ((kEO & 2) != 0) {
           double2 us[N];
           eo_apply<N, false>(in, us, z3);
 #pragma unroll
@@ -574,7 +574,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
         for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
         mirror_fence<G * T < GL>();  // the mirrors of a lane have read the same two lines
-        if constexpr (kEO) {
+        if constexpr ((kEO & 4) != 0) {
           double2 r0[NP], r1[NP];
           eo_apply_rows<N, false>(v0, v1, r0, r1, z2);
 #pragma unroll
@@ -603,7 +603,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double2 v0[NP], v1[NP];
   #pragma unroll
         for (int c = 0; c < NP; c++) v0[c] = B0[oa + (c ^ sa)], v1[c] = B0[ob + (c ^ sb)];
-        if constexpr (kEO) {
+        if constexpr ((kEO & 4) != 0) {
           double2 r0[NP], r1[NP];
           eo_apply_rows<N, false>(v0, v1, r0, r1, z2);
 #pragma unroll
@@ -623,7 +623,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
         double2 in[N];
   #pragma unroll
         for (int l = 0; l < N; l++) in[l] = B0[L::at(q, l, p)];
-        if constexpr (kEO) {
+        if constexpr ((kEO & 2) != 0) {
           double2 us[N];
           eo_apply<N, false>(in, us, z3);
 #pragma unroll
@@ -682,7 +682,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
     }
     // ---- S5: w = D_t^T wt along the k-column, in registers --------------------------------------------
     double2 wacc[N];
-    if constexpr (kEO) {
+    if constexpr ((kEO & 8) != 0) {
       eo_apply<N, true>(col, wacc, z5);
     } else {
       static_for(SeqN{}, [&](auto A) {
@@ -698,7 +698,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 #pragma unroll
       for (int c = 0; c < NP; c++) v0[c] = B1[oa + (c ^ sa)], v1[c] = B1[ob + (c ^ sb)];
       if constexpr (kTwoBuf) mirror_fence<G * T < GL>();  // B1 is B0: in place, mirrors must have read first
-      if constexpr (kEO) {
+      if constexpr ((kEO & 16) != 0) {
         double2 r0[NP], r1[NP];
         eo_apply_rows<N, true>(v0, v1, r0, r1, z6);
 #pragma unroll
@@ -721,7 +721,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
       double2 in[N];
 #pragma unroll
       for (int l = 0; l < N; l++) in[l] = B2[L::at(q, l, p)];
-      if constexpr (kEO) {
+      if constexpr ((kEO & 32) != 0) {
         double2 ws[N];
         eo_apply<N, true>(in, ws, z7);
 #pragma unroll
@@ -783,7 +783,7 @@ ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__
 }
 
 template <int N, int G, int W, int GPC, int GA, int PF, bool ST, int MB, bool DOT = false, bool PERSISTENT = true,
-          bool TWOBUF = false, int PFMODE = 0, int PIN = 0, bool EO = false>
+          bool TWOBUF = false, int PFMODE = 0, int PIN = 0, int EO = 0>
 int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_t stream, AxDotArgs dot = AxDotArgs()) {
   using L = Layout<N>;
   auto kern = ax_kernel<N, G, W, GPC, GA, PF, ST, MB, DOT, PERSISTENT, TWOBUF, false, PFMODE, PIN, EO>;
@@ -805,7 +805,7 @@ int launch_ax(size_t E, const double *u, const double *g, double *w, cudaStream_
   return NOMPK_OK;
 }
 
-template <int N, int G, int W, int GPC, int GA, int PF, int MB, bool EO = false>
+template <int N, int G, int W, int GPC, int GA, int PF, int MB, int EO = 0>
 int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream, AxDotArgs dot, AxXpayArgs xp) {
   using L = Layout<N>;
   auto kern = ax_kernel<N, G, W, GPC, GA, PF, false, MB, true, true, false, true, (N == 8 ? 0 : 3), 0, EO>;
@@ -827,6 +827,9 @@ int launch_ax_xpay_dot(size_t E, const double *g, double *w, cudaStream_t stream
   return NOMPK_OK;
 }
 
+// kEO is a mask of the stages that take the even-odd form: 1 S1, 2 S3, 4 S2, 8 S5, 16 S6, 32 S7.
+constexpr int kEOAll = 63;
+
 // Group shapes: <elements per group, warps per group, groups per CTA>.
 template <int N> struct Shape;
 template <> struct Shape<6> { static constexpr int G = 7, W = 4, GPC = 1; };    // 126 / 128 lanes
@@ -836,8 +839,12 @@ template <> struct Shape<12> { static constexpr int G = 2, W = 5, GPC = 1; };   
 
 #if NOMPK_AX_PART == 0
 // Ax fused with u . A u (production shapes only).
-// Even-odd contractions where they pay (interleaved sweeps, profiles/r02_even_odd.jsonl): n = 8 and n = 10.
-template <int N> constexpr bool kUseEO = (N == 8 || N == 10);
+// Even-odd contractions where they pay (interleaved sweeps, profiles/r02_even_odd.jsonl): n = 8 and n = 10 in every
+// stage; n = 12 in S1, S2, S5, S6 (kEO = 29: the full form spills 100 bytes more at 128 registers and gains nothing,
+// this one +6 %); n = 6 not at all.  The plain, the dot-fused and the xpay-fused kernel of an n use the same mask: same
+// arithmetic, same bits.
+template <int N> constexpr bool kUseEO = (N == 8 || N == 10 || N == 12);
+constexpr int kEO12 = 29;
 
 template <int N> int dispatch_ax_dot(int variant, bool eo, size_t E, const double *u, const double *g, double *w, cudaStream_t s, AxDotArgs dot) {
   constexpr int G = Shape<N>::G, W = Shape<N>::W, GPC = Shape<N>::GPC;
@@ -845,10 +852,11 @@ template <int N> int dispatch_ax_dot(int variant, bool eo, size_t E, const doubl
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
   if constexpr (kUseEO<N>) {
     if (eo && variant == 0) {
-      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 0, 0, true>(E, u, g, w, s, dot);
+      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 0, 0, kEOAll>(E, u, g, w, s, dot);
+      else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), true, true, true, 4, 0, kEO12>(E, u, g, w, s, dot);
       // n = 10: with the even-odd stages the shape of the xpay-fused kernel (three buffers, three slabs in flight, 168
       // registers, two CTAs) beats the three-CTA shape for the fused dot product: 0.87 against 0.78 of the peak
-      else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
+      else return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, kEOAll>(E, u, g, w, s, dot);
     }
   }
   // kept for profiling (tools/ax_sweep.py axdot): round 1's three-buffer shape, two CTAs with the local window, three
@@ -857,8 +865,8 @@ template <int N> int dispatch_ax_dot(int variant, bool eo, size_t E, const doubl
   if (variant == 70 || variant == 71) {
     if constexpr (kUseEO<N>) {
       if (eo) {
-        if (variant == 70) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
-        return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 3, 0, true>(E, u, g, w, s, dot);
+        if (variant == 70) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3, 0, kEOAll>(E, u, g, w, s, dot);
+        return launch_ax<N, G, W, GPC, 2, 4, false, MB168, true, true, false, 3, 0, kEOAll>(E, u, g, w, s, dot);
       }
     }
     if (variant == 70) return launch_ax<N, G, W, GPC, 3, 6, false, MB168, true, true, false, 3>(E, u, g, w, s, dot);
@@ -884,8 +892,9 @@ template <int N> int dispatch_ax_xpay_dot(bool eo, size_t E, const double *g, do
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
   if constexpr (kUseEO<N>) {
     if (eo) {
-      if constexpr (N == 8) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168, true>(E, g, w, s, dot, xp);
-      else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168, true>(E, g, w, s, dot, xp);
+      if constexpr (N == 8) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168, kEOAll>(E, g, w, s, dot, xp);
+      else if constexpr (N == 12) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168, kEO12>(E, g, w, s, dot, xp);
+      else return launch_ax_xpay_dot<N, G, W, GPC, 3, 6, MB168, kEOAll>(E, g, w, s, dot, xp);
     }
   }
   if constexpr (N == 8 || N == 12) return launch_ax_xpay_dot<N, G, W, GPC, 2, 4, MB168>(E, g, w, s, dot, xp);   // n = 12: no spills this way
@@ -912,8 +921,9 @@ template <int N> int dispatch_ax(bool eo, size_t E, const double *u, const doubl
   constexpr int MB168 = 65536 / (168 * kThreads) > 0 ? 65536 / (168 * kThreads) : 1;
   if constexpr (kUseEO<N>) {
     if (eo) {
-      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, true>(E, u, g, w, s);
-      else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, true>(E, u, g, w, s);
+      if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, kEOAll>(E, u, g, w, s);
+      else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, kEO12>(E, u, g, w, s);
+      else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, kEOAll>(E, u, g, w, s);
     }
   }
   // production choice (interleaved sweeps of round 2, profiles/r02_kernel_sweeps.jsonl)
@@ -989,13 +999,16 @@ template <int N> int dispatch_ax_variants(int variant, size_t E, const double *u
   case 52: return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 1>(E, u, g, w, s);
   // even-odd contractions (kEO) on the production shapes; D must be centro-antisymmetric
   case 54:
-    if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, true>(E, u, g, w, s);
-    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, true>(E, u, g, w, s);
-    else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, true>(E, u, g, w, s);
+    if constexpr (N == 8) return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 0, 0, kEOAll>(E, u, g, w, s);
+    else if constexpr (N == 12) return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, kEOAll>(E, u, g, w, s);
+    else return launch_ax<N, G, W, GPC, 2, 4, false, (MB168 + 1), false, true, true, 3, 0, kEOAll>(E, u, g, w, s);
   case 55:   // ... with the 168-register budget (two CTAs per SM for n = 10, 12)
-    return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true, 3, 0, true>(E, u, g, w, s);
-  case 56: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 3, 0, true>(E, u, g, w, s);   // ... three buffers
-  case 57: return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, true, false, 3, 0, true>(E, u, g, w, s);   // ... three slabs in flight
+    return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, true, 3, 0, kEOAll>(E, u, g, w, s);
+  case 56: return launch_ax<N, G, W, GPC, 2, 4, false, MB168, false, true, false, 3, 0, kEOAll>(E, u, g, w, s);   // ... three buffers
+  case 57: return launch_ax<N, G, W, GPC, 3, 6, false, MB168, false, true, false, 3, 0, kEOAll>(E, u, g, w, s);   // ... three slabs in flight
+  // ... in some of the stages only (n = 12: the full form spills): S1, S5, S6 / S1, S2, S5, S6, on n = 12's production shape
+  case 58: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, 25>(E, u, g, w, s);
+  case 59: return launch_ax<N, G, W, GPC, 2, 6, false, (MB168 + 1), false, true, true, 4, 0, 29>(E, u, g, w, s);
 #endif
   default: return NOMPK_AX_NO_SUCH_VARIANT;
   }
@@ -1036,7 +1049,7 @@ NOMPK_AX_VARIANTS_DECL_(NOMPK_AX_PART, NOMPK_AX_N) {
   using namespace nompk;
   constexpr int n = NOMPK_AX_N;
   if (!((NOMPK_AX_PART == 1 && ((variant >= 1 && variant <= 17) || (variant >= 21 && variant <= 23))) ||
-        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 57)))
+        (NOMPK_AX_PART == 2 && variant >= 30 && variant <= 59)))
     return NOMPK_AX_NO_SUCH_VARIANT;   // before D is staged for nothing
   NOMPK_CUDA_TRY(cudaMemcpyToSymbolAsync(nompk_ax_cD, D, sizeof(double) * n * n, 0, cudaMemcpyDeviceToDevice, stream));
   if (variant >= 54) NOMPK_CUDA_TRY(stage_eo(D, n, stream));

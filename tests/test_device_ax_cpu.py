@@ -22,18 +22,20 @@ KERNELS = ROOT / "libnomp_b200" / "csrc" / "kernels"
 SHAPES = {6: (7, 4, 1), 8: (1, 1, 4), 10: (3, 5, 1), 12: (2, 5, 1)}
 
 
-# what the emulated kernels instantiate: (geometric slabs in flight, fused p.Ap, two shared buffers, kPfMode, kPin, kEO)
-VARIANTS = {0: (2, False, False, 0, 0, False),      # three buffers, wrapping prefetch window (n = 8 in production)
-            1: (2, True, False, 0, 0, False),       # ... with the fused p.Ap
-            2: (2, False, True, 0, 0, False),       # two buffers
-            3: (1, False, True, 0, 0, False),       # two buffers, one slab in flight
-            4: (2, False, True, 4, 0, False),       # local prefetch window, last-use demand loads
-            5: (2, True, True, 3, 0, False),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
-            6: (2, True, True, 5, 1, False),        # ... first slabs prefetched too, ring fill pinned in front of S4
-            7: (2, False, True, 5, 1, False),       # the same without the dot product
-            8: (2, True, True, 3, 1, True),         # even-odd contractions (centro-antisymmetric D)
-            9: (2, False, False, 0, 0, True),       # ... on three buffers: n = 8 in production
-            10: (3, True, False, 3, 0, True)}       # fused p.Ap, three buffers, three slabs in flight, local window: n = 10
+# what the emulated kernels instantiate: (geometric slabs in flight, fused p.Ap, two shared buffers, kPfMode, kPin, kEO: mask of the even-odd stages)
+VARIANTS = {0: (2, False, False, 0, 0, 0),      # three buffers, wrapping prefetch window (n = 8 in production)
+            1: (2, True, False, 0, 0, 0),       # ... with the fused p.Ap
+            2: (2, False, True, 0, 0, 0),       # two buffers
+            3: (1, False, True, 0, 0, 0),       # two buffers, one slab in flight
+            4: (2, False, True, 4, 0, 0),       # local prefetch window, last-use demand loads
+            5: (2, True, True, 3, 0, 0),        # two buffers, fused p.Ap, local window (production: n = 6, 12)
+            6: (2, True, True, 5, 1, 0),        # ... first slabs prefetched too, ring fill pinned in front of S4
+            7: (2, False, True, 5, 1, 0),       # the same without the dot product
+            8: (2, True, True, 3, 1, 63),         # even-odd contractions (centro-antisymmetric D)
+            9: (2, False, False, 0, 0, 63),       # ... on three buffers: n = 8 in production
+            10: (3, True, False, 3, 0, 63),       # fused p.Ap, three buffers, three slabs in flight, local window: n = 10
+            11: (2, False, True, 4, 0, 25),       # even-odd in S1, S5, S6 only
+            12: (2, True, True, 4, 0, 29)}        # even-odd in S1, S2, S5, S6, fused p.Ap: n = 12 in production
 DOT_VARIANTS = [v for v, spec in VARIANTS.items() if spec[1]]
 
 
@@ -78,7 +80,7 @@ def device_source():
                 f"  __syncthreads();\n"
                 f"  nompk::AxDotArgs d; d.workspace = ws; d.result = res; d.result_host = nullptr; d.host_seq = 0;\n"
                 f"  nompk::ax_kernel<{n_}, {G}, {W}, {GPC}, {ga}, 4, false, 1, {'true' if with_dot else 'false'}, true,"
-                f" {'true' if twobuf else 'false'}, false, {pfmode}, {pin}, {'true' if eo else 'false'}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
+                f" {'true' if twobuf else 'false'}, false, {pfmode}, {pin}, {eo}>(u, g, w, E, d, stride, nompk::AxNoXpay());\n}}\n")
         # p <- r + beta p fused in front of the operator (always with the dot product); p is read and written in place
         wrappers.append(
             f"static void axx{n_}(double *p, const double *r, double beta, const double *beta_dev, const double *g, const double *D,"

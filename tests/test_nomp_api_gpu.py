@@ -637,7 +637,7 @@ def test_ax_closed_form_on_a_sheared_element(n):
     assert abs(pap.value - float(u @ want)) <= 1e-10 * abs(float(u @ want))
 
 
-@pytest.mark.parametrize("n", [8, 10])
+@pytest.mark.parametrize("n", [8, 10, 12])
 def test_ax_takes_the_even_odd_path_for_an_antisymmetric_D(n):
     """The backend reads D from the device once per version: a centro-antisymmetric D (every GLL matrix) runs the even-odd
     kernels -- the bits of nompk_ax_f64(..., NOMPK_AX_D_ANTISYMMETRIC) --, any other D the general ones; the decision
