@@ -55,9 +55,10 @@ def template_args(mangled):
 def main():
     print("# Ax kernels: static figures from the built objects (`tools/sass_stats.py`)\n")
     print("Template arguments: n, elements per group, warps per group, groups per CTA, geometric slabs in flight, L2 prefetch "
-          "distance, streaming loads, min CTAs/SM, fused dot, persistent grid, two shared buffers, fused direction update.\n")
-    print("| n | G,W,GPC | GA | PF | minCTA | dot | persistent | two-buf | xpay | registers | stack B | instructions | DFMA | with UR operand | LDS | STS | LDG | STG | LDCU |")
-    print("|---|---|---|---|---|---|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+          "distance, streaming loads, min CTAs/SM, fused dot, persistent grid, two shared buffers, fused direction update, prefetch "
+          "mode (kPfMode), pinned ring fill (kPin), even-odd stage mask (kEO: 63 = all six stages).\n")
+    print("| n | G,W,GPC | GA | PF | minCTA | dot | persistent | two-buf | xpay | pfmode | pin | EO | registers | stack B | instructions | DFMA | with UR operand | LDS | STS | LDG | STG | LDCU |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for n in (6, 8, 10, 12):
         res, mix = {}, {}
         for obj in (OBJ / f"ax_n{n}.cu.o", OBJ / f"ax_n{n}_p1.cu.o", OBJ / f"ax_n{n}_p2.cu.o"):   # production + profiling shapes
@@ -69,12 +70,12 @@ def main():
             a = template_args(name)
             if a is None or len(a) < 11:
                 continue
-            a = a + ["0"] * (12 - len(a))
+            a = a + ["0"] * (15 - len(a))
             s = mix.get(name, {})
             rows.append((a, r, s))
         rows.sort(key=lambda x: [int(v) for v in x[0]])
         for a, r, s in rows:
-            print(f"| {a[0]} | {a[1]},{a[2]},{a[3]} | {a[4]} | {a[5]} | {a[7]} | {a[8]} | {a[9]} | {a[10]} | {a[11]} | {r['reg']} | {r['stack']} | "
+            print(f"| {a[0]} | {a[1]},{a[2]},{a[3]} | {a[4]} | {a[5]} | {a[7]} | {a[8]} | {a[9]} | {a[10]} | {a[11]} | {a[12]} | {a[13]} | {a[14]} | {r['reg']} | {r['stack']} | "
                   f"{s.get('total', 0)} | {s.get('dfma', 0)} | {s.get('dfma_ur', 0)} | {s.get('lds', 0)} | {s.get('sts', 0)} | {s.get('ldg', 0)} | "
                   f"{s.get('stg', 0)} | {s.get('ldcu', 0)} |")
 
