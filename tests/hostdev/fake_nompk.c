@@ -198,9 +198,14 @@ static int run_ax(void *blob) {
   return f(c->n, c->E, c->u, c->g, c->D, c->w) ? NOMPK_EINVAL : NOMPK_OK;
 }
 
+/* the flags of the last Ax call of any kind (what the backend found out about D): tests/test_hostdev_cpu.py */
+static unsigned last_ax_flags;
+EXPORT unsigned nomp_hostdev_last_ax_flags(void) { return last_ax_flags; }
+
 EXPORT int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w, unsigned flags,
                         void *stream) {
-  (void)flags, (void)stream;
+  (void)stream;
+  last_ax_flags = flags;
   ax_call_t c = {n, E, u, g, D, w};
   calls++;
   if (nomp_hostdev_record(run_ax, &c, sizeof(c))) return NOMPK_OK;
@@ -210,7 +215,8 @@ EXPORT int nompk_ax_f64(int n, size_t E, const double *u, const double *g, const
 EXPORT int nompk_ax_dot_peers_f64(int n, size_t E, const double *u, const double *g, const double *D, double *w,
                                   double *result, double *result_host_mapped, unsigned long long host_seq,
                                   void *workspace, const nompk_peers_t *peers, unsigned flags, void *stream) {
-  (void)workspace, (void)flags, (void)stream;
+  (void)workspace, (void)stream;
+  last_ax_flags = flags;
   reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, u, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0, NULL, NULL}, NULL, NULL, 0.0};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;
@@ -222,7 +228,8 @@ EXPORT int nompk_ax_xpay_dot_peers_f64(int n, size_t E, double *p, const double 
                                        const double *g, const double *D, double *w, double *result, double *result_host_mapped,
                                        unsigned long long host_seq, void *workspace, const nompk_peers_t *peers, unsigned flags,
                                        void *stream) {
-  (void)workspace, (void)flags, (void)stream;
+  (void)workspace, (void)stream;
+  last_ax_flags = flags;
   reduce_call_t c = {NOMPK_RED_SUM, NOMPK_F64, n, E, p, NULL, g, D, w, result, result_host_mapped, host_seq, {NULL, 0, 1, 0, NULL, NULL}, r, beta_dev, beta};
   if (peers && peers->world > 1) c.peers = *peers;
   calls++;

@@ -164,6 +164,62 @@ def test_jit_cache_serves_a_second_process(double, tmp_path):
     assert sorted(p.name for p in (tmp_path / "cache").iterdir()) == entries
 
 
+SYMMETRY_SCRIPT = r"""
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, "%(root)s")
+sys.path.insert(0, "%(root)s/libnomp_b200/python")
+from libnomp_b200 import capi
+from nomp_bridge.families import AX_KERNEL_SOURCE, AX_DOT_KERNEL_SOURCE
+from oracle import ffi
+fake = C.CDLL(None)
+fake.nomp_hostdev_last_ax_flags.restype = C.c_uint
+P, I, F, JIT = capi.NOMP_PTR, capi.NOMP_INT, capi.NOMP_FLOAT, capi.NOMP_JIT
+capi.check(capi.init())
+n, E = 8, 3
+u, g = np.ones(E * n ** 3), np.ones(E * 6 * n ** 3)
+D = np.ascontiguousarray(ffi.gll_derivative(n)[0].ravel())
+w = np.zeros_like(u)
+args = [("w", 8, P), ("u", 8, P), ("g", 8, P), ("D", 8, P), ("E", 4, I), ("n", 4, I | JIT, C.c_int(n))]
+err, kid = capi.jit(AX_KERNEL_SOURCE, capi.clauses(), args)
+capi.check(err)
+err, kdot = capi.jit(AX_DOT_KERNEL_SOURCE, capi.clauses(("reduce", "pap", "+")), args + [("pap", 8, F)])
+capi.check(err)
+for a in (u, g, D, w):
+    capi.check(capi.update(a.ctypes.data, 0, a.size, 8, capi.NOMP_TO))
+seen = []
+def run(k=kid):
+    extra = (C.c_double(0.0),) if k == kdot else ()
+    capi.check(capi.run(k, w.ctypes.data, u.ctypes.data, g.ctypes.data, D.ctypes.data, C.c_int(E), *extra))
+    seen.append(fake.nomp_hostdev_last_ax_flags())
+run(); run(); run(kdot)                       # GLL matrix: antisymmetric (2), staged once (1 = cached from the second run on)
+D[1] += 0.25
+capi.check(capi.update(D.ctypes.data, 0, D.size, 8, capi.NOMP_TO))
+run(); run()                                  # any other matrix: the general kernels
+D[1] -= 0.25
+capi.check(capi.update(D.ctypes.data, 0, D.size, 8, capi.NOMP_TO))
+run(kdot)                                     # the decision follows the contents
+print("FLAGS", seen)
+capi.nomp().nomp_finalize_excluding_interpreter()
+"""
+
+
+def test_backend_finds_out_whether_D_is_antisymmetric(double, monkeypatch):
+    """backends/cuda.c: ax_D_antisymmetric reads the device image of D once per version and hands
+    NOMPK_AX_D_ANTISYMMETRIC (2) to the kernel library for a GLL matrix only; NOMPK_AX_D_CACHED (1) from the second
+    launch with the same D.  The test double records the flags of the native calls."""
+    so, env = double
+    env = dict(env, LD_PRELOAD=str(so), NOMP_HOSTDEV_ACTIVE="1")
+    r = subprocess.run([sys.executable, "-c", SYMMETRY_SCRIPT % {"root": str(ROOT)}], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("FLAGS")][-1]
+    assert line == "FLAGS [2, 3, 3, 0, 1, 2]", line
+    r = subprocess.run([sys.executable, "-c", SYMMETRY_SCRIPT % {"root": str(ROOT)}], cwd=ROOT,
+                       env=dict(env, NOMP_B200_NO_EVEN_ODD="1"), capture_output=True, text=True, timeout=600)
+    assert [ln for ln in r.stdout.splitlines() if ln.startswith("FLAGS")][-1] == "FLAGS [0, 1, 1, 0, 1, 0]", r.stdout[-500:]
+
+
 # API-level tests of the GPU tier whose sizes the emulator finishes in seconds; the rest need the real device
 # (2^25-element reductions, 256 MiB transfers, throughput floors, direct libnompk calls on torch tensors, NCCL / IPC).
 API_TESTS = ["tests/test_nomp_api_gpu.py", "tests/test_jit_cache_gpu.py", "tests/test_sem_annotations_gpu.py",
