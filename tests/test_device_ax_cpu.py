@@ -108,8 +108,13 @@ def run_ax(n, E, u, g, D, dot, blocks):
     return w, res[0], ws
 
 
-@pytest.mark.parametrize("n", [6, 8, 10, 12])
-@pytest.mark.parametrize("dot", sorted(VARIANTS))
+# every variant at n = 10 (three elements on five warps: mirrors, element strides, the row table); the other sizes run the
+# three-buffer kernels, their own production shapes and the even-odd forms they use
+CASES = [(n, v) for v in sorted(VARIANTS) for n in (6, 8, 10, 12)
+         if n == 10 or v in {6: (0, 1, 3, 5), 8: (0, 1, 2, 9), 12: (0, 1, 4, 5, 8, 11, 12)}[n]]
+
+
+@pytest.mark.parametrize("n,dot", CASES)
 def test_ax_kernel_on_the_host(n, dot):
     """Exact-integer data: bitwise the oracle's w (and u . w) for element counts that are not multiples of the group
     size, with a persistent grid in which every CTA loops (two CTAs) and with one CTA per group."""

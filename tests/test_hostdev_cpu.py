@@ -253,6 +253,9 @@ def test_api_level_gpu_tests_run_on_the_cuda_test_double(double):
 
 # ---- several ranks: one process per rank, shared memory standing in for NVLink peer memory -------------------------------
 
+_RUN_IDS = __import__("itertools").count()      # (next() on a count is atomic in CPython: the cases below run in threads)
+
+
 def run_ranks(world, args, env, so, extra=None, timeout=600):
     """`world` processes of examples/cg_poisson.c on the test double: NCCL double through LD_LIBRARY_PATH, "device" memory
     in POSIX shared memory so that CUDA IPC handles work between the processes.  Returns the JSON lines of every rank."""
@@ -261,7 +264,7 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
     if not exe.exists():
         pytest.skip("examples/cg_poisson was not built")
     work = Path(env["NOMP_HOSTDEV_DIR"])
-    idfile = work / f"id-{os.getpid()}-{len(list(work.glob('id-*')))}"
+    idfile = work / f"id-{os.getpid()}-{next(_RUN_IDS)}"
     procs = []
     for r in range(world):
         e = dict(env, LD_PRELOAD=str(so), LD_LIBRARY_PATH=str(so.parent), NOMP_HOSTDEV_SHARED="1", NOMP_HOSTDEV_DEVICES=str(world),
@@ -274,10 +277,24 @@ def run_ranks(world, args, env, so, extra=None, timeout=600):
     return [[json.loads(line) for line in o.splitlines() if line.startswith("{")] for o in outs]
 
 
-@pytest.mark.parametrize("path,scalars", [("fused", "host"), ("fused", "device"), ("fused", "device3"), ("standalone", "host"),
-                                          ("standalone", "device"), ("nccl", "host"), ("nccl", "device3"), ("fused", "fused"), ("fused", "device_fused"),
-                                          ("fused", "graph"), ("standalone", "graph")])
-def test_two_ranks_of_the_cg_example(double, path, scalars):
+TWO_RANK_CASES = [("fused", "host"), ("fused", "device"), ("fused", "device3"), ("standalone", "host"), ("standalone", "device"),
+                  ("nccl", "host"), ("nccl", "device3"), ("fused", "fused"), ("fused", "device_fused"), ("fused", "graph"),
+                  ("standalone", "graph")]
+
+
+def test_two_ranks_of_the_cg_example(double):
+    """Eleven combinations of how a reduce clause is all-reduced and where the scalars live (see _two_rank_case), four at
+    a time; every failure is reported with its case."""
+    if not (ROOT / "libnomp_b200" / "build" / "cg_poisson").exists():
+        pytest.skip("examples/cg_poisson was not built")
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        futures = {case: ex.submit(_two_rank_case, double, *case) for case in TWO_RANK_CASES}
+    failed = {case: repr(f.exception())[:2000] for case, f in futures.items() if f.exception() is not None}
+    assert not failed, failed
+    assert not list(Path("/dev/shm").glob("nomp-hostdev-*")), "a rank left shared-memory objects behind"
+
+
+def _two_rank_case(double, path, scalars):
     """src/comm.c end to end without GPUs -- file rendezvous of the NCCL id, CUDA-IPC exchange of the ranks' buffers, the
     agreement all-reduce -- and the three ways a reduce clause is all-reduced (fused into the reduction kernel,
     stand-alone kernel after it, ncclAllReduce), each with the scalars on the host and in device memory
@@ -301,7 +318,6 @@ def test_two_ranks_of_the_cg_example(double, path, scalars):
         assert abs(lines[-1]["rr_final"] - ref_final) <= 1e-9 * ref_final
     assert per_rank[0][1:] and [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[0]] == \
         [{k: v for k, v in d.items() if k not in ("seconds", "ms_per_iter", "GDOF_per_s_per_rank")} for d in per_rank[1]]
-    assert not list(Path("/dev/shm").glob("nomp-hostdev-*")), "a rank left shared-memory objects behind"
 
 
 def test_four_ranks_mixing_host_and_device_results(double):
